@@ -1,0 +1,63 @@
+"""TEST INFRASTRUCTURE ONLY — import the UNMODIFIED reference from /root/reference (build container only).
+
+The reference is flat scripts; `model.py:5` imports an uninstalled, unused package (`block`), and
+`model.py:224` loads `./soundnet8_final.pth` relative to the cwd.  Nothing is
+copied: the modules are imported in place with a stub for `block` and a temporary chdir.
+The GPU box has no /root/reference: callers must check `available()` first.
+"""
+import contextlib
+import os
+import sys
+import types
+
+REF_DIR = os.environ.get("VINET_REFERENCE_DIR", "/root/reference")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_DIR, "model.py"))
+
+
+@contextlib.contextmanager
+def _cwd(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)
+
+
+_cache = {}
+
+
+def load():
+    """Returns (ref_model_module, ref_loss_module)."""
+    if "m" in _cache:
+        return _cache["m"], _cache["l"]
+    if not available():
+        raise RuntimeError("reference sources not present at %s" % REF_DIR)
+    blk = types.ModuleType("block")
+    blk.fusions = types.ModuleType("block.fusions")
+    sys.modules.setdefault("block", blk)
+    sys.modules.setdefault("block.fusions", blk.fusions)
+    sys.path.insert(0, REF_DIR)
+    try:
+        with _cwd(REF_DIR):
+            import importlib
+            m = importlib.import_module("model")
+            l = importlib.import_module("loss")
+    finally:
+        sys.path.remove(REF_DIR)
+    _cache["m"], _cache["l"] = m, l
+    return m, l
+
+
+def build_vinet(num_clips=32):
+    m, _ = load()
+    return m.VideoSaliencyModel(num_clips=num_clips)
+
+
+def build_avinet():
+    m, _ = load()
+    with _cwd(REF_DIR):
+        return m.VideoAudioSaliencyModel()
