@@ -1,0 +1,357 @@
+/*
+ * vinet_b200.h — C-ABI of the B200-native ViNet/AViNet hot path.
+ *
+ * The reference (samyak0210/ViNet) has no FFI for this path: every device op is a torch.nn call made
+ * from model.py / model_utils.py / loss.py.  This header is the boundary a maintainer binds instead
+ * (ctypes stub in INTEGRATION.md; `vinet_b200/lib.py` is that binding).  Each entry point names the
+ * reference call site it replaces.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - activations are NDHWC ("channels last"): element (b,t,h,w,c) of a view lives at
+ *     ptr[(((b*T + t)*H + h)*W + w)*ld + c]; `ptr` already includes the view's channel offset and
+ *     `ld` is the channel count of the underlying buffer, so channel slices of a concat buffer are views;
+ *   - every function only enqueues work on `stream` (a cudaStream_t) and returns 0, or a negative
+ *     error code with a message retrievable through vinet_last_error(); nothing allocates;
+ *   - entry points are re-entrant (no global mutable state besides the thread-local error string).
+ */
+#ifndef VINET_B200_H
+#define VINET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vinet_stream_t; /* cudaStream_t */
+
+enum { VINET_BF16 = 0, VINET_F32 = 1 };
+/* transform applied to a source element when it is read ("pending" BN/ReLU of the producer layer) */
+enum { VINET_XF_IDENT = 0, VINET_XF_RELU = 1, VINET_XF_AFFINE = 2, VINET_XF_AFFINE_RELU = 3 };
+enum { VINET_GATHER_FPROP = 0, VINET_GATHER_DGRAD = 1 };
+/* VINET_ENGINE_TC: bf16 tcgen05.mma with fp32 TMEM accumulators; VINET_ENGINE_SIMT: fp32 FFMA (parity mode) */
+enum { VINET_ENGINE_TC = 0, VINET_ENGINE_SIMT = 1 };
+enum { VINET_ACT_NONE = 0, VINET_ACT_RELU = 1, VINET_ACT_SIGMOID = 2 };
+enum { VINET_LOSS_KLDIV = 0, VINET_LOSS_CC = 1, VINET_LOSS_SIM = 2, VINET_LOSS_NSS = 3 };
+
+#define VINET_MAX_TAPS 64
+#define VINET_TC_BLOCK_M 128
+#define VINET_TC_BLOCK_K 64
+
+/* One source of a virtual concat along T (torch.cat(..., 2), model.py:290,296,302). */
+typedef struct vinet_src {
+  const void* ptr;
+  const float* scale; /* per-channel, for VINET_XF_AFFINE*; may be NULL otherwise */
+  const float* shift;
+  int64_t ld;
+  int32_t T;     /* frames held by this source */
+  int32_t xform; /* VINET_XF_* */
+} vinet_src_t;
+
+/*
+ * Implicit-GEMM operand gather.  GEMM rows enumerate (b, tr, h, w) over [B,Tr,Hr,Wr]; the row's
+ * frame is t = tr*row_tstep + row_toff.  The K index enumerates (tap, c) with c < Cs, tap < ntaps;
+ * tap[i] = (dt,dh,dw) is a kernel index of the forward convolution.
+ *   FPROP: source position = (t*st - pt + dt, h*sh - ph + dh, w*sw - pw + dw)
+ *   DGRAD: source position = ((t + pt - dt)/st, ...) when divisible, i.e. the transposed convolution;
+ * out-of-range positions read as 0 (zero padding is applied AFTER the source transform).
+ */
+typedef struct vinet_gather {
+  int32_t mode;  /* VINET_GATHER_* */
+  int32_t dtype; /* storage type of both sources */
+  int32_t B, Tr, Hr, Wr;
+  int32_t row_tstep, row_toff;
+  int32_t Ts, Hs, Ws; /* source extent; Ts = src[0].T + src[1].T */
+  int32_t Cs;         /* channels per tap, multiple of 8 */
+  int32_t ntaps;
+  int32_t st, sh, sw, pt, ph, pw;
+  int8_t tap[VINET_MAX_TAPS][4];
+  vinet_src_t src[2]; /* src[1].ptr == NULL when there is no concat */
+} vinet_gather_t;
+
+/*
+ * out[rows, N] (+)= act( gather(rows, K) x W[K, N] * ep_scale + ep_shift )
+ * Replaces nn.Conv3d forward (model_utils.py:131,144,148; model.py:256-281) in FPROP mode and its
+ * autograd data-gradient in DGRAD mode.  Rows whose frame t < out_T[0] are written to out[0] (frame t),
+ * the others to out[1] (frame t - out_T[0]): the data-gradient of a T-concat lands in both producers.
+ */
+typedef struct vinet_conv {
+  vinet_gather_t g;
+  const void* w;    /* from vinet_pack_weights with the same engine/block_n/n_tiles */
+  int32_t N;        /* real output channels */
+  int32_t block_n;  /* TC engine: UMMA N per tile (multiple of 16, <= 256) */
+  int32_t n_tiles;  /* TC engine: tiles along N */
+  int32_t k_blocks; /* ceil(ntaps*Cs / 64) */
+  void* out[2];
+  int64_t ldo[2];
+  int32_t out_T[2];
+  int32_t out_dtype;
+  int32_t accumulate; /* 1: out += result (fp32 outputs only) */
+  const float* ep_scale; /* per-output-channel, may be NULL */
+  const float* ep_shift; /* per-output-channel (bias), may be NULL */
+  int32_t ep_act;        /* VINET_ACT_* */
+} vinet_conv_t;
+int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stream_t stream);
+
+/*
+ * dwp[(tap,c), n] += sum_rows gather(row,(tap,c)) * dy[row, n]   (fp32 atomics; caller zeroes dwp)
+ * Replaces the autograd weight-gradient of nn.Conv3d.  g must be an FPROP gather whose rows are the
+ * conv's output positions; dy is the materialised gradient w.r.t. the raw conv output.
+ */
+typedef struct vinet_wgrad {
+  vinet_gather_t g;
+  const void* dy;
+  int64_t lddy;
+  int32_t dy_dtype;
+  int32_t N;
+  float* dwp;    /* [round_up(ntaps*Cs,128)][lddw] */
+  int32_t lddw;  /* >= round_up(N,64) */
+  int32_t splits; /* CTAs along the row (reduction) dimension */
+} vinet_wgrad_t;
+int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream);
+
+/* Weight (re)packing: PyTorch (Cout,Cin,kt,kh,kw) fp32 -> GEMM B operand. */
+typedef struct vinet_pack {
+  const float* w;
+  int32_t Cout, Cin, kt, kh, kw;
+  int32_t cs;    /* channels per tap in the packed K index (>= Cin for FPROP when the input is channel-padded) */
+  int32_t mode;  /* FPROP: n=cout,k=(tap,cin); DGRAD: n=cin,k=(tap,cout) */
+  int32_t ntaps;
+  int8_t tap[VINET_MAX_TAPS][4];
+  int32_t engine, block_n, n_tiles, k_blocks;
+  void* out; /* TC: bf16 [n_tiles][k_blocks][block_n][64] 128B-swizzled; SIMT: fp32 [k_blocks*64][round_up(N,64)] */
+} vinet_pack_t;
+int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
+size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks);
+
+/* grad[co][ci][tap] = dwp[(tap*cs + ci)*lddw + co]  (taps in natural (dt,dh,dw) order) */
+int vinet_unpack_wgrad(const float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
+                       int32_t ntaps, vinet_stream_t stream);
+
+/* (B,C,T,H,W) strided fp32 clip (train.py:205 hands a permuted view) -> NDHWC with C padded to cpad. */
+typedef struct vinet_pack_input {
+  const float* x;
+  int64_t sb, sc, st, sh, sw; /* element strides */
+  int32_t B, C, T, H, W;
+  int32_t cpad;
+  void* out;
+  int32_t out_dtype;
+} vinet_pack_input_t;
+int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream);
+
+/* ---- BatchNorm3d / BatchNorm2d (model_utils.py:132,145,149; model.py:752...) ---- */
+typedef struct vinet_bn_stats {
+  const void* y;
+  int64_t ld;
+  int32_t dtype;
+  int64_t rows;
+  int32_t C;
+  double* sums; /* [2][C]: sum, sum of squares; caller zeroes */
+} vinet_bn_stats_t;
+int vinet_bn_stats(const vinet_bn_stats_t* d, vinet_stream_t stream);
+
+typedef struct vinet_bn_finalize {
+  const double* sums;
+  int64_t rows;
+  int32_t C;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean; /* training: updated in place (unbiased variance) */
+  float* running_var;
+  int32_t training; /* 0: scale/shift from the running statistics */
+  float* scale;     /* gamma * invstd */
+  float* shift;     /* beta - mean * scale */
+  float* mean;
+  float* invstd;
+} vinet_bn_finalize_t;
+int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream);
+
+/* Backward of y_hat = relu?(scale*y + shift) w.r.t. the raw conv output y. */
+typedef struct vinet_bn_bwd {
+  const float* g; /* grad w.r.t. the activated output, fp32 */
+  int64_t ldg;
+  const void* y;
+  int64_t ldy;
+  int32_t dtype;
+  int64_t rows;
+  int32_t C;
+  int32_t relu;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  double* sums; /* [2][C]: sum(g*m), sum(g*m*y_norm); caller zeroes */
+  float* dgamma;
+  float* dbeta;
+  void* dy;
+  int64_t lddy;
+  int32_t dy_dtype;
+  int32_t training; /* 0: eval-mode BN (running stats): dy = g*m*scale, no mean/projection terms */
+} vinet_bn_bwd_t;
+int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream);
+int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream);
+
+/* ---- nn.MaxPool3d (model.py:696-714, model_utils.py:178...; model.py:229) ---- */
+typedef struct vinet_pool {
+  const void* x;
+  int64_t ldx;
+  int32_t dtype;
+  const float* scale;
+  const float* shift;
+  int32_t xform;
+  int32_t B, Ti, Hi, Wi, C;
+  int32_t kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int32_t To, Ho, Wo;
+  void* out;
+  int64_t ldo;
+  int32_t out_dtype;
+  const float* gout; /* backward: grad w.r.t. out, fp32 */
+  int64_t ldgo;
+  float* gin; /* backward: grad w.r.t. the activated input, fp32, accumulated with atomics */
+  int64_t ldgi;
+} vinet_pool_t;
+int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream);
+int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream);
+
+/* ---- relu? + nn.Upsample((1,2,2),'trilinear') (model.py:254): per-frame 2x bilinear ---- */
+typedef struct vinet_upsample {
+  const void* z;
+  int64_t ldz;
+  int32_t dtype;
+  int32_t relu;
+  int32_t B, T, h, w, C;
+  void* u; /* [B,T,2h,2w,C] */
+  int64_t ldu;
+  int32_t u_dtype;
+  const float* gu; /* backward in: fp32 grad w.r.t. u */
+  int64_t ldgu;
+  void* dz; /* backward out: grad w.r.t. raw z (ReLU-masked) */
+  int64_t lddz;
+  int32_t dz_dtype;
+} vinet_upsample_t;
+int vinet_upsample_fwd(const vinet_upsample_t* d, vinet_stream_t stream);
+int vinet_upsample_bwd(const vinet_upsample_t* d, vinet_stream_t stream);
+
+/* ---- decoder head: relu? -> Conv3d(C,1,1x1x1,bias) -> Sigmoid (model.py:280-283) ---- */
+typedef struct vinet_head {
+  const void* x;
+  int64_t ldx;
+  int32_t dtype;
+  int32_t relu;
+  int64_t rows;
+  int32_t C; /* <= 64 */
+  const float* w;
+  const float* b;
+  float* out;        /* [rows] */
+  const float* gout; /* backward */
+  void* dx;          /* grad w.r.t. x (ReLU-masked) */
+  int64_t lddx;
+  int32_t dx_dtype;
+  float* dw; /* [C], atomics; caller zeroes */
+  float* db; /* [1] */
+} vinet_head_t;
+int vinet_head_fwd(const vinet_head_t* d, vinet_stream_t stream);
+int vinet_head_bwd(const vinet_head_t* d, vinet_stream_t stream);
+
+/* ---- losses (loss.py:13-120): mean over the batch of a per-sample reduction ---- */
+typedef struct vinet_loss {
+  int32_t kind; /* VINET_LOSS_* */
+  const float* s; /* [B,n] prediction */
+  const float* g; /* [B,n] ground truth / fixation map */
+  int32_t B;
+  int32_t n;
+  float* per_sample; /* [B][8] workspace: value + saved reductions for the backward */
+  float* out;        /* [1] */
+  int32_t* counter;  /* [1] zero-initialised once; left at zero */
+  const float* gout; /* backward: device scalar */
+  float* grad_s;     /* [B,n] */
+} vinet_loss_t;
+int vinet_loss_fwd(const vinet_loss_t* d, vinet_stream_t stream);
+int vinet_loss_bwd(const vinet_loss_t* d, vinet_stream_t stream);
+
+/* ---- SoundNet 1-D convs (model.py:750-786) and the audio-visual bilinear fusion (model.py:229-237) ---- */
+typedef struct vinet_conv1d {
+  const float* x; /* [B,Cin,Lin] fp32 */
+  const float* w; /* [Cout,Cin,k] */
+  const float* bias;
+  int32_t B, Cin, Lin, Cout, Lout, k, stride, pad;
+  float* y; /* [B,Cout,Lout] raw conv output (+bias) */
+  const float* dy; /* backward */
+  float* dx;       /* [B,Cin,Lin] (may be NULL) */
+  float* dw;       /* [Cout,Cin,k] */
+  float* dbias;    /* [Cout] */
+} vinet_conv1d_t;
+int vinet_conv1d_fwd(const vinet_conv1d_t* d, vinet_stream_t stream);
+int vinet_conv1d_bwd(const vinet_conv1d_t* d, vinet_stream_t stream);
+
+/* BatchNorm2d(+ReLU)(+MaxPool (p,1)) on [B,C,L] fp32, materialised (the audio branch is 0.19 GFLOP). */
+typedef struct vinet_bn1d {
+  const float* y; /* raw conv output [B,C,L] */
+  int32_t B, C, L, pool;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int32_t training;
+  float* mean;   /* [C] saved */
+  float* invstd; /* [C] saved */
+  float* out;    /* [B,C,L/pool] */
+  const float* gout; /* backward */
+  float* dy;         /* [B,C,L] */
+  float* dgamma;
+  float* dbeta;
+} vinet_bn1d_t;
+int vinet_bn1d_fwd(const vinet_bn1d_t* d, vinet_stream_t stream);
+int vinet_bn1d_bwd(const vinet_bn1d_t* d, vinet_stream_t stream);
+
+/* fused[b,c,o] = sum_ij v[b,c,i] W[o,i,j] a[b,c,j] + bias[o]; v = max over 4 frames / every 2nd column of y0. */
+typedef struct vinet_avfuse {
+  const void* y0; /* [B,4,7,12,C] NDHWC view with pending transform */
+  int64_t ld;
+  int32_t dtype;
+  const float* scale;
+  const float* shift;
+  int32_t xform;
+  const float* audio; /* [B,C,3] */
+  const float* w;     /* [336,42,3] */
+  const float* bias;  /* [336] */
+  int32_t B, C;
+  float* vbuf; /* [B,C,42] pooled visual features (written by fwd, read by bwd) */
+  void* out; /* [B,4,7,12,C] NDHWC, identity transform */
+  int64_t ldo;
+  int32_t out_dtype;
+  const float* gout; /* backward: fp32 grad w.r.t. out [B,4,7,12,C] */
+  int64_t ldgo;
+  float* gy0; /* fp32 grad w.r.t. activated y0 (atomics) */
+  int64_t ldgy0;
+  float* gaudio; /* [B,C,3] */
+  float* dw;     /* [336,42,3] atomics; caller zeroes */
+  float* dbias;  /* [336] */
+} vinet_avfuse_t;
+int vinet_avfuse_fwd(const vinet_avfuse_t* d, vinet_stream_t stream);
+int vinet_avfuse_bwd(const vinet_avfuse_t* d, vinet_stream_t stream);
+
+/* ---- misc ---- */
+int vinet_memset_async(void* ptr, int value, size_t bytes, vinet_stream_t stream);
+/* dst[i] = src[i] (+ dst[i] if accumulate); fp32 */
+int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t accumulate, vinet_stream_t stream);
+/* column sums of a [rows, C] view -> out[C] fp32 (bias gradients) */
+int vinet_colsum(const void* x, int64_t ld, int32_t dtype, int64_t rows, int32_t C, double* ws, float* out,
+                 vinet_stream_t stream);
+const char* vinet_last_error(void);
+const char* vinet_version(void);
+int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* sizeof() of every struct above, in declaration order (host-only; lets a binding check its layout) */
+int vinet_abi_sizes(int64_t* out, int32_t n);
+/* development switch (key 0: tcgen05 descriptor-encoding experiments, see csrc/conv_tc.cu); 0 in production */
+int vinet_debug_set(int32_t key, int32_t value);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t vinet_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINET_B200_H */

@@ -1,0 +1,336 @@
+"""TEST INFRASTRUCTURE ONLY — executable specification of every kernel behind include/vinet_b200.h.
+
+A slow numpy re-statement of what each C-ABI entry point must compute, operating on HOST memory
+through the very same ctypes descriptors (fp32 storage only).  Two uses, both in ``tests/``:
+  * ``Spec`` can be injected into ``vinet_b200.engine.Engine(backend=Spec())`` so the whole host-side
+    plan (descriptor construction, channel-slice/ld arithmetic, tape order, backward formulas) is
+    checked on the CPU against the PyTorch oracle without a GPU;
+  * GPU tests run the same descriptor through the CUDA kernel and through this spec and compare.
+It is never imported by the product package.
+"""
+import ctypes as C
+
+import numpy as np
+
+from vinet_b200 import lib as L
+
+EPS = np.float32(2.2204e-16)
+
+
+def _arr(ptr, n, dtype=np.float32):
+    if not ptr or n == 0:
+        return None
+    ct = {np.float32: C.c_float, np.float64: C.c_double, np.int32: C.c_int32, np.uint8: C.c_uint8}[dtype]
+    return np.ctypeslib.as_array((ct * int(n)).from_address(int(ptr)))
+
+
+def _rows_view(ptr, rows, ld, c):
+    """[rows, c] strided view of a channel slice whose row stride is ld."""
+    a = _arr(ptr, (rows - 1) * ld + c)
+    return np.lib.stride_tricks.as_strided(a, shape=(rows, c), strides=(ld * 4, 4))
+
+
+def _xform(v, xf, scale, shift, c0, c):
+    if xf & 2:
+        v = v * _arr(scale, c0 + c)[c0:] + _arr(shift, c0 + c)[c0:]
+    if xf & 1:
+        v = np.maximum(v, 0)
+    return v.astype(np.float32)
+
+
+def _taps(g):
+    return [(g.tap[i][0], g.tap[i][1], g.tap[i][2]) for i in range(g.ntaps)]
+
+
+def _row_coords(g):
+    rows = g.B * g.Tr * g.Hr * g.Wr
+    r = np.arange(rows)
+    w = r % g.Wr; r //= g.Wr
+    h = r % g.Hr; r //= g.Hr
+    tr = r % g.Tr; b = r // g.Tr
+    return b, tr * g.row_tstep + g.row_toff, h, w
+
+
+def gather_matrix(g):
+    """A[rows, ntaps*Cs] of the implicit GEMM described by a vinet_gather_t."""
+    assert g.dtype == L.F32, "the spec handles fp32 storage only"
+    b, t, h, w = _row_coords(g)
+    rows = b.shape[0]
+    A = np.zeros((rows, g.ntaps * g.Cs), np.float32)
+    T0 = g.src[0].T
+    for ti, (dt, dh, dw) in enumerate(_taps(g)):
+        if g.mode == L.GATHER_FPROP:
+            ts, hs, ws = t * g.st - g.pt + dt, h * g.sh - g.ph + dh, w * g.sw - g.pw + dw
+            ok = np.ones(rows, bool)
+        else:
+            nt, nh, nw = t + g.pt - dt, h + g.ph - dh, w + g.pw - dw
+            ok = (nt >= 0) & (nh >= 0) & (nw >= 0) & (nt % g.st == 0) & (nh % g.sh == 0) & (nw % g.sw == 0)
+            ts, hs, ws = nt // g.st, nh // g.sh, nw // g.sw
+        ok &= (ts >= 0) & (ts < g.Ts) & (hs >= 0) & (hs < g.Hs) & (ws >= 0) & (ws < g.Ws)
+        for si in (0, 1):
+            s = g.src[si]
+            if not s.ptr or s.T == 0:
+                continue
+            sel = ok & ((ts < T0) if si == 0 else (ts >= T0))
+            if not sel.any():
+                continue
+            tl = ts[sel] - (T0 if si else 0)
+            pos = ((b[sel] * s.T + tl) * g.Hs + hs[sel]) * g.Ws + ws[sel]
+            src = _rows_view(s.ptr, g.B * s.T * g.Hs * g.Ws, s.ld, g.Cs)
+            A[np.nonzero(sel)[0], ti * g.Cs:(ti + 1) * g.Cs] = _xform(src[pos], s.xform, s.scale, s.shift, 0, g.Cs)
+    return A
+
+
+class Spec:
+    """Drop-in for vinet_b200.lib.Library on host memory."""
+
+    def __init__(self):
+        self.fn = {"vinet_packed_weight_bytes": self._packed_bytes}
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    @staticmethod
+    def _packed_bytes(engine, n, block_n, n_tiles, k_blocks):
+        return k_blocks * 64 * (-(-n // 64) * 64) * 4
+
+    def call(self, name, *args):
+        args = [a._obj if hasattr(a, "_obj") else a for a in args]
+        self.launches += 1
+        getattr(self, name[len("vinet_"):])(*args)
+
+    # ------------------------------------------------------------------ misc
+    def memset_async(self, ptr, value, nbytes, stream):
+        C.memset(int(ptr), value, int(nbytes))
+
+    def axpy_f32(self, dst, src, n, acc, stream):
+        d, s = _arr(dst, n), _arr(src, n)
+        d[:] = d + s if acc else s
+
+    def colsum(self, x, ld, dtype, rows, c, ws, out, stream):
+        _arr(out, c)[:] = _rows_view(x, rows, ld, c).astype(np.float64).sum(0)
+
+    # ------------------------------------------------------------------ packing
+    def pack_input(self, d, stream):
+        n = d.B * d.T * d.H * d.W
+        out = _arr(d.out, n * d.cpad).reshape(d.B, d.T, d.H, d.W, d.cpad)
+        out[:] = 0
+        span = (d.B - 1) * d.sb + (d.C - 1) * d.sc + (d.T - 1) * d.st + (d.H - 1) * d.sh + (d.W - 1) * d.sw + 1
+        x = np.lib.stride_tricks.as_strided(_arr(d.x, span), shape=(d.B, d.C, d.T, d.H, d.W),
+                                            strides=tuple(4 * s for s in (d.sb, d.sc, d.st, d.sh, d.sw)))
+        out[..., :d.C] = np.transpose(x, (0, 2, 3, 4, 1))
+
+    def pack_weights(self, d, stream):
+        assert d.engine == L.ENGINE_SIMT
+        w = _arr(d.w, d.Cout * d.Cin * d.kt * d.kh * d.kw).reshape(d.Cout, d.Cin, d.kt, d.kh, d.kw)
+        n = d.Cout if d.mode == L.GATHER_FPROP else d.Cin
+        npad = -(-n // 64) * 64
+        out = _arr(d.out, d.k_blocks * 64 * npad).reshape(d.k_blocks * 64, npad)
+        out[:] = 0
+        for ti in range(d.ntaps):
+            dt, dh, dw = d.tap[ti][0], d.tap[ti][1], d.tap[ti][2]
+            if d.mode == L.GATHER_FPROP:
+                out[ti * d.cs:ti * d.cs + d.Cin, :d.Cout] = w[:, :, dt, dh, dw].T
+            else:
+                out[ti * d.cs:ti * d.cs + d.Cout, :d.Cin] = w[:, :, dt, dh, dw]
+
+    def unpack_wgrad(self, dwp, lddw, cs, grad, cout, cin, ntaps, stream):
+        rows = -(-(ntaps * cs) // 128) * 128
+        p = _arr(dwp, rows * lddw).reshape(rows, lddw)
+        g = _arr(grad, cout * cin * ntaps).reshape(cout, cin, ntaps)
+        for t in range(ntaps):
+            g[:, :, t] = p[t * cs:t * cs + cin, :cout].T
+
+    # ------------------------------------------------------------------ convolution
+    def conv_gemm(self, d, engine, stream):
+        A = gather_matrix(d.g)
+        npad = -(-d.N // 64) * 64
+        W = _arr(d.w, d.k_blocks * 64 * npad).reshape(d.k_blocks * 64, npad)
+        acc = A @ W[:A.shape[1], :d.N]
+        if d.ep_scale:
+            acc = acc * _arr(d.ep_scale, d.N)
+        if d.ep_shift:
+            acc = acc + _arr(d.ep_shift, d.N)
+        if d.ep_act == L.ACT_RELU:
+            acc = np.maximum(acc, 0)
+        elif d.ep_act == L.ACT_SIGMOID:
+            acc = 1 / (1 + np.exp(-acc))
+        assert d.out_dtype == L.F32
+        g = d.g
+        b, t, h, w = _row_coords(g)
+        for i in (0, 1):
+            if not d.out[i]:
+                continue
+            sel = (t < d.out_T[0]) if i == 0 else (t >= d.out_T[0])
+            if not sel.any():
+                continue
+            tl = t[sel] - (d.out_T[0] if i else 0)
+            pos = ((b[sel] * d.out_T[i] + tl) * g.Hr + h[sel]) * g.Wr + w[sel]
+            out = _rows_view(d.out[i], g.B * d.out_T[i] * g.Hr * g.Wr, d.ldo[i], d.N)
+            out[pos] = (out[pos] + acc[sel]) if d.accumulate else acc[sel]
+
+    def conv_wgrad(self, d, engine, stream):
+        A = gather_matrix(d.g)
+        rows = A.shape[0]
+        dy = _rows_view(d.dy, rows, d.lddy, d.N)
+        k = A.shape[1]
+        kp = -(-k // 128) * 128
+        dwp = _arr(d.dwp, kp * d.lddw).reshape(kp, d.lddw)
+        dwp[:k, :d.N] += A.T @ dy
+
+    # ------------------------------------------------------------------ batch norm
+    def bn_stats(self, d, stream):
+        y = _rows_view(d.y, d.rows, d.ld, d.C).astype(np.float64)
+        s = _arr(d.sums, 2 * d.C, np.float64)
+        s[:d.C] += y.sum(0)
+        s[d.C:] += (y * y).sum(0)
+
+    def bn_finalize(self, d, stream):
+        c = d.C
+        if d.training:
+            s = _arr(d.sums, 2 * c, np.float64)
+            mean = s[:c] / d.rows
+            var = np.maximum(s[c:] / d.rows - mean * mean, 0)
+            invstd = 1 / np.sqrt(var + d.eps)
+            if d.running_mean:
+                unb = var * d.rows / (d.rows - 1) if d.rows > 1 else var
+                rm, rv = _arr(d.running_mean, c), _arr(d.running_var, c)
+                rm[:] = (1 - d.momentum) * rm + d.momentum * mean
+                rv[:] = (1 - d.momentum) * rv + d.momentum * unb
+        else:
+            mean = _arr(d.running_mean, c).astype(np.float64)
+            invstd = 1 / np.sqrt(_arr(d.running_var, c).astype(np.float64) + d.eps)
+        sc = _arr(d.gamma, c) * invstd
+        _arr(d.scale, c)[:] = sc
+        _arr(d.shift, c)[:] = _arr(d.beta, c) - mean * sc
+        _arr(d.mean, c)[:] = mean
+        _arr(d.invstd, c)[:] = invstd
+
+    def _bn_bwd_terms(self, d):
+        c = d.C
+        y = _rows_view(d.y, d.rows, d.ldy, c)
+        g = _rows_view(d.g, d.rows, d.ldg, c)
+        sc, sh = _arr(d.scale, c), _arr(d.shift, c)
+        yh = y * sc + sh
+        gm = np.where((yh > 0) | (d.relu == 0), g, 0).astype(np.float32)
+        yn = (y - _arr(d.mean, c)) * _arr(d.invstd, c)
+        return gm, yn, sc
+
+    def bn_bwd_reduce(self, d, stream):
+        gm, yn, _ = self._bn_bwd_terms(d)
+        _arr(d.dbeta, d.C)[:] = gm.astype(np.float64).sum(0)
+        _arr(d.dgamma, d.C)[:] = (gm.astype(np.float64) * yn).sum(0)
+
+    def bn_bwd_apply(self, d, stream):
+        gm, yn, sc = self._bn_bwd_terms(d)
+        assert d.dy_dtype == L.F32
+        dy = _rows_view(d.dy, d.rows, d.lddy, d.C)
+        if d.training:
+            dy[:] = sc * (gm - _arr(d.dbeta, d.C) / d.rows - yn * _arr(d.dgamma, d.C) / d.rows)
+        else:
+            dy[:] = sc * gm
+
+    # ------------------------------------------------------------------ pooling
+    def _pool_scan(self, d):
+        n_in = d.B * d.Ti * d.Hi * d.Wi
+        x = _xform(_rows_view(d.x, n_in, d.ldx, d.C), d.xform, d.scale, d.shift, 0, d.C)
+        x = x.reshape(d.B, d.Ti, d.Hi, d.Wi, d.C)
+        best = np.full((d.B, d.To, d.Ho, d.Wo, d.C), -np.inf, np.float32)
+        arg = np.full(best.shape, -1, np.int64)
+        bi = np.arange(d.B)[:, None, None, None]
+        to, ho, wo = np.arange(d.To)[None, :, None, None], np.arange(d.Ho)[None, None, :, None], np.arange(d.Wo)[None, None, None, :]
+        for dt in range(d.kt):
+            for dh in range(d.kh):
+                for dw in range(d.kw):
+                    t, h, w = to * d.st - d.pt + dt, ho * d.sh - d.ph + dh, wo * d.sw - d.pw + dw
+                    ok = (t >= 0) & (t < d.Ti) & (h >= 0) & (h < d.Hi) & (w >= 0) & (w < d.Wi)
+                    ok = np.broadcast_to(ok, best.shape[:4])
+                    tc, hc, wc = np.clip(t, 0, d.Ti - 1), np.clip(h, 0, d.Hi - 1), np.clip(w, 0, d.Wi - 1)
+                    v = x[bi, tc, hc, wc]
+                    pos = np.broadcast_to(((bi * d.Ti + tc) * d.Hi + hc) * d.Wi + wc, best.shape[:4])[..., None]
+                    upd = ok[..., None] & (v > best)
+                    best = np.where(upd, v, best)
+                    arg = np.where(upd, pos, arg)
+        return best, arg
+
+    def maxpool_fwd(self, d, stream):
+        best, _ = self._pool_scan(d)
+        n_out = d.B * d.To * d.Ho * d.Wo
+        _rows_view(d.out, n_out, d.ldo, d.C)[:] = best.reshape(n_out, d.C)
+
+    def maxpool_bwd(self, d, stream):
+        _, arg = self._pool_scan(d)
+        n_out = d.B * d.To * d.Ho * d.Wo
+        g = _rows_view(d.gout, n_out, d.ldgo, d.C)
+        gin = _rows_view(d.gin, d.B * d.Ti * d.Hi * d.Wi, d.ldgi, d.C)
+        arg = arg.reshape(n_out, d.C)
+        cc = np.broadcast_to(np.arange(d.C), arg.shape)
+        ok = arg >= 0
+        np.add.at(gin, (arg[ok], cc[ok]), g[ok])
+
+    # ------------------------------------------------------------------ upsample
+    @staticmethod
+    def _up_matrix(n):
+        """[2n, n] interpolation matrix of the 2x bilinear resize with align_corners=False."""
+        m = np.zeros((2 * n, n), np.float32)
+        for Y in range(2 * n):
+            src = max((Y + 0.5) * 0.5 - 0.5, 0.0)
+            i0 = int(src); i1 = min(i0 + 1, n - 1); l1 = src - i0
+            m[Y, i0] += 1 - l1
+            m[Y, i1] += l1
+        return m
+
+    def upsample_fwd(self, d, stream):
+        z = _rows_view(d.z, d.B * d.T * d.h * d.w, d.ldz, d.C).reshape(d.B * d.T, d.h, d.w, d.C)
+        if d.relu:
+            z = np.maximum(z, 0)
+        u = np.einsum("Yy,nyxc,Xx->nYXc", self._up_matrix(d.h), z, self._up_matrix(d.w))
+        _rows_view(d.u, d.B * d.T * 4 * d.h * d.w, d.ldu, d.C)[:] = u.reshape(-1, d.C)
+
+    def upsample_bwd(self, d, stream):
+        gu = _rows_view(d.gu, d.B * d.T * 4 * d.h * d.w, d.ldgu, d.C).reshape(d.B * d.T, 2 * d.h, 2 * d.w, d.C)
+        dz = np.einsum("Yy,nYXc,Xx->nyxc", self._up_matrix(d.h), gu, self._up_matrix(d.w)).reshape(-1, d.C)
+        if d.relu:
+            z = _rows_view(d.z, d.B * d.T * d.h * d.w, d.ldz, d.C)
+            dz = np.where(z > 0, dz, 0)
+        assert d.dz_dtype == L.F32
+        _rows_view(d.dz, d.B * d.T * d.h * d.w, d.lddz, d.C)[:] = dz
+
+    # ------------------------------------------------------------------ head
+    def head_fwd(self, d, stream):
+        x = _rows_view(d.x, d.rows, d.ldx, d.C)
+        if d.relu:
+            x = np.maximum(x, 0)
+        logit = x @ _arr(d.w, d.C) + (_arr(d.b, 1)[0] if d.b else 0)
+        _arr(d.out, d.rows)[:] = 1 / (1 + np.exp(-logit))
+
+    def head_bwd(self, d, stream):
+        x = _rows_view(d.x, d.rows, d.ldx, d.C)
+        on = (x > 0) | (d.relu == 0)
+        a = np.where(on, x, 0)
+        o = _arr(d.out, d.rows)
+        dl = _arr(d.gout, d.rows) * o * (1 - o)
+        assert d.dx_dtype == L.F32
+        _rows_view(d.dx, d.rows, d.lddx, d.C)[:] = np.where(on, dl[:, None] * _arr(d.w, d.C)[None, :], 0)
+        _arr(d.dw, d.C)[:] += (dl[:, None].astype(np.float64) * a).sum(0)
+        _arr(d.db, 1)[0] += dl.astype(np.float64).sum()
+
+    # ------------------------------------------------------------------ losses (torch autograd of the oracle)
+    def _loss(self, d, want_grad):
+        import torch
+        from . import torch_oracle as O
+        s = torch.from_numpy(_arr(d.s, d.B * d.n).reshape(d.B, 1, d.n).copy()).requires_grad_(want_grad)
+        g = torch.from_numpy(_arr(d.g, d.B * d.n).reshape(d.B, 1, d.n).copy())
+        fn = {L.LOSS_KLDIV: O.kldiv, L.LOSS_CC: O.cc, L.LOSS_SIM: O.similarity, L.LOSS_NSS: O.nss}[d.kind]
+        return s, fn(s, g)
+
+    def loss_fwd(self, d, stream):
+        _, v = self._loss(d, False)
+        _arr(d.out, 1)[0] = v.item()
+
+    def loss_bwd(self, d, stream):
+        import torch
+        s, v = self._loss(d, True)
+        (gr,) = torch.autograd.grad(v, s)
+        _arr(d.grad_s, d.B * d.n)[:] = gr.numpy().reshape(-1) * _arr(d.gout, 1)[0]

@@ -1,0 +1,138 @@
+"""Small engine-level scenarios run identically on (cpu, numpy kernel spec) and (cuda, real kernels)."""
+import torch
+import torch.nn.functional as F
+
+from vinet_b200 import lib as L
+from vinet_b200 import model as M
+from vinet_b200.engine import ConvGeom, Engine
+
+
+def ncdhw(t):
+    return t.detach().float().permute(0, 4, 1, 2, 3).contiguous().cpu()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def make_engine(device, precision, backend=None):
+    e = Engine(precision, backend=backend)
+    e.begin(torch.device(device), True, True)
+    return e
+
+
+def fill_act(e, name, B, T, H, W, C, gen, affine):
+    a = e.new_act(name, B, T, H, W, C, affine=affine)
+    a.buf.copy_(bf16r(torch.randn(a.buf.shape, generator=gen)))
+    if affine:
+        a.scale.copy_(torch.rand(C, generator=gen) + 0.5)
+        a.shift.copy_(torch.randn(C, generator=gen) * 0.3)
+        a.xform = L.XF_AFFINE_RELU
+    return a
+
+
+def run_tape(e, out, gen):
+    for g in e.grad_bufs:
+        g.zero_()
+    go = bf16r(torch.randn(out.grad.shape, generator=gen))
+    out.grad.copy_(go)
+    for fn in reversed(e.tape):
+        fn()
+    if e.device.type == "cuda":
+        torch.cuda.synchronize()
+    return go
+
+
+def conv_up(device, precision, backend=None, B=2, T0=1, T1=2, H=6, W=5, Cin=16, Cout=24, kt=3, seed=0):
+    """decoder stage: conv over a T-concat of (identity, affine+relu) sources -> relu -> 2x upsample."""
+    gen = torch.Generator().manual_seed(seed)
+    e = make_engine(device, precision, backend)
+    u = fill_act(e, "u", B, T0, H, W, Cin, gen, False)
+    y = fill_act(e, "y", B, T1, H, W, Cin, gen, True)
+    w = bf16r(torch.randn(Cout, Cin, kt, 3, 3, generator=gen) * (2.0 / (Cin * kt * 9)) ** 0.5).to(device)
+    out = e.conv_relu_up("c", [u, y], w, ConvGeom((kt, 3, 3), (kt, 1, 1), (0, 1, 1)))
+    run_tape(e, out, gen)
+    return {"out": ncdhw(out.buf), "dW": e.param_grads["c.weight"].cpu(), "du": ncdhw(u.grad), "dy": ncdhw(y.grad)}
+
+
+def conv_up_torch(B=2, T0=1, T1=2, H=6, W=5, Cin=16, Cout=24, kt=3, seed=0):
+    """The same scenario in plain PyTorch fp32 (the torch reference of the kernels)."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def rnd(*s):
+        return bf16r(torch.randn(*s, generator=gen))
+    ub = rnd(B, T0, H, W, Cin)
+    yb = rnd(B, T1, H, W, Cin)
+    sc = torch.rand(Cin, generator=gen) + 0.5
+    sh = torch.randn(Cin, generator=gen) * 0.3
+    w = bf16r(torch.randn(Cout, Cin, kt, 3, 3, generator=gen) * (2.0 / (Cin * kt * 9)) ** 0.5).requires_grad_(True)
+    xu = ub.permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    xy = F.relu(yb.permute(0, 4, 1, 2, 3) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    xy.retain_grad() if xy.requires_grad else None
+    xy = xy.detach().requires_grad_(True)
+    z = F.conv3d(torch.cat([xu, xy], 2), w, None, (kt, 1, 1), (0, 1, 1))
+    o = F.interpolate(F.relu(z), scale_factor=(1, 2, 2), mode="trilinear")
+    go = bf16r(torch.randn(B, T0 and o.shape[2], o.shape[3], o.shape[4], Cout, generator=gen)).permute(0, 4, 1, 2, 3)
+    o.backward(go)
+    return {"out": o.detach(), "dW": w.grad, "du": xu.grad, "dy": xy.grad}
+
+
+def mixed(device, precision, backend=None, name="3b", B=2, T=3, H=5, W=4, seed=0):
+    from oracle import torch_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    ref = O.Inception(name)
+    O.randomize_(ref, seed + 1)
+    m = M.Mixed(name)
+    m.load_state_dict(ref.state_dict())
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 5:
+                p.copy_(bf16r(p))
+    m.to(device)
+    cin = M.arch.MIXED[name][0]
+    e = make_engine(device, precision, backend)
+    x = fill_act(e, "x", B, T, H, W, cin, gen, True)
+    out = M._mixed(e, "mx", x, m)
+    run_tape(e, out, gen)
+    res = {"out": ncdhw(out.buf), "scale": out.scale.detach().cpu().clone(), "shift": out.shift.detach().cpu().clone(),
+           "dx": ncdhw(x.grad)}
+    for k, v in e.param_grads.items():
+        res["g/" + k] = v.detach().cpu()
+    return res
+
+
+def stem(device, precision, backend=None, B=1, T=8, H=32, W=32, seed=0):
+    """pack_input + SepConv3d(3,64,k7,s2,p3) + MaxPool(1,3,3)/(1,2,2): strided convs, channel padding."""
+    from oracle import torch_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    ref = O.SepConv(3, 64, 7, 2, 3)
+    O.randomize_(ref, seed + 2)
+    m = M.SepConv3d(3, 64, 7, 2, 3)
+    m.load_state_dict(ref.state_dict())
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 5:
+                p.copy_(bf16r(p))
+    m.to(device)
+    e = make_engine(device, precision, backend)
+    x = bf16r(torch.randn(B, T, 3, H, W, generator=gen)).permute(0, 2, 1, 3, 4).to(device)
+    xin = M.pack_input(e, x)
+    a = M._sepconv(e, "stem", [xin], m, cin_real=3)
+    out = e.maxpool("pool", a, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    run_tape(e, out, gen)
+    res = {"out": ncdhw(out.buf), "raw": ncdhw(a.buf)}
+    for k, v in e.param_grads.items():
+        res["g/" + k] = v.detach().cpu()
+    return res
+
+
+def compare(a, b, rtol, what=""):
+    """max|a-b| <= rtol * max|b| per entry; returns the list of failures."""
+    bad = []
+    for k in b:
+        ref = b[k].float()
+        err = (a[k].float() - ref).abs().max().item()
+        scale = ref.abs().max().item() + 1e-20
+        if not err <= rtol * scale:
+            bad.append("%s%s: err %.3e vs scale %.3e" % (what, k, err, scale))
+    return bad

@@ -1,0 +1,99 @@
+// C-ABI glue: error string, engine dispatch, small utilities.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vinet {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int conv_gemm_simt(const vinet_conv_t* d, cudaStream_t stream);
+int conv_wgrad_simt(const vinet_wgrad_t* d, cudaStream_t stream);
+int conv_gemm_tc(const vinet_conv_t* d, cudaStream_t stream);
+int conv_wgrad_tc(const vinet_wgrad_t* d, cudaStream_t stream);
+int tc_debug_set(unsigned int v);
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = accumulate ? dst[i] + src[i] : src[i];
+}
+
+}  // namespace vinet
+using namespace vinet;
+
+extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stream_t stream) {
+  VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_gemm: bad tap count");
+  VINET_CHECK(d->g.B > 0 && d->g.Tr > 0 && d->g.Hr > 0 && d->g.Wr > 0, "conv_gemm: empty row space");
+  VINET_CHECK(d->g.st > 0 && d->g.sh > 0 && d->g.sw > 0 && d->g.row_tstep > 0, "conv_gemm: bad strides");
+  if (engine == VINET_ENGINE_TC) return conv_gemm_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);
+  set_error("conv_gemm: unknown engine %d", engine);
+  return -1;
+}
+
+extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream) {
+  VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_wgrad: bad tap count");
+  VINET_CHECK(d->splits >= 1, "conv_wgrad: splits");
+  VINET_CHECK(d->lddw >= d->N, "conv_wgrad: lddw");
+  if (engine == VINET_ENGINE_TC) return conv_wgrad_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_SIMT) return conv_wgrad_simt(d, (cudaStream_t)stream);
+  set_error("conv_wgrad: unknown engine %d", engine);
+  return -1;
+}
+
+extern "C" int vinet_memset_async(void* ptr, int value, size_t bytes, vinet_stream_t stream) {
+  cudaError_t e = cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream);
+  VINET_CHECK(e == cudaSuccess, "memset: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t accumulate, vinet_stream_t stream) {
+  int64_t nb = cdiv(n, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  axpy_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dst, src, n, accumulate);
+  VINET_LAUNCH_OK("axpy");
+  return 0;
+}
+
+extern "C" const char* vinet_last_error(void) { return g_err; }
+extern "C" const char* vinet_version(void) { return "vinet_b200 0.1 (sm_100a; tcgen05+TMEM conv, fp32 SIMT parity engine)"; }
+extern "C" int64_t vinet_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  VINET_CHECK(e == cudaSuccess, "device_info: %s", cudaGetErrorString(e));
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  VINET_CHECK(e == cudaSuccess, "device_info: %s", cudaGetErrorString(e));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
+  const int64_t sizes[] = {sizeof(vinet_src_t),      sizeof(vinet_gather_t),     sizeof(vinet_conv_t),     sizeof(vinet_wgrad_t),
+                           sizeof(vinet_pack_t),     sizeof(vinet_pack_input_t), sizeof(vinet_bn_stats_t), sizeof(vinet_bn_finalize_t),
+                           sizeof(vinet_bn_bwd_t),   sizeof(vinet_pool_t),       sizeof(vinet_upsample_t), sizeof(vinet_head_t),
+                           sizeof(vinet_loss_t),     sizeof(vinet_conv1d_t),     sizeof(vinet_bn1d_t),     sizeof(vinet_avfuse_t)};
+  const int32_t m = (int32_t)(sizeof(sizes) / sizeof(sizes[0]));
+  for (int32_t i = 0; i < n && i < m; ++i) out[i] = sizes[i];
+  return m;
+}
+
+extern "C" int vinet_debug_set(int32_t key, int32_t value) {
+  VINET_CHECK(key == 0, "debug_set: unknown key %d", key);
+  VINET_CHECK(tc_debug_set((unsigned int)value) == 0, "debug_set: cudaMemcpyToSymbol failed");
+  return 0;
+}

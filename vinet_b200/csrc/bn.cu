@@ -1,0 +1,228 @@
+// BatchNorm3d statistics / finalize / backward on NDHWC views (model_utils.py:132,145,149).
+// The normalisation itself is never a kernel: consumers apply scale/shift(+ReLU) when they read.
+#include "common.cuh"
+
+namespace vinet {
+
+// Column reduction skeleton: blockDim = (G = C/8 channel groups, Ry rows in flight).
+// Each thread accumulates NV fp32 partial vectors of 8 channels over its rows, the block combines
+// them in shared memory and issues one double atomicAdd per channel.
+template <int NV, typename F>
+__device__ __forceinline__ void column_reduce(int64_t rows, int C, int64_t rows_per_block, double* sums, F&& body) {
+  extern __shared__ float red[];  // [Ry][NV][C]
+  const int gx = threadIdx.x, ry = threadIdx.y, Ry = blockDim.y;
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  for (int64_t r = r_begin + ry; r < r_end; r += Ry) body(r, gx * 8, acc);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[((size_t)ry * NV + v) * C + gx * 8 + e] = acc[v][e];
+  __syncthreads();
+  const int tid = ry * blockDim.x + gx, nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < NV * C; i += nthr) {
+    double s = 0.0;
+    for (int y = 0; y < Ry; ++y) s += (double)red[(size_t)y * NV * C + i];
+    atomicAdd(sums + i, s);
+  }
+}
+
+template <typename T>
+__global__ void bn_stats_kernel(const __grid_constant__ vinet_bn_stats_t d, int64_t rows_per_block) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8];
+    load8(y + r * d.ld + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += v[e];
+      acc[1][e] = fmaf(v[e], v[e], acc[1][e]);
+    }
+  });
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int C, double* sums,
+                              int64_t rows_per_block) {
+  column_reduce<1>(rows, C, rows_per_block, sums, [&](int64_t r, int c, float (&acc)[1][8]) {
+    float v[8];
+    load8(x + r * ld + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] += v[e];
+  });
+}
+
+__global__ void colsum_finish_kernel(const double* sums, float* out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (float)sums[c];
+}
+
+__global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.C) return;
+  float mean, invstd;
+  if (d.training) {
+    const double n = (double)d.rows;
+    const double m = d.sums[c] / n;
+    double var = d.sums[d.C + c] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)d.eps));
+    if (d.running_mean) {
+      const double unbiased = (d.rows > 1) ? var * n / (n - 1.0) : var;
+      d.running_mean[c] = (float)((1.0 - d.momentum) * d.running_mean[c] + d.momentum * m);
+      d.running_var[c] = (float)((1.0 - d.momentum) * d.running_var[c] + d.momentum * unbiased);
+    }
+  } else {
+    mean = d.running_mean[c];
+    invstd = 1.0f / sqrtf(d.running_var[c] + d.eps);
+  }
+  const float sc = d.gamma[c] * invstd;
+  d.scale[c] = sc;
+  d.shift[c] = d.beta[c] - mean * sc;
+  d.mean[c] = mean;
+  d.invstd[c] = invstd;
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8], g[8];
+    load8(y + r * d.ldy + c, v);
+    load8(d.g + r * d.ldg + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float yh = fmaf(v[e], __ldg(d.scale + c + e), __ldg(d.shift + c + e));
+      const float gm = (d.relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - __ldg(d.mean + c + e)) * __ldg(d.invstd + c + e);
+      acc[0][e] += gm;
+      acc[1][e] = fmaf(gm, yn, acc[1][e]);
+    }
+  });
+}
+
+__global__ void bn_bwd_finish_kernel(const double* sums, float* dgamma, float* dbeta, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[C + c];
+  }
+}
+
+template <typename T, typename TD>
+__global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  TD* __restrict__ dy = reinterpret_cast<TD*>(d.dy);
+  const int G = d.C / 8;
+  const int64_t total = d.rows * G;
+  const float inv_n = 1.0f / (float)d.rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float v[8], g[8], o[8];
+    load8(y + r * d.ldy + c, v);
+    load8(d.g + r * d.ldg + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sc = __ldg(d.scale + c + e);
+      const float yh = fmaf(v[e], sc, __ldg(d.shift + c + e));
+      const float gm = (d.relu && !(yh > 0.f)) ? 0.f : g[e];
+      if (d.training) {
+        const float yn = (v[e] - __ldg(d.mean + c + e)) * __ldg(d.invstd + c + e);
+        o[e] = sc * (gm - __ldg(d.dbeta + c + e) * inv_n - yn * __ldg(d.dgamma + c + e) * inv_n);
+      } else {
+        o[e] = sc * gm;
+      }
+    }
+    store8(dy + r * d.lddy + c, o);
+  }
+}
+
+struct ColGrid {
+  dim3 block;
+  unsigned grid;
+  int64_t rows_per_block;
+  size_t smem;
+};
+static ColGrid col_grid(int64_t rows, int C, int nv) {
+  ColGrid g;
+  const int G = C / 8;
+  int Ry = 256 / G;
+  if (Ry < 1) Ry = 1;
+  if (Ry > 64) Ry = 64;
+  g.block = dim3(G, Ry);
+  int64_t rpb = (int64_t)Ry * 64;  // <= 64 rows per thread per block
+  int64_t nb = cdiv(rows, rpb);
+  if (nb > 148 * 8) {
+    nb = 148 * 8;
+    rpb = round_up(cdiv(rows, nb), Ry);
+    nb = cdiv(rows, rpb);
+  }
+  g.grid = (unsigned)(nb < 1 ? 1 : nb);
+  g.rows_per_block = rpb;
+  g.smem = (size_t)Ry * nv * C * sizeof(float);
+  return g;
+}
+
+}  // namespace vinet
+
+using namespace vinet;
+
+extern "C" int vinet_bn_stats(const vinet_bn_stats_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_stats: C %d", d->C);
+  ColGrid g = col_grid(d->rows, d->C, 2);
+  VINET_DISPATCH_DTYPE(d->dtype, T, {
+    if (g.smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
+  });
+  VINET_LAUNCH_OK("bn_stats");
+  return 0;
+}
+
+extern "C" int vinet_colsum(const void* x, int64_t ld, int32_t dtype, int64_t rows, int32_t C, double* ws, float* out,
+                            vinet_stream_t stream) {
+  VINET_CHECK(C % 8 == 0 && C <= 1024, "colsum: C %d", C);
+  cudaMemsetAsync(ws, 0, sizeof(double) * C, (cudaStream_t)stream);
+  ColGrid g = col_grid(rows, C, 1);
+  VINET_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
+                                     reinterpret_cast<const T*>(x), ld, rows, C, ws, g.rows_per_block)));
+  VINET_LAUNCH_OK("colsum");
+  colsum_finish_kernel<<<(unsigned)cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(ws, out, C);
+  VINET_LAUNCH_OK("colsum_finish");
+  return 0;
+}
+
+extern "C" int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream) {
+  bn_finalize_kernel<<<(unsigned)cdiv(d->C, 128), 128, 0, (cudaStream_t)stream>>>(*d);
+  VINET_LAUNCH_OK("bn_finalize");
+  return 0;
+}
+
+extern "C" int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd: C %d", d->C);
+  ColGrid g = col_grid(d->rows, d->C, 2);
+  VINET_DISPATCH_DTYPE(d->dtype, T, {
+    if (g.smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
+  });
+  VINET_LAUNCH_OK("bn_bwd_reduce");
+  bn_bwd_finish_kernel<<<(unsigned)cdiv(d->C, 128), 128, 0, (cudaStream_t)stream>>>(d->sums, d->dgamma, d->dbeta, d->C);
+  VINET_LAUNCH_OK("bn_bwd_finish");
+  return 0;
+}
+
+extern "C" int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
+  const int64_t total = d->rows * (d->C / 8);
+  int64_t nb = cdiv(total, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD,
+      (bn_bwd_apply_kernel<T, TD><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d))));
+  VINET_LAUNCH_OK("bn_bwd_apply");
+  return 0;
+}

@@ -1,0 +1,89 @@
+// Implicit-GEMM operand gather shared by the SIMT and tcgen05 conv kernels.
+// Semantics are defined in include/vinet_b200.h (vinet_gather_t).
+#pragma once
+#include "common.cuh"
+
+namespace vinet {
+
+struct RowCoord {
+  int b, t, h, w;  // b < 0: row beyond the problem (reads as zero)
+};
+
+__device__ __forceinline__ int64_t gather_rows(const vinet_gather_t& g) {
+  return (int64_t)g.B * g.Tr * g.Hr * g.Wr;
+}
+
+__device__ __forceinline__ RowCoord decode_row(const vinet_gather_t& g, int64_t row, int64_t M) {
+  RowCoord rc;
+  if (row >= M) {
+    rc.b = -1; rc.t = rc.h = rc.w = 0;
+    return rc;
+  }
+  rc.w = (int)(row % g.Wr); row /= g.Wr;
+  rc.h = (int)(row % g.Hr); row /= g.Hr;
+  int tr = (int)(row % g.Tr);
+  rc.b = (int)(row / g.Tr);
+  rc.t = tr * g.row_tstep + g.row_toff;
+  return rc;
+}
+
+// Locate the source element (b, tap-shifted position, channel 0). Returns false for zero fill.
+__device__ __forceinline__ bool gather_locate(const vinet_gather_t& g, const RowCoord& rc, int tap, int& si,
+                                              int64_t& off) {
+  if (rc.b < 0 || tap >= g.ntaps) return false;
+  const int dt = g.tap[tap][0], dh = g.tap[tap][1], dw = g.tap[tap][2];
+  int ts, hs, ws;
+  if (g.mode == VINET_GATHER_FPROP) {
+    ts = rc.t * g.st - g.pt + dt;
+    hs = rc.h * g.sh - g.ph + dh;
+    ws = rc.w * g.sw - g.pw + dw;
+  } else {
+    int nt = rc.t + g.pt - dt, nh = rc.h + g.ph - dh, nw = rc.w + g.pw - dw;
+    if (nt < 0 || nh < 0 || nw < 0) return false;
+    ts = nt / g.st; hs = nh / g.sh; ws = nw / g.sw;
+    if (ts * g.st != nt || hs * g.sh != nh || ws * g.sw != nw) return false;
+  }
+  if ((unsigned)ts >= (unsigned)g.Ts || (unsigned)hs >= (unsigned)g.Hs || (unsigned)ws >= (unsigned)g.Ws)
+    return false;
+  si = (ts >= g.src[0].T) ? 1 : 0;
+  if (si) ts -= g.src[0].T;
+  off = ((((int64_t)rc.b * g.src[si].T + ts) * g.Hs + hs) * g.Ws + ws) * g.src[si].ld;
+  return true;
+}
+
+// Gather V (4 or 8) consecutive K elements starting at flattened index k = tap*Cs + c (k % V == 0).
+template <typename T, int V>
+__device__ __forceinline__ void gather_vec(const vinet_gather_t& g, const RowCoord& rc, int k, float (&v)[V]) {
+  const int tap = k / g.Cs;
+  const int c = k - tap * g.Cs;
+  int si;
+  int64_t off;
+  if (!gather_locate(g, rc, tap, si, off)) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = 0.f;
+    return;
+  }
+  const vinet_src_t& s = g.src[si];
+  const T* p = reinterpret_cast<const T*>(s.ptr) + off + c;
+  if constexpr (V == 8) load8(p, v); else load4(p, v);
+  apply_xform<V>(v, s.xform, s.scale, s.shift, c);
+}
+
+// output row -> destination pointer (two destinations split on the frame index)
+template <typename TO>
+__device__ __forceinline__ TO* out_row_ptr(const vinet_conv_t& d, const RowCoord& rc) {
+  int i = (rc.t >= d.out_T[0]) ? 1 : 0;
+  int t = rc.t - (i ? d.out_T[0] : 0);
+  int64_t pos = (((int64_t)rc.b * d.out_T[i] + t) * d.g.Hr + rc.h) * d.g.Wr + rc.w;
+  return reinterpret_cast<TO*>(d.out[i]) + pos * d.ldo[i];
+}
+
+__device__ __forceinline__ float epilogue_value(const vinet_conv_t& d, float acc, int n) {
+  if (d.ep_scale) acc *= __ldg(d.ep_scale + n);
+  if (d.ep_shift) acc += __ldg(d.ep_shift + n);
+  if (d.ep_act == VINET_ACT_RELU) acc = fmaxf(acc, 0.f);
+  else if (d.ep_act == VINET_ACT_SIGMOID) acc = 1.f / (1.f + __expf(-acc));
+  return acc;
+}
+
+}  // namespace vinet

@@ -1,0 +1,127 @@
+// Layout conversion kernels: clip -> NDHWC, PyTorch conv weights -> GEMM B operand, packed wgrad -> PyTorch.
+#include "common.cuh"
+
+namespace vinet {
+
+// ------------------------------------------------------------------ input clip
+// One thread per (b,t,h,w): reads C strided fp32 values, writes cpad contiguous channels.
+template <typename TO>
+__global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) {
+  const int64_t total = (int64_t)d.B * d.T * d.H * d.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int w = (int)(r % d.W); r /= d.W;
+    const int h = (int)(r % d.H); r /= d.H;
+    const int t = (int)(r % d.T);
+    const int b = (int)(r / d.T);
+    const float* src = d.x + b * d.sb + t * d.st + h * d.sh + w * d.sw;
+    TO* dst = reinterpret_cast<TO*>(d.out) + i * d.cpad;
+    for (int c0 = 0; c0 < d.cpad; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (c0 + e < d.C) ? __ldg(src + (c0 + e) * d.sc) : 0.f;
+      store8(dst + c0, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weights
+// element (n, k) of the GEMM B operand, k = tap_idx*cs + c
+__device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k) {
+  const int tap = k / d.cs, c = k - tap * d.cs;
+  if (tap >= d.ntaps) return 0.f;
+  int co, ci;
+  if (d.mode == VINET_GATHER_FPROP) { co = n; ci = c; } else { co = c; ci = n; }
+  if (co >= d.Cout || ci >= d.Cin) return 0.f;
+  const int dt = d.tap[tap][0], dh = d.tap[tap][1], dw = d.tap[tap][2];
+  return __ldg(d.w + ((((int64_t)co * d.Cin + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
+}
+
+// TC: one thread per 16-byte chunk (8 consecutive k) of [n_tiles][k_blocks][block_n][64], 128B-swizzled.
+__global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
+  const int64_t chunks = (int64_t)d.n_tiles * d.k_blocks * d.block_n * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    int64_t r = i >> 3;
+    const int nl = (int)(r % d.block_n); r /= d.block_n;
+    const int kb = (int)(r % d.k_blocks);
+    const int nt = (int)(r / d.k_blocks);
+    const int n = nt * d.block_n + nl;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = weight_elem(d, n, kb * 64 + j * 8 + e);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
+    uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
+  }
+}
+
+// SIMT: fp32 [k_blocks*64][npad]
+__global__ void pack_weights_simt_kernel(const __grid_constant__ vinet_pack_t d, int npad) {
+  const int64_t total = (int64_t)d.k_blocks * 64 * npad;
+  float* out = reinterpret_cast<float*>(d.out);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % npad);
+    const int k = (int)(i / npad);
+    out[i] = weight_elem(d, n, k);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int lddw, int cs, float* __restrict__ grad, int Cout,
+                                    int Cin, int ntaps) {
+  const int64_t total = (int64_t)Cout * Cin * ntaps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % ntaps);
+    int64_t r = i / ntaps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    grad[i] = dwp[((int64_t)tap * cs + ci) * lddw + co];
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int block) {
+  int64_t g = cdiv(n, block);
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace vinet
+
+using namespace vinet;
+
+extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->cpad % 8 == 0 && d->cpad >= d->C, "pack_input: cpad %d", d->cpad);
+  const int64_t total = (int64_t)d->B * d->T * d->H * d->W;
+  VINET_DISPATCH_DTYPE(d->out_dtype, TO, (pack_input_kernel<TO><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d)));
+  VINET_LAUNCH_OK("pack_input");
+  return 0;
+}
+
+extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks) {
+  if (engine == VINET_ENGINE_TC) return (size_t)n_tiles * k_blocks * block_n * 128;
+  return (size_t)k_blocks * 64 * round_up(N, 64) * sizeof(float);
+}
+
+extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
+  VINET_CHECK((int64_t)d->k_blocks * 64 >= (int64_t)d->ntaps * d->cs, "pack_weights: k_blocks too small");
+  if (d->engine == VINET_ENGINE_TC) {
+    const int64_t chunks = (int64_t)d->n_tiles * d->k_blocks * d->block_n * 8;
+    pack_weights_tc_kernel<<<grid_for(chunks, 256), 256, 0, (cudaStream_t)stream>>>(*d);
+  } else {
+    const int N = (d->mode == VINET_GATHER_FPROP) ? d->Cout : d->Cin;
+    const int npad = (int)round_up(N, 64);
+    pack_weights_simt_kernel<<<grid_for((int64_t)d->k_blocks * 64 * npad, 256), 256, 0, (cudaStream_t)stream>>>(*d, npad);
+  }
+  VINET_LAUNCH_OK("pack_weights");
+  return 0;
+}
+
+extern "C" int vinet_unpack_wgrad(const float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
+                                  int32_t ntaps, vinet_stream_t stream) {
+  const int64_t total = (int64_t)Cout * Cin * ntaps;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dwp, lddw, cs, grad, Cout, Cin, ntaps);
+  VINET_LAUNCH_OK("unpack_wgrad");
+  return 0;
+}

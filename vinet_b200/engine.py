@@ -1,0 +1,401 @@
+"""Host-side executor of the hot path: turns layers into C-ABI kernel calls (no torch compute ops).
+
+PyTorch is used for device memory (the caching allocator), streams and parameters only; every
+arithmetic step is a kernel of ``libvinet_b200.so`` reached through ``vinet_b200.lib``.
+
+Data model
+  * ``Act``  — a channel view of an NDHWC buffer together with the *pending transform* of its producer
+    (BatchNorm scale/shift and/or ReLU, applied by whoever reads it) and, when training, an fp32 buffer
+    holding the gradient w.r.t. the activated value.
+  * forward ops append closures to ``Engine.tape``; ``Engine.backward()`` runs them in reverse.  This is
+    a purpose-built replacement for autograd on this path: conv dgrad/wgrad, BN, pool,
+    upsample, head and loss backward are all explicit kernels.
+
+Precision modes
+  * ``bf16`` : bf16 storage, tcgen05 tensor-core GEMMs (fp32 accumulation in TMEM)   — throughput mode
+  * ``fp32`` : fp32 storage, fp32 FFMA GEMMs                                          — parity mode
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def cdiv(a, b):
+    return -(-a // b)
+
+
+def round_up(a, b):
+    return cdiv(a, b) * b
+
+
+class Act:
+    def __init__(self, buf, B, T, H, W, C_, choff=0, xform=L.XF_IDENT, scale=None, shift=None):
+        self.buf, self.B, self.T, self.H, self.W, self.C, self.choff = buf, B, T, H, W, C_, choff
+        self.ld = buf.shape[-1]
+        self.xform, self.scale, self.shift = xform, scale, shift
+        self.grad = None      # fp32 [B,T,H,W,ldg]
+        self.gchoff = 0
+        self.needs_grad = False
+
+    @property
+    def rows(self):
+        return self.B * self.T * self.H * self.W
+
+    def ptr(self):
+        return self.buf.data_ptr() + self.choff * self.buf.element_size()
+
+    def gptr(self):
+        return self.grad.data_ptr() + self.gchoff * 4
+
+    @property
+    def ldg(self):
+        return self.grad.shape[-1]
+
+    def slice(self, c0, c):
+        a = Act(self.buf, self.B, self.T, self.H, self.W, c, self.choff + c0, self.xform,
+                None if self.scale is None else self.scale[c0:c0 + c],
+                None if self.shift is None else self.shift[c0:c0 + c])
+        a.grad, a.gchoff, a.needs_grad = self.grad, self.gchoff + c0, self.needs_grad
+        return a
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _taps(kt, kh, kw):
+    return [(a, b, c) for a in range(kt) for b in range(kh) for c in range(kw)]
+
+
+def _fill_taps(field, taps):
+    for i, (a, b, c) in enumerate(taps):
+        field[i][0], field[i][1], field[i][2], field[i][3] = a, b, c, 0
+
+
+class ConvGeom:
+    def __init__(self, k, s, p):
+        (self.kt, self.kh, self.kw), (self.st, self.sh, self.sw), (self.pt, self.ph, self.pw) = k, s, p
+
+    def out_dims(self, T, H, W):
+        return ((T + 2 * self.pt - self.kt) // self.st + 1, (H + 2 * self.ph - self.kh) // self.sh + 1,
+                (W + 2 * self.pw - self.kw) // self.sw + 1)
+
+
+class Engine:
+    def __init__(self, precision="bf16", backend=None):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.eng = L.ENGINE_TC if precision == "bf16" else L.ENGINE_SIMT
+        self.dt = L.BF16 if precision == "bf16" else L.F32
+        self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.lib = backend if backend is not None else L.get()   # tests may inject the numpy kernel spec
+        self.pool = {}
+        self.wcache = {}
+        self.tape = []
+        self.grad_bufs = []
+        self.zero_list = []
+        self.param_grads = {}
+        self.device = None
+        self.training = False
+        self.record = False
+
+    # ------------------------------------------------------------------ plumbing
+    def stream(self):
+        if self.device.type != "cuda":
+            return None
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def call(self, name, desc):
+        self.lib.call(name, C.byref(desc), self.stream())
+
+    def buf(self, name, shape, dtype):
+        t = self.pool.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.pool[name] = t
+        return t
+
+    def memset(self, t):
+        self.lib.call("vinet_memset_async", t.data_ptr(), 0, t.numel() * t.element_size(), self.stream())
+
+    def begin(self, device, training, record):
+        self.device, self.training, self.record = device, training, record
+        self.tape, self.grad_bufs, self.zero_list, self.param_grads = [], [], [], {}
+
+    def new_act(self, name, B, T, H, W, C_, xform=L.XF_IDENT, affine=False, dtype=None):
+        buf = self.buf(name, (B, T, H, W, C_), dtype or self.tdtype)
+        sc = sh = None
+        if affine:
+            ss = self.buf(name + ".ss", (2, C_), torch.float32)
+            sc, sh = ss[0], ss[1]
+        a = Act(buf, B, T, H, W, C_, 0, xform, sc, sh)
+        if self.record:
+            self.want_grad(a, name)
+        return a
+
+    def want_grad(self, a, name):
+        a.grad = self.buf(name + ".grad", (a.B, a.T, a.H, a.W, a.C), torch.float32)
+        a.gchoff, a.needs_grad = 0, True
+        self.grad_bufs.append(a.grad)
+
+    # ------------------------------------------------------------------ descriptors
+    def _src(self, s, a):
+        s.ptr, s.scale, s.shift, s.ld, s.T, s.xform = a.ptr(), _ptr(a.scale), _ptr(a.shift), a.ld, a.T, a.xform
+
+    def _gather_fprop(self, g, srcs, geom, cs, To, Ho, Wo):
+        a0 = srcs[0]
+        g.mode, g.dtype = L.GATHER_FPROP, self.dt
+        g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, To, Ho, Wo, 1, 0
+        g.Ts, g.Hs, g.Ws, g.Cs = sum(s.T for s in srcs), a0.H, a0.W, cs
+        taps = _taps(geom.kt, geom.kh, geom.kw)
+        g.ntaps = len(taps)
+        _fill_taps(g.tap, taps)
+        g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
+        self._src(g.src[0], srcs[0])
+        if len(srcs) > 1:
+            self._src(g.src[1], srcs[1])
+        else:
+            g.src[1].ptr, g.src[1].T = None, 0
+
+    @staticmethod
+    def tiling(n):
+        n16 = round_up(n, 16)
+        n_tiles = cdiv(n16, 256)
+        return round_up(cdiv(n16, n_tiles), 16), n_tiles
+
+    def packed_weight(self, w, key, mode, taps, cs, n):
+        """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version."""
+        ck = (key, mode, tuple(taps), self.eng)
+        block_n, n_tiles = self.tiling(n)
+        k_blocks = cdiv(len(taps) * cs, L.TC_BLOCK_K)
+        hit = self.wcache.get(ck)
+        if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] is w:
+            return hit[1], block_n, n_tiles, k_blocks
+        nbytes = self.lib.fn["vinet_packed_weight_bytes"](self.eng, n, block_n, n_tiles, k_blocks)
+        out = hit[1] if hit is not None and hit[1].numel() == nbytes and hit[1].device == w.device else \
+            torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        d = L.Pack()
+        wc = w.detach()
+        assert wc.is_contiguous() and wc.dtype == torch.float32
+        d.w, d.Cout, d.Cin, d.kt, d.kh, d.kw = wc.data_ptr(), *wc.shape
+        d.cs, d.mode, d.ntaps = cs, mode, len(taps)
+        _fill_taps(d.tap, taps)
+        d.engine, d.block_n, d.n_tiles, d.k_blocks, d.out = self.eng, block_n, n_tiles, k_blocks, out.data_ptr()
+        self.call("vinet_pack_weights", d)
+        self.wcache[ck] = (w._version, out, None, w)
+        return out, block_n, n_tiles, k_blocks
+
+    # ------------------------------------------------------------------ convolution
+    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None):
+        """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY."""
+        a0 = srcs[0]
+        cs = a0.C
+        Cout = w.shape[0]
+        To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
+        assert (To, Ho, Wo, Cout) == (out.T, out.H, out.W, out.C), (name, (To, Ho, Wo, Cout), (out.T, out.H, out.W, out.C))
+        assert w.shape[1] == (cin_real or cs), name
+        taps = _taps(geom.kt, geom.kh, geom.kw)
+        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout)
+        d = L.Conv()
+        self._gather_fprop(d.g, srcs, geom, cs, To, Ho, Wo)
+        d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
+        d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
+        d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
+        d.out_dtype, d.accumulate = self.dt, 0
+        d.ep_scale, d.ep_shift, d.ep_act = None, _ptr(bias), L.ACT_NONE
+        self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream())
+        if not self.record:
+            return None
+
+        def backward(dy, lddy):
+            # ---- weight gradient
+            ktot = len(taps) * cs
+            lddw = round_up(Cout, 64)
+            dwp = self.buf(name + ".dwp", (round_up(ktot, 128), lddw), torch.float32)
+            self.memset(dwp)
+            wg = L.Wgrad()
+            self._gather_fprop(wg.g, srcs, geom, cs, To, Ho, Wo)
+            wg.dy, wg.lddy, wg.dy_dtype, wg.N, wg.dwp, wg.lddw = dy, lddy, self.dt, Cout, dwp.data_ptr(), lddw
+            rows = a0.B * To * Ho * Wo
+            if self.eng == L.ENGINE_TC:
+                tiles = cdiv(ktot, 128) * self.tiling(Cout)[1]
+                chunks = cdiv(rows, 64)
+            else:
+                tiles = cdiv(ktot, 64) * cdiv(Cout, 64)
+                chunks = cdiv(rows, 16)
+            wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
+            self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream())
+            gw = torch.empty_like(w)
+            self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, cs, gw.data_ptr(), Cout, w.shape[1], len(taps),
+                          self.stream())
+            self.param_grads[name + ".weight"] = gw
+            if bias is not None:
+                gb = torch.empty_like(bias)
+                ws = self.buf("colsum.ws", (1024,), torch.float64)
+                self.lib.call("vinet_colsum", dy, lddy, self.dt, rows, Cout, ws.data_ptr(), gb.data_ptr(), self.stream())
+                self.param_grads[name + ".bias"] = gb
+            # ---- data gradient, one launch per temporal phase of the transposed convolution
+            if not any(s.needs_grad for s in srcs):
+                return
+            Ti = sum(s.T for s in srcs)
+            for rho in range(geom.st):
+                dts = [dt for dt in range(geom.kt) if dt % geom.st == rho]
+                t0 = (rho - geom.pt) % geom.st
+                frames = len(range(t0, Ti, geom.st))
+                if not dts or frames == 0:
+                    continue
+                ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
+                n = w.shape[1]
+                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n)
+                dd = L.Conv()
+                g = dd.g
+                g.mode, g.dtype = L.GATHER_DGRAD, self.dt
+                g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, frames, a0.H, a0.W, geom.st, t0
+                g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = To, Ho, Wo, Cout, len(ptaps)
+                _fill_taps(g.tap, ptaps)
+                g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
+                g.src[0].ptr, g.src[0].scale, g.src[0].shift = dy, None, None
+                g.src[0].ld, g.src[0].T, g.src[0].xform = lddy, To, L.XF_IDENT
+                g.src[1].ptr, g.src[1].T = None, 0
+                dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
+                for i, s in enumerate(srcs):
+                    dd.out[i], dd.ldo[i], dd.out_T[i] = s.gptr(), s.ldg, s.T
+                if len(srcs) == 1:
+                    dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
+                dd.out_dtype, dd.accumulate = L.F32, 1
+                dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
+                self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream())
+        return backward
+
+    # ------------------------------------------------------------------ conv + BatchNorm (+ReLU pending)
+    def conv_bn(self, name_conv, name_bn, srcs, w, bn, geom, out, cin_real=None):
+        """BasicConv3d / one half of SepConv3d (model_utils.py:128-160): raw conv into `out`, batch statistics
+        -> out.scale/out.shift; consumers apply scale/shift + ReLU on read."""
+        conv_bwd = self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real)
+        Cn = out.C
+        rows = out.rows
+        st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)      # mean, invstd
+        fin = L.BnFinalize()
+        if self.training:
+            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64)
+            self.memset(sums)
+            sd = L.BnStats()
+            sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = out.ptr(), out.ld, self.dt, rows, Cn, sums.data_ptr()
+            self.call("vinet_bn_stats", sd)
+            fin.sums = sums.data_ptr()
+        fin.rows, fin.C, fin.gamma, fin.beta = rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
+        fin.eps, fin.momentum = bn.eps, bn.momentum
+        fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        fin.training = 1 if self.training else 0
+        fin.scale, fin.shift, fin.mean, fin.invstd = out.scale.data_ptr(), out.shift.data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+        self.call("vinet_bn_finalize", fin)
+        if self.training:
+            bn.num_batches_tracked += 1          # host-side counter buffer (nn.BatchNorm semantics)
+        out.xform = L.XF_AFFINE_RELU
+        if not self.record:
+            return
+        training = self.training
+
+        def backward():
+            bsums = self.buf(name_bn + ".bsums", (2, Cn), torch.float64)
+            self.memset(bsums)
+            dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+            dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
+            b = L.BnBwd()
+            b.g, b.ldg, b.y, b.ldy, b.dtype, b.rows, b.C, b.relu = out.gptr(), out.ldg, out.ptr(), out.ld, self.dt, rows, Cn, 1
+            b.scale, b.shift, b.mean, b.invstd = out.scale.data_ptr(), out.shift.data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+            b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+            b.dy, b.lddy, b.dy_dtype, b.training = dy.data_ptr(), Cn, self.dt, 1 if training else 0
+            self.call("vinet_bn_bwd_reduce", b)
+            self.call("vinet_bn_bwd_apply", b)
+            self.param_grads[name_bn + ".weight"] = dgamma
+            self.param_grads[name_bn + ".bias"] = dbeta
+            conv_bwd(dy.data_ptr(), Cn)
+        self.tape.append(backward)
+
+    # ------------------------------------------------------------------ max pooling
+    def maxpool(self, name, a, k, s, p):
+        To, Ho, Wo = ConvGeom(k, s, p).out_dims(a.T, a.H, a.W)
+        out = self.new_act(name, a.B, To, Ho, Wo, a.C)
+        d = L.Pool()
+        d.x, d.ldx, d.dtype, d.scale, d.shift, d.xform = a.ptr(), a.ld, self.dt, _ptr(a.scale), _ptr(a.shift), a.xform
+        d.B, d.Ti, d.Hi, d.Wi, d.C = a.B, a.T, a.H, a.W, a.C
+        (d.kt, d.kh, d.kw), (d.st, d.sh, d.sw), (d.pt, d.ph, d.pw) = k, s, p
+        d.To, d.Ho, d.Wo, d.out, d.ldo, d.out_dtype = To, Ho, Wo, out.ptr(), out.ld, self.dt
+        self.call("vinet_maxpool_fwd", d)
+        if self.record and a.needs_grad:
+            def backward():
+                d.gout, d.ldgo, d.gin, d.ldgi = out.gptr(), out.ldg, a.gptr(), a.ldg
+                self.call("vinet_maxpool_bwd", d)
+            self.tape.append(backward)
+        return out
+
+    # ------------------------------------------------------------------ decoder: conv -> ReLU -> 2x bilinear
+    def conv_relu_up(self, name, srcs, w, geom):
+        a0 = srcs[0]
+        To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
+        Cout = w.shape[0]
+        z = Act(self.buf(name + ".z", (a0.B, To, Ho, Wo, Cout), self.tdtype), a0.B, To, Ho, Wo, Cout, 0, L.XF_RELU)
+        conv_bwd = self.conv(name, srcs, w, geom, z)
+        u = self.new_act(name + ".up", a0.B, To, 2 * Ho, 2 * Wo, Cout)
+        d = L.Upsample()
+        d.z, d.ldz, d.dtype, d.relu, d.B, d.T, d.h, d.w, d.C = z.ptr(), z.ld, self.dt, 1, a0.B, To, Ho, Wo, Cout
+        d.u, d.ldu, d.u_dtype = u.ptr(), u.ld, self.dt
+        self.call("vinet_upsample_fwd", d)
+        if self.record:
+            def backward():
+                dz = self.buf("dy.%d" % (z.rows * Cout), (z.rows, Cout), self.tdtype)
+                d.gu, d.ldgu, d.dz, d.lddz, d.dz_dtype = u.gptr(), u.ldg, dz.data_ptr(), Cout, self.dt
+                self.call("vinet_upsample_bwd", d)
+                conv_bwd(dz.data_ptr(), Cout)
+            self.tape.append(backward)
+        return u
+
+    # ------------------------------------------------------------------ decoder tail
+    def conv_relu(self, name, srcs, w, geom, bias=None):
+        """Conv3d (+bias) whose ReLU is applied by the consumer (the head); returns (act, conv backward)."""
+        a0 = srcs[0]
+        To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
+        Cout = w.shape[0]
+        h = Act(self.buf(name + ".h", (a0.B, To, Ho, Wo, Cout), self.tdtype), a0.B, To, Ho, Wo, Cout, 0, L.XF_RELU)
+        return h, self.conv(name, srcs, w, geom, h, bias=bias)
+
+    def head(self, name, a, w, b, conv_bwd=None):
+        """relu? -> Conv3d(C,1,1) + bias -> Sigmoid -> (B,H,W) fp32 (model.py:282-283 + the final view)."""
+        assert a.T == 1, "the decoder collapses time to one frame before the head"
+        out = torch.empty((a.B, a.H, a.W), dtype=torch.float32, device=self.device)
+        d = L.Head()
+        relu = 1 if a.xform == L.XF_RELU else 0
+        assert a.xform in (L.XF_RELU, L.XF_IDENT)
+        d.x, d.ldx, d.dtype, d.relu, d.rows, d.C = a.ptr(), a.ld, self.dt, relu, a.rows, a.C
+        d.w, d.b, d.out = w.data_ptr(), b.data_ptr(), out.data_ptr()
+        self.call("vinet_head_fwd", d)
+        if self.record:
+            def backward(gout):
+                gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+                d.gout, d.dw, d.db = gout.data_ptr(), gw.data_ptr(), gb.data_ptr()
+                if conv_bwd is not None:        # input is a raw conv output: dx is that conv's dY
+                    dx = self.buf("dy.%d" % (a.rows * a.C), (a.rows, a.C), self.tdtype)
+                    d.dx, d.lddx, d.dx_dtype = dx.data_ptr(), a.C, self.dt
+                else:                           # input is a materialised activation: dx is its fp32 gradient
+                    d.dx, d.lddx, d.dx_dtype = a.gptr(), a.ldg, L.F32
+                self.call("vinet_head_bwd", d)
+                self.param_grads[name + ".weight"] = gw
+                self.param_grads[name + ".bias"] = gb
+                if conv_bwd is not None:
+                    conv_bwd(dx.data_ptr(), a.C)
+            self.head_backward = backward
+        return out
+
+    # ------------------------------------------------------------------ backward driver
+    def backward(self, gout):
+        """gout: fp32 (B,H,W) gradient w.r.t. the saliency map. Fills self.param_grads."""
+        for g in self.grad_bufs:
+            self.memset(g)
+        self.head_backward(gout)
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        return self.param_grads

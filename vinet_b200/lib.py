@@ -1,0 +1,213 @@
+"""ctypes binding of the C-ABI in ``include/vinet_b200.h`` (the drop-in boundary).
+
+The product path has NO fallback: if ``libvinet_b200.so`` is missing or a call fails, this raises.
+Structures mirror the header field by field; ``tests/test_abi.py`` checks ``sizeof`` of every struct
+against the values compiled into the library is not possible without a compute call, so it checks
+that every symbol declared in the header is exported and that the field lists agree with the header.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvinet_b200.so")
+
+BF16, F32 = 0, 1
+XF_IDENT, XF_RELU, XF_AFFINE, XF_AFFINE_RELU = 0, 1, 2, 3
+GATHER_FPROP, GATHER_DGRAD = 0, 1
+ENGINE_TC, ENGINE_SIMT = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+LOSS_KLDIV, LOSS_CC, LOSS_SIM, LOSS_NSS = 0, 1, 2, 3
+MAX_TAPS = 64
+TC_BLOCK_M, TC_BLOCK_K = 128, 64
+
+_p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class Src(C.Structure):
+    _fields_ = [("ptr", _p), ("scale", _p), ("shift", _p), ("ld", _i64), ("T", _i32), ("xform", _i32)]
+
+
+class Gather(C.Structure):
+    _fields_ = [("mode", _i32), ("dtype", _i32), ("B", _i32), ("Tr", _i32), ("Hr", _i32), ("Wr", _i32),
+                ("row_tstep", _i32), ("row_toff", _i32), ("Ts", _i32), ("Hs", _i32), ("Ws", _i32),
+                ("Cs", _i32), ("ntaps", _i32), ("st", _i32), ("sh", _i32), ("sw", _i32),
+                ("pt", _i32), ("ph", _i32), ("pw", _i32), ("tap", (C.c_int8 * 4) * MAX_TAPS), ("src", Src * 2)]
+
+
+class Conv(C.Structure):
+    _fields_ = [("g", Gather), ("w", _p), ("N", _i32), ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32),
+                ("out", _p * 2), ("ldo", _i64 * 2), ("out_T", _i32 * 2), ("out_dtype", _i32), ("accumulate", _i32),
+                ("ep_scale", _p), ("ep_shift", _p), ("ep_act", _i32)]
+
+
+class Wgrad(C.Structure):
+    _fields_ = [("g", Gather), ("dy", _p), ("lddy", _i64), ("dy_dtype", _i32), ("N", _i32), ("dwp", _p),
+                ("lddw", _i32), ("splits", _i32)]
+
+
+class Pack(C.Structure):
+    _fields_ = [("w", _p), ("Cout", _i32), ("Cin", _i32), ("kt", _i32), ("kh", _i32), ("kw", _i32), ("cs", _i32),
+                ("mode", _i32), ("ntaps", _i32), ("tap", (C.c_int8 * 4) * MAX_TAPS), ("engine", _i32),
+                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p)]
+
+
+class PackInput(C.Structure):
+    _fields_ = [("x", _p), ("sb", _i64), ("sc", _i64), ("st", _i64), ("sh", _i64), ("sw", _i64), ("B", _i32),
+                ("C", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("cpad", _i32), ("out", _p), ("out_dtype", _i32)]
+
+
+class BnStats(C.Structure):
+    _fields_ = [("y", _p), ("ld", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32), ("sums", _p)]
+
+
+class BnFinalize(C.Structure):
+    _fields_ = [("sums", _p), ("rows", _i64), ("C", _i32), ("gamma", _p), ("beta", _p), ("eps", _f32),
+                ("momentum", _f32), ("running_mean", _p), ("running_var", _p), ("training", _i32), ("scale", _p),
+                ("shift", _p), ("mean", _p), ("invstd", _p)]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [("g", _p), ("ldg", _i64), ("y", _p), ("ldy", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32),
+                ("relu", _i32), ("scale", _p), ("shift", _p), ("mean", _p), ("invstd", _p), ("gamma", _p),
+                ("sums", _p), ("dgamma", _p), ("dbeta", _p), ("dy", _p), ("lddy", _i64), ("dy_dtype", _i32),
+                ("training", _i32)]
+
+
+class Pool(C.Structure):
+    _fields_ = [("x", _p), ("ldx", _i64), ("dtype", _i32), ("scale", _p), ("shift", _p), ("xform", _i32),
+                ("B", _i32), ("Ti", _i32), ("Hi", _i32), ("Wi", _i32), ("C", _i32),
+                ("kt", _i32), ("kh", _i32), ("kw", _i32), ("st", _i32), ("sh", _i32), ("sw", _i32),
+                ("pt", _i32), ("ph", _i32), ("pw", _i32), ("To", _i32), ("Ho", _i32), ("Wo", _i32),
+                ("out", _p), ("ldo", _i64), ("out_dtype", _i32), ("gout", _p), ("ldgo", _i64), ("gin", _p),
+                ("ldgi", _i64)]
+
+
+class Upsample(C.Structure):
+    _fields_ = [("z", _p), ("ldz", _i64), ("dtype", _i32), ("relu", _i32), ("B", _i32), ("T", _i32), ("h", _i32),
+                ("w", _i32), ("C", _i32), ("u", _p), ("ldu", _i64), ("u_dtype", _i32), ("gu", _p), ("ldgu", _i64),
+                ("dz", _p), ("lddz", _i64), ("dz_dtype", _i32)]
+
+
+class Head(C.Structure):
+    _fields_ = [("x", _p), ("ldx", _i64), ("dtype", _i32), ("relu", _i32), ("rows", _i64), ("C", _i32), ("w", _p),
+                ("b", _p), ("out", _p), ("gout", _p), ("dx", _p), ("lddx", _i64), ("dx_dtype", _i32), ("dw", _p),
+                ("db", _p)]
+
+
+class Loss(C.Structure):
+    _fields_ = [("kind", _i32), ("s", _p), ("g", _p), ("B", _i32), ("n", _i32), ("per_sample", _p), ("out", _p),
+                ("counter", _p), ("gout", _p), ("grad_s", _p)]
+
+
+class Conv1d(C.Structure):
+    _fields_ = [("x", _p), ("w", _p), ("bias", _p), ("B", _i32), ("Cin", _i32), ("Lin", _i32), ("Cout", _i32),
+                ("Lout", _i32), ("k", _i32), ("stride", _i32), ("pad", _i32), ("y", _p), ("dy", _p), ("dx", _p),
+                ("dw", _p), ("dbias", _p)]
+
+
+class Bn1d(C.Structure):
+    _fields_ = [("y", _p), ("B", _i32), ("C", _i32), ("L", _i32), ("pool", _i32), ("gamma", _p), ("beta", _p),
+                ("eps", _f32), ("momentum", _f32), ("running_mean", _p), ("running_var", _p), ("training", _i32),
+                ("mean", _p), ("invstd", _p), ("out", _p), ("gout", _p), ("dy", _p), ("dgamma", _p), ("dbeta", _p)]
+
+
+class AvFuse(C.Structure):
+    _fields_ = [("y0", _p), ("ld", _i64), ("dtype", _i32), ("scale", _p), ("shift", _p), ("xform", _i32),
+                ("audio", _p), ("w", _p), ("bias", _p), ("B", _i32), ("C", _i32), ("vbuf", _p), ("out", _p),
+                ("ldo", _i64), ("out_dtype", _i32), ("gout", _p), ("ldgo", _i64), ("gy0", _p), ("ldgy0", _i64),
+                ("gaudio", _p), ("dw", _p), ("dbias", _p)]
+
+
+# name -> (restype, argtypes); every function declared in include/vinet_b200.h
+_S = C.c_void_p  # stream
+SIGNATURES = {
+    "vinet_conv_gemm": (C.c_int, [C.POINTER(Conv), _i32, _S]),
+    "vinet_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), _i32, _S]),
+    "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
+    "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
+    "vinet_unpack_wgrad": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _S]),
+    "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
+    "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
+    "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
+    "vinet_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwd), _S]),
+    "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
+    "vinet_maxpool_fwd": (C.c_int, [C.POINTER(Pool), _S]),
+    "vinet_maxpool_bwd": (C.c_int, [C.POINTER(Pool), _S]),
+    "vinet_upsample_fwd": (C.c_int, [C.POINTER(Upsample), _S]),
+    "vinet_upsample_bwd": (C.c_int, [C.POINTER(Upsample), _S]),
+    "vinet_head_fwd": (C.c_int, [C.POINTER(Head), _S]),
+    "vinet_head_bwd": (C.c_int, [C.POINTER(Head), _S]),
+    "vinet_loss_fwd": (C.c_int, [C.POINTER(Loss), _S]),
+    "vinet_loss_bwd": (C.c_int, [C.POINTER(Loss), _S]),
+    "vinet_conv1d_fwd": (C.c_int, [C.POINTER(Conv1d), _S]),
+    "vinet_conv1d_bwd": (C.c_int, [C.POINTER(Conv1d), _S]),
+    "vinet_bn1d_fwd": (C.c_int, [C.POINTER(Bn1d), _S]),
+    "vinet_bn1d_bwd": (C.c_int, [C.POINTER(Bn1d), _S]),
+    "vinet_avfuse_fwd": (C.c_int, [C.POINTER(AvFuse), _S]),
+    "vinet_avfuse_bwd": (C.c_int, [C.POINTER(AvFuse), _S]),
+    "vinet_memset_async": (C.c_int, [_p, C.c_int, C.c_size_t, _S]),
+    "vinet_axpy_f32": (C.c_int, [_p, _p, _i64, _i32, _S]),
+    "vinet_colsum": (C.c_int, [_p, _i64, _i32, _i64, _i32, _p, _p, _S]),
+    "vinet_last_error": (C.c_char_p, []),
+    "vinet_version": (C.c_char_p, []),
+    "vinet_device_info": (C.c_int, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "vinet_launch_count": (_i64, []),
+    "vinet_abi_sizes": (C.c_int, [C.POINTER(_i64), _i32]),
+    "vinet_debug_set": (C.c_int, [_i32, _i32]),
+}
+
+# declaration order of the structs in the header (vinet_abi_sizes)
+ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnBwd, Pool, Upsample, Head, Loss,
+               Conv1d, Bn1d, AvFuse]
+
+
+class VinetError(RuntimeError):
+    pass
+
+
+class Library:
+    """Loaded ``libvinet_b200.so``; ``call(name, *args)`` raises VinetError on a non-zero status."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.isfile(path):
+            raise VinetError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for this path)" % path)
+        self.path = path
+        self.dll = C.CDLL(path)
+        self.fn = {}
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(self.dll, name)
+            f.restype, f.argtypes = res, args
+            self.fn[name] = f
+        sizes = (_i64 * len(ABI_STRUCTS))()
+        n = self.fn["vinet_abi_sizes"](sizes, len(ABI_STRUCTS))
+        mine = [C.sizeof(t) for t in ABI_STRUCTS]
+        if n != len(ABI_STRUCTS) or list(sizes) != mine:
+            raise VinetError("ABI mismatch between lib.py and %s: %s vs %s" % (path, list(sizes), mine))
+
+    def call(self, name, *args):
+        rc = self.fn[name](*args)
+        if rc != 0:
+            raise VinetError("%s failed (%d): %s" % (name, rc, self.fn["vinet_last_error"]().decode()))
+
+    def version(self):
+        return self.fn["vinet_version"]().decode()
+
+    def launch_count(self):
+        return int(self.fn["vinet_launch_count"]())
+
+    def device_info(self):
+        a, b, c = _i32(), _i32(), _i32()
+        self.call("vinet_device_info", C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+
+_lib = None
+
+
+def get():
+    global _lib
+    if _lib is None:
+        _lib = Library()
+    return _lib

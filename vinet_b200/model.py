@@ -1,0 +1,300 @@
+"""Drop-in ``VideoSaliencyModel`` / ``VideoAudioSaliencyModel`` (reference model.py:72-112, :191-249).
+
+Same constructor keywords, ``forward()`` signatures, sub-module attribute tree and ``state_dict`` layout
+as the reference, so ``train.py`` / ``generate_result*.py`` can import these classes instead of the
+reference's.  The sub-modules are *parameter holders only* (they have no ``forward``): the computation
+is one fused plan executed by ``vinet_b200.engine.Engine`` through the C-ABI kernels, wrapped in a single
+``torch.autograd.Function`` so ``loss.backward()`` / optimizers / DDP see ordinary ``.grad`` tensors.
+
+Reference sites: BasicConv3d/SepConv3d/Mixed_* model_utils.py:128-420; BackBoneS3D model.py:690-743;
+DecoderConvUp{,8,16,48} model.py:251-499; SoundNet model.py:746-825.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import arch
+from . import lib as L
+from .engine import Act, ConvGeom, Engine
+
+BN_EPS, BN_MOM = 1e-3, 1e-3   # model_utils.py:132
+
+
+# ----------------------------------------------------------------------------- parameter holders
+class ConvParams(nn.Module):
+    """Holds a Conv3d/Conv2d weight (+bias) with PyTorch's default initialisation; never computes."""
+
+    def __init__(self, cin, cout, k, bias=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, *k))
+        self.bias = nn.Parameter(torch.empty(cout)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            bound = 1.0 / math.sqrt(cin * math.prod(k))
+            nn.init.uniform_(self.bias, -bound, bound)
+
+
+class BNParams(nn.Module):
+    def __init__(self, c, eps=BN_EPS, momentum=BN_MOM):
+        super().__init__()
+        self.eps, self.momentum = eps, momentum
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class Marker(nn.Module):
+    """Parameter-less placeholder keeping nn.Sequential indices equal to the reference's
+    (MaxPool3d / ReLU / Upsample / Sigmoid entries)."""
+
+    def __init__(self, what):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return self.what
+
+
+class BasicConv3d(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = ConvParams(cin, cout, (1, 1, 1))
+        self.bn = BNParams(cout)
+
+
+class SepConv3d(nn.Module):
+    def __init__(self, cin, cout, k, stride, padding):
+        super().__init__()
+        self.k, self.stride, self.padding = k, stride, padding
+        self.conv_s = ConvParams(cin, cout, (1, k, k))
+        self.bn_s = BNParams(cout)
+        self.conv_t = ConvParams(cout, cout, (k, 1, 1))
+        self.bn_t = BNParams(cout)
+
+
+class Mixed(nn.Module):
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+        cin, b0, b1r, b1, b2r, b2, b3 = arch.MIXED[name]
+        self.branch0 = nn.Sequential(BasicConv3d(cin, b0))
+        self.branch1 = nn.Sequential(BasicConv3d(cin, b1r), SepConv3d(b1r, b1, 3, 1, 1))
+        self.branch2 = nn.Sequential(BasicConv3d(cin, b2r), SepConv3d(b2r, b2, 3, 1, 1))
+        self.branch3 = nn.Sequential(Marker("MaxPool3d(3,1,1)"), BasicConv3d(cin, b3))
+
+
+class BackBoneS3D(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.base1 = nn.Sequential(SepConv3d(3, 64, 7, 2, 3), Marker("MaxPool3d((1,3,3),(1,2,2),(0,1,1))"),
+                                   BasicConv3d(64, 64), SepConv3d(64, 192, 3, 1, 1))
+        self.maxp2 = Marker("MaxPool3d((1,3,3),(1,2,2),(0,1,1))")
+        self.base2 = nn.Sequential(*[Mixed(n) for n in arch.STAGES["base2"]])
+        self.maxp3 = Marker("MaxPool3d(3,2,1)")
+        self.base3 = nn.Sequential(*[Mixed(n) for n in arch.STAGES["base3"]])
+        self.maxt4 = Marker("MaxPool3d((2,1,1),(2,1,1))")
+        self.maxp4 = Marker("MaxPool3d((1,2,2),(1,2,2))")
+        self.base4 = nn.Sequential(*[Mixed(n) for n in arch.STAGES["base4"]])
+
+
+class DecoderConvUp(nn.Module):
+    """Parameter layout of DecoderConvUp / DecoderConvUp8 / 16 / 48 (model.py:251-499)."""
+
+    def __init__(self, num_clips=32):
+        super().__init__()
+        self.num_clips = num_clips
+        self.upsampling = Marker("Upsample((1,2,2),trilinear)")
+        heads = [[ConvParams(cin, cout, (kt, 3, 3)), Marker("ReLU"), self.upsampling]
+                 for cin, cout, kt in arch.DECODER_HEAD]
+        tail = []
+        for item in arch.decoder_tail(num_clips):
+            if isinstance(item, str):
+                tail.append(self.upsampling if item == "up" else Marker(item))
+            else:
+                _, cin, cout, k, _, _, bias = item
+                tail.append(ConvParams(cin, cout, k, bias=bias))
+        self.convtsp1 = nn.Sequential(*heads[0])
+        self.convtsp2 = nn.Sequential(*heads[1])
+        self.convtsp3 = nn.Sequential(*heads[2])
+        self.convtsp4 = nn.Sequential(*(heads[3] + tail))
+
+
+# ----------------------------------------------------------------------------- the fused plan
+def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
+    a0 = srcs[0]
+    k, s, p = m.k, m.stride, m.padding
+    gs = ConvGeom((1, k, k), (1, s, s), (0, p, p))
+    To, Ho, Wo = gs.out_dims(a0.T, a0.H, a0.W)
+    cout = m.conv_s.weight.shape[0]
+    mid = e.new_act(pfx + ".s", a0.B, To, Ho, Wo, cout, affine=True)
+    e.conv_bn(pfx + ".conv_s", pfx + ".bn_s", srcs, m.conv_s.weight, m.bn_s, gs, mid, cin_real=cin_real)
+    gt = ConvGeom((k, 1, 1), (s, 1, 1), (p, 0, 0))
+    To2, _, _ = gt.out_dims(To, Ho, Wo)
+    if out is None:
+        out = e.new_act(pfx + ".t", a0.B, To2, Ho, Wo, cout, affine=True)
+    e.conv_bn(pfx + ".conv_t", pfx + ".bn_t", [mid], m.conv_t.weight, m.bn_t, gt, out)
+    return out
+
+
+_G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
+
+
+def _basic(e, pfx, x, m, out=None):
+    if out is None:
+        out = e.new_act(pfx + ".o", x.B, x.T, x.H, x.W, m.conv.weight.shape[0], affine=True)
+    e.conv_bn(pfx + ".conv", pfx + ".bn", [x], m.conv.weight, m.bn, _G1, out)
+    return out
+
+
+def _mixed(e, pfx, x, m):
+    cin, b0, b1r, b1, b2r, b2, b3 = arch.MIXED[m.name]
+    out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3, affine=True)
+    _basic(e, pfx + ".branch0.0", x, m.branch0[0], out.slice(0, b0))
+    t = _basic(e, pfx + ".branch1.0", x, m.branch1[0])
+    _sepconv(e, pfx + ".branch1.1", [t], m.branch1[1], out.slice(b0, b1))
+    t = _basic(e, pfx + ".branch2.0", x, m.branch2[0])
+    _sepconv(e, pfx + ".branch2.1", [t], m.branch2[1], out.slice(b0 + b1, b2))
+    p = e.maxpool(pfx + ".branch3.pool", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    _basic(e, pfx + ".branch3.1", p, m.branch3[1], out.slice(b0 + b1 + b2, b3))
+    out.xform = L.XF_AFFINE_RELU
+    return out
+
+
+def backbone_plan(e, pfx, bb, x):
+    """BackBoneS3D.forward (model.py:720-743): returns [y0, y1, y2, y3] as Acts."""
+    a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
+    a = e.maxpool(pfx + "base1.1", a, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    a = _basic(e, pfx + "base1.2", a, bb.base1[2])
+    y3 = _sepconv(e, pfx + "base1.3", [a], bb.base1[3])
+    a = e.maxpool(pfx + "maxp2", y3, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    for i, m in enumerate(bb.base2):
+        a = _mixed(e, pfx + "base2.%d" % i, a, m)
+    y2 = a
+    a = e.maxpool(pfx + "maxp3", y2, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    for i, m in enumerate(bb.base3):
+        a = _mixed(e, pfx + "base3.%d" % i, a, m)
+    y1 = a
+    # maxt4 (2,1,1) followed by maxp4 (1,2,2) == one (2,2,2)/2 max pool
+    a = e.maxpool(pfx + "maxt4p4", y1, (2, 2, 2), (2, 2, 2), (0, 0, 0))
+    for i, m in enumerate(bb.base4):
+        a = _mixed(e, pfx + "base4.%d" % i, a, m)
+    return [a, y1, y2, y3]
+
+
+def decoder_plan(e, pfx, dec, y0, y1, y2, y3):
+    """DecoderConvUp*.forward (model.py:286-311): returns the (B,H,W) fp32 saliency map tensor."""
+    heads = [dec.convtsp1[0], dec.convtsp2[0], dec.convtsp3[0], dec.convtsp4[0]]
+    names = ["convtsp1.0", "convtsp2.0", "convtsp3.0", "convtsp4.0"]
+    skips = [None, y1, y2, y3]
+    z = y0
+    for m, nm, skip in zip(heads, names, skips):
+        kt = m.weight.shape[2]
+        srcs = [z] if skip is None else [z, skip]
+        z = e.conv_relu_up(pfx + nm, srcs, m.weight, ConvGeom((kt, 3, 3), (kt, 1, 1), (0, 1, 1)))
+    tail = arch.decoder_tail(dec.num_clips)
+    convs = [(i + 3, it) for i, it in enumerate(tail) if not isinstance(it, str)]
+    # first tail conv: conv -> relu -> up
+    idx, (_, cin, cout, k, s, p, bias) = convs[0]
+    z = e.conv_relu_up(pfx + "convtsp4.%d" % idx, [z], dec.convtsp4[idx].weight, ConvGeom(k, s, (0, p, p)))
+    conv_bwd = None
+    if len(convs) == 3:      # (kt,1,1) time-collapsing conv -> relu, then the 1x1x1 head
+        idx, (_, cin, cout, k, s, p, bias) = convs[1]
+        m = dec.convtsp4[idx]
+        z, conv_bwd = e.conv_relu(pfx + "convtsp4.%d" % idx, [z], m.weight, ConvGeom(k, s, (0, p, p)), bias=m.bias)
+    idx, _ = convs[-1]
+    m = dec.convtsp4[idx]
+    return e.head(pfx + "convtsp4.%d" % idx, z, m.weight, m.bias, conv_bwd)
+
+
+class _PlanFunction(torch.autograd.Function):
+    """One autograd node for the whole model: forward runs the plan, backward runs the tape."""
+
+    @staticmethod
+    def forward(ctx, model, record, names, x, *extra_and_params):
+        e = model._engine_for(x.device)
+        out = model._run_plan(e, record, x, *extra_and_params[:model._n_extra])
+        ctx.engine, ctx.names, ctx.gen, ctx.n_extra = e, names, e.generation, model._n_extra
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        e = ctx.engine
+        if ctx.gen != e.generation:
+            raise RuntimeError("vinet_b200: backward() of a stale forward (one outstanding forward per model)")
+        grads = e.backward(gout.contiguous().float())
+        return (None, None, None, None) + (None,) * ctx.n_extra + tuple(grads.get(n) for n in ctx.names)
+
+
+class _PlanModule(nn.Module):
+    """Shared machinery: engine cache (per device), parameter list, autograd wiring."""
+
+    precision = "bf16"
+    _n_extra = 0
+
+    def set_precision(self, precision):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.__dict__.pop("_engines", None)
+        return self
+
+    def _engine_for(self, device):
+        engines = self.__dict__.setdefault("_engines", {})
+        key = (str(device), self.precision)
+        if key not in engines:
+            engines[key] = Engine(self.precision, backend=self.__dict__.get("_backend"))
+            engines[key].generation = 0
+        return engines[key]
+
+    def _call_plan(self, x, *extra):
+        if x.device.type != "cuda" and self.__dict__.get("_backend") is None:
+            raise RuntimeError("vinet_b200 has no CPU path: move the model and inputs to a CUDA device")
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and self._plan_uses(n)]
+        names = tuple(n for n, _ in named)
+        record = torch.is_grad_enabled() and len(named) > 0
+        return _PlanFunction.apply(self, record, names, x, *extra, *[p for _, p in named])
+
+    def _plan_uses(self, name):
+        return True
+
+
+class VideoSaliencyModel(_PlanModule):
+    """ViNet (model.py:72-112). Only the default ``use_upsample=True, num_hier=3`` family is on the hot
+    path; other settings raise, like the reference does for ``use_upsample=False``."""
+
+    def __init__(self, transformer_in_channel=32, nhead=4, use_upsample=True, num_hier=3, num_clips=32):
+        super().__init__()
+        if not use_upsample:
+            raise NameError("name 'DecoderConvT' is not defined")      # model.py:101 — same failure as the reference
+        if num_hier != 3:
+            raise NotImplementedError("num_hier=%r ablation decoders are out of the hot-path scope" % (num_hier,))
+        self.backbone = BackBoneS3D()
+        self.num_hier = num_hier
+        self.decoder = DecoderConvUp(num_clips)
+
+    def forward(self, x):
+        return self._call_plan(x)
+
+    def _run_plan(self, e, record, x, prefix=""):
+        e.generation += 1
+        e.begin(x.device, self.training, record)
+        xin = pack_input(e, x)
+        ys = backbone_plan(e, prefix + "backbone.", self.backbone, xin)
+        return decoder_plan(e, prefix + "decoder.", self.decoder, *ys)
+
+
+def pack_input(e, x):
+    """(B,3,T,H,W) fp32, any strides (train.py:205 passes a permuted view) -> NDHWC, C padded 3->8."""
+    assert x.dim() == 5 and x.shape[1] == 3 and x.dtype == torch.float32, "expected a (B,3,T,H,W) fp32 clip"
+    B, _, T, H, W = x.shape
+    assert H % 32 == 0 and W % 32 == 0, "H and W must be multiples of 32 (the reference fails otherwise)"
+    buf = e.buf("input.packed", (B, T, H, W, 8), e.tdtype)
+    d = L.PackInput()
+    d.x = x.data_ptr()
+    d.sb, d.sc, d.st, d.sh, d.sw = x.stride()
+    d.B, d.C, d.T, d.H, d.W, d.cpad, d.out, d.out_dtype = B, 3, T, H, W, 8, buf.data_ptr(), e.dt
+    e.call("vinet_pack_input", d)
+    return Act(buf, B, T, H, W, 8)
