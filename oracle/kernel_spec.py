@@ -331,6 +331,7 @@ class Spec:
 
     def loss_bwd(self, d, stream):
         import torch
-        s, v = self._loss(d, True)
-        (gr,) = torch.autograd.grad(v, s)
+        with torch.enable_grad():
+            s, v = self._loss(d, True)
+            (gr,) = torch.autograd.grad(v, s)
         _arr(d.grad_s, d.B * d.n)[:] = gr.numpy().reshape(-1) * _arr(d.gout, 1)[0]

@@ -1,0 +1,75 @@
+"""GPU: every CUDA kernel, called through the C-ABI via the engine, against the numpy kernel spec run on
+the CPU with the same seeded inputs (fp32 engine: tight; bf16 tcgen05 engine: bf16-rounding tolerance)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenarios as S
+from oracle import torch_oracle as O
+from oracle.kernel_spec import Spec
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+CONV_CASES = [dict(), dict(T0=1, T1=4, kt=5, Cin=24, Cout=16, H=4, W=7),
+              dict(B=1, T0=4, T1=8, kt=3, Cin=64, Cout=96, H=14, W=24),
+              dict(B=2, T0=2, T1=4, kt=3, Cin=192, Cout=288, H=8, W=12)]
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 2e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("case", range(len(CONV_CASES)))
+def test_conv_concat_relu_upsample(precision, rtol, case):
+    kw = CONV_CASES[case]
+    ref = S.conv_up("cpu", "fp32", Spec(), **kw)
+    got = S.conv_up("cuda", precision, **kw)
+    bad = S.compare(got, ref, rtol)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("name", ["3b", "4c", "5c"])
+def test_mixed_block(precision, rtol, name):
+    ref = S.mixed("cpu", "fp32", Spec(), name=name)
+    got = S.mixed("cuda", precision, name=name)
+    bad = S.compare(got, ref, rtol)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_stem_sepconv_and_pool(precision, rtol):
+    ref = S.stem("cpu", "fp32", Spec())
+    got = S.stem("cuda", precision)
+    bad = S.compare(got, ref, rtol)
+    assert not bad, bad
+
+
+def test_losses_against_reference_goldens():
+    """north_star: loss scalars within 1e-5 relative of the reference."""
+    from vinet_b200 import loss as PL
+    z = np.load(os.path.join(GOLD, "losses.npz"))
+    for tag in O.LOSS_CASES:
+        s, gt, fix = O.make_loss_inputs(tag)
+        s = s.cuda().requires_grad_(True)
+        for nm, fn, tgt in [("kldiv", PL.kldiv, gt), ("cc", PL.cc, gt), ("sim", PL.similarity, gt), ("nss", PL.nss, fix)]:
+            v = fn(s, tgt.cuda())
+            (g,) = torch.autograd.grad(v, s)
+            ref = float(z[f"{tag}/{nm}"])
+            assert abs(v.item() - ref) <= 1e-5 * abs(ref) + 1e-9, (tag, nm, v.item(), ref)
+            gg = g.cpu().numpy() if tag == "a" else g.cpu().numpy()[:, ::7, ::5]
+            rg = z[f"{tag}/{nm}_grad"]
+            assert np.allclose(gg, rg, rtol=2e-3, atol=2e-5 * np.abs(rg).max()), (tag, nm, np.abs(gg - rg).max())
+
+
+def test_loss_func_contract():
+    from vinet_b200 import loss as PL
+
+    class A:
+        kldiv, cc, sim, l1 = True, True, True, False
+        kldiv_coeff, cc_coeff, sim_coeff, batch_size = 1.0, -1.0, -1.0, 3
+    s, gt, _ = O.make_loss_inputs("a")
+    out = PL.loss_func(s.cuda(), gt.cuda(), A)
+    assert out.shape == (1,) and out.is_cuda
+    ref = O.kldiv(s, gt) - O.cc(s, gt) - O.similarity(s, gt)
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-6
