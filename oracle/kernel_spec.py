@@ -335,3 +335,121 @@ class Spec:
             s, v = self._loss(d, True)
             (gr,) = torch.autograd.grad(v, s)
         _arr(d.grad_s, d.B * d.n)[:] = gr.numpy().reshape(-1) * _arr(d.gout, 1)[0]
+
+
+# ----------------------------------------------------------------------------- audio branch (AViNet)
+def _t(ptr, shape):
+    import torch
+    n = int(np.prod(shape))
+    return torch.from_numpy(_arr(ptr, n).reshape(shape))
+
+
+def _conv1d_fwd(self, d, stream):
+    import torch.nn.functional as F
+    x, w = _t(d.x, (d.B, d.Cin, d.Lin)), _t(d.w, (d.Cout, d.Cin, d.k))
+    b = _t(d.bias, (d.Cout,)) if d.bias else None
+    _t(d.y, (d.B, d.Cout, d.Lout))[:] = F.conv1d(x, w, b, d.stride, d.pad)
+
+
+def _conv1d_bwd(self, d, stream):
+    import torch
+    import torch.nn.functional as F
+    x = _t(d.x, (d.B, d.Cin, d.Lin)).clone().requires_grad_(True)
+    w = _t(d.w, (d.Cout, d.Cin, d.k)).clone().requires_grad_(True)
+    b = _t(d.bias, (d.Cout,)).clone().requires_grad_(True)
+    with torch.enable_grad():
+        y = F.conv1d(x, w, b, d.stride, d.pad)
+        gx, gw, gb = torch.autograd.grad(y, (x, w, b), _t(d.dy, (d.B, d.Cout, d.Lout)))
+    if d.dx:
+        _t(d.dx, (d.B, d.Cin, d.Lin))[:] = gx
+    _t(d.dw, (d.Cout, d.Cin, d.k))[:] = gw
+    if d.dbias:
+        _t(d.dbias, (d.Cout,))[:] = gb
+
+
+def _bn1d(d, y, train_stats):
+    import torch
+    import torch.nn.functional as F
+    g, b = _t(d.gamma, (d.C,)), _t(d.beta, (d.C,))
+    if d.training:
+        mean, var = train_stats if train_stats else (y.mean((0, 2)), y.var((0, 2), unbiased=False))
+    else:
+        mean, var = _t(d.running_mean, (d.C,)), _t(d.running_var, (d.C,))
+    invstd = 1 / torch.sqrt(var + d.eps)
+    o = F.relu((y - mean[None, :, None]) * invstd[None, :, None] * g[None, :, None] + b[None, :, None])
+    if d.pool > 1:
+        o = F.max_pool1d(o, d.pool, d.pool)
+    return o, mean, var, invstd
+
+
+def _bn1d_fwd(self, d, stream):
+    import torch
+    y = _t(d.y, (d.B, d.C, d.L))
+    o, mean, var, invstd = _bn1d(d, y, None)
+    _t(d.out, (d.B, d.C, d.L // d.pool))[:] = o
+    _t(d.mean, (d.C,))[:] = mean
+    _t(d.invstd, (d.C,))[:] = invstd
+    if d.training and d.running_mean:
+        n = d.B * d.L
+        rm, rv = _t(d.running_mean, (d.C,)), _t(d.running_var, (d.C,))
+        rm[:] = (1 - d.momentum) * rm + d.momentum * mean
+        rv[:] = (1 - d.momentum) * rv + d.momentum * var * n / (n - 1)
+
+
+def _bn1d_bwd(self, d, stream):
+    import torch
+    import torch.nn.functional as F
+    y = _t(d.y, (d.B, d.C, d.L)).clone().requires_grad_(True)
+    g = _t(d.gamma, (d.C,)).clone().requires_grad_(True)
+    b = _t(d.beta, (d.C,)).clone().requires_grad_(True)
+    with torch.enable_grad():
+        if d.training:
+            o = F.relu(F.batch_norm(y, None, None, g, b, True, 0.0, d.eps))
+        else:
+            o = F.relu(F.batch_norm(y, _t(d.running_mean, (d.C,)), _t(d.running_var, (d.C,)), g, b, False, 0.0, d.eps))
+        if d.pool > 1:
+            o = F.max_pool1d(o, d.pool, d.pool)
+        gy, gg, gb = torch.autograd.grad(o, (y, g, b), _t(d.gout, (d.B, d.C, d.L // d.pool)))
+    _t(d.dy, (d.B, d.C, d.L))[:] = gy
+    _t(d.dgamma, (d.C,))[:] = gg
+    _t(d.dbeta, (d.C,))[:] = gb
+
+
+def _av_inputs(d):
+    import torch
+    y0 = torch.from_numpy(_xform(_rows_view(d.y0, d.B * 4 * 7 * 12, d.ld, d.C), d.xform, d.scale, d.shift, 0, d.C))
+    return y0.reshape(d.B, 4, 7, 12, d.C).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _avfuse_fwd(self, d, stream):
+    import torch
+    import torch.nn.functional as F
+    y0 = _av_inputs(d)
+    v = F.max_pool3d(y0, (4, 1, 1), (2, 1, 2)).flatten(2)
+    _t(d.vbuf, (d.B, d.C, 42))[:] = v
+    o = F.bilinear(v, _t(d.audio, (d.B, d.C, 3)), _t(d.w, (336, 42, 3)), _t(d.bias, (336,)))     # (B,C,336)
+    assert d.out_dtype == L.F32
+    _rows_view(d.out, d.B * 336, d.ldo, d.C)[:] = o.permute(0, 2, 1).reshape(d.B * 336, d.C).numpy()
+
+
+def _avfuse_bwd(self, d, stream):
+    import torch
+    import torch.nn.functional as F
+    y0 = _av_inputs(d).requires_grad_(True)
+    a = _t(d.audio, (d.B, d.C, 3)).clone().requires_grad_(True)
+    w = _t(d.w, (336, 42, 3)).clone().requires_grad_(True)
+    b = _t(d.bias, (336,)).clone().requires_grad_(True)
+    go = torch.from_numpy(_rows_view(d.gout, d.B * 336, d.ldgo, d.C).copy()).reshape(d.B, 336, d.C).permute(0, 2, 1)
+    with torch.enable_grad():
+        o = F.bilinear(F.max_pool3d(y0, (4, 1, 1), (2, 1, 2)).flatten(2), a, w, b)
+        gy, ga, gw, gb = torch.autograd.grad(o, (y0, a, w, b), go)
+    gy0 = _rows_view(d.gy0, d.B * 4 * 7 * 12, d.ldgy0, d.C)
+    gy0 += gy.permute(0, 2, 3, 4, 1).reshape(-1, d.C).numpy()
+    _t(d.gaudio, (d.B, d.C, 3))[:] = ga
+    _t(d.dw, (336, 42, 3))[:] = gw
+    _t(d.dbias, (336,))[:] = gb
+
+
+Spec.conv1d_fwd, Spec.conv1d_bwd = _conv1d_fwd, _conv1d_bwd
+Spec.bn1d_fwd, Spec.bn1d_bwd = _bn1d_fwd, _bn1d_bwd
+Spec.avfuse_fwd, Spec.avfuse_bwd = _avfuse_fwd, _avfuse_bwd

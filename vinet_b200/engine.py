@@ -85,11 +85,12 @@ class ConvGeom:
 
 class Engine:
     def __init__(self, precision="bf16", backend=None):
-        assert precision in ("bf16", "fp32")
+        # "bf16_simt": bf16 storage with the fp32 FFMA engine — the on-device cross-check of the tcgen05 path
+        assert precision in ("bf16", "fp32", "bf16_simt")
         self.precision = precision
         self.eng = L.ENGINE_TC if precision == "bf16" else L.ENGINE_SIMT
-        self.dt = L.BF16 if precision == "bf16" else L.F32
-        self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dt = L.F32 if precision == "fp32" else L.BF16
+        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.lib = backend if backend is not None else L.get()   # tests may inject the numpy kernel spec
         self.pool = {}
         self.wcache = {}
@@ -100,6 +101,8 @@ class Engine:
         self.device = None
         self.training = False
         self.record = False
+        self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
+        self.l2_flush = None
 
     # ------------------------------------------------------------------ plumbing
     def stream(self):
@@ -116,6 +119,19 @@ class Engine:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self.pool[name] = t
         return t
+
+    def timed(self, label, kind, flops, fn):
+        """Run one kernel call; when profiling, bracket it with CUDA events on the launching stream (after
+        evicting L2 by overwriting a buffer larger than it)."""
+        if self.profile is None:
+            return fn()
+        if self.l2_flush is not None:
+            self.memset(self.l2_flush)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.profile.append((label, kind, flops, e0, e1))
 
     def memset(self, t):
         self.lib.call("vinet_memset_async", t.data_ptr(), 0, t.numel() * t.element_size(), self.stream())
@@ -205,7 +221,9 @@ class Engine:
         d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
         d.out_dtype, d.accumulate = self.dt, 0
         d.ep_scale, d.ep_shift, d.ep_act = None, _ptr(bias), L.ACT_NONE
-        self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream())
+        cin_r = w.shape[1]
+        flops = 2.0 * a0.B * To * Ho * Wo * len(taps) * cin_r * Cout
+        self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
         if not self.record:
             return None
 
@@ -226,7 +244,7 @@ class Engine:
                 tiles = cdiv(ktot, 64) * cdiv(Cout, 64)
                 chunks = cdiv(rows, 16)
             wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
-            self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream())
+            self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
             gw = torch.empty_like(w)
             self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, cs, gw.data_ptr(), Cout, w.shape[1], len(taps),
                           self.stream())
@@ -266,7 +284,8 @@ class Engine:
                     dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
                 dd.out_dtype, dd.accumulate = L.F32, 1
                 dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
-                self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream())
+                dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
+                self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
         return backward
 
     # ------------------------------------------------------------------ conv + BatchNorm (+ReLU pending)

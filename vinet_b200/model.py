@@ -236,7 +236,7 @@ class _PlanModule(nn.Module):
     _n_extra = 0
 
     def set_precision(self, precision):
-        assert precision in ("bf16", "fp32")
+        assert precision in ("bf16", "fp32", "bf16_simt")
         self.precision = precision
         self.__dict__.pop("_engines", None)
         return self
