@@ -10,7 +10,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 pids=()
 for f in $SRC/*.cu; do
   o=build/$(basename ${f%.cu}).o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ $SRC/common.cuh -nt "$o" ] || [ $SRC/gather.cuh -nt "$o" ] || [ include/vinet_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ $SRC/common.cuh -nt "$o" ] || [ $SRC/gather.cuh -nt "$o" ] || [ $SRC/tc_ptx.cuh -nt "$o" ] || [ include/vinet_b200.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
     pids+=($!)
   fi

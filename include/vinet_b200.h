@@ -33,6 +33,13 @@ enum { VINET_GATHER_FPROP = 0, VINET_GATHER_DGRAD = 1 };
 enum { VINET_ENGINE_TC = 0, VINET_ENGINE_SIMT = 1 };
 enum { VINET_ACT_NONE = 0, VINET_ACT_RELU = 1, VINET_ACT_SIGMOID = 2 };
 enum { VINET_LOSS_KLDIV = 0, VINET_LOSS_CC = 1, VINET_LOSS_SIM = 2, VINET_LOSS_NSS = 3 };
+/* TC engine operand feed. GATHER: producer warps gather A through registers (any stride, pending transforms).
+ * TMA: A/dy tiles fetched by cp.async.bulk.tensor (5-D tiled tensor maps, hardware zero fill = conv padding),
+ * persistent CTAs, double-buffered TMEM accumulators; needs bf16 sources with VINET_XF_IDENT and spatial stride 1. */
+enum { VINET_KERNEL_GATHER = 0, VINET_KERNEL_TMA = 1 };
+/* K index of packed weights / packed weight gradients. DENSE: k = tap*cs + c.  TAP64: every tap is padded to a
+ * multiple of 64 channels, k = (tap*ceil(cs/64) + c/64)*64 + c%64 (one 64-wide K block per TMA box). */
+enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1 };
 
 #define VINET_MAX_TAPS 64
 #define VINET_TC_BLOCK_M 128
@@ -81,7 +88,7 @@ typedef struct vinet_conv {
   int32_t N;        /* real output channels */
   int32_t block_n;  /* TC engine: UMMA N per tile (multiple of 16, <= 256) */
   int32_t n_tiles;  /* TC engine: tiles along N */
-  int32_t k_blocks; /* ceil(ntaps*Cs / 64) */
+  int32_t k_blocks; /* DENSE: ceil(ntaps*Cs / 64); TAP64: ntaps*ceil(Cs/64) */
   void* out[2];
   int64_t ldo[2];
   int32_t out_T[2];
@@ -90,6 +97,7 @@ typedef struct vinet_conv {
   const float* ep_scale; /* per-output-channel, may be NULL */
   const float* ep_shift; /* per-output-channel (bias), may be NULL */
   int32_t ep_act;        /* VINET_ACT_* */
+  int32_t kernel;        /* VINET_KERNEL_* (TC engine); TMA expects w packed with VINET_KLAYOUT_TAP64 */
 } vinet_conv_t;
 int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stream_t stream);
 
@@ -104,9 +112,10 @@ typedef struct vinet_wgrad {
   int64_t lddy;
   int32_t dy_dtype;
   int32_t N;
-  float* dwp;    /* [round_up(ntaps*Cs,128)][lddw] */
+  float* dwp;    /* [round_up(K,128)][lddw], K = ntaps*Cs (GATHER) or ntaps*round_up(Cs,64) (TMA: TAP64 rows) */
   int32_t lddw;  /* >= round_up(N,64) */
   int32_t splits; /* CTAs along the row (reduction) dimension */
+  int32_t kernel; /* VINET_KERNEL_* (TC engine) */
 } vinet_wgrad_t;
 int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream);
 
@@ -120,6 +129,7 @@ typedef struct vinet_pack {
   int8_t tap[VINET_MAX_TAPS][4];
   int32_t engine, block_n, n_tiles, k_blocks;
   void* out; /* TC: bf16 [n_tiles][k_blocks][block_n][64] 128B-swizzled; SIMT: fp32 [k_blocks*64][round_up(N,64)] */
+  int32_t layout; /* VINET_KLAYOUT_* */
 } vinet_pack_t;
 int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
 size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks);
@@ -166,6 +176,23 @@ typedef struct vinet_bn_finalize {
   float* invstd;
 } vinet_bn_finalize_t;
 int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream);
+
+/* out = relu?(scale*y + shift): materialises BatchNorm(+ReLU) of a raw conv output (possibly into a channel
+ * slice of a concat buffer, model_utils.py:187), so that consumers read it untransformed (TMA-fed kernels). */
+typedef struct vinet_bn_apply {
+  const void* y;
+  int64_t ldy;
+  int32_t dtype;
+  int64_t rows;
+  int32_t C;
+  int32_t relu;
+  const float* scale;
+  const float* shift;
+  void* out;
+  int64_t ldo;
+  int32_t out_dtype;
+} vinet_bn_apply_t;
+int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream);
 
 /* Backward of y_hat = relu?(scale*y + shift) w.r.t. the raw conv output y. */
 typedef struct vinet_bn_bwd {

@@ -122,7 +122,7 @@ class Spec:
         out[..., :d.C] = np.transpose(x, (0, 2, 3, 4, 1))
 
     def pack_weights(self, d, stream):
-        assert d.engine == L.ENGINE_SIMT
+        assert d.engine == L.ENGINE_SIMT and d.layout == L.KLAYOUT_DENSE
         w = _arr(d.w, d.Cout * d.Cin * d.kt * d.kh * d.kw).reshape(d.Cout, d.Cin, d.kt, d.kh, d.kw)
         n = d.Cout if d.mode == L.GATHER_FPROP else d.Cin
         npad = -(-n // 64) * 64
@@ -206,6 +206,14 @@ class Spec:
         _arr(d.shift, c)[:] = _arr(d.beta, c) - mean * sc
         _arr(d.mean, c)[:] = mean
         _arr(d.invstd, c)[:] = invstd
+
+    def bn_apply(self, d, stream):
+        assert d.dtype == L.F32 and d.out_dtype == L.F32
+        y = _rows_view(d.y, d.rows, d.ldy, d.C)
+        v = y * _arr(d.scale, d.C) + _arr(d.shift, d.C)
+        if d.relu:
+            v = np.maximum(v, 0)
+        _rows_view(d.out, d.rows, d.ldo, d.C)[:] = v.astype(np.float32)
 
     def _bn_bwd_terms(self, d):
         c = d.C

@@ -20,6 +20,8 @@ int conv_gemm_simt(const vinet_conv_t* d, cudaStream_t stream);
 int conv_wgrad_simt(const vinet_wgrad_t* d, cudaStream_t stream);
 int conv_gemm_tc(const vinet_conv_t* d, cudaStream_t stream);
 int conv_wgrad_tc(const vinet_wgrad_t* d, cudaStream_t stream);
+int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream);
+int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream);
 int tc_debug_set(unsigned int v);
 
 __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, int accumulate) {
@@ -34,7 +36,8 @@ extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stre
   VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_gemm: bad tap count");
   VINET_CHECK(d->g.B > 0 && d->g.Tr > 0 && d->g.Hr > 0 && d->g.Wr > 0, "conv_gemm: empty row space");
   VINET_CHECK(d->g.st > 0 && d->g.sh > 0 && d->g.sw > 0 && d->g.row_tstep > 0, "conv_gemm: bad strides");
-  if (engine == VINET_ENGINE_TC) return conv_gemm_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC)
+    return d->kernel == VINET_KERNEL_TMA ? conv_gemm_tma(d, (cudaStream_t)stream) : conv_gemm_tc(d, (cudaStream_t)stream);
   if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);
   set_error("conv_gemm: unknown engine %d", engine);
   return -1;
@@ -44,7 +47,8 @@ extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_st
   VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_wgrad: bad tap count");
   VINET_CHECK(d->splits >= 1, "conv_wgrad: splits");
   VINET_CHECK(d->lddw >= d->N, "conv_wgrad: lddw");
-  if (engine == VINET_ENGINE_TC) return conv_wgrad_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC)
+    return d->kernel == VINET_KERNEL_TMA ? conv_wgrad_tma(d, (cudaStream_t)stream) : conv_wgrad_tc(d, (cudaStream_t)stream);
   if (engine == VINET_ENGINE_SIMT) return conv_wgrad_simt(d, (cudaStream_t)stream);
   set_error("conv_wgrad: unknown engine %d", engine);
   return -1;
@@ -66,7 +70,7 @@ extern "C" int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t a
 }
 
 extern "C" const char* vinet_last_error(void) { return g_err; }
-extern "C" const char* vinet_version(void) { return "vinet_b200 0.1 (sm_100a; tcgen05+TMEM conv, fp32 SIMT parity engine)"; }
+extern "C" const char* vinet_version(void) { return "vinet_b200 0.2 (sm_100a; TMA-fed persistent tcgen05+TMEM conv, fp32 SIMT parity engine)"; }
 extern "C" int64_t vinet_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
@@ -85,7 +89,7 @@ extern "C" int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* 
 extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
   const int64_t sizes[] = {sizeof(vinet_src_t),      sizeof(vinet_gather_t),     sizeof(vinet_conv_t),     sizeof(vinet_wgrad_t),
                            sizeof(vinet_pack_t),     sizeof(vinet_pack_input_t), sizeof(vinet_bn_stats_t), sizeof(vinet_bn_finalize_t),
-                           sizeof(vinet_bn_bwd_t),   sizeof(vinet_pool_t),       sizeof(vinet_upsample_t), sizeof(vinet_head_t),
+                           sizeof(vinet_bn_apply_t), sizeof(vinet_bn_bwd_t),   sizeof(vinet_pool_t),       sizeof(vinet_upsample_t), sizeof(vinet_head_t),
                            sizeof(vinet_loss_t),     sizeof(vinet_conv1d_t),     sizeof(vinet_bn1d_t),     sizeof(vinet_avfuse_t)};
   const int32_t m = (int32_t)(sizeof(sizes) / sizeof(sizes[0]));
   for (int32_t i = 0; i < n && i < m; ++i) out[i] = sizes[i];

@@ -144,6 +144,22 @@ __global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d) {
   }
 }
 
+template <typename T, typename TO>
+__global__ void bn_apply_kernel(const __grid_constant__ vinet_bn_apply_t d) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  TO* __restrict__ out = reinterpret_cast<TO*>(d.out);
+  const int G = d.C / 8;
+  const int64_t total = d.rows * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float v[8];
+    load8(y + r * d.ldy + c, v);
+    apply_xform<8>(v, d.relu ? VINET_XF_AFFINE_RELU : VINET_XF_AFFINE, d.scale, d.shift, c);
+    store8(out + r * d.ldo + c, v);
+  }
+}
+
 struct ColGrid {
   dim3 block;
   unsigned grid;
@@ -201,6 +217,18 @@ extern "C" int vinet_colsum(const void* x, int64_t ld, int32_t dtype, int64_t ro
 extern "C" int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream) {
   bn_finalize_kernel<<<(unsigned)cdiv(d->C, 128), 128, 0, (cudaStream_t)stream>>>(*d);
   VINET_LAUNCH_OK("bn_finalize");
+  return 0;
+}
+
+extern "C" int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0, "bn_apply: C %d", d->C);
+  const int64_t total = d->rows * (d->C / 8);
+  int64_t nb = cdiv(total, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
+      (bn_apply_kernel<T, TO><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d))));
+  VINET_LAUNCH_OK("bn_apply");
   return 0;
 }
 

@@ -1,0 +1,562 @@
+// TMA-fed persistent tcgen05 implicit-GEMM convolution for sm_100a (engine VINET_ENGINE_TC, kernel VINET_KERNEL_TMA).
+//
+// The activation operand is never gathered by threads: every (tap, 64-channel block) of the implicit GEMM is ONE
+// cp.async.bulk.tensor.5d box {64 ch, bw, bh, 1 frame, 1 clip} of the NDHWC source, addressed at the tap-shifted
+// tile origin.  Hardware out-of-bound zero fill IS the convolution's zero padding (spatial and temporal), and the
+// 128-byte-swizzled box is exactly the canonical UMMA shared-memory layout: rows = output positions, 128 B = 64 ch.
+//
+//   conv_gemm_tma_kernel  (fprop + dgrad)   D[128 positions, block_n] = sum_(tap,cblk) A_box x W_blk^T
+//     persistent CTAs (one per SM), static round-robin tile schedule, 3 roles:
+//       warp 0      TMA producer  : A box (tensor map) + packed weight block (cp.async.bulk) per pipeline stage
+//       warp 1      MMA issuer    : tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 accumulator buffers
+//       warps 2..5  epilogue      : tcgen05.ld -> scale/shift/act -> NDHWC store (overlaps the next tile's main loop)
+//   conv_wgrad_tma_kernel                   D[(tap,cblk pair) 128, block_n] += sum_positions A_box^T x dY_box
+//     both operands are the same boxes read MN-major; split over position chunks, fp32 red.add into the packed
+//     TAP64 weight gradient.
+//
+// A tile of output positions is a bw x bh rectangle of ONE frame (chosen per layer to maximise 128-row use).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+namespace vinet {
+
+constexpr int TMA_THREADS = 192;
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+struct ConvTmaParams {
+  CUtensorMap tmA[2];  // the two sources of the virtual T-concat (tmA[1] == tmA[0] without a concat)
+  vinet_conv_t d;
+  int32_t bw, bh, tiles_w, tiles_h, ncb, stages, num_tiles;
+  uint32_t acc_cols, idesc, a_bytes, b_bytes;
+};
+
+struct TileCoord {
+  int nt, b, t, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTmaParams& p, int tile) {
+  TileCoord c;
+  c.nt = tile % p.d.n_tiles;
+  int m = tile / p.d.n_tiles;
+  const int tw = m % p.tiles_w; m /= p.tiles_w;
+  const int th = m % p.tiles_h; m /= p.tiles_h;
+  const int tr = m % p.d.g.Tr;
+  c.b = m / p.d.g.Tr;
+  c.t = tr * p.d.g.row_tstep + p.d.g.row_toff;
+  c.h0 = th * p.bh;
+  c.w0 = tw * p.bw;
+  return c;
+}
+
+// Source frame read by rows of frame t through temporal tap dt: false when it lies in the temporal padding
+// (or, for the transposed convolution, off the stride lattice) - the whole (tile, tap) contributes nothing.
+__device__ __forceinline__ bool tap_frame(const vinet_gather_t& g, int t, int dt, int& si, int& tl) {
+  int ts;
+  if (g.mode == VINET_GATHER_FPROP) {
+    ts = t * g.st - g.pt + dt;
+  } else {
+    const int nt = t + g.pt - dt;
+    if (nt < 0) return false;
+    ts = nt / g.st;
+    if (ts * g.st != nt) return false;
+  }
+  if ((unsigned)ts >= (unsigned)g.Ts) return false;
+  si = (ts >= g.src[0].T) ? 1 : 0;
+  tl = ts - (si ? g.src[0].T : 0);
+  return true;
+}
+
+__device__ __forceinline__ bool tile_has_work(const vinet_gather_t& g, int t) {
+  int si, tl;
+  for (int tap = 0; tap < g.ntaps; ++tap)
+    if (tap_frame(g, t, g.tap[tap][0], si, tl)) return true;
+  return false;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  uint8_t* sA = base;
+  uint8_t* sB = sA + (size_t)stages * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)stages * p.b_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, tfull0 = empty0 + 8 * stages, tempty0 = tfull0 + 16;
+  const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const vinet_gather_t& g = p.d.g;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmA[1]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull0 + 8 * a, 1);
+        mbar_init(tempty0 + 8 * a, 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 2 * p.acc_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (one elected thread)
+    if (lane == 0) {
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.d.w);
+      const int KB = p.d.k_blocks;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+          int si, tl;
+          if (!tap_frame(g, tc.t, g.tap[tap][0], si, tl)) continue;
+          const int dh = g.tap[tap][1], dw = g.tap[tap][2];
+          const int hc = (g.mode == VINET_GATHER_FPROP) ? tc.h0 - g.ph + dh : tc.h0 + g.ph - dh;
+          const int wc = (g.mode == VINET_GATHER_FPROP) ? tc.w0 - g.pw + dw : tc.w0 + g.pw - dw;
+          const uint8_t* wtap = wbase + ((size_t)tc.nt * KB + (size_t)tap * p.ncb) * p.b_bytes;
+          for (int cb = 0; cb < p.ncb; ++cb) {
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(full0 + 8 * s, p.a_bytes + p.b_bytes);
+            tma_load_5d(sA0 + (uint32_t)s * TC_A_BYTES, &p.tmA[si], full0 + 8 * s, cb * 64, wc, hc, tl, tc.b);
+            bulk_copy_g2s(sB0 + (uint32_t)s * p.b_bytes, wtap + (size_t)cb * p.b_bytes, p.b_bytes, full0 + 8 * s);
+            if (++s == stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    int s = 0;
+    uint32_t ph = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      if (!tile_has_work(g, tc.t)) continue;
+      const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+      mbar_wait(tempty0 + 8 * as, aph ^ 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * p.acc_cols;
+      uint32_t acc = 0;
+      for (int tap = 0; tap < g.ntaps; ++tap) {
+        int si, tl;
+        if (!tap_frame(g, tc.t, g.tap[tap][0], si, tl)) continue;
+        for (int cb = 0; cb < p.ncb; ++cb) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const int rem = g.Cs - cb * 64;
+            const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+            const uint32_t a_stage = sA0 + (uint32_t)s * TC_A_BYTES;
+            const uint32_t b_stage = sB0 + (uint32_t)s * p.b_bytes;
+            for (int kk = 0; kk < nk; ++kk) {
+              umma_bf16(tacc, desc_kmajor_sw128(a_stage + kk * 32, 0), desc_kmajor_sw128(b_stage + kk * 32, 0), p.idesc, acc);
+              acc = 1;
+            }
+            umma_commit(empty0 + 8 * s);
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+      if (lane == 0) umma_commit(tfull0 + 8 * as);
+      __syncwarp();
+      ++lt;
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: TMEM -> registers -> global
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int rh = row / p.bw, rw = row - rh * p.bw;
+    const int BN = p.d.block_n;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const bool any = tile_has_work(g, tc.t);
+      const int h = tc.h0 + rh, w = tc.w0 + rw;
+      const bool valid = row < p.bw * p.bh && h < g.Hr && w < g.Wr;
+      TO* orow = nullptr;
+      if (valid) {
+        RowCoord rc;
+        rc.b = tc.b; rc.t = tc.t; rc.h = h; rc.w = w;
+        orow = out_row_ptr<TO>(p.d, rc);
+      }
+      const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+      if (any) {
+        mbar_wait(tfull0 + 8 * as, aph);
+        tc_fence_after();
+      }
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.acc_cols;
+      for (int gi = 0; gi < BN / 16; ++gi) {
+        uint32_t r[16];
+        if (any) {
+          tmem_ld16(tacc + (uint32_t)(gi * 16), r);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = 0u;
+        }
+        if (!valid) continue;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int n = tc.nt * BN + gi * 16 + hh * 8;
+          if (n >= p.d.N) continue;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = epilogue_value(p.d, __uint_as_float(r[hh * 8 + e]), n + e);
+          if constexpr (sizeof(TO) == 4) {
+            if (p.d.accumulate) {
+              float o[8];
+              load8(reinterpret_cast<const float*>(orow) + n, o);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += o[e];
+            }
+          }
+          store8(orow + n, v);
+        }
+      }
+      if (any) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        ++lt;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * p.acc_cols);
+  }
+}
+
+// =====================================================================================================
+// wgrad
+// =====================================================================================================
+struct WgradTmaParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmDy;
+  vinet_wgrad_t d;
+  int32_t bw, bh, tiles_w, tiles_h, ncb, nunits, stages, block_n, nblk, R, splits;
+  uint32_t tmem_cols, idesc, unit_bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(TMA_THREADS, 1) conv_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p) {
+  const vinet_gather_t& g = p.d.g;
+  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
+  const int64_t per = cdiv(nchunks, p.splits);
+  const int64_t c_begin = (int64_t)blockIdx.z * per;
+  const int64_t c_end = min(nchunks, c_begin + per);
+  if (c_end <= c_begin) return;  // uniform for the CTA
+  const int KB = (int)(c_end - c_begin);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * p.stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, accum_bar = empty0 + 8 * stages;
+  const uint32_t s0 = smem_u32(base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.block_n;
+  const int n0 = blockIdx.y * BN;
+  const int u0 = blockIdx.x * 2;
+  const int nu = min(2, p.nunits - u0);
+  const int nblk_eff = min(p.nblk, (min(BN, p.d.N - n0) + 63) / 64);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmDy);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, 1);
+      }
+      mbar_init(accum_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(nu + nblk_eff) * p.unit_bytes;
+      for (int kb = 0; kb < KB; ++kb) {
+        int64_t m = c_begin + kb;
+        const int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
+        const int th = (int)(m % p.tiles_h); m /= p.tiles_h;
+        const int tr = (int)(m % g.Tr);
+        const int t = tr * g.row_tstep + g.row_toff;
+        const int b = (int)(m / g.Tr);
+        const int h0 = th * p.bh, w0 = tw * p.bw;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(full0 + 8 * s, tx);
+        const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
+        for (int j = 0; j < nu; ++j) {
+          const int u = u0 + j;
+          const int tap = u / p.ncb, cb = u - tap * p.ncb;
+          const int ts = t * g.st - g.pt + g.tap[tap][0];
+          // frames outside [0,Ts) are addressed out of bounds on purpose: TMA zero-fills the temporal padding
+          const int si = (g.src[1].ptr != nullptr && ts >= g.src[0].T) ? 1 : 0;
+          const int tl = ts - (si ? g.src[0].T : 0);
+          tma_load_5d(stage + (uint32_t)j * p.unit_bytes, &p.tmA[si], full0 + 8 * s, cb * 64, w0 - g.pw + g.tap[tap][2],
+                      h0 - g.ph + g.tap[tap][1], tl, b);
+        }
+        for (int nb = 0; nb < nblk_eff; ++nb)
+          tma_load_5d(stage + (uint32_t)(2 + nb) * p.unit_bytes, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_stage = s0 + (uint32_t)s * p.stage_bytes;
+        const uint32_t b_stage = a_stage + 2u * p.unit_bytes;
+        for (int kk = 0; kk < p.R / 16; ++kk) {
+          // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B; 64-wide MN blocks unit_bytes apart
+          umma_bf16(tmem_base, desc_mnmajor_sw128(a_stage + kk * 2048, p.unit_bytes, 0),
+                    desc_mnmajor_sw128(b_stage + kk * 2048, p.unit_bytes, 0), p.idesc, (uint32_t)((kb | kk) != 0));
+        }
+        umma_commit(empty0 + 8 * s);
+        if (kb == KB - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = blockIdx.x * 128 + q * 32 + lane;
+    const bool mvalid = m < p.nunits * 64;
+    float* drow = p.d.dwp + (int64_t)m * p.d.lddw;
+    for (int gi = 0; gi < BN / 16; ++gi) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * 16), r);
+      if (!mvalid) continue;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int n = n0 + gi * 16 + e;
+        if (n < p.d.N) atomicAdd(drow + n, __uint_as_float(r[e]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static std::atomic<void*> cached{nullptr};
+  void* f = cached.load(std::memory_order_acquire);
+  if (f == nullptr) {
+    cudaDriverEntryPointQueryResult q;
+    void* sym = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    cached.store(sym, std::memory_order_release);
+    f = sym;
+  }
+  return reinterpret_cast<EncodeTiledFn>(f);
+}
+
+// NDHWC bf16 view [B][T][H][W][C] with row stride ld -> 5-D tiled map, box {64, bw, bh, 1, 1}, 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int bw, int bh) {
+  EncodeTiledFn enc = encode_fn();
+  VINET_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from the driver");
+  VINET_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0, "conv_tma: source must be 16-byte aligned (ld %lld)",
+              (long long)ld);
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2,
+                                 (cuuint64_t)T * H * W * ld * 2};
+  const cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VINET_CHECK(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d,%d] ld %lld box %dx%d", (int)r,
+              B, T, H, W, C, (long long)ld, bw, bh);
+  return 0;
+}
+
+// bw x bh rectangle (<= max_rows positions, rows a multiple of `mult`) maximising the fraction of useful rows;
+// ties go to more rows per box, then to wider boxes (longer contiguous runs for the TMA engine).
+static void pick_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out) {
+  double best = -1.0;
+  int bbw = 1, bbh = 1;
+  for (int bw = 1; bw <= W && bw <= max_rows; ++bw) {
+    for (int bh = 1; bw * bh <= max_rows && bh <= 256; ++bh) {
+      if ((bw * bh) % mult != 0) continue;
+      if (bh > H && ((bh - 1) >= H && (bw * (bh - 1)) % mult == 0)) break;  // taller only adds zero-filled rows
+      const double tiles = (double)cdiv(H, bh) * (double)cdiv(W, bw);
+      const double cost = tiles * (full_tile_cost ? (double)max_rows : (double)(bw * bh));
+      const double util = (double)H * W / cost;
+      const double score = util + 1e-6 * (bw * bh) + 1e-9 * bw;
+      if (score > best) { best = score; bbw = bw; bbh = bh; }
+    }
+  }
+  *bw_out = bbw;
+  *bh_out = bbh;
+}
+
+static int sm_count() {
+  static std::atomic<int> cached{0};
+  int n = cached.load();
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cached.store(n);
+  }
+  return n;
+}
+
+static int check_tma_gather(const vinet_gather_t& g, const char* what) {
+  VINET_CHECK(g.dtype == VINET_BF16, "%s: the TMA kernel needs bf16 sources", what);
+  VINET_CHECK(g.sh == 1 && g.sw == 1, "%s: the TMA kernel needs spatial stride 1 (got %d,%d)", what, g.sh, g.sw);
+  VINET_CHECK(g.Cs % 8 == 0, "%s: Cs %d must be a multiple of 8", what, g.Cs);
+  VINET_CHECK(g.src[0].xform == VINET_XF_IDENT && (g.src[1].ptr == nullptr || g.src[1].xform == VINET_XF_IDENT),
+              "%s: the TMA kernel cannot apply pending source transforms", what);
+  VINET_CHECK(g.src[0].T + (g.src[1].ptr ? g.src[1].T : 0) == g.Ts, "%s: Ts %d != sum of source frames", what, g.Ts);
+  return 0;
+}
+
+int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
+  const vinet_gather_t& g = d->g;
+  if (check_tma_gather(g, "conv_gemm_tma")) return -1;
+  VINET_CHECK(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "conv_gemm_tma: bad block_n %d", d->block_n);
+  VINET_CHECK(d->N % 8 == 0, "conv_gemm_tma: N %d must be a multiple of 8", d->N);
+  VINET_CHECK(!(d->accumulate && d->out_dtype != VINET_F32), "conv_gemm_tma: accumulate needs fp32 outputs");
+  ConvTmaParams p;
+  p.d = *d;
+  p.ncb = (g.Cs + 63) / 64;
+  VINET_CHECK(d->k_blocks == g.ntaps * p.ncb, "conv_gemm_tma: k_blocks %d != ntaps*ceil(Cs/64) = %d (TAP64 weights expected)",
+              d->k_blocks, g.ntaps * p.ncb);
+  pick_box(g.Hr, g.Wr, TC_BM, 1, true, &p.bw, &p.bh);
+  p.tiles_w = (int)cdiv(g.Wr, p.bw);
+  p.tiles_h = (int)cdiv(g.Hr, p.bh);
+  const int64_t tiles = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w * d->n_tiles;
+  VINET_CHECK(tiles < (1ll << 31), "conv_gemm_tma: too many tiles");
+  p.num_tiles = (int)tiles;
+  p.a_bytes = (uint32_t)(p.bw * p.bh * 128);
+  p.b_bytes = (uint32_t)d->block_n * 128u;
+  p.acc_cols = tmem_cols_for(d->block_n);
+  p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
+  const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 64;
+  for (int i = 0; i < 2; ++i) {
+    const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, p.bw, p.bh)) return -1;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
+#define LAUNCH_TMA(TO)                                                                                  \
+  do {                                                                                                  \
+    auto kern = conv_gemm_tma_kernel<TO>;                                                               \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+    kern<<<grid, TMA_THREADS, smem, stream>>>(p);                                                       \
+  } while (0)
+  VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_TMA(TO));
+#undef LAUNCH_TMA
+  VINET_LAUNCH_OK("conv_gemm_tma");
+  return 0;
+}
+
+int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
+  const vinet_gather_t& g = d->g;
+  if (check_tma_gather(g, "conv_wgrad_tma")) return -1;
+  VINET_CHECK(g.mode == VINET_GATHER_FPROP, "conv_wgrad_tma: needs an FPROP gather");
+  VINET_CHECK(d->dy_dtype == VINET_BF16 && d->N % 8 == 0 && d->lddy % 8 == 0, "conv_wgrad_tma: dy must be bf16, N %d lddy %lld",
+              d->N, (long long)d->lddy);
+  WgradTmaParams p;
+  p.d = *d;
+  p.ncb = (g.Cs + 63) / 64;
+  p.nunits = g.ntaps * p.ncb;
+  const int n16 = (int)round_up(d->N, 16);
+  const int n_tiles = (int)cdiv(n16, 256);
+  p.block_n = (int)round_up(cdiv(n16, n_tiles), 16);
+  p.nblk = (p.block_n + 63) / 64;
+  const int max_rows = (p.nblk <= 2) ? 128 : 64;  // keep >= 3 pipeline stages in shared memory
+  pick_box(g.Hr, g.Wr, max_rows, 16, false, &p.bw, &p.bh);
+  p.R = p.bw * p.bh;
+  p.tiles_w = (int)cdiv(g.Wr, p.bw);
+  p.tiles_h = (int)cdiv(g.Hr, p.bh);
+  p.unit_bytes = (uint32_t)p.R * 128u;
+  p.stage_bytes = (uint32_t)(2 + p.nblk) * p.unit_bytes;
+  p.tmem_cols = tmem_cols_for(p.block_n);
+  p.idesc = make_idesc(TC_BM, p.block_n, 1, 1);
+  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
+  const int mblocks = (int)cdiv(p.nunits, 2);
+  int64_t splits = cdiv(2 * sm_count(), (int64_t)mblocks * n_tiles);
+  splits = std::max<int64_t>(1, std::min<int64_t>(splits, cdiv(nchunks, 2)));
+  VINET_CHECK(splits <= 65535, "conv_wgrad_tma: splits");
+  p.splits = (int)splits;
+  int stages = (int)((200 * 1024) / p.stage_bytes);
+  stages = std::max(2, std::min(stages, 6));
+  stages = (int)std::max<int64_t>(1, std::min<int64_t>(stages, cdiv(nchunks, splits)));
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * p.stage_bytes + 8 * (2 * stages + 1) + 64;
+  for (int i = 0; i < 2; ++i) {
+    const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, p.bw, p.bh)) return -1;
+  }
+  if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, p.bw, p.bh)) return -1;
+  dim3 grid((unsigned)mblocks, (unsigned)n_tiles, (unsigned)splits);
+  cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  conv_wgrad_tma_kernel<<<grid, TMA_THREADS, smem, stream>>>(p);
+  VINET_LAUNCH_OK("conv_wgrad_tma");
+  return 0;
+}
+
+}  // namespace vinet

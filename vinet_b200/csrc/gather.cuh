@@ -67,6 +67,14 @@ __device__ __forceinline__ void gather_vec(const vinet_gather_t& g, const RowCoo
   const T* p = reinterpret_cast<const T*>(s.ptr) + off + c;
   if constexpr (V == 8) load8(p, v); else load4(p, v);
   apply_xform<V>(v, s.xform, s.scale, s.shift, c);
+  if constexpr (sizeof(T) == 2) {
+    // bf16 storage: the tensor-core engine feeds bf16 operands, so the fp32-FFMA cross-check engine rounds the
+    // transformed value at the same point (otherwise ReLU masks downstream differ by more than accumulation order)
+    if (s.xform & 2) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    }
+  }
 }
 
 // output row -> destination pointer (two destinations split on the frame index)

@@ -26,10 +26,11 @@ __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) 
 }
 
 // ------------------------------------------------------------------ weights
-// element (n, k) of the GEMM B operand, k = tap_idx*cs + c
+// element (n, k) of the GEMM B operand; DENSE: k = tap_idx*cs + c, TAP64: k = tap_idx*round_up(cs,64) + c
 __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k) {
-  const int tap = k / d.cs, c = k - tap * d.cs;
-  if (tap >= d.ntaps) return 0.f;
+  const int csk = (d.layout == VINET_KLAYOUT_TAP64) ? ((d.cs + 63) / 64) * 64 : d.cs;
+  const int tap = k / csk, c = k - tap * csk;
+  if (tap >= d.ntaps || c >= d.cs) return 0.f;
   int co, ci;
   if (d.mode == VINET_GATHER_FPROP) { co = n; ci = c; } else { co = c; ci = n; }
   if (co >= d.Cout || ci >= d.Cin) return 0.f;
@@ -105,7 +106,9 @@ extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t b
 
 extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
-  VINET_CHECK((int64_t)d->k_blocks * 64 >= (int64_t)d->ntaps * d->cs, "pack_weights: k_blocks too small");
+  VINET_CHECK(d->layout == VINET_KLAYOUT_DENSE || d->layout == VINET_KLAYOUT_TAP64, "pack_weights: layout %d", d->layout);
+  const int64_t csk = d->layout == VINET_KLAYOUT_TAP64 ? round_up(d->cs, 64) : d->cs;
+  VINET_CHECK((int64_t)d->k_blocks * 64 >= (int64_t)d->ntaps * csk, "pack_weights: k_blocks too small");
   if (d->engine == VINET_ENGINE_TC) {
     const int64_t chunks = (int64_t)d->n_tiles * d->k_blocks * d->block_n * 8;
     pack_weights_tc_kernel<<<grid_for(chunks, 256), 256, 0, (cudaStream_t)stream>>>(*d);

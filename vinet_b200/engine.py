@@ -101,6 +101,7 @@ class Engine:
         self.device = None
         self.training = False
         self.record = False
+        self.use_tma = True     # False: force the register-gather tcgen05 kernels (tests / A-B timing)
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
 
@@ -181,11 +182,14 @@ class Engine:
         n_tiles = cdiv(n16, 256)
         return round_up(cdiv(n16, n_tiles), 16), n_tiles
 
-    def packed_weight(self, w, key, mode, taps, cs, n):
+    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE):
         """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version."""
-        ck = (key, mode, tuple(taps), self.eng)
+        ck = (key, mode, tuple(taps), self.eng, layout)
         block_n, n_tiles = self.tiling(n)
-        k_blocks = cdiv(len(taps) * cs, L.TC_BLOCK_K)
+        if layout == L.KLAYOUT_TAP64:
+            k_blocks = len(taps) * cdiv(cs, L.TC_BLOCK_K)
+        else:
+            k_blocks = cdiv(len(taps) * cs, L.TC_BLOCK_K)
         hit = self.wcache.get(ck)
         if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] is w:
             return hit[1], block_n, n_tiles, k_blocks
@@ -199,28 +203,42 @@ class Engine:
         d.cs, d.mode, d.ntaps = cs, mode, len(taps)
         _fill_taps(d.tap, taps)
         d.engine, d.block_n, d.n_tiles, d.k_blocks, d.out = self.eng, block_n, n_tiles, k_blocks, out.data_ptr()
+        d.layout = layout
         self.call("vinet_pack_weights", d)
         self.wcache[ck] = (w._version, out, None, w)
         return out, block_n, n_tiles, k_blocks
 
     # ------------------------------------------------------------------ convolution
-    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None):
-        """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY."""
+    def tma_ok(self, srcs, geom):
+        """The TMA-fed kernels need bf16 sources without pending transforms and spatial stride 1."""
+        return (self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
+                and all(s.xform == L.XF_IDENT for s in srcs))
+
+    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None):
+        """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY.
+        ep = (scale, shift, act): fused per-channel epilogue (inference-mode BatchNorm folding)."""
         a0 = srcs[0]
         cs = a0.C
         Cout = w.shape[0]
+        tma = self.tma_ok(srcs, geom)
+        kern = L.KERNEL_TMA if tma else L.KERNEL_GATHER
+        layout = L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE
         To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
         assert (To, Ho, Wo, Cout) == (out.T, out.H, out.W, out.C), (name, (To, Ho, Wo, Cout), (out.T, out.H, out.W, out.C))
         assert w.shape[1] == (cin_real or cs), name
         taps = _taps(geom.kt, geom.kh, geom.kw)
-        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout)
+        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout)
         d = L.Conv()
+        d.kernel = kern
         self._gather_fprop(d.g, srcs, geom, cs, To, Ho, Wo)
         d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
         d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
         d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
         d.out_dtype, d.accumulate = self.dt, 0
         d.ep_scale, d.ep_shift, d.ep_act = None, _ptr(bias), L.ACT_NONE
+        if ep is not None:
+            assert bias is None
+            d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * len(taps) * cin_r * Cout
         self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
@@ -229,11 +247,13 @@ class Engine:
 
         def backward(dy, lddy):
             # ---- weight gradient
-            ktot = len(taps) * cs
+            csk = round_up(cs, 64) if tma else cs          # TAP64 rows of the packed gradient
+            ktot = len(taps) * csk
             lddw = round_up(Cout, 64)
             dwp = self.buf(name + ".dwp", (round_up(ktot, 128), lddw), torch.float32)
             self.memset(dwp)
             wg = L.Wgrad()
+            wg.kernel = kern
             self._gather_fprop(wg.g, srcs, geom, cs, To, Ho, Wo)
             wg.dy, wg.lddy, wg.dy_dtype, wg.N, wg.dwp, wg.lddw = dy, lddy, self.dt, Cout, dwp.data_ptr(), lddw
             rows = a0.B * To * Ho * Wo
@@ -246,7 +266,7 @@ class Engine:
             wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
             self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
             gw = torch.empty_like(w)
-            self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, cs, gw.data_ptr(), Cout, w.shape[1], len(taps),
+            self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
                           self.stream())
             self.param_grads[name + ".weight"] = gw
             if bias is not None:
@@ -266,8 +286,11 @@ class Engine:
                     continue
                 ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
                 n = w.shape[1]
-                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n)
+                dtma = self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
+                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
+                                                        L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE)
                 dd = L.Conv()
+                dd.kernel = L.KERNEL_TMA if dtma else L.KERNEL_GATHER
                 g = dd.g
                 g.mode, g.dtype = L.GATHER_DGRAD, self.dt
                 g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, frames, a0.H, a0.W, geom.st, t0
@@ -290,29 +313,42 @@ class Engine:
 
     # ------------------------------------------------------------------ conv + BatchNorm (+ReLU pending)
     def conv_bn(self, name_conv, name_bn, srcs, w, bn, geom, out, cin_real=None):
-        """BasicConv3d / one half of SepConv3d (model_utils.py:128-160): raw conv into `out`, batch statistics
-        -> out.scale/out.shift; consumers apply scale/shift + ReLU on read."""
-        conv_bwd = self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real)
+        """BasicConv3d / one half of SepConv3d (model_utils.py:128-160).
+        Training: raw conv -> batch statistics -> finalize (scale/shift, running stats) -> materialise
+        relu(scale*y+shift) into `out` (possibly a channel slice of a Mixed concat buffer).  Consumers then read
+        plain activations, which is what lets the TMA-fed kernels fetch them.  Pure inference (no tape, running
+        statistics): scale/shift/ReLU are folded into the conv epilogue and nothing else is launched."""
         Cn = out.C
         rows = out.rows
         st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)      # mean, invstd
+        ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)        # scale, shift
         fin = L.BnFinalize()
-        if self.training:
-            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64)
-            self.memset(sums)
-            sd = L.BnStats()
-            sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = out.ptr(), out.ld, self.dt, rows, Cn, sums.data_ptr()
-            self.call("vinet_bn_stats", sd)
-            fin.sums = sums.data_ptr()
         fin.rows, fin.C, fin.gamma, fin.beta = rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
         fin.eps, fin.momentum = bn.eps, bn.momentum
         fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
         fin.training = 1 if self.training else 0
-        fin.scale, fin.shift, fin.mean, fin.invstd = out.scale.data_ptr(), out.shift.data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+        fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+        out.xform, out.scale, out.shift = L.XF_IDENT, None, None
+        if not self.training and not self.record:
+            self.call("vinet_bn_finalize", fin)
+            self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
+            return
+        raw = Act(self.buf(name_conv + ".raw", (out.B, out.T, out.H, out.W, Cn), self.tdtype), out.B, out.T, out.H, out.W, Cn)
+        conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real)
+        if self.training:
+            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64)
+            self.memset(sums)
+            sd = L.BnStats()
+            sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
+            self.call("vinet_bn_stats", sd)
+            fin.sums = sums.data_ptr()
         self.call("vinet_bn_finalize", fin)
         if self.training:
             bn.num_batches_tracked += 1          # host-side counter buffer (nn.BatchNorm semantics)
-        out.xform = L.XF_AFFINE_RELU
+        ap = L.BnApply()
+        ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
+        ap.scale, ap.shift, ap.out, ap.ldo, ap.out_dtype = ss[0].data_ptr(), ss[1].data_ptr(), out.ptr(), out.ld, self.dt
+        self.call("vinet_bn_apply", ap)
         if not self.record:
             return
         training = self.training
@@ -323,8 +359,8 @@ class Engine:
             dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
             dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
             b = L.BnBwd()
-            b.g, b.ldg, b.y, b.ldy, b.dtype, b.rows, b.C, b.relu = out.gptr(), out.ldg, out.ptr(), out.ld, self.dt, rows, Cn, 1
-            b.scale, b.shift, b.mean, b.invstd = out.scale.data_ptr(), out.shift.data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+            b.g, b.ldg, b.y, b.ldy, b.dtype, b.rows, b.C, b.relu = out.gptr(), out.ldg, raw.ptr(), raw.ld, self.dt, rows, Cn, 1
+            b.scale, b.shift, b.mean, b.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
             b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
             b.dy, b.lddy, b.dy_dtype, b.training = dy.data_ptr(), Cn, self.dt, 1 if training else 0
             self.call("vinet_bn_bwd_reduce", b)

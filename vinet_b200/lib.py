@@ -17,6 +17,8 @@ GATHER_FPROP, GATHER_DGRAD = 0, 1
 ENGINE_TC, ENGINE_SIMT = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 LOSS_KLDIV, LOSS_CC, LOSS_SIM, LOSS_NSS = 0, 1, 2, 3
+KERNEL_GATHER, KERNEL_TMA = 0, 1
+KLAYOUT_DENSE, KLAYOUT_TAP64 = 0, 1
 MAX_TAPS = 64
 TC_BLOCK_M, TC_BLOCK_K = 128, 64
 
@@ -37,18 +39,18 @@ class Gather(C.Structure):
 class Conv(C.Structure):
     _fields_ = [("g", Gather), ("w", _p), ("N", _i32), ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32),
                 ("out", _p * 2), ("ldo", _i64 * 2), ("out_T", _i32 * 2), ("out_dtype", _i32), ("accumulate", _i32),
-                ("ep_scale", _p), ("ep_shift", _p), ("ep_act", _i32)]
+                ("ep_scale", _p), ("ep_shift", _p), ("ep_act", _i32), ("kernel", _i32)]
 
 
 class Wgrad(C.Structure):
     _fields_ = [("g", Gather), ("dy", _p), ("lddy", _i64), ("dy_dtype", _i32), ("N", _i32), ("dwp", _p),
-                ("lddw", _i32), ("splits", _i32)]
+                ("lddw", _i32), ("splits", _i32), ("kernel", _i32)]
 
 
 class Pack(C.Structure):
     _fields_ = [("w", _p), ("Cout", _i32), ("Cin", _i32), ("kt", _i32), ("kh", _i32), ("kw", _i32), ("cs", _i32),
                 ("mode", _i32), ("ntaps", _i32), ("tap", (C.c_int8 * 4) * MAX_TAPS), ("engine", _i32),
-                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p)]
+                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p), ("layout", _i32)]
 
 
 class PackInput(C.Structure):
@@ -64,6 +66,11 @@ class BnFinalize(C.Structure):
     _fields_ = [("sums", _p), ("rows", _i64), ("C", _i32), ("gamma", _p), ("beta", _p), ("eps", _f32),
                 ("momentum", _f32), ("running_mean", _p), ("running_var", _p), ("training", _i32), ("scale", _p),
                 ("shift", _p), ("mean", _p), ("invstd", _p)]
+
+
+class BnApply(C.Structure):
+    _fields_ = [("y", _p), ("ldy", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32), ("relu", _i32), ("scale", _p),
+                ("shift", _p), ("out", _p), ("ldo", _i64), ("out_dtype", _i32)]
 
 
 class BnBwd(C.Structure):
@@ -129,6 +136,7 @@ SIGNATURES = {
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
+    "vinet_bn_apply": (C.c_int, [C.POINTER(BnApply), _S]),
     "vinet_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_maxpool_fwd": (C.c_int, [C.POINTER(Pool), _S]),
@@ -157,7 +165,7 @@ SIGNATURES = {
 }
 
 # declaration order of the structs in the header (vinet_abi_sizes)
-ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnBwd, Pool, Upsample, Head, Loss,
+ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
                Conv1d, Bn1d, AvFuse]
 
 

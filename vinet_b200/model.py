@@ -130,12 +130,12 @@ def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
     gs = ConvGeom((1, k, k), (1, s, s), (0, p, p))
     To, Ho, Wo = gs.out_dims(a0.T, a0.H, a0.W)
     cout = m.conv_s.weight.shape[0]
-    mid = e.new_act(pfx + ".s", a0.B, To, Ho, Wo, cout, affine=True)
+    mid = e.new_act(pfx + ".s", a0.B, To, Ho, Wo, cout)
     e.conv_bn(pfx + ".conv_s", pfx + ".bn_s", srcs, m.conv_s.weight, m.bn_s, gs, mid, cin_real=cin_real)
     gt = ConvGeom((k, 1, 1), (s, 1, 1), (p, 0, 0))
     To2, _, _ = gt.out_dims(To, Ho, Wo)
     if out is None:
-        out = e.new_act(pfx + ".t", a0.B, To2, Ho, Wo, cout, affine=True)
+        out = e.new_act(pfx + ".t", a0.B, To2, Ho, Wo, cout)
     e.conv_bn(pfx + ".conv_t", pfx + ".bn_t", [mid], m.conv_t.weight, m.bn_t, gt, out)
     return out
 
@@ -145,14 +145,14 @@ _G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
 
 def _basic(e, pfx, x, m, out=None):
     if out is None:
-        out = e.new_act(pfx + ".o", x.B, x.T, x.H, x.W, m.conv.weight.shape[0], affine=True)
+        out = e.new_act(pfx + ".o", x.B, x.T, x.H, x.W, m.conv.weight.shape[0])
     e.conv_bn(pfx + ".conv", pfx + ".bn", [x], m.conv.weight, m.bn, _G1, out)
     return out
 
 
 def _mixed(e, pfx, x, m):
     cin, b0, b1r, b1, b2r, b2, b3 = arch.MIXED[m.name]
-    out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3, affine=True)
+    out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3)
     _basic(e, pfx + ".branch0.0", x, m.branch0[0], out.slice(0, b0))
     t = _basic(e, pfx + ".branch1.0", x, m.branch1[0])
     _sepconv(e, pfx + ".branch1.1", [t], m.branch1[1], out.slice(b0, b1))
@@ -160,7 +160,6 @@ def _mixed(e, pfx, x, m):
     _sepconv(e, pfx + ".branch2.1", [t], m.branch2[1], out.slice(b0 + b1, b2))
     p = e.maxpool(pfx + ".branch3.pool", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     _basic(e, pfx + ".branch3.1", p, m.branch3[1], out.slice(b0 + b1 + b2, b3))
-    out.xform = L.XF_AFFINE_RELU
     return out
 
 
