@@ -93,7 +93,7 @@ typedef struct vinet_conv {
   int64_t ldo[2];
   int32_t out_T[2];
   int32_t out_dtype;
-  int32_t accumulate; /* 1: out += result (fp32 outputs only) */
+  int32_t accumulate; /* bit i set: out[i] += result (read-modify-write); clear: out[i] = result */
   const float* ep_scale; /* per-output-channel, may be NULL */
   const float* ep_shift; /* per-output-channel (bias), may be NULL */
   int32_t ep_act;        /* VINET_ACT_* */
@@ -196,7 +196,7 @@ int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream);
 
 /* Backward of y_hat = relu?(scale*y + shift) w.r.t. the raw conv output y. */
 typedef struct vinet_bn_bwd {
-  const float* g; /* grad w.r.t. the activated output, fp32 */
+  const void* g; /* grad w.r.t. the activated output (g_dtype) */
   int64_t ldg;
   const void* y;
   int64_t ldy;
@@ -216,6 +216,7 @@ typedef struct vinet_bn_bwd {
   int64_t lddy;
   int32_t dy_dtype;
   int32_t training; /* 0: eval-mode BN (running stats): dy = g*m*scale, no mean/projection terms */
+  int32_t g_dtype;
 } vinet_bn_bwd_t;
 int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream);
 int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream);
@@ -234,10 +235,11 @@ typedef struct vinet_pool {
   void* out;
   int64_t ldo;
   int32_t out_dtype;
-  const float* gout; /* backward: grad w.r.t. out, fp32 */
+  const void* gout; /* backward: grad w.r.t. out (gout_dtype) */
   int64_t ldgo;
-  float* gin; /* backward: grad w.r.t. the activated input, fp32, accumulated with atomics */
+  void* gin; /* backward: grad w.r.t. the activated input (gin_dtype), accumulated with atomics (caller initialises) */
   int64_t ldgi;
+  int32_t gout_dtype, gin_dtype;
 } vinet_pool_t;
 int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream);
 int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream);
@@ -252,11 +254,12 @@ typedef struct vinet_upsample {
   void* u; /* [B,T,2h,2w,C] */
   int64_t ldu;
   int32_t u_dtype;
-  const float* gu; /* backward in: fp32 grad w.r.t. u */
+  const void* gu; /* backward in: grad w.r.t. u (gu_dtype) */
   int64_t ldgu;
   void* dz; /* backward out: grad w.r.t. raw z (ReLU-masked) */
   int64_t lddz;
   int32_t dz_dtype;
+  int32_t gu_dtype;
 } vinet_upsample_t;
 int vinet_upsample_fwd(const vinet_upsample_t* d, vinet_stream_t stream);
 int vinet_upsample_bwd(const vinet_upsample_t* d, vinet_stream_t stream);

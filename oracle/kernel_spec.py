@@ -168,7 +168,7 @@ class Spec:
             tl = t[sel] - (d.out_T[0] if i else 0)
             pos = ((b[sel] * d.out_T[i] + tl) * g.Hr + h[sel]) * g.Wr + w[sel]
             out = _rows_view(d.out[i], g.B * d.out_T[i] * g.Hr * g.Wr, d.ldo[i], d.N)
-            out[pos] = (out[pos] + acc[sel]) if d.accumulate else acc[sel]
+            out[pos] = (out[pos] + acc[sel]) if (d.accumulate >> i) & 1 else acc[sel]
 
     def conv_wgrad(self, d, engine, stream):
         A = gather_matrix(d.g)

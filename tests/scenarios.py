@@ -21,8 +21,8 @@ def make_engine(device, precision, backend=None):
     return e
 
 
-def fill_act(e, name, B, T, H, W, C, gen, affine):
-    a = e.new_act(name, B, T, H, W, C, affine=affine)
+def fill_act(e, name, B, T, H, W, C, gen, affine, gdtype=None):
+    a = e.new_act(name, B, T, H, W, C, affine=affine, gdtype=gdtype)
     a.buf.copy_(bf16r(torch.randn(a.buf.shape, generator=gen)))
     if affine:
         a.scale.copy_(torch.rand(C, generator=gen) + 0.5)
@@ -34,6 +34,7 @@ def fill_act(e, name, B, T, H, W, C, gen, affine):
 def run_tape(e, out, gen):
     for g in e.grad_bufs:
         g.zero_()
+    e.gwritten = {g.data_ptr() for g in e.grad_bufs}      # everything is initialised: writers accumulate
     go = bf16r(torch.randn(out.grad.shape, generator=gen))
     out.grad.copy_(go)
     for fn in reversed(e.tape):
@@ -160,7 +161,7 @@ def audio_fuse(device, precision, backend=None, B=2, seed=0):
     e = make_engine(device, precision, backend)
     audio = O.make_inputs(B, 8, 32, 32, seed, audio=True)["audio"].to(device)
     a, ga = AV.soundnet_plan(e, "audionet.", net, audio)
-    y0 = fill_act(e, "y0", B, 4, 7, 12, 1024, gen, True)
+    y0 = fill_act(e, "y0", B, 4, 7, 12, 1024, gen, True, gdtype=torch.float32)
     out = AV.avfuse_plan(e, "bilinear", y0, a, ga, bil)
     run_tape(e, out, gen)
     res = {"a": a.detach().cpu().clone(), "out": ncdhw(out.buf), "dy0": ncdhw(y0.grad)}

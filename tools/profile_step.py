@@ -1,0 +1,51 @@
+"""Per-kernel device-time table of one training step (torch.profiler / CUPTI; concurrent, warm caches)."""
+import os
+import sys
+import collections
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import profile, ProfilerActivity
+from vinet_b200 import VideoSaliencyModel, kldiv
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = torch.device("cuda")
+torch.manual_seed(0)
+model = VideoSaliencyModel().to(dev).train()
+opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+x = torch.randn(B, 32, 3, 224, 384, device=dev)
+gt = torch.rand(B, 224, 384, device=dev) + 1e-3
+
+
+def step():
+    loss = kldiv(model(x.permute(0, 2, 1, 3, 4)), gt)
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+print("wall ms/step %.2f" % ((time.perf_counter() - t0) / 3 * 1e3))
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step()
+    torch.cuda.synchronize()
+tot = collections.defaultdict(float)
+cnt = collections.Counter()
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", ev.name))
+        tot[name] += ev.device_time / 1e3 if hasattr(ev, "device_time") else ev.cuda_time / 1e3
+        cnt[name] += 1
+s = sum(tot.values())
+print("device total ms %.2f over %d launches" % (s, sum(cnt.values())))
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:40]:
+    print("%-70s %5d %9.3f ms %5.1f%%" % (k[:70], cnt[k], v, 100 * v / s))

@@ -90,17 +90,20 @@ def avfuse_plan(e, name, y0, a, ga, bil):
     """MaxPool3d((4,1,1),stride=(2,1,2)) + nn.Bilinear(42,3,336) + view(B,1024,4,7,12) (model.py:235-237)."""
     assert (y0.T, y0.H, y0.W, y0.C) == (4, 7, 12, 1024), "AViNet is hard-wired to 32x224x384 clips (model.py:230,237)"
     B = y0.B
-    out = e.new_act(name + ".fused", B, 4, 7, 12, 1024)
+    out = e.new_act(name + ".fused", B, 4, 7, 12, 1024, gdtype=torch.float32)
     vbuf = e.buf(name + ".v", (B, 1024, 42), torch.float32)
     d = L.AvFuse()
     d.y0, d.ld, d.dtype, d.xform = y0.ptr(), y0.ld, e.dt, y0.xform
-    d.scale, d.shift = y0.scale.data_ptr(), y0.shift.data_ptr()
+    d.scale = None if y0.scale is None else y0.scale.data_ptr()
+    d.shift = None if y0.shift is None else y0.shift.data_ptr()
     d.audio, d.w, d.bias, d.B, d.C = a.data_ptr(), bil.weight.data_ptr(), bil.bias.data_ptr(), B, 1024
     d.vbuf, d.out, d.ldo, d.out_dtype = vbuf.data_ptr(), out.ptr(), out.ld, e.dt
     e.lib.call("vinet_avfuse_fwd", C.byref(d), e.stream())
     if e.record:
         def backward():
             gw, gb = torch.empty_like(bil.weight), torch.empty_like(bil.bias)
+            assert out.gdt == L.F32 and y0.gdt == L.F32, "the AV fusion kernel keeps fp32 gradients"
+            e.ensure_init(y0)
             d.gout, d.ldgo, d.gy0, d.ldgy0 = out.gptr(), out.ldg, y0.gptr(), y0.ldg
             d.gaudio, d.dw, d.dbias = ga.data_ptr(), gw.data_ptr(), gb.data_ptr()
             e.lib.call("vinet_avfuse_bwd", C.byref(d), e.stream())
@@ -145,6 +148,7 @@ class VideoAudioSaliencyModel(_PlanModule):
         e.begin(x.device, self.training, record)
         a, ga = soundnet_plan(e, "audionet.", self.audionet, audio)
         xin = pack_input(e, x)
-        y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin)
+        y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin,
+                                       y0_gdtype=torch.float32)
         fused = avfuse_plan(e, "bilinear", y0, a, ga, self.bilinear)
         return decoder_plan(e, "visual_model.decoder.", self.visual_model.decoder, fused, y1, y2, y3)

@@ -89,13 +89,14 @@ __global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d
   d.invstd[c] = invstd;
 }
 
-template <typename T>
+template <typename T, typename TG>
 __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
   column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
     float v[8], g[8];
     load8(y + r * d.ldy + c, v);
-    load8(d.g + r * d.ldg + c, g);
+    load8(gp + r * d.ldg + c, g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float yh = fmaf(v[e], __ldg(d.scale + c + e), __ldg(d.shift + c + e));
@@ -115,9 +116,10 @@ __global__ void bn_bwd_finish_kernel(const double* sums, float* dgamma, float* d
   }
 }
 
-template <typename T, typename TD>
+template <typename T, typename TD, typename TG>
 __global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
   TD* __restrict__ dy = reinterpret_cast<TD*>(d.dy);
   const int G = d.C / 8;
   const int64_t total = d.rows * G;
@@ -127,7 +129,7 @@ __global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d) {
     const int c = (int)(i - r * G) * 8;
     float v[8], g[8], o[8];
     load8(y + r * d.ldy + c, v);
-    load8(d.g + r * d.ldg + c, g);
+    load8(gp + r * d.ldg + c, g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float sc = __ldg(d.scale + c + e);
@@ -235,10 +237,11 @@ extern "C" int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream) 
 extern "C" int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd: C %d", d->C);
   ColGrid g = col_grid(d->rows, d->C, 2);
-  VINET_DISPATCH_DTYPE(d->dtype, T, {
-    if (g.smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    bn_bwd_reduce_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
-  });
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->g_dtype, TG, {
+    if (g.smem > 48 * 1024)
+      cudaFuncSetAttribute(bn_bwd_reduce_kernel<T, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    bn_bwd_reduce_kernel<T, TG><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
+  }));
   VINET_LAUNCH_OK("bn_bwd_reduce");
   bn_bwd_finish_kernel<<<(unsigned)cdiv(d->C, 128), 128, 0, (cudaStream_t)stream>>>(d->sums, d->dgamma, d->dbeta, d->C);
   VINET_LAUNCH_OK("bn_bwd_finish");
@@ -249,8 +252,8 @@ extern "C" int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream
   const int64_t total = d->rows * (d->C / 8);
   int64_t nb = cdiv(total, 256);
   if (nb > 148 * 16) nb = 148 * 16;
-  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD,
-      (bn_bwd_apply_kernel<T, TD><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d))));
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, VINET_DISPATCH_DTYPE(d->g_dtype, TG,
+      (bn_bwd_apply_kernel<T, TD, TG><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d)))));
   VINET_LAUNCH_OK("bn_bwd_apply");
   return 0;
 }

@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const __grid_consta
     if (row >= M) continue;
     const RowCoord orc = decode_row(d.g, row, M);
     TO* p = out_row_ptr<TO>(d, orc);
+    const bool accum = (d.accumulate >> out_index(d, orc)) & 1;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= d.N) continue;
       float v = epilogue_value(d, acc[i][j], n);
-      if (d.accumulate) v += load1(p + n);
+      if (accum) v += load1(p + n);
       store1(p + n, v);
     }
   }
@@ -128,7 +129,6 @@ int conv_gemm_simt(const vinet_conv_t* d, cudaStream_t stream) {
   const int64_t M = (int64_t)d->g.B * d->g.Tr * d->g.Hr * d->g.Wr;
   const int npad = (int)round_up(d->N, SM_BN);
   dim3 grid((unsigned)cdiv(M, SM_BM), (unsigned)(npad / SM_BN));
-  VINET_CHECK(!(d->accumulate && d->out_dtype != VINET_F32), "conv_gemm: accumulate needs fp32 outputs");
   VINET_DISPATCH_DTYPE(d->g.dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
       (conv_gemm_simt_kernel<T, TO><<<grid, 256, 0, stream>>>(*d, npad))));
   VINET_LAUNCH_OK("conv_gemm_simt");

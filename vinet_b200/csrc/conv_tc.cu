@@ -164,6 +164,7 @@ conv_gemm_tc_kernel(const __grid_constant__ vinet_conv_t d, int stages, uint32_t
     RowCoord orc;
     orc.b = ri.x; orc.t = ri.y; orc.h = ri.z; orc.w = ri.w;
     TO* orow = (orc.b >= 0) ? out_row_ptr<TO>(d, orc) : nullptr;
+    const bool accum = (orc.b >= 0) && ((d.accumulate >> out_index(d, orc)) & 1);
     for (int g = half; g < BN / 16; g += 2) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), r);
@@ -175,13 +176,11 @@ conv_gemm_tc_kernel(const __grid_constant__ vinet_conv_t d, int stages, uint32_t
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = epilogue_value(d, __uint_as_float(r[h * 8 + e]), n + e);
-        if constexpr (sizeof(TO) == 4) {
-          if (d.accumulate) {
-            float o[8];
-            load8(reinterpret_cast<const float*>(orow) + n, o);
+        if (accum) {
+          float o[8];
+          load8(orow + n, o);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += o[e];
-          }
+          for (int e = 0; e < 8; ++e) v[e] += o[e];
         }
         store8(orow + n, v);
       }
@@ -398,7 +397,6 @@ int conv_gemm_tc(const vinet_conv_t* d, cudaStream_t stream) {
   VINET_CHECK(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "conv_gemm_tc: bad block_n %d", d->block_n);
   VINET_CHECK(d->g.Cs % 8 == 0, "conv_gemm_tc: Cs %d must be a multiple of 8", d->g.Cs);
   VINET_CHECK(d->N % 8 == 0, "conv_gemm_tc: N %d must be a multiple of 8", d->N);
-  VINET_CHECK(!(d->accumulate && d->out_dtype != VINET_F32), "conv_gemm: accumulate needs fp32 outputs");
   VINET_CHECK(d->k_blocks >= 1, "conv_gemm_tc: k_blocks");
   const int64_t M = (int64_t)d->g.B * d->g.Tr * d->g.Hr * d->g.Wr;
   const size_t stage_bytes = TC_A_BYTES + (size_t)d->block_n * 128;

@@ -200,10 +200,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       const int h = tc.h0 + rh, w = tc.w0 + rw;
       const bool valid = row < p.bw * p.bh && h < g.Hr && w < g.Wr;
       TO* orow = nullptr;
+      bool accum = false;
       if (valid) {
         RowCoord rc;
         rc.b = tc.b; rc.t = tc.t; rc.h = h; rc.w = w;
         orow = out_row_ptr<TO>(p.d, rc);
+        accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
       }
       const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
       if (any) {
@@ -227,13 +229,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = epilogue_value(p.d, __uint_as_float(r[hh * 8 + e]), n + e);
-          if constexpr (sizeof(TO) == 4) {
-            if (p.d.accumulate) {
-              float o[8];
-              load8(reinterpret_cast<const float*>(orow) + n, o);
+          if (accum) {
+            float o[8];
+            load8(orow + n, o);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += o[e];
-            }
+            for (int e = 0; e < 8; ++e) v[e] += o[e];
           }
           store8(orow + n, v);
         }
@@ -474,7 +474,6 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   if (check_tma_gather(g, "conv_gemm_tma")) return -1;
   VINET_CHECK(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "conv_gemm_tma: bad block_n %d", d->block_n);
   VINET_CHECK(d->N % 8 == 0, "conv_gemm_tma: N %d must be a multiple of 8", d->N);
-  VINET_CHECK(!(d->accumulate && d->out_dtype != VINET_F32), "conv_gemm_tma: accumulate needs fp32 outputs");
   ConvTmaParams p;
   p.d = *d;
   p.ncb = (g.Cs + 63) / 64;

@@ -78,6 +78,9 @@ __device__ __forceinline__ void gather_vec(const vinet_gather_t& g, const RowCoo
 }
 
 // output row -> destination pointer (two destinations split on the frame index)
+__device__ __forceinline__ int out_index(const vinet_conv_t& d, const RowCoord& rc) {
+  return (rc.t >= d.out_T[0]) ? 1 : 0;
+}
 template <typename TO>
 __device__ __forceinline__ TO* out_row_ptr(const vinet_conv_t& d, const RowCoord& rc) {
   int i = (rc.t >= d.out_T[0]) ? 1 : 0;

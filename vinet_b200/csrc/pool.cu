@@ -5,7 +5,8 @@
 
 namespace vinet {
 
-template <typename T, typename TO, bool BWD>
+// TO: forward output type / backward gout type; TGI: backward gin type
+template <typename T, typename TO, typename TGI, bool BWD>
 __global__ void maxpool_kernel(const __grid_constant__ vinet_pool_t d) {
   const T* __restrict__ x = reinterpret_cast<const T*>(d.x);
   const int G = d.C / 8;
@@ -45,10 +46,20 @@ __global__ void maxpool_kernel(const __grid_constant__ vinet_pool_t d) {
       store8(reinterpret_cast<TO*>(d.out) + opos * d.ldo + c, best);
     } else {
       float g[8];
-      load8(d.gout + opos * d.ldgo + c, g);
+      load8(reinterpret_cast<const TO*>(d.gout) + opos * d.ldgo + c, g);
+      TGI* gin = reinterpret_cast<TGI*>(d.gin);
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (arg[e] >= 0) atomicAdd(d.gin + arg[e] * d.ldgi + c + e, g[e]);
+      for (int e = 0; e < 8; ++e) {
+        if (arg[e] < 0) continue;
+        if constexpr (sizeof(TGI) == 4) {
+          atomicAdd(gin + arg[e] * d.ldgi + c + e, g[e]);
+        } else {
+          // bf16 gradients: native red.add.bf16x2 on the aligned pair holding channel c+e
+          const __nv_bfloat16 z = __float2bfloat16_rn(0.f), v = __float2bfloat16_rn(g[e]);
+          __nv_bfloat162 pair = (e & 1) ? __halves2bfloat162(z, v) : __halves2bfloat162(v, z);
+          atomicAdd(reinterpret_cast<__nv_bfloat162*>(gin + arg[e] * d.ldgi + c + (e & ~1)), pair);
+        }
+      }
     }
   }
 }
@@ -66,14 +77,15 @@ static unsigned pool_grid(const vinet_pool_t* d) {
 extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0, "maxpool: C %d", d->C);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
-      (maxpool_kernel<T, TO, false><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d))));
+      (maxpool_kernel<T, TO, float, false><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d))));
   VINET_LAUNCH_OK("maxpool_fwd");
   return 0;
 }
 
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0, "maxpool: C %d", d->C);
-  VINET_DISPATCH_DTYPE(d->dtype, T, (maxpool_kernel<T, float, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)));
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
+      (maxpool_kernel<T, TGO, TGI, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)))));
   VINET_LAUNCH_OK("maxpool_bwd");
   return 0;
 }

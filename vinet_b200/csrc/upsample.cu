@@ -55,9 +55,10 @@ __device__ __forceinline__ float up_weight(int Y, int n, int i) {
   return w;
 }
 
-template <typename T, typename TD>
+template <typename T, typename TD, typename TG>
 __global__ void upsample_bwd_kernel(const __grid_constant__ vinet_upsample_t d) {
   const T* __restrict__ z = reinterpret_cast<const T*>(d.z);
+  const TG* __restrict__ gu = reinterpret_cast<const TG*>(d.gu);
   TD* __restrict__ dz = reinterpret_cast<TD*>(d.dz);
   const int G = d.C / 8, H2 = 2 * d.h, W2 = 2 * d.w;
   const int64_t total = (int64_t)d.B * d.T * d.h * d.w * G;
@@ -76,7 +77,7 @@ __global__ void upsample_bwd_kernel(const __grid_constant__ vinet_upsample_t d) 
         const float wx = up_weight(X, d.w, x);
         if (wx == 0.f) continue;
         float g[8];
-        load8(d.gu + ((r * H2 + Y) * W2 + X) * d.ldgu + c, g);
+        load8(gu + ((r * H2 + Y) * W2 + X) * d.ldgu + c, g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy * wx, g[e], acc[e]);
       }
@@ -113,8 +114,8 @@ extern "C" int vinet_upsample_fwd(const vinet_upsample_t* d, vinet_stream_t stre
 extern "C" int vinet_upsample_bwd(const vinet_upsample_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0, "upsample: C %d", d->C);
   const int64_t total = (int64_t)d->B * d->T * d->h * d->w * (d->C / 8);
-  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dz_dtype, TD,
-      (upsample_bwd_kernel<T, TD><<<up_grid(total), 256, 0, (cudaStream_t)stream>>>(*d))));
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dz_dtype, TD, VINET_DISPATCH_DTYPE(d->gu_dtype, TG,
+      (upsample_bwd_kernel<T, TD, TG><<<up_grid(total), 256, 0, (cudaStream_t)stream>>>(*d)))));
   VINET_LAUNCH_OK("upsample_bwd");
   return 0;
 }

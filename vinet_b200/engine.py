@@ -35,8 +35,9 @@ class Act:
         self.buf, self.B, self.T, self.H, self.W, self.C, self.choff = buf, B, T, H, W, C_, choff
         self.ld = buf.shape[-1]
         self.xform, self.scale, self.shift = xform, scale, shift
-        self.grad = None      # fp32 [B,T,H,W,ldg]
+        self.grad = None      # [B,T,H,W,ldg] in the engine's storage type (bf16 / fp32), or fp32 when forced
         self.gchoff = 0
+        self.gdt = L.F32
         self.needs_grad = False
 
     @property
@@ -47,7 +48,7 @@ class Act:
         return self.buf.data_ptr() + self.choff * self.buf.element_size()
 
     def gptr(self):
-        return self.grad.data_ptr() + self.gchoff * 4
+        return self.grad.data_ptr() + self.gchoff * self.grad.element_size()
 
     @property
     def ldg(self):
@@ -57,7 +58,7 @@ class Act:
         a = Act(self.buf, self.B, self.T, self.H, self.W, c, self.choff + c0, self.xform,
                 None if self.scale is None else self.scale[c0:c0 + c],
                 None if self.shift is None else self.shift[c0:c0 + c])
-        a.grad, a.gchoff, a.needs_grad = self.grad, self.gchoff + c0, self.needs_grad
+        a.grad, a.gchoff, a.needs_grad, a.gdt = self.grad, self.gchoff + c0, self.needs_grad, self.gdt
         return a
 
 
@@ -81,6 +82,9 @@ class ConvGeom:
     def out_dims(self, T, H, W):
         return ((T + 2 * self.pt - self.kt) // self.st + 1, (H + 2 * self.ph - self.kh) // self.sh + 1,
                 (W + 2 * self.pw - self.kw) // self.sw + 1)
+
+
+_G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
 
 
 class Engine:
@@ -140,8 +144,9 @@ class Engine:
     def begin(self, device, training, record):
         self.device, self.training, self.record = device, training, record
         self.tape, self.grad_bufs, self.zero_list, self.param_grads = [], [], [], {}
+        self.gwritten = set()
 
-    def new_act(self, name, B, T, H, W, C_, xform=L.XF_IDENT, affine=False, dtype=None):
+    def new_act(self, name, B, T, H, W, C_, xform=L.XF_IDENT, affine=False, dtype=None, gdtype=None):
         buf = self.buf(name, (B, T, H, W, C_), dtype or self.tdtype)
         sc = sh = None
         if affine:
@@ -149,13 +154,36 @@ class Engine:
             sc, sh = ss[0], ss[1]
         a = Act(buf, B, T, H, W, C_, 0, xform, sc, sh)
         if self.record:
-            self.want_grad(a, name)
+            self.want_grad(a, name, gdtype)
         return a
 
-    def want_grad(self, a, name):
-        a.grad = self.buf(name + ".grad", (a.B, a.T, a.H, a.W, a.C), torch.float32)
+    def want_grad(self, a, name, dtype=None):
+        """Gradient w.r.t. the activated value, in the storage type (bf16 mode: bf16 gradients)."""
+        dtype = dtype or self.tdtype
+        a.grad = self.buf(name + ".grad", (a.B, a.T, a.H, a.W, a.C), dtype)
         a.gchoff, a.needs_grad = 0, True
+        a.gdt = L.F32 if dtype == torch.float32 else L.BF16
         self.grad_bufs.append(a.grad)
+
+    # Gradient buffers are never zeroed up front: the first writer of a buffer STORES (a convolution's data
+    # gradient covers every element), later writers accumulate.  Scatter-style writers (max-pool backward)
+    # and partial-coverage writers ask for an initialised buffer instead.
+    def first_write(self, a):
+        """True when `a` is the first (and full-coverage) writer of its gradient buffer."""
+        key = a.grad.data_ptr()
+        if key in self.gwritten:
+            return False
+        self.gwritten.add(key)
+        if a.gchoff == 0 and a.C == a.ldg:
+            return True
+        self.memset(a.grad)
+        return False
+
+    def ensure_init(self, a):
+        key = a.grad.data_ptr()
+        if key not in self.gwritten:
+            self.gwritten.add(key)
+            self.memset(a.grad)
 
     # ------------------------------------------------------------------ descriptors
     def _src(self, s, a):
@@ -278,12 +306,20 @@ class Engine:
             if not any(s.needs_grad for s in srcs):
                 return
             Ti = sum(s.T for s in srcs)
+            gdt = srcs[0].gdt
+            assert all(s.gdt == gdt for s in srcs)
+            phases = []
             for rho in range(geom.st):
                 dts = [dt for dt in range(geom.kt) if dt % geom.st == rho]
                 t0 = (rho - geom.pt) % geom.st
                 frames = len(range(t0, Ti, geom.st))
-                if not dts or frames == 0:
-                    continue
+                if dts and frames:
+                    phases.append((dts, t0, frames))
+            if len(phases) < min(geom.st, Ti):          # some frames receive no gradient from this conv
+                for s in srcs:
+                    self.ensure_init(s)
+            accmask = sum((0 if self.first_write(s) else 1) << i for i, s in enumerate(srcs))
+            for dts, t0, frames in phases:
                 ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
                 n = w.shape[1]
                 dtma = self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
@@ -305,7 +341,7 @@ class Engine:
                     dd.out[i], dd.ldo[i], dd.out_T[i] = s.gptr(), s.ldg, s.T
                 if len(srcs) == 1:
                     dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
-                dd.out_dtype, dd.accumulate = L.F32, 1
+                dd.out_dtype, dd.accumulate = gdt, accmask
                 dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
                 dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
                 self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
@@ -319,7 +355,17 @@ class Engine:
         plain activations, which is what lets the TMA-fed kernels fetch them.  Pure inference (no tape, running
         statistics): scale/shift/ReLU are folded into the conv epilogue and nothing else is launched."""
         Cn = out.C
-        rows = out.rows
+        if not self.training and not self.record:
+            ss = self._bn_finalize(name_bn, bn, out.rows, Cn, None)[1]
+            out.xform, out.scale, out.shift = L.XF_IDENT, None, None
+            self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
+            return
+        raw = Act(self.buf(name_conv + ".raw", (out.B, out.T, out.H, out.W, Cn), self.tdtype), out.B, out.T, out.H, out.W, Cn)
+        conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real)
+        self._bn_tail(name_bn, bn, raw, out, conv_bwd, None)
+
+    def _bn_finalize(self, name_bn, bn, rows, Cn, raw):
+        """Batch statistics of `raw` (training) or the running statistics -> (mean/invstd, scale/shift) buffers."""
         st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)      # mean, invstd
         ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)        # scale, shift
         fin = L.BnFinalize()
@@ -328,13 +374,6 @@ class Engine:
         fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
         fin.training = 1 if self.training else 0
         fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
-        out.xform, out.scale, out.shift = L.XF_IDENT, None, None
-        if not self.training and not self.record:
-            self.call("vinet_bn_finalize", fin)
-            self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
-            return
-        raw = Act(self.buf(name_conv + ".raw", (out.B, out.T, out.H, out.W, Cn), self.tdtype), out.B, out.T, out.H, out.W, Cn)
-        conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real)
         if self.training:
             sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64)
             self.memset(sums)
@@ -345,6 +384,14 @@ class Engine:
         self.call("vinet_bn_finalize", fin)
         if self.training:
             bn.num_batches_tracked += 1          # host-side counter buffer (nn.BatchNorm semantics)
+        return st, ss
+
+    def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot):
+        """BatchNorm + ReLU of the raw conv output `raw` into `out`, and its backward.  The backward either
+        hands dY to `conv_bwd` (own conv) or writes it into `dy_slot` = (ptr, ld) of a fused group's dY buffer."""
+        Cn, rows = out.C, out.rows
+        st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw)
+        out.xform, out.scale, out.shift = L.XF_IDENT, None, None
         ap = L.BnApply()
         ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
         ap.scale, ap.shift, ap.out, ap.ldo, ap.out_dtype = ss[0].data_ptr(), ss[1].data_ptr(), out.ptr(), out.ld, self.dt
@@ -357,18 +404,64 @@ class Engine:
             bsums = self.buf(name_bn + ".bsums", (2, Cn), torch.float64)
             self.memset(bsums)
             dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
-            dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
+            if dy_slot is None:
+                dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
+                dy_ptr, lddy = dy.data_ptr(), Cn
+            else:
+                dy_ptr, lddy = dy_slot
             b = L.BnBwd()
             b.g, b.ldg, b.y, b.ldy, b.dtype, b.rows, b.C, b.relu = out.gptr(), out.ldg, raw.ptr(), raw.ld, self.dt, rows, Cn, 1
             b.scale, b.shift, b.mean, b.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
             b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
-            b.dy, b.lddy, b.dy_dtype, b.training = dy.data_ptr(), Cn, self.dt, 1 if training else 0
+            b.dy, b.lddy, b.dy_dtype, b.training = dy_ptr, lddy, self.dt, 1 if training else 0
+            b.g_dtype = out.gdt
             self.call("vinet_bn_bwd_reduce", b)
             self.call("vinet_bn_bwd_apply", b)
             self.param_grads[name_bn + ".weight"] = dgamma
             self.param_grads[name_bn + ".bias"] = dbeta
-            conv_bwd(dy.data_ptr(), Cn)
+            if conv_bwd is not None:
+                conv_bwd(dy_ptr, lddy)
         self.tape.append(backward)
+
+    def conv_bn_group(self, gname, x, members):
+        """Horizontally fused 1x1x1 BasicConv3d's that read the same input (Mixed_* branch0 / branch1.0 /
+        branch2.0, model_utils.py:182-185): ONE GEMM with the concatenated weights computes all raw outputs
+        (x is read once instead of three times), each member keeps its own BatchNorm; backward runs ONE
+        weight-gradient and ONE data-gradient GEMM over the concatenated dY.
+        members: [(name_conv, name_bn, conv_weight, bn, out_act)]."""
+        if not self.training and not self.record:          # inference: per-member convs with folded BatchNorm
+            for nc, nb, w, bn, out in members:
+                self.conv_bn(nc, nb, [x], w, bn, _G1, out)
+            return
+        couts = [w.shape[0] for _, _, w, _, _ in members]
+        tot = sum(couts)
+        key = gname + ".wcat"
+        vers = tuple(w._version for _, _, w, _, _ in members)
+        hit = self.wcache.get(key)
+        if hit is None or hit[0] != vers or any(a is not b[2] for a, b in zip(hit[2], members)):
+            with torch.no_grad():
+                wcat = torch.cat([w.detach() for _, _, w, _, _ in members], 0).contiguous()
+            self.wcache[key] = (vers, wcat, [w for _, _, w, _, _ in members])
+        wcat = self.wcache[key][1]
+        rawcat = Act(self.buf(gname + ".raw", (x.B, x.T, x.H, x.W, tot), self.tdtype), x.B, x.T, x.H, x.W, tot)
+        conv_bwd = self.conv(gname, [x], wcat, _G1, rawcat)
+        dycat = None
+        if self.record:
+            dycat = self.buf(gname + ".dy", (rawcat.rows, tot), self.tdtype)
+
+            def group_backward():
+                conv_bwd(dycat.data_ptr(), tot)
+                gw = self.param_grads.pop(gname + ".weight")
+                off = 0
+                for (nc, _, _, _, _), c in zip(members, couts):
+                    self.param_grads[nc + ".weight"] = gw[off:off + c]
+                    off += c
+            self.tape.append(group_backward)      # appended first => runs after every member's BatchNorm backward
+        off = 0
+        for (nc, nb, w, bn, out), c in zip(members, couts):
+            slot = None if dycat is None else (dycat.data_ptr() + off * dycat.element_size(), tot)
+            self._bn_tail(nb, bn, rawcat.slice(off, c), out, None, slot)
+            off += c
 
     # ------------------------------------------------------------------ max pooling
     def maxpool(self, name, a, k, s, p):
@@ -382,7 +475,9 @@ class Engine:
         self.call("vinet_maxpool_fwd", d)
         if self.record and a.needs_grad:
             def backward():
+                self.ensure_init(a)
                 d.gout, d.ldgo, d.gin, d.ldgi = out.gptr(), out.ldg, a.gptr(), a.ldg
+                d.gout_dtype, d.gin_dtype = out.gdt, a.gdt
                 self.call("vinet_maxpool_bwd", d)
             self.tape.append(backward)
         return out
@@ -403,6 +498,7 @@ class Engine:
             def backward():
                 dz = self.buf("dy.%d" % (z.rows * Cout), (z.rows, Cout), self.tdtype)
                 d.gu, d.ldgu, d.dz, d.lddz, d.dz_dtype = u.gptr(), u.ldg, dz.data_ptr(), Cout, self.dt
+                d.gu_dtype = u.gdt
                 self.call("vinet_upsample_bwd", d)
                 conv_bwd(dz.data_ptr(), Cout)
             self.tape.append(backward)
@@ -435,7 +531,8 @@ class Engine:
                     dx = self.buf("dy.%d" % (a.rows * a.C), (a.rows, a.C), self.tdtype)
                     d.dx, d.lddx, d.dx_dtype = dx.data_ptr(), a.C, self.dt
                 else:                           # input is a materialised activation: dx is its fp32 gradient
-                    d.dx, d.lddx, d.dx_dtype = a.gptr(), a.ldg, L.F32
+                    assert self.first_write(a), "the head must be the only consumer of its input"
+                    d.dx, d.lddx, d.dx_dtype = a.gptr(), a.ldg, a.gdt
                 self.call("vinet_head_bwd", d)
                 self.param_grads[name + ".weight"] = gw
                 self.param_grads[name + ".bias"] = gb
@@ -447,8 +544,7 @@ class Engine:
     # ------------------------------------------------------------------ backward driver
     def backward(self, gout):
         """gout: fp32 (B,H,W) gradient w.r.t. the saliency map. Fills self.param_grads."""
-        for g in self.grad_bufs:
-            self.memset(g)
+        self.gwritten = set()
         self.head_backward(gout)
         for fn in reversed(self.tape):
             fn()

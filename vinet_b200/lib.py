@@ -77,7 +77,7 @@ class BnBwd(C.Structure):
     _fields_ = [("g", _p), ("ldg", _i64), ("y", _p), ("ldy", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32),
                 ("relu", _i32), ("scale", _p), ("shift", _p), ("mean", _p), ("invstd", _p), ("gamma", _p),
                 ("sums", _p), ("dgamma", _p), ("dbeta", _p), ("dy", _p), ("lddy", _i64), ("dy_dtype", _i32),
-                ("training", _i32)]
+                ("training", _i32), ("g_dtype", _i32)]
 
 
 class Pool(C.Structure):
@@ -86,13 +86,13 @@ class Pool(C.Structure):
                 ("kt", _i32), ("kh", _i32), ("kw", _i32), ("st", _i32), ("sh", _i32), ("sw", _i32),
                 ("pt", _i32), ("ph", _i32), ("pw", _i32), ("To", _i32), ("Ho", _i32), ("Wo", _i32),
                 ("out", _p), ("ldo", _i64), ("out_dtype", _i32), ("gout", _p), ("ldgo", _i64), ("gin", _p),
-                ("ldgi", _i64)]
+                ("ldgi", _i64), ("gout_dtype", _i32), ("gin_dtype", _i32)]
 
 
 class Upsample(C.Structure):
     _fields_ = [("z", _p), ("ldz", _i64), ("dtype", _i32), ("relu", _i32), ("B", _i32), ("T", _i32), ("h", _i32),
                 ("w", _i32), ("C", _i32), ("u", _p), ("ldu", _i64), ("u_dtype", _i32), ("gu", _p), ("ldgu", _i64),
-                ("dz", _p), ("lddz", _i64), ("dz_dtype", _i32)]
+                ("dz", _p), ("lddz", _i64), ("dz_dtype", _i32), ("gu_dtype", _i32)]
 
 
 class Head(C.Structure):

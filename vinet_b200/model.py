@@ -150,20 +150,26 @@ def _basic(e, pfx, x, m, out=None):
     return out
 
 
-def _mixed(e, pfx, x, m):
+def _mixed(e, pfx, x, m, gdtype=None):
+    """Mixed_3b..5c (model_utils.py:162-420).  Launch order differs from the reference's textual order (pool
+    branch first, the three 1x1 convs on x fused into one GEMM); the arithmetic per branch is unchanged."""
     cin, b0, b1r, b1, b2r, b2, b3 = arch.MIXED[m.name]
-    out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3)
-    _basic(e, pfx + ".branch0.0", x, m.branch0[0], out.slice(0, b0))
-    t = _basic(e, pfx + ".branch1.0", x, m.branch1[0])
-    _sepconv(e, pfx + ".branch1.1", [t], m.branch1[1], out.slice(b0, b1))
-    t = _basic(e, pfx + ".branch2.0", x, m.branch2[0])
-    _sepconv(e, pfx + ".branch2.1", [t], m.branch2[1], out.slice(b0 + b1, b2))
+    out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3, gdtype=gdtype)
+    # pool branch first: its backward (a scatter-add) then runs after the convs' data gradients have written x.grad
     p = e.maxpool(pfx + ".branch3.pool", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     _basic(e, pfx + ".branch3.1", p, m.branch3[1], out.slice(b0 + b1 + b2, b3))
+    t1 = e.new_act(pfx + ".branch1.0.o", x.B, x.T, x.H, x.W, b1r)
+    t2 = e.new_act(pfx + ".branch2.0.o", x.B, x.T, x.H, x.W, b2r)
+    e.conv_bn_group(pfx + ".fused1x1", x, [
+        (pfx + ".branch0.0.conv", pfx + ".branch0.0.bn", m.branch0[0].conv.weight, m.branch0[0].bn, out.slice(0, b0)),
+        (pfx + ".branch1.0.conv", pfx + ".branch1.0.bn", m.branch1[0].conv.weight, m.branch1[0].bn, t1),
+        (pfx + ".branch2.0.conv", pfx + ".branch2.0.bn", m.branch2[0].conv.weight, m.branch2[0].bn, t2)])
+    _sepconv(e, pfx + ".branch1.1", [t1], m.branch1[1], out.slice(b0, b1))
+    _sepconv(e, pfx + ".branch2.1", [t2], m.branch2[1], out.slice(b0 + b1, b2))
     return out
 
 
-def backbone_plan(e, pfx, bb, x):
+def backbone_plan(e, pfx, bb, x, y0_gdtype=None):
     """BackBoneS3D.forward (model.py:720-743): returns [y0, y1, y2, y3] as Acts."""
     a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
     a = e.maxpool(pfx + "base1.1", a, (1, 3, 3), (1, 2, 2), (0, 1, 1))
@@ -180,7 +186,7 @@ def backbone_plan(e, pfx, bb, x):
     # maxt4 (2,1,1) followed by maxp4 (1,2,2) == one (2,2,2)/2 max pool
     a = e.maxpool(pfx + "maxt4p4", y1, (2, 2, 2), (2, 2, 2), (0, 0, 0))
     for i, m in enumerate(bb.base4):
-        a = _mixed(e, pfx + "base4.%d" % i, a, m)
+        a = _mixed(e, pfx + "base4.%d" % i, a, m, gdtype=y0_gdtype if i == len(bb.base4) - 1 else None)
     return [a, y1, y2, y3]
 
 
