@@ -76,7 +76,7 @@ struct TcSmem {
 // =====================================================================================================
 // fprop / dgrad
 // =====================================================================================================
-template <typename T, typename TO>
+template <typename T, typename TO, bool EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ vinet_conv_t d, int stages, uint32_t tmem_cols, uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
@@ -173,16 +173,7 @@ conv_gemm_tc_kernel(const __grid_constant__ vinet_conv_t d, int stages, uint32_t
       for (int h = 0; h < 2; ++h) {
         const int n = nt * BN + g * 16 + h * 8;
         if (n >= d.N) continue;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = epilogue_value(d, __uint_as_float(r[h * 8 + e]), n + e);
-        if (accum) {
-          float o[8];
-          load8(orow + n, o);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += o[e];
-        }
-        store8(orow + n, v);
+        epilogue_store8<TO, EPI>(d, orow + n, r + h * 8, n, accum);
       }
     }
     tc_fence_before();
@@ -407,7 +398,7 @@ int conv_gemm_tc(const vinet_conv_t* d, cudaStream_t stream) {
   dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)d->n_tiles);
 #define LAUNCH_GEMM(T, TO)                                                                                     \
   do {                                                                                                         \
-    auto kern = conv_gemm_tc_kernel<T, TO>;                                                                    \
+    auto kern = conv_has_epilogue(*d) ? conv_gemm_tc_kernel<T, TO, true> : conv_gemm_tc_kernel<T, TO, false>;  \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
     kern<<<grid, TC_THREADS, smem, stream>>>(*d, stages, cols, idesc);                                         \
   } while (0)

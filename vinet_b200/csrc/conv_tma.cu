@@ -23,7 +23,8 @@
 
 namespace vinet {
 
-constexpr int TMA_THREADS = 192;
+constexpr int TMA_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TMA_WGRAD_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -86,7 +87,7 @@ __device__ __forceinline__ bool tile_has_work(const vinet_gather_t& g, int t) {
   return false;
 }
 
-template <typename TO>
+template <typename TO, bool EPI>
 __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull0 + 8 * a, 1);
-        mbar_init(tempty0 + 8 * a, 4);
+        mbar_init(tempty0 + 8 * a, 8);
       }
       fence_barrier_init();
     }
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     }
   } else {
     // ---------------------------------------------------------------- epilogue: TMEM -> registers -> global
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int row = q * 32 + lane;
     const int rh = row / p.bw, rw = row - rh * p.bw;
     const int BN = p.d.block_n;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       if (valid) {
         RowCoord rc;
         rc.b = tc.b; rc.t = tc.t; rc.h = h; rc.w = w;
-        orow = out_row_ptr<TO>(p.d, rc);
+        orow = out_row_ptr<TO>(p.d, rc) + tc.nt * BN;
         accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
       }
       const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
@@ -213,7 +215,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         tc_fence_after();
       }
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.acc_cols;
-      for (int gi = 0; gi < BN / 16; ++gi) {
+      const int nlim = p.d.N - tc.nt * BN;  // columns of this tile that exist
+      for (int gi = half; gi < BN / 16; gi += 2) {
         uint32_t r[16];
         if (any) {
           tmem_ld16(tacc + (uint32_t)(gi * 16), r);
@@ -222,21 +225,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           for (int e = 0; e < 16; ++e) r[e] = 0u;
         }
         if (!valid) continue;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int n = tc.nt * BN + gi * 16 + hh * 8;
-          if (n >= p.d.N) continue;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = epilogue_value(p.d, __uint_as_float(r[hh * 8 + e]), n + e);
-          if (accum) {
-            float o[8];
-            load8(orow + n, o);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += o[e];
-          }
-          store8(orow + n, v);
-        }
+        const int c0 = gi * 16;
+        if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, tc.nt * BN + c0, accum);
+        if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, tc.nt * BN + c0 + 8, accum);
       }
       if (any) {
         tc_fence_before();
@@ -265,7 +256,7 @@ struct WgradTmaParams {
   uint32_t tmem_cols, idesc, unit_bytes, stage_bytes;
 };
 
-__global__ void __launch_bounds__(TMA_THREADS, 1) conv_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p) {
+__global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p) {
   const vinet_gather_t& g = p.d.g;
   const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
   const int64_t per = cdiv(nchunks, p.splits);
@@ -502,7 +493,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
 #define LAUNCH_TMA(TO)                                                                                  \
   do {                                                                                                  \
-    auto kern = conv_gemm_tma_kernel<TO>;                                                               \
+    auto kern = conv_has_epilogue(*d) ? conv_gemm_tma_kernel<TO, true> : conv_gemm_tma_kernel<TO, false>; \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     kern<<<grid, TMA_THREADS, smem, stream>>>(p);                                                       \
   } while (0)
@@ -553,7 +544,7 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, p.bw, p.bh)) return -1;
   dim3 grid((unsigned)mblocks, (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  conv_wgrad_tma_kernel<<<grid, TMA_THREADS, smem, stream>>>(p);
+  conv_wgrad_tma_kernel<<<grid, TMA_WGRAD_THREADS, smem, stream>>>(p);
   VINET_LAUNCH_OK("conv_wgrad_tma");
   return 0;
 }

@@ -89,6 +89,44 @@ __device__ __forceinline__ TO* out_row_ptr(const vinet_conv_t& d, const RowCoord
   return reinterpret_cast<TO*>(d.out[i]) + pos * d.ldo[i];
 }
 
+// Epilogue of 8 consecutive output channels [n, n+8) of one row: optional per-channel scale/shift/activation
+// (EPI; vector loads, branches hoisted out of the element loop), optional read-modify-write, one 16/32-byte store.
+template <typename TO, bool EPI>
+__device__ __forceinline__ void epilogue_store8(const vinet_conv_t& d, TO* p, const uint32_t* r, int n, bool accum) {
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
+  if constexpr (EPI) {
+    if (d.ep_scale) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(d.ep_scale + n));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(d.ep_scale + n) + 1);
+      v[0] *= a.x; v[1] *= a.y; v[2] *= a.z; v[3] *= a.w; v[4] *= b.x; v[5] *= b.y; v[6] *= b.z; v[7] *= b.w;
+    }
+    if (d.ep_shift) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(d.ep_shift + n));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(d.ep_shift + n) + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (d.ep_act == VINET_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    } else if (d.ep_act == VINET_ACT_SIGMOID) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
+    }
+  }
+  if (accum) {
+    float o[8];
+    load8(p, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += o[e];
+  }
+  store8(p, v);
+}
+__host__ __device__ static inline bool conv_has_epilogue(const vinet_conv_t& d) {
+  return d.ep_scale != nullptr || d.ep_shift != nullptr || d.ep_act != VINET_ACT_NONE;
+}
+
 __device__ __forceinline__ float epilogue_value(const vinet_conv_t& d, float acc, int n) {
   if (d.ep_scale) acc *= __ldg(d.ep_scale + n);
   if (d.ep_shift) acc += __ldg(d.ep_shift + n);
