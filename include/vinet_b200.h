@@ -38,8 +38,10 @@ enum { VINET_LOSS_KLDIV = 0, VINET_LOSS_CC = 1, VINET_LOSS_SIM = 2, VINET_LOSS_N
  * persistent CTAs, double-buffered TMEM accumulators; needs bf16 sources with VINET_XF_IDENT and spatial stride 1. */
 enum { VINET_KERNEL_GATHER = 0, VINET_KERNEL_TMA = 1 };
 /* K index of packed weights / packed weight gradients. DENSE: k = tap*cs + c.  TAP64: every tap is padded to a
- * multiple of 64 channels, k = (tap*ceil(cs/64) + c/64)*64 + c%64 (one 64-wide K block per TMA box). */
-enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1 };
+ * multiple of 64 channels, k = (tap*ceil(cs/64) + c/64)*64 + c%64 (one 64-wide K block per TMA box).
+ * WIN8 (stem, Cin <= 8, kw <= 8): the gather's taps enumerate dh only and one 64-wide K block holds the whole
+ * (dw, c) window of a padded NDHWC8 row: k = dh*64 + dw*8 + c.  The matching source view has Cs = 64, ld = 8*sw. */
+enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1, VINET_KLAYOUT_WIN8 = 2 };
 
 #define VINET_MAX_TAPS 64
 #define VINET_TC_BLOCK_M 128
@@ -53,6 +55,8 @@ typedef struct vinet_src {
   int64_t ld;
   int32_t T;     /* frames held by this source */
   int32_t xform; /* VINET_XF_* */
+  int64_t ldh;   /* elements between consecutive h rows; 0 = dense (Ws*ld).  Only the TMA kernels accept a
+                    non-dense pitch or ld < Cs (overlapping sliding-window rows, see vinet_pack_input_t) */
 } vinet_src_t;
 
 /*
@@ -134,6 +138,9 @@ typedef struct vinet_pack {
 int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
 size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks);
 
+/* WIN8 variant: grad[co][ci][0][dh][dw] = dwp[(dh*64 + dw*8 + ci)*lddw + co] */
+int vinet_unpack_wgrad_win8(const float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                            vinet_stream_t stream);
 /* grad[co][ci][tap] = dwp[(tap*cs + ci)*lddw + co]  (taps in natural (dt,dh,dw) order) */
 int vinet_unpack_wgrad(const float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
                        int32_t ntaps, vinet_stream_t stream);
@@ -146,6 +153,8 @@ typedef struct vinet_pack_input {
   int32_t cpad;
   void* out;
   int32_t out_dtype;
+  int32_t wl, Wp; /* rows are written Wp >= wl + W pixels wide: wl zero pixels, the W pixels, zeros (0,0 = dense).
+                     With explicit zero columns the stem conv can address a row as overlapping windows (WIN8). */
 } vinet_pack_input_t;
 int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream);
 

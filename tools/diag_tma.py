@@ -96,6 +96,7 @@ def child_check():
 
 
 PERF = [  # name, case (B=8 layers of the north-star workload)
+    ("base1.0.conv_s", None),
     ("base1.3.conv_s", (8, 16, 0, 56, 96, 64, 192, (1, 3, 3), 1, (0, 1, 1))),
     ("base1.3.conv_t", (8, 16, 0, 56, 96, 192, 192, (3, 1, 1), 1, (1, 0, 0))),
     ("base1.0.conv_t", (8, 32, 0, 112, 192, 64, 64, (7, 1, 1), 2, (3, 0, 0))),
@@ -109,19 +110,34 @@ PERF = [  # name, case (B=8 layers of the north-star workload)
 ]
 
 
+def build_stem(use_tma, B=8, T=32, H=224, W=384):
+    import torch
+    from vinet_b200 import model as M
+    from vinet_b200.engine import ConvGeom, Engine
+    e = Engine("bf16")
+    e.use_tma = use_tma
+    e.begin(torch.device("cuda"), True, True)
+    x = torch.randn(B, T, 3, H, W, device="cuda").permute(0, 2, 1, 3, 4)
+    xin = M.pack_input(e, x)
+    w = (torch.randn(64, 3, 1, 7, 7, device="cuda") / 147 ** 0.5).to(torch.bfloat16).float()
+    geom = ConvGeom((1, 7, 7), (1, 2, 2), (0, 3, 3))
+    out = e.new_act("o", B, T, H // 2, W // 2, 64)
+    return e, [xin], w, geom, out, None
+
+
 def child_perf():
     import torch
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     print("%-16s %8s | %21s | %21s | %21s" % ("layer", "GFLOP", "fprop ms (TF/s)", "dgrad ms (TF/s)", "wgrad ms (TF/s)"))
     for name, c in PERF:
         for use_tma in (True, False):
-            e, srcs, w, geom, out, g = build("bf16", use_tma, *c)
+            e, srcs, w, geom, out, g = build_stem(use_tma) if c is None else build("bf16", use_tma, *c)
             e.profile = []
             e.l2_flush = flush
             dy = torch.randn(out.buf.shape, device="cuda").to(e.tdtype)
             for it in range(3):
                 e.profile = []
-                bwd = e.conv("c", srcs, w, geom, out)
+                bwd = e.conv("c", srcs, w, geom, out, cin_real=3 if c is None else None)
                 bwd(dy.data_ptr(), out.C)
             torch.cuda.synchronize()
             agg = {}

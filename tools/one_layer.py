@@ -11,10 +11,10 @@ import diag_tma as D
 name = sys.argv[1] if len(sys.argv) > 1 else "base1.3.conv_s"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 case = dict(D.PERF)[name]
-e, srcs, w, geom, out, g = D.build("bf16", True, *case)
+e, srcs, w, geom, out, g = D.build_stem(True) if case is None else D.build("bf16", True, *case)
 dy = torch.randn(out.buf.shape, device="cuda").to(e.tdtype)
 for it in range(iters):
-    bwd = e.conv("c", srcs, w, geom, out)
+    bwd = e.conv("c", srcs, w, geom, out, cin_real=3 if case is None else None)
     bwd(dy.data_ptr(), out.C)
 torch.cuda.synchronize()
 print("done", name)

@@ -24,6 +24,17 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream);
 int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream);
 int tc_debug_set(unsigned int v);
 
+// the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
+static bool dense_sources(const vinet_gather_t& g) {
+  for (int i = 0; i < 2; ++i) {
+    const vinet_src_t& s = g.src[i];
+    if (s.ptr == nullptr) continue;
+    if (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) return false;
+    if (s.ld < g.Cs) return false;
+  }
+  return true;
+}
+
 __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, int accumulate) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = accumulate ? dst[i] + src[i] : src[i];
@@ -36,8 +47,9 @@ extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stre
   VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_gemm: bad tap count");
   VINET_CHECK(d->g.B > 0 && d->g.Tr > 0 && d->g.Hr > 0 && d->g.Wr > 0, "conv_gemm: empty row space");
   VINET_CHECK(d->g.st > 0 && d->g.sh > 0 && d->g.sw > 0 && d->g.row_tstep > 0, "conv_gemm: bad strides");
-  if (engine == VINET_ENGINE_TC)
-    return d->kernel == VINET_KERNEL_TMA ? conv_gemm_tma(d, (cudaStream_t)stream) : conv_gemm_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA) return conv_gemm_tma(d, (cudaStream_t)stream);
+  VINET_CHECK(dense_sources(d->g), "conv_gemm: only the TMA kernel reads pitched / sliding-window sources");
+  if (engine == VINET_ENGINE_TC) return conv_gemm_tc(d, (cudaStream_t)stream);
   if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);
   set_error("conv_gemm: unknown engine %d", engine);
   return -1;
@@ -47,8 +59,9 @@ extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_st
   VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_wgrad: bad tap count");
   VINET_CHECK(d->splits >= 1, "conv_wgrad: splits");
   VINET_CHECK(d->lddw >= d->N, "conv_wgrad: lddw");
-  if (engine == VINET_ENGINE_TC)
-    return d->kernel == VINET_KERNEL_TMA ? conv_wgrad_tma(d, (cudaStream_t)stream) : conv_wgrad_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA) return conv_wgrad_tma(d, (cudaStream_t)stream);
+  VINET_CHECK(dense_sources(d->g), "conv_wgrad: only the TMA kernel reads pitched / sliding-window sources");
+  if (engine == VINET_ENGINE_TC) return conv_wgrad_tc(d, (cudaStream_t)stream);
   if (engine == VINET_ENGINE_SIMT) return conv_wgrad_simt(d, (cudaStream_t)stream);
   set_error("conv_wgrad: unknown engine %d", engine);
   return -1;

@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           int si, tl;
           if (!tap_frame(g, tc.t, g.tap[tap][0], si, tl)) continue;
           const int dh = g.tap[tap][1], dw = g.tap[tap][2];
-          const int hc = (g.mode == VINET_GATHER_FPROP) ? tc.h0 - g.ph + dh : tc.h0 + g.ph - dh;
-          const int wc = (g.mode == VINET_GATHER_FPROP) ? tc.w0 - g.pw + dw : tc.w0 + g.pw - dw;
+          // FPROP boxes step through the source with the conv's spatial stride (tensor-map element strides)
+          const int hc = (g.mode == VINET_GATHER_FPROP) ? tc.h0 * g.sh - g.ph + dh : tc.h0 + g.ph - dh;
+          const int wc = (g.mode == VINET_GATHER_FPROP) ? tc.w0 * g.sw - g.pw + dw : tc.w0 + g.pw - dw;
           const uint8_t* wtap = wbase + ((size_t)tc.nt * KB + (size_t)tap * p.ncb) * p.b_bytes;
           for (int cb = 0; cb < p.ncb; ++cb) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -324,8 +325,8 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
           // frames outside [0,Ts) are addressed out of bounds on purpose: TMA zero-fills the temporal padding
           const int si = (g.src[1].ptr != nullptr && ts >= g.src[0].T) ? 1 : 0;
           const int tl = ts - (si ? g.src[0].T : 0);
-          tma_load_5d(stage + (uint32_t)j * p.unit_bytes, &p.tmA[si], full0 + 8 * s, cb * 64, w0 - g.pw + g.tap[tap][2],
-                      h0 - g.ph + g.tap[tap][1], tl, b);
+          tma_load_5d(stage + (uint32_t)j * p.unit_bytes, &p.tmA[si], full0 + 8 * s, cb * 64,
+                      w0 * g.sw - g.pw + g.tap[tap][2], h0 * g.sh - g.ph + g.tap[tap][1], tl, b);
         }
         for (int nb = 0; nb < nblk_eff; ++nb)
           tma_load_5d(stage + (uint32_t)(2 + nb) * p.unit_bytes, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
@@ -398,17 +399,20 @@ static EncodeTiledFn encode_fn() {
   return reinterpret_cast<EncodeTiledFn>(f);
 }
 
-// NDHWC bf16 view [B][T][H][W][C] with row stride ld -> 5-D tiled map, box {64, bw, bh, 1, 1}, 128B swizzle
-static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int bw, int bh) {
+// NDHWC bf16 view [B][T][H][W][C] (pixel stride ld, row pitch ldh) -> 5-D tiled map, box {64, bw, bh, 1, 1} taking every
+// esw-th / esh-th pixel (strided convolutions), 128B swizzle.  ld < C gives overlapping sliding-window rows (WIN8).
+static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
+                    int esw = 1, int esh = 1) {
   EncodeTiledFn enc = encode_fn();
   VINET_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from the driver");
   VINET_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0, "conv_tma: source must be 16-byte aligned (ld %lld)",
               (long long)ld);
   const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
-  const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2,
-                                 (cuuint64_t)T * H * W * ld * 2};
-  const cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  if (ldh == 0) ldh = (int64_t)W * ld;
+  VINET_CHECK(ldh % 8 == 0 && bw * esw <= 256 && bh * esh <= 256 && esw <= 8 && esh <= 8, "conv_tma: bad pitch / box");
+  const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ldh * 2, (cuuint64_t)H * ldh * 2, (cuuint64_t)T * H * ldh * 2};
+  const cuuint32_t box[5] = {64, (cuuint32_t)(bw * esw), (cuuint32_t)(bh * esh), 1, 1};
+  const cuuint32_t es[5] = {1, (cuuint32_t)esw, (cuuint32_t)esh, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -452,7 +456,8 @@ static int sm_count() {
 
 static int check_tma_gather(const vinet_gather_t& g, const char* what) {
   VINET_CHECK(g.dtype == VINET_BF16, "%s: the TMA kernel needs bf16 sources", what);
-  VINET_CHECK(g.sh == 1 && g.sw == 1, "%s: the TMA kernel needs spatial stride 1 (got %d,%d)", what, g.sh, g.sw);
+  VINET_CHECK((g.sh == 1 && g.sw == 1) || g.mode == VINET_GATHER_FPROP,
+              "%s: the TMA kernel handles spatial strides (%d,%d) only for FPROP gathers", what, g.sh, g.sw);
   VINET_CHECK(g.Cs % 8 == 0, "%s: Cs %d must be a multiple of 8", what, g.Cs);
   VINET_CHECK(g.src[0].xform == VINET_XF_IDENT && (g.src[1].ptr == nullptr || g.src[1].xform == VINET_XF_IDENT),
               "%s: the TMA kernel cannot apply pending source transforms", what);
@@ -488,7 +493,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   const size_t smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 64;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, p.bw, p.bh)) return -1;
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
 #define LAUNCH_TMA(TO)                                                                                  \
@@ -539,9 +544,9 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)stages * p.stage_bytes + 8 * (2 * stages + 1) + 64;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, p.bw, p.bh)) return -1;
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
   }
-  if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, p.bw, p.bh)) return -1;
+  if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, p.bw, p.bh)) return -1;
   dim3 grid((unsigned)mblocks, (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   conv_wgrad_tma_kernel<<<grid, TMA_WGRAD_THREADS, smem, stream>>>(p);

@@ -7,19 +7,21 @@ namespace vinet {
 // One thread per (b,t,h,w): reads C strided fp32 values, writes cpad contiguous channels.
 template <typename TO>
 __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) {
-  const int64_t total = (int64_t)d.B * d.T * d.H * d.W;
+  const int Wp = d.Wp > 0 ? d.Wp : d.W;
+  const int64_t total = (int64_t)d.B * d.T * d.H * Wp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i;
-    const int w = (int)(r % d.W); r /= d.W;
+    const int w = (int)(r % Wp) - d.wl; r /= Wp;
     const int h = (int)(r % d.H); r /= d.H;
     const int t = (int)(r % d.T);
     const int b = (int)(r / d.T);
-    const float* src = d.x + b * d.sb + t * d.st + h * d.sh + w * d.sw;
+    const bool in = (unsigned)w < (unsigned)d.W;
+    const float* src = d.x + b * d.sb + t * d.st + h * d.sh + (in ? w : 0) * d.sw;
     TO* dst = reinterpret_cast<TO*>(d.out) + i * d.cpad;
     for (int c0 = 0; c0 < d.cpad; c0 += 8) {
       float v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (c0 + e < d.C) ? __ldg(src + (c0 + e) * d.sc) : 0.f;
+      for (int e = 0; e < 8; ++e) v[e] = (in && c0 + e < d.C) ? __ldg(src + (c0 + e) * d.sc) : 0.f;
       store8(dst + c0, v);
     }
   }
@@ -28,6 +30,12 @@ __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) 
 // ------------------------------------------------------------------ weights
 // element (n, k) of the GEMM B operand; DENSE: k = tap_idx*cs + c, TAP64: k = tap_idx*round_up(cs,64) + c
 __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k) {
+  if (d.layout == VINET_KLAYOUT_WIN8) {  // k = dh_tap*64 + dw*8 + ci; FPROP only
+    const int tap = k >> 6, dw = (k >> 3) & 7, ci = k & 7;
+    if (tap >= d.ntaps || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
+    const int dt = d.tap[tap][0], dh = d.tap[tap][1];
+    return __ldg(d.w + ((((int64_t)n * d.Cin + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
+  }
   const int csk = (d.layout == VINET_KLAYOUT_TAP64) ? ((d.cs + 63) / 64) * 64 : d.cs;
   const int tap = k / csk, c = k - tap * csk;
   if (tap >= d.ntaps || c >= d.cs) return 0.f;
@@ -80,6 +88,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int lddw, int
   }
 }
 
+__global__ void unpack_wgrad_win8_kernel(const float* __restrict__ dwp, int lddw, float* __restrict__ grad, int Cout, int Cin,
+                                         int kh, int kw) {
+  const int64_t total = (int64_t)Cout * Cin * kh * kw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int dw = (int)(i % kw);
+    int64_t r = i / kw;
+    const int dh = (int)(r % kh); r /= kh;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    grad[i] = dwp[((int64_t)dh * 64 + dw * 8 + ci) * lddw + co];
+  }
+}
+
 static inline unsigned grid_for(int64_t n, int block) {
   int64_t g = cdiv(n, block);
   if (g > 148 * 16) g = 148 * 16;
@@ -93,7 +114,8 @@ using namespace vinet;
 
 extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->cpad % 8 == 0 && d->cpad >= d->C, "pack_input: cpad %d", d->cpad);
-  const int64_t total = (int64_t)d->B * d->T * d->H * d->W;
+  VINET_CHECK(d->Wp == 0 || d->Wp >= d->wl + d->W, "pack_input: Wp %d < wl %d + W %d", d->Wp, d->wl, d->W);
+  const int64_t total = (int64_t)d->B * d->T * d->H * (d->Wp > 0 ? d->Wp : d->W);
   VINET_DISPATCH_DTYPE(d->out_dtype, TO, (pack_input_kernel<TO><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d)));
   VINET_LAUNCH_OK("pack_input");
   return 0;
@@ -106,8 +128,10 @@ extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t b
 
 extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
-  VINET_CHECK(d->layout == VINET_KLAYOUT_DENSE || d->layout == VINET_KLAYOUT_TAP64, "pack_weights: layout %d", d->layout);
-  const int64_t csk = d->layout == VINET_KLAYOUT_TAP64 ? round_up(d->cs, 64) : d->cs;
+  VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN8, "pack_weights: layout %d", d->layout);
+  VINET_CHECK(d->layout != VINET_KLAYOUT_WIN8 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 8 && d->kw <= 8 && d->cs == 64),
+              "pack_weights: WIN8 needs an FPROP pack with Cin <= 8, kw <= 8, cs == 64");
+  const int64_t csk = d->layout == VINET_KLAYOUT_DENSE ? d->cs : round_up(d->cs, 64);
   VINET_CHECK((int64_t)d->k_blocks * 64 >= (int64_t)d->ntaps * csk, "pack_weights: k_blocks too small");
   if (d->engine == VINET_ENGINE_TC) {
     const int64_t chunks = (int64_t)d->n_tiles * d->k_blocks * d->block_n * 8;
@@ -118,6 +142,15 @@ extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) 
     pack_weights_simt_kernel<<<grid_for((int64_t)d->k_blocks * 64 * npad, 256), 256, 0, (cudaStream_t)stream>>>(*d, npad);
   }
   VINET_LAUNCH_OK("pack_weights");
+  return 0;
+}
+
+extern "C" int vinet_unpack_wgrad_win8(const float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh,
+                                       int32_t kw, vinet_stream_t stream) {
+  VINET_CHECK(Cin <= 8 && kw <= 8, "unpack_wgrad_win8: Cin %d kw %d", Cin, kw);
+  const int64_t total = (int64_t)Cout * Cin * kh * kw;
+  unpack_wgrad_win8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dwp, lddw, grad, Cout, Cin, kh, kw);
+  VINET_LAUNCH_OK("unpack_wgrad_win8");
   return 0;
 }
 

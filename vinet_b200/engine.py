@@ -62,6 +62,15 @@ class Act:
         return a
 
 
+class WinAct(Act):
+    """The packed input clip stored with explicit zero columns ([B,T,H,Wp,8], image at columns wl..wl+W) so that
+    the TMA-fed stem conv can address every row as overlapping sliding windows (VINET_KLAYOUT_WIN8)."""
+
+    def __init__(self, buf, B, T, H, W, wl, Wp):
+        super().__init__(buf, B, T, H, W, 8)
+        self.wl, self.Wp = wl, Wp
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -214,7 +223,7 @@ class Engine:
         """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version."""
         ck = (key, mode, tuple(taps), self.eng, layout)
         block_n, n_tiles = self.tiling(n)
-        if layout == L.KLAYOUT_TAP64:
+        if layout != L.KLAYOUT_DENSE:
             k_blocks = len(taps) * cdiv(cs, L.TC_BLOCK_K)
         else:
             k_blocks = cdiv(len(taps) * cs, L.TC_BLOCK_K)
@@ -248,17 +257,39 @@ class Engine:
         a0 = srcs[0]
         cs = a0.C
         Cout = w.shape[0]
-        tma = self.tma_ok(srcs, geom)
+        win = isinstance(a0, WinAct)
+        tma = win or self.tma_ok(srcs, geom)
         kern = L.KERNEL_TMA if tma else L.KERNEL_GATHER
-        layout = L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE
+        layout = L.KLAYOUT_WIN8 if win else (L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE)
         To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
         assert (To, Ho, Wo, Cout) == (out.T, out.H, out.W, out.C), (name, (To, Ho, Wo, Cout), (out.T, out.H, out.W, out.C))
         assert w.shape[1] == (cin_real or cs), name
         taps = _taps(geom.kt, geom.kh, geom.kw)
+        nreal = len(taps)
+        if win:
+            # stem: one 64-wide K block per kernel row dh holds the (dw, c) window of 8 pixels x 8 channels;
+            # output column wo reads padded pixels wo*sw .. wo*sw+7, i.e. consecutive windows overlap
+            assert len(srcs) == 1 and geom.kt == 1 and geom.st == 1 and geom.kw <= 8 and geom.pw == a0.wl and w.shape[1] <= 8
+            assert (Wo - 1) * geom.sw + 8 <= a0.Wp
+            taps, cs = [(0, dh, 0) for dh in range(geom.kh)], 64
+
+        def fill_gather(g):
+            if not win:
+                return self._gather_fprop(g, srcs, geom, cs, To, Ho, Wo)
+            g.mode, g.dtype = L.GATHER_FPROP, self.dt
+            g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, To, Ho, Wo, 1, 0
+            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = a0.T, a0.H, Wo, 64, len(taps)
+            _fill_taps(g.tap, taps)
+            g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
+            s0 = g.src[0]
+            s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = a0.buf.data_ptr(), None, None, 8 * geom.sw, a0.T, L.XF_IDENT
+            s0.ldh = a0.Wp * 8
+            g.src[1].ptr, g.src[1].T = None, 0
+
         wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout)
         d = L.Conv()
         d.kernel = kern
-        self._gather_fprop(d.g, srcs, geom, cs, To, Ho, Wo)
+        fill_gather(d.g)
         d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
         d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
         d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
@@ -268,7 +299,7 @@ class Engine:
             assert bias is None
             d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
         cin_r = w.shape[1]
-        flops = 2.0 * a0.B * To * Ho * Wo * len(taps) * cin_r * Cout
+        flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
         self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
         if not self.record:
             return None
@@ -282,7 +313,7 @@ class Engine:
             self.memset(dwp)
             wg = L.Wgrad()
             wg.kernel = kern
-            self._gather_fprop(wg.g, srcs, geom, cs, To, Ho, Wo)
+            fill_gather(wg.g)
             wg.dy, wg.lddy, wg.dy_dtype, wg.N, wg.dwp, wg.lddw = dy, lddy, self.dt, Cout, dwp.data_ptr(), lddw
             rows = a0.B * To * Ho * Wo
             if self.eng == L.ENGINE_TC:
@@ -294,8 +325,12 @@ class Engine:
             wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
             self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
             gw = torch.empty_like(w)
-            self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
-                          self.stream())
+            if win:
+                self.lib.call("vinet_unpack_wgrad_win8", dwp.data_ptr(), lddw, gw.data_ptr(), Cout, w.shape[1], geom.kh,
+                              geom.kw, self.stream())
+            else:
+                self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
+                              self.stream())
             self.param_grads[name + ".weight"] = gw
             if bias is not None:
                 gb = torch.empty_like(bias)

@@ -18,7 +18,7 @@ ENGINE_TC, ENGINE_SIMT = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 LOSS_KLDIV, LOSS_CC, LOSS_SIM, LOSS_NSS = 0, 1, 2, 3
 KERNEL_GATHER, KERNEL_TMA = 0, 1
-KLAYOUT_DENSE, KLAYOUT_TAP64 = 0, 1
+KLAYOUT_DENSE, KLAYOUT_TAP64, KLAYOUT_WIN8 = 0, 1, 2
 MAX_TAPS = 64
 TC_BLOCK_M, TC_BLOCK_K = 128, 64
 
@@ -26,7 +26,7 @@ _p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", _p), ("scale", _p), ("shift", _p), ("ld", _i64), ("T", _i32), ("xform", _i32)]
+    _fields_ = [("ptr", _p), ("scale", _p), ("shift", _p), ("ld", _i64), ("T", _i32), ("xform", _i32), ("ldh", _i64)]
 
 
 class Gather(C.Structure):
@@ -55,7 +55,8 @@ class Pack(C.Structure):
 
 class PackInput(C.Structure):
     _fields_ = [("x", _p), ("sb", _i64), ("sc", _i64), ("st", _i64), ("sh", _i64), ("sw", _i64), ("B", _i32),
-                ("C", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("cpad", _i32), ("out", _p), ("out_dtype", _i32)]
+                ("C", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("cpad", _i32), ("out", _p), ("out_dtype", _i32),
+                ("wl", _i32), ("Wp", _i32)]
 
 
 class BnStats(C.Structure):
@@ -133,6 +134,7 @@ SIGNATURES = {
     "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
     "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
     "vinet_unpack_wgrad": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _S]),
+    "vinet_unpack_wgrad_win8": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _S]),
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),

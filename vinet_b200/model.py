@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import arch
 from . import lib as L
-from .engine import Act, ConvGeom, Engine
+from .engine import Act, ConvGeom, Engine, WinAct
 
 BN_EPS, BN_MOM = 1e-3, 1e-3   # model_utils.py:132
 
@@ -296,10 +296,13 @@ def pack_input(e, x):
     assert x.dim() == 5 and x.shape[1] == 3 and x.dtype == torch.float32, "expected a (B,3,T,H,W) fp32 clip"
     B, _, T, H, W = x.shape
     assert H % 32 == 0 and W % 32 == 0, "H and W must be multiples of 32 (the reference fails otherwise)"
-    buf = e.buf("input.packed", (B, T, H, W, 8), e.tdtype)
+    win = e.eng == L.ENGINE_TC and e.use_tma      # TMA engine: rows padded with zero columns (3 left, 5 right)
+    wl, Wp = (3, W + 8) if win else (0, W)
+    buf = e.buf("input.packed", (B, T, H, Wp, 8), e.tdtype)
     d = L.PackInput()
     d.x = x.data_ptr()
     d.sb, d.sc, d.st, d.sh, d.sw = x.stride()
     d.B, d.C, d.T, d.H, d.W, d.cpad, d.out, d.out_dtype = B, 3, T, H, W, 8, buf.data_ptr(), e.dt
+    d.wl, d.Wp = (wl, Wp) if win else (0, 0)
     e.call("vinet_pack_input", d)
-    return Act(buf, B, T, H, W, 8)
+    return WinAct(buf, B, T, H, W, wl, Wp) if win else Act(buf, B, T, H, W, 8)
