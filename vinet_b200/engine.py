@@ -16,10 +16,14 @@ Precision modes
   * ``fp32`` : fp32 storage, fp32 FFMA GEMMs                                          — parity mode
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import lib as L
+
+
+_POISON = bool(os.environ.get("VINET_POISON"))
 
 
 def cdiv(a, b):
@@ -131,6 +135,8 @@ class Engine:
         t = self.pool.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device:
             t = torch.empty(shape, dtype=dtype, device=self.device)
+            if _POISON and t.is_floating_point():
+                t.fill_(float("nan"))       # debug aid: reads of never-written scratch surface as NaN
             self.pool[name] = t
         return t
 
@@ -559,7 +565,7 @@ class Engine:
         d.w, d.b, d.out = w.data_ptr(), b.data_ptr(), out.data_ptr()
         self.call("vinet_head_fwd", d)
         if self.record:
-            def backward(gout):
+            def backward(gout, _keep=out):       # the descriptor holds a raw pointer to `out` (sigmoid output): keep it alive
                 gw, gb = torch.zeros_like(w), torch.zeros_like(b)
                 d.gout, d.dw, d.db = gout.data_ptr(), gw.data_ptr(), gb.data_ptr()
                 if conv_bwd is not None:        # input is a raw conv output: dx is that conv's dY
