@@ -249,6 +249,8 @@ typedef struct vinet_pool {
   void* gin; /* backward: grad w.r.t. the activated input (gin_dtype), accumulated with atomics (caller initialises) */
   int64_t ldgi;
   int32_t gout_dtype, gin_dtype;
+  uint8_t* idx; /* optional [B,To,Ho,Wo,C] bytes: forward records the winning tap ((dt*kh+dh)*kw+dw, first maximum in
+                   scan order), backward scatters with it; NULL: backward recomputes the arg-max */
 } vinet_pool_t;
 int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream);
 int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream);

@@ -18,6 +18,7 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int C, int64_t rows_
     for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r_end = min(rows, r_begin + rows_per_block);
+#pragma unroll 4
   for (int64_t r = r_begin + ry; r < r_end; r += Ry) body(r, gx * 8, acc);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -93,15 +94,25 @@ template <typename T, typename TG>
 __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
   const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
+  float sc[8], sh[8], mu[8], is[8];  // this thread's 8 channels never change: keep their constants in registers
+  {
+    const int c = threadIdx.x * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e);
+      mu[e] = __ldg(d.mean + c + e); is[e] = __ldg(d.invstd + c + e);
+    }
+  }
+  const bool relu = d.relu != 0;
   column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
     float v[8], g[8];
     load8(y + r * d.ldy + c, v);
     load8(gp + r * d.ldg + c, g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float yh = fmaf(v[e], __ldg(d.scale + c + e), __ldg(d.shift + c + e));
-      const float gm = (d.relu && !(yh > 0.f)) ? 0.f : g[e];
-      const float yn = (v[e] - __ldg(d.mean + c + e)) * __ldg(d.invstd + c + e);
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
       acc[0][e] += gm;
       acc[1][e] = fmaf(gm, yn, acc[1][e]);
     }
@@ -116,48 +127,62 @@ __global__ void bn_bwd_finish_kernel(const double* sums, float* dgamma, float* d
   }
 }
 
+// Elementwise passes use the same (channel group, row) thread layout as the reductions: a thread owns 8 channels,
+// keeps their per-channel constants in registers and walks rows with several 128-bit loads in flight.
 template <typename T, typename TD, typename TG>
-__global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d) {
+__global__ void bn_bwd_apply_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
   const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
   TD* __restrict__ dy = reinterpret_cast<TD*>(d.dy);
-  const int G = d.C / 8;
-  const int64_t total = d.rows * G;
+  const int c = threadIdx.x * 8, Ry = blockDim.y;
   const float inv_n = 1.0f / (float)d.rows;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / G;
-    const int c = (int)(i - r * G) * 8;
+  float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e);
+    mu[e] = __ldg(d.mean + c + e); is[e] = __ldg(d.invstd + c + e);
+    k1[e] = d.training ? __ldg(d.dbeta + c + e) * inv_n : 0.f;
+    k2[e] = d.training ? __ldg(d.dgamma + c + e) * inv_n : 0.f;
+  }
+  const bool relu = d.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(d.rows, r_begin + rows_per_block);
+#pragma unroll 4
+  for (int64_t r = r_begin + threadIdx.y; r < r_end; r += Ry) {
     float v[8], g[8], o[8];
     load8(y + r * d.ldy + c, v);
     load8(gp + r * d.ldg + c, g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float sc = __ldg(d.scale + c + e);
-      const float yh = fmaf(v[e], sc, __ldg(d.shift + c + e));
-      const float gm = (d.relu && !(yh > 0.f)) ? 0.f : g[e];
-      if (d.training) {
-        const float yn = (v[e] - __ldg(d.mean + c + e)) * __ldg(d.invstd + c + e);
-        o[e] = sc * (gm - __ldg(d.dbeta + c + e) * inv_n - yn * __ldg(d.dgamma + c + e) * inv_n);
-      } else {
-        o[e] = sc * gm;
-      }
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
+      o[e] = sc[e] * (gm - k1[e] - yn * k2[e]);
     }
     store8(dy + r * d.lddy + c, o);
   }
 }
 
 template <typename T, typename TO>
-__global__ void bn_apply_kernel(const __grid_constant__ vinet_bn_apply_t d) {
+__global__ void bn_apply_kernel(const __grid_constant__ vinet_bn_apply_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
   TO* __restrict__ out = reinterpret_cast<TO*>(d.out);
-  const int G = d.C / 8;
-  const int64_t total = d.rows * G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / G;
-    const int c = (int)(i - r * G) * 8;
+  const int c = threadIdx.x * 8, Ry = blockDim.y;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e); }
+  const bool relu = d.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(d.rows, r_begin + rows_per_block);
+#pragma unroll 4
+  for (int64_t r = r_begin + threadIdx.y; r < r_end; r += Ry) {
     float v[8];
     load8(y + r * d.ldy + c, v);
-    apply_xform<8>(v, d.relu ? VINET_XF_AFFINE_RELU : VINET_XF_AFFINE, d.scale, d.shift, c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = fmaf(v[e], sc[e], sh[e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
     store8(out + r * d.ldo + c, v);
   }
 }
@@ -173,9 +198,9 @@ static ColGrid col_grid(int64_t rows, int C, int nv) {
   const int G = C / 8;
   int Ry = 256 / G;
   if (Ry < 1) Ry = 1;
-  if (Ry > 64) Ry = 64;
+  if (Ry > 128) Ry = 128;
   g.block = dim3(G, Ry);
-  int64_t rpb = (int64_t)Ry * 64;  // <= 64 rows per thread per block
+  int64_t rpb = (int64_t)Ry * 16;  // >= 16 rows per thread when the tensor is large enough
   int64_t nb = cdiv(rows, rpb);
   if (nb > 148 * 8) {
     nb = 148 * 8;
@@ -224,12 +249,10 @@ extern "C" int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t st
 
 extern "C" int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0, "bn_apply: C %d", d->C);
-  const int64_t total = d->rows * (d->C / 8);
-  int64_t nb = cdiv(total, 256);
-  if (nb > 148 * 16) nb = 148 * 16;
-  if (nb < 1) nb = 1;
+  VINET_CHECK(d->C <= 1024, "bn_apply: C %d", d->C);
+  ColGrid g = col_grid(d->rows, d->C, 0);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
-      (bn_apply_kernel<T, TO><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d))));
+      (bn_apply_kernel<T, TO><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(*d, g.rows_per_block))));
   VINET_LAUNCH_OK("bn_apply");
   return 0;
 }
@@ -249,11 +272,10 @@ extern "C" int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t strea
 }
 
 extern "C" int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
-  const int64_t total = d->rows * (d->C / 8);
-  int64_t nb = cdiv(total, 256);
-  if (nb > 148 * 16) nb = 148 * 16;
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd_apply: C %d", d->C);
+  ColGrid g = col_grid(d->rows, d->C, 0);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, VINET_DISPATCH_DTYPE(d->g_dtype, TG,
-      (bn_bwd_apply_kernel<T, TD, TG><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(*d)))));
+      (bn_bwd_apply_kernel<T, TD, TG><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(*d, g.rows_per_block)))));
   VINET_LAUNCH_OK("bn_bwd_apply");
   return 0;
 }

@@ -41,6 +41,7 @@ struct ConvTmaParams {
   CUtensorMap tmA[2];  // the two sources of the virtual T-concat (tmA[1] == tmA[0] without a concat)
   vinet_conv_t d;
   int32_t bw, bh, tiles_w, tiles_h, ncb, stages, num_tiles;
+  int32_t wres;  // 1: the whole packed weight (one N tile) stays resident in shared memory for the CTA's lifetime
   uint32_t acc_cols, idesc, a_bytes, b_bytes;
 };
 
@@ -93,10 +94,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   uint8_t* sA = base;
-  uint8_t* sB = sA + (size_t)stages * TC_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)stages * p.b_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint8_t* sB = sA + (size_t)stages * TC_A_BYTES;  // per-stage weight blocks, or all k_blocks of them when resident
+  const int nb_slots = p.wres ? p.d.k_blocks : stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_slots * p.b_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, tfull0 = empty0 + 8 * stages, tempty0 = tfull0 + 16;
+  const uint32_t wbar = tempty0 + 16;
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const vinet_gather_t& g = p.d.g;
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         mbar_init(tfull0 + 8 * a, 1);
         mbar_init(tempty0 + 8 * a, 8);
       }
+      mbar_init(wbar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -132,6 +136,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       const int KB = p.d.k_blocks;
       int s = 0;
       uint32_t ph = 0;
+      if (p.wres) {  // fetch the whole weight once (n_tiles == 1): the main loop then only streams activations
+        mbar_arrive_expect_tx(wbar, (uint32_t)KB * p.b_bytes);
+        for (int kb = 0; kb < KB; ++kb) bulk_copy_g2s(sB0 + (uint32_t)kb * p.b_bytes, wbase + (size_t)kb * p.b_bytes, p.b_bytes, wbar);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int tap = 0; tap < g.ntaps; ++tap) {
@@ -144,9 +152,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           const uint8_t* wtap = wbase + ((size_t)tc.nt * KB + (size_t)tap * p.ncb) * p.b_bytes;
           for (int cb = 0; cb < p.ncb; ++cb) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(full0 + 8 * s, p.a_bytes + p.b_bytes);
+            mbar_arrive_expect_tx(full0 + 8 * s, p.wres ? p.a_bytes : p.a_bytes + p.b_bytes);
             tma_load_5d(sA0 + (uint32_t)s * TC_A_BYTES, &p.tmA[si], full0 + 8 * s, cb * 64, wc, hc, tl, tc.b);
-            bulk_copy_g2s(sB0 + (uint32_t)s * p.b_bytes, wtap + (size_t)cb * p.b_bytes, p.b_bytes, full0 + 8 * s);
+            if (!p.wres) bulk_copy_g2s(sB0 + (uint32_t)s * p.b_bytes, wtap + (size_t)cb * p.b_bytes, p.b_bytes, full0 + 8 * s);
             if (++s == stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     // ---------------------------------------------------------------- MMA issuer
     int s = 0;
     uint32_t ph = 0, lt = 0;
+    if (p.wres) mbar_wait(wbar, 0);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       if (!tile_has_work(g, tc.t)) continue;
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
             const int rem = g.Cs - cb * 64;
             const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
             const uint32_t a_stage = sA0 + (uint32_t)s * TC_A_BYTES;
-            const uint32_t b_stage = sB0 + (uint32_t)s * p.b_bytes;
+            const uint32_t b_stage = sB0 + (uint32_t)(p.wres ? tap * p.ncb + cb : s) * p.b_bytes;
             for (int kk = 0; kk < nk; ++kk) {
               umma_bf16(tacc, desc_kmajor_sw128(a_stage + kk * 32, 0), desc_kmajor_sw128(b_stage + kk * 32, 0), p.idesc, acc);
               acc = 1;
@@ -253,10 +262,12 @@ struct WgradTmaParams {
   CUtensorMap tmA[2];
   CUtensorMap tmDy;
   vinet_wgrad_t d;
-  int32_t bw, bh, tiles_w, tiles_h, ncb, nunits, stages, block_n, nblk, R, splits;
-  uint32_t tmem_cols, idesc, unit_bytes, stage_bytes;
+  int32_t bw, bh, tiles_w, tiles_h, ncb, nunits, stages, block_n, nblk, R, splits, mb, transpose;
+  uint32_t acc_cols, idesc, unit_bytes, stage_bytes;
 };
 
+// One CTA accumulates `mb` (1 or 2) 128-row blocks of the packed gradient = 2*mb (tap, 64-channel) units against ONE
+// dY tile per position chunk (the dY box is fetched once for all of them), over its share of the position chunks.
 __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p) {
   const vinet_gather_t& g = p.d.g;
   const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
@@ -276,8 +287,10 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.block_n;
   const int n0 = blockIdx.y * BN;
-  const int u0 = blockIdx.x * 2;
-  const int nu = min(2, p.nunits - u0);
+  const int upc = 2 * p.mb;  // unit slots per CTA
+  const int u0 = blockIdx.x * upc;
+  const int nu = min(upc, p.nunits - u0);
+  const int nmb = (nu + 1) >> 1;  // 128-row accumulators in use
   const int nblk_eff = min(p.nblk, (min(BN, p.d.N - n0) + 63) / 64);
 
   if (warp == 0 && lane == 0) {
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    tmem_alloc(smem_u32(tmem_slot), p.acc_cols * p.mb);
   }
   tc_fence_before();
   __syncthreads();
@@ -304,33 +317,50 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
 
   if (warp == 0) {
     if (lane == 0) {
+      // first chunk decoded with divisions once, then walked incrementally (tw fastest, then th, frame, clip)
+      int64_t m = c_begin;
+      int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
+      int th = (int)(m % p.tiles_h); m /= p.tiles_h;
+      int tr = (int)(m % g.Tr);
+      int b = (int)(m / g.Tr);
+      // per-unit constants
+      int u_cb[4], u_dt[4], u_dh[4], u_dw[4];
+      for (int j = 0; j < nu; ++j) {
+        const int u = u0 + j;
+        const int tap = u / p.ncb;
+        u_cb[j] = (u - tap * p.ncb) * 64;
+        u_dt[j] = g.tap[tap][0];
+        u_dh[j] = g.tap[tap][1] - g.ph;
+        u_dw[j] = g.tap[tap][2] - g.pw;
+      }
+      const bool cat = g.src[1].ptr != nullptr;
+      const int T0 = g.src[0].T;
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = (uint32_t)(nu + nblk_eff) * p.unit_bytes;
       for (int kb = 0; kb < KB; ++kb) {
-        int64_t m = c_begin + kb;
-        const int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
-        const int th = (int)(m % p.tiles_h); m /= p.tiles_h;
-        const int tr = (int)(m % g.Tr);
         const int t = tr * g.row_tstep + g.row_toff;
-        const int b = (int)(m / g.Tr);
         const int h0 = th * p.bh, w0 = tw * p.bw;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(full0 + 8 * s, tx);
         const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
         for (int j = 0; j < nu; ++j) {
-          const int u = u0 + j;
-          const int tap = u / p.ncb, cb = u - tap * p.ncb;
-          const int ts = t * g.st - g.pt + g.tap[tap][0];
+          const int ts = t * g.st - g.pt + u_dt[j];
           // frames outside [0,Ts) are addressed out of bounds on purpose: TMA zero-fills the temporal padding
-          const int si = (g.src[1].ptr != nullptr && ts >= g.src[0].T) ? 1 : 0;
-          const int tl = ts - (si ? g.src[0].T : 0);
-          tma_load_5d(stage + (uint32_t)j * p.unit_bytes, &p.tmA[si], full0 + 8 * s, cb * 64,
-                      w0 * g.sw - g.pw + g.tap[tap][2], h0 * g.sh - g.ph + g.tap[tap][1], tl, b);
+          const int si = (cat && ts >= T0) ? 1 : 0;
+          tma_load_5d(stage + (uint32_t)j * p.unit_bytes, &p.tmA[si], full0 + 8 * s, u_cb[j], w0 * g.sw + u_dw[j],
+                      h0 * g.sh + u_dh[j], ts - (si ? T0 : 0), b);
         }
         for (int nb = 0; nb < nblk_eff; ++nb)
-          tma_load_5d(stage + (uint32_t)(2 + nb) * p.unit_bytes, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
+          tma_load_5d(stage + (uint32_t)(upc + nb) * p.unit_bytes, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
         if (++s == stages) { s = 0; ph ^= 1u; }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            if (++tr == g.Tr) { tr = 0; ++b; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -341,11 +371,15 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_stage = s0 + (uint32_t)s * p.stage_bytes;
-        const uint32_t b_stage = a_stage + 2u * p.unit_bytes;
-        for (int kk = 0; kk < p.R / 16; ++kk) {
-          // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B; 64-wide MN blocks unit_bytes apart
-          umma_bf16(tmem_base, desc_mnmajor_sw128(a_stage + kk * 2048, p.unit_bytes, 0),
-                    desc_mnmajor_sw128(b_stage + kk * 2048, p.unit_bytes, 0), p.idesc, (uint32_t)((kb | kk) != 0));
+        const uint32_t b_stage = a_stage + (uint32_t)upc * p.unit_bytes;
+        for (int mbi = 0; mbi < nmb; ++mbi) {
+          const uint32_t a_mb = a_stage + (uint32_t)(2 * mbi) * p.unit_bytes;
+          const uint32_t tacc = tmem_base + (uint32_t)mbi * p.acc_cols;
+          for (int kk = 0; kk < p.R / 16; ++kk) {
+            // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B; 64-wide MN blocks unit_bytes apart
+            umma_bf16(tacc, desc_mnmajor_sw128(a_mb + kk * 2048, p.unit_bytes, 0),
+                      desc_mnmajor_sw128(b_stage + kk * 2048, p.unit_bytes, 0), p.idesc, (uint32_t)((kb | kk) != 0));
+          }
         }
         umma_commit(empty0 + 8 * s);
         if (kb == KB - 1) umma_commit(accum_bar);
@@ -354,20 +388,44 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
       if (++s == stages) { s = 0; ph ^= 1u; }
     }
   } else {
-    mbar_wait(accum_bar, 0);
+    mbar_wait(accum_bar, 0);  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
     tc_fence_after();
+    fence_proxy_async();
     const int q = warp & 3;
-    const int m = blockIdx.x * 128 + q * 32 + lane;
-    const bool mvalid = m < p.nunits * 64;
-    float* drow = p.d.dwp + (int64_t)m * p.d.lddw;
-    for (int gi = 0; gi < BN / 16; ++gi) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * 16), r);
-      if (!mvalid) continue;
+    // Transposing epilogue: a lane owns one accumulator ROW in TMEM, but rows of the packed gradient are lddw floats
+    // apart, so direct red.add would touch 32 lines per instruction.  Each warp parks its 32 rows in (its own part
+    // of) the free stage ring and re-reads them row by row: 32 lanes = 32 consecutive columns = one 128-byte red.
+    const int P = BN + 1;  // odd pitch: conflict-free column-wise writes
+    float* stile = reinterpret_cast<float*>(base) + (size_t)(q * 32) * P;
+    for (int mbi = 0; mbi < nmb; ++mbi) {
+      const int m0 = (u0 + 2 * mbi) * 64 + q * 32;
+      for (int gi = 0; gi < BN / 16; ++gi) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mbi * p.acc_cols + (uint32_t)(gi * 16), r);
+        if (p.transpose) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int n = n0 + gi * 16 + e;
-        if (n < p.d.N) atomicAdd(drow + n, __uint_as_float(r[e]));
+          for (int e = 0; e < 16; ++e) stile[lane * P + gi * 16 + e] = __uint_as_float(r[e]);
+        } else {
+          const int m = m0 + lane;
+          if (m < p.nunits * 64) {
+            float* drow = p.d.dwp + (int64_t)m * p.d.lddw;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int n = n0 + gi * 16 + e;
+              if (n < p.d.N) atomicAdd(drow + n, __uint_as_float(r[e]));
+            }
+          }
+        }
+      }
+      if (p.transpose) {
+        __syncwarp();
+        const int ncols = min(BN, p.d.N - n0);
+        const int rows = min(32, p.nunits * 64 - m0);
+        for (int rr = 0; rr < rows; ++rr) {
+          float* drow = p.d.dwp + (int64_t)(m0 + rr) * p.d.lddw + n0;
+          for (int col = lane; col < ncols; col += 32) atomicAdd(drow + col, stile[rr * P + col]);
+        }
+        __syncwarp();
       }
     }
   }
@@ -375,7 +433,7 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    tmem_dealloc(tmem_base, p.acc_cols * p.mb);
   }
 }
 
@@ -485,12 +543,14 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   p.b_bytes = (uint32_t)d->block_n * 128u;
   p.acc_cols = tmem_cols_for(d->block_n);
   p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
-  const size_t stage_bytes = TC_A_BYTES + p.b_bytes;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t wbytes = (size_t)d->k_blocks * p.b_bytes;
+  p.wres = (d->n_tiles == 1 && wbytes <= 96 * 1024 && tiles > 2 * (int64_t)sm_count()) ? 1 : 0;
+  const size_t stage_bytes = p.wres ? TC_A_BYTES : TC_A_BYTES + p.b_bytes;
+  int stages = (int)((200 * 1024 - (p.wres ? wbytes : 0)) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 64;
+  const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
@@ -522,32 +582,45 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   const int n_tiles = (int)cdiv(n16, 256);
   p.block_n = (int)round_up(cdiv(n16, n_tiles), 16);
   p.nblk = (p.block_n + 63) / 64;
-  const int max_rows = (p.nblk <= 2) ? 128 : 64;  // keep >= 3 pipeline stages in shared memory
+  p.acc_cols = tmem_cols_for(p.block_n);
+  const int mblocks = (int)cdiv(p.nunits, 2);
+  p.mb = mblocks >= 2 ? 2 : 1;  // two accumulators share every dY tile: halves the dY traffic per FLOP
+  // position chunk: as many rows as leave >= 3 pipeline stages in shared memory
+  const int slots = 2 * p.mb + p.nblk;
+  const int max_rows = (slots * 128 * 128 * 3 <= 200 * 1024) ? 128 : 64;
   pick_box(g.Hr, g.Wr, max_rows, 16, false, &p.bw, &p.bh);
   p.R = p.bw * p.bh;
   p.tiles_w = (int)cdiv(g.Wr, p.bw);
   p.tiles_h = (int)cdiv(g.Hr, p.bh);
   p.unit_bytes = (uint32_t)p.R * 128u;
-  p.stage_bytes = (uint32_t)(2 + p.nblk) * p.unit_bytes;
-  p.tmem_cols = tmem_cols_for(p.block_n);
+  p.stage_bytes = (uint32_t)slots * p.unit_bytes;
   p.idesc = make_idesc(TC_BM, p.block_n, 1, 1);
   const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
-  const int mblocks = (int)cdiv(p.nunits, 2);
-  int64_t splits = cdiv(2 * sm_count(), (int64_t)mblocks * n_tiles);
-  splits = std::max<int64_t>(1, std::min<int64_t>(splits, cdiv(nchunks, 2)));
-  VINET_CHECK(splits <= 65535, "conv_wgrad_tma: splits");
+  const int gx = (int)cdiv(mblocks, p.mb);
+  // split the position chunks so that the CTA count fills whole waves of the machine (1 CTA per SM)
+  const int64_t base_ctas = (int64_t)gx * n_tiles;
+  const int sms = sm_count();
+  const int64_t smax = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nchunks / 4, 128), 65535));
+  int64_t splits = 1;
+  double best = 1e30;
+  for (int64_t sp = 1; sp <= smax; ++sp) {
+    // time in chunk units: waves x (main loop + ~3 chunks of prologue / transposing red.add epilogue)
+    const double t = (double)cdiv(base_ctas * sp, sms) * ((double)cdiv(nchunks, sp) + 3.0);
+    if (t < best * 0.999) { best = t; splits = sp; }
+  }
   p.splits = (int)splits;
   int stages = (int)((200 * 1024) / p.stage_bytes);
-  stages = std::max(2, std::min(stages, 6));
+  stages = std::max(2, std::min(stages, 8));
   stages = (int)std::max<int64_t>(1, std::min<int64_t>(stages, cdiv(nchunks, splits)));
   p.stages = stages;
+  p.transpose = ((size_t)stages * p.stage_bytes >= (size_t)128 * (p.block_n + 1) * sizeof(float)) ? 1 : 0;
   const size_t smem = 1024 + (size_t)stages * p.stage_bytes + 8 * (2 * stages + 1) + 64;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
   }
   if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, p.bw, p.bh)) return -1;
-  dim3 grid((unsigned)mblocks, (unsigned)n_tiles, (unsigned)splits);
+  dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   conv_wgrad_tma_kernel<<<grid, TMA_WGRAD_THREADS, smem, stream>>>(p);
   VINET_LAUNCH_OK("conv_wgrad_tma");

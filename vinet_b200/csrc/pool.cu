@@ -1,65 +1,203 @@
-// nn.MaxPool3d on NDHWC views with the producer's pending transform applied on read
-// (model.py:696-714 stage pools, model_utils.py:178 3x3x3 stride-1 branch pools, model.py:229 AV pool).
-// Backward recomputes the arg-max (first maximum in (t,h,w) scan order, like ATen) instead of storing indices.
+// nn.MaxPool3d on NDHWC views (model.py:696-714 stage pools, model_utils.py:178 3x3x3 stride-1 branch pools,
+// model.py:229 AV pool).  One thread = one output position x 8 channels (one 128-bit vector per tap).
+// Forward optionally records, per output element, the index of the winning tap (first maximum in (t,h,w) scan
+// order, like ATen) as one byte; backward then scatters the gradient without re-scanning the window.  Without a
+// recorded index (inference-only forward / legacy callers) backward recomputes the arg-max.
 #include "common.cuh"
 
 namespace vinet {
 
-// TO: forward output type / backward gout type; TGI: backward gin type
-template <typename T, typename TO, typename TGI, bool BWD>
-__global__ void maxpool_kernel(const __grid_constant__ vinet_pool_t d) {
+struct PoolItem {
+  int c, wo, ho, to, b;
+};
+
+__device__ __forceinline__ PoolItem pool_decode(const vinet_pool_t& d, int64_t i, int G) {
+  PoolItem it;
+  // items < 2^31 for every tensor of this workload; keep the divisions 32-bit when they are
+  if (i < (int64_t)0x7fffffff) {
+    unsigned r = (unsigned)i;
+    it.c = (int)(r % (unsigned)G) * 8; r /= (unsigned)G;
+    it.wo = (int)(r % (unsigned)d.Wo); r /= (unsigned)d.Wo;
+    it.ho = (int)(r % (unsigned)d.Ho); r /= (unsigned)d.Ho;
+    it.to = (int)(r % (unsigned)d.To);
+    it.b = (int)(r / (unsigned)d.To);
+  } else {
+    int64_t r = i;
+    it.c = (int)(r % G) * 8; r /= G;
+    it.wo = (int)(r % d.Wo); r /= d.Wo;
+    it.ho = (int)(r % d.Ho); r /= d.Ho;
+    it.to = (int)(r % d.To);
+    it.b = (int)(r / d.To);
+  }
+  return it;
+}
+
+// running maximum + winning tap for 8 channels
+template <typename T>
+struct Max8;
+
+template <>
+struct Max8<float> {
+  float best[8];
+  unsigned idx[8];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; idx[e] = 0xffu; }
+  }
+  __device__ __forceinline__ void update(const float* p, const vinet_pool_t& d, int c, unsigned tap) {
+    float v[8];
+    load8(p, v);
+    apply_xform<8>(v, d.xform, d.scale, d.shift, c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (v[e] > best[e]) { best[e] = v[e]; idx[e] = tap; }
+  }
+  __device__ __forceinline__ void values(float (&v)[8]) const {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = best[e];
+  }
+  __device__ __forceinline__ unsigned tap_of(int e) const { return idx[e]; }
+};
+
+template <>
+struct Max8<__nv_bfloat16> {
+  // packed bf16x2 compare / max; tap indices ride in the two 16-bit lanes of a 32-bit word
+  __nv_bfloat162 best[4];
+  unsigned idx[4];
+  float fbest[8];  // only used when the source carries a pending transform (values are then compared in fp32)
+  unsigned fidx[8];
+  bool plain;
+  __device__ __forceinline__ void init() {
+    const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16(0xff80), __ushort_as_bfloat16(0xff80));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { best[q] = ninf; idx[q] = 0x00ff00ffu; }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { fbest[e] = -INFINITY; fidx[e] = 0xffu; }
+    plain = true;
+  }
+  __device__ __forceinline__ void update(const __nv_bfloat16* p, const vinet_pool_t& d, int c, unsigned tap) {
+    if (d.xform == VINET_XF_IDENT) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+      const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const unsigned tap2 = tap | (tap << 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned m = __hgt2_mask(v[q], best[q]);
+        idx[q] = (idx[q] & ~m) | (tap2 & m);
+        best[q] = __hmax2(best[q], v[q]);
+      }
+    } else {
+      plain = false;
+      float v[8];
+      load8(p, v);
+      apply_xform<8>(v, d.xform, d.scale, d.shift, c);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v[e] > fbest[e]) { fbest[e] = v[e]; fidx[e] = tap; }
+    }
+  }
+  __device__ __forceinline__ void values(float (&v)[8]) const {
+    if (plain) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[2 * q] = __low2float(best[q]);
+        v[2 * q + 1] = __high2float(best[q]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fbest[e];
+    }
+  }
+  __device__ __forceinline__ unsigned tap_of(int e) const {
+    return plain ? ((idx[e >> 1] >> ((e & 1) * 16)) & 0xffu) : fidx[e];
+  }
+};
+
+// scan the window of one output position; returns the source offset (elements, without channel) of its origin
+template <typename T>
+__device__ __forceinline__ void pool_scan(const vinet_pool_t& d, const T* __restrict__ x, const PoolItem& it, Max8<T>& acc) {
+  const int t0 = it.to * d.st - d.pt, h0 = it.ho * d.sh - d.ph, w0 = it.wo * d.sw - d.pw;
+  const int dt_lo = max(0, -t0), dt_hi = min(d.kt, d.Ti - t0);
+  const int dh_lo = max(0, -h0), dh_hi = min(d.kh, d.Hi - h0);
+  const int dw_lo = max(0, -w0), dw_hi = min(d.kw, d.Wi - w0);
+  acc.init();
+  for (int dt = dt_lo; dt < dt_hi; ++dt) {
+    for (int dh = dh_lo; dh < dh_hi; ++dh) {
+      const int64_t row = (((int64_t)it.b * d.Ti + (t0 + dt)) * d.Hi + (h0 + dh)) * d.Wi + w0;
+      const T* p = x + (row + dw_lo) * d.ldx + it.c;
+      unsigned tap = (unsigned)((dt * d.kh + dh) * d.kw + dw_lo);
+      for (int dw = dw_lo; dw < dw_hi; ++dw, ++tap, p += d.ldx) acc.update(p, d, it.c, tap);
+    }
+  }
+}
+
+template <typename T, typename TO, bool IDX>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __grid_constant__ vinet_pool_t d) {
   const T* __restrict__ x = reinterpret_cast<const T*>(d.x);
   const int G = d.C / 8;
   const int64_t total = (int64_t)d.B * d.To * d.Ho * d.Wo * G;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i;
-    const int c = (int)(r % G) * 8; r /= G;
-    const int wo = (int)(r % d.Wo); r /= d.Wo;
-    const int ho = (int)(r % d.Ho); r /= d.Ho;
-    const int to = (int)(r % d.To);
-    const int b = (int)(r / d.To);
+    const PoolItem it = pool_decode(d, i, G);
+    Max8<T> acc;
+    pool_scan<T>(d, x, it, acc);
+    const int64_t opos = (((int64_t)it.b * d.To + it.to) * d.Ho + it.ho) * d.Wo + it.wo;
     float best[8];
-    int64_t arg[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = -1; }
-    for (int dt = 0; dt < d.kt; ++dt) {
-      const int t = to * d.st - d.pt + dt;
-      if ((unsigned)t >= (unsigned)d.Ti) continue;
-      for (int dh = 0; dh < d.kh; ++dh) {
-        const int h = ho * d.sh - d.ph + dh;
-        if ((unsigned)h >= (unsigned)d.Hi) continue;
-        for (int dw = 0; dw < d.kw; ++dw) {
-          const int w = wo * d.sw - d.pw + dw;
-          if ((unsigned)w >= (unsigned)d.Wi) continue;
-          const int64_t pos = (((int64_t)b * d.Ti + t) * d.Hi + h) * d.Wi + w;
-          float v[8];
-          load8(x + pos * d.ldx + c, v);
-          apply_xform<8>(v, d.xform, d.scale, d.shift, c);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (v[e] > best[e]) { best[e] = v[e]; arg[e] = pos; }
-        }
-      }
+    acc.values(best);
+    store8(reinterpret_cast<TO*>(d.out) + opos * d.ldo + it.c, best);
+    if constexpr (IDX) {
+      uint2 pk;
+      pk.x = acc.tap_of(0) | (acc.tap_of(1) << 8) | (acc.tap_of(2) << 16) | (acc.tap_of(3) << 24);
+      pk.y = acc.tap_of(4) | (acc.tap_of(5) << 8) | (acc.tap_of(6) << 16) | (acc.tap_of(7) << 24);
+      *reinterpret_cast<uint2*>(d.idx + opos * d.C + it.c) = pk;
     }
-    const int64_t opos = (((int64_t)b * d.To + to) * d.Ho + ho) * d.Wo + wo;
-    if constexpr (!BWD) {
-      store8(reinterpret_cast<TO*>(d.out) + opos * d.ldo + c, best);
-    } else {
-      float g[8];
-      load8(reinterpret_cast<const TO*>(d.gout) + opos * d.ldgo + c, g);
-      TGI* gin = reinterpret_cast<TGI*>(d.gin);
+  }
+}
+
+template <typename TGI>
+__device__ __forceinline__ void grad_atomic_add(TGI* gin, int e, float g) {
+  if constexpr (sizeof(TGI) == 4) {
+    atomicAdd(gin + e, g);
+  } else {
+    // bf16 gradients: native red.add.bf16x2 on the aligned pair holding channel e
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f), v = __float2bfloat16_rn(g);
+    const __nv_bfloat162 pair = (e & 1) ? __halves2bfloat162(z, v) : __halves2bfloat162(v, z);
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(gin + (e & ~1)), pair);
+  }
+}
+
+// T: activation type (arg-max recompute when no index was recorded), TGO / TGI: gradient types
+template <typename T, typename TGO, typename TGI, bool IDX>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __grid_constant__ vinet_pool_t d) {
+  const T* __restrict__ x = reinterpret_cast<const T*>(d.x);
+  const int G = d.C / 8;
+  const int khw = d.kh * d.kw;
+  const int64_t total = (int64_t)d.B * d.To * d.Ho * d.Wo * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const PoolItem it = pool_decode(d, i, G);
+    const int64_t opos = (((int64_t)it.b * d.To + it.to) * d.Ho + it.ho) * d.Wo + it.wo;
+    unsigned taps[8];
+    if constexpr (IDX) {
+      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(d.idx + opos * d.C + it.c));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (arg[e] < 0) continue;
-        if constexpr (sizeof(TGI) == 4) {
-          atomicAdd(gin + arg[e] * d.ldgi + c + e, g[e]);
-        } else {
-          // bf16 gradients: native red.add.bf16x2 on the aligned pair holding channel c+e
-          const __nv_bfloat16 z = __float2bfloat16_rn(0.f), v = __float2bfloat16_rn(g[e]);
-          __nv_bfloat162 pair = (e & 1) ? __halves2bfloat162(z, v) : __halves2bfloat162(v, z);
-          atomicAdd(reinterpret_cast<__nv_bfloat162*>(gin + arg[e] * d.ldgi + c + (e & ~1)), pair);
-        }
-      }
+      for (int e = 0; e < 4; ++e) { taps[e] = (pk.x >> (8 * e)) & 0xffu; taps[4 + e] = (pk.y >> (8 * e)) & 0xffu; }
+    } else {
+      Max8<T> acc;
+      pool_scan<T>(d, x, it, acc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) taps[e] = acc.tap_of(e);
+    }
+    float g[8];
+    load8(reinterpret_cast<const TGO*>(d.gout) + opos * d.ldgo + it.c, g);
+    const int t0 = it.to * d.st - d.pt, h0 = it.ho * d.sh - d.ph, w0 = it.wo * d.sw - d.pw;
+    TGI* gin = reinterpret_cast<TGI*>(d.gin);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned tap = taps[e];
+      if (tap == 0xffu) continue;
+      const int dt = (int)tap / khw, r = (int)tap - dt * khw;
+      const int dh = r / d.kw, dw = r - dh * d.kw;
+      const int64_t pos = (((int64_t)it.b * d.Ti + (t0 + dt)) * d.Hi + (h0 + dh)) * d.Wi + (w0 + dw);
+      grad_atomic_add<TGI>(gin + pos * d.ldgi + it.c, e, g[e]);
     }
   }
 }
@@ -70,22 +208,38 @@ using namespace vinet;
 static unsigned pool_grid(const vinet_pool_t* d) {
   int64_t total = (int64_t)d->B * d->To * d->Ho * d->Wo * (d->C / 8);
   int64_t nb = cdiv(total, 256);
-  if (nb > 148 * 32) nb = 148 * 32;
+  if (nb > 148 * 64) nb = 148 * 64;
   return (unsigned)(nb < 1 ? 1 : nb);
 }
 
-extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
+static int pool_check(const vinet_pool_t* d) {
   VINET_CHECK(d->C % 8 == 0, "maxpool: C %d", d->C);
-  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
-      (maxpool_kernel<T, TO, float, false><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d))));
+  VINET_CHECK(d->kt * d->kh * d->kw < 255, "maxpool: window of %d taps does not fit the byte index", d->kt * d->kh * d->kw);
+  return 0;
+}
+
+extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
+  if (pool_check(d)) return -1;
+  if (d->idx) {
+    VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
+        (maxpool_fwd_kernel<T, TO, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d))));
+  } else {
+    VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
+        (maxpool_fwd_kernel<T, TO, false><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d))));
+  }
   VINET_LAUNCH_OK("maxpool_fwd");
   return 0;
 }
 
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
-  VINET_CHECK(d->C % 8 == 0, "maxpool: C %d", d->C);
-  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
-      (maxpool_kernel<T, TGO, TGI, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)))));
+  if (pool_check(d)) return -1;
+  if (d->idx) {
+    VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
+        (maxpool_bwd_kernel<T, TGO, TGI, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)))));
+  } else {
+    VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
+        (maxpool_bwd_kernel<T, TGO, TGI, false><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)))));
+  }
   VINET_LAUNCH_OK("maxpool_bwd");
   return 0;
 }

@@ -513,6 +513,8 @@ class Engine:
         d.B, d.Ti, d.Hi, d.Wi, d.C = a.B, a.T, a.H, a.W, a.C
         (d.kt, d.kh, d.kw), (d.st, d.sh, d.sw), (d.pt, d.ph, d.pw) = k, s, p
         d.To, d.Ho, d.Wo, d.out, d.ldo, d.out_dtype = To, Ho, Wo, out.ptr(), out.ld, self.dt
+        if self.record and a.needs_grad:       # remember the winning tap per output element for the backward scatter
+            d.idx = self.buf(name + ".idx", (a.B, To, Ho, Wo, a.C), torch.uint8).data_ptr()
         self.call("vinet_maxpool_fwd", d)
         if self.record and a.needs_grad:
             def backward():

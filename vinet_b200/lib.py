@@ -87,7 +87,7 @@ class Pool(C.Structure):
                 ("kt", _i32), ("kh", _i32), ("kw", _i32), ("st", _i32), ("sh", _i32), ("sw", _i32),
                 ("pt", _i32), ("ph", _i32), ("pw", _i32), ("To", _i32), ("Ho", _i32), ("Wo", _i32),
                 ("out", _p), ("ldo", _i64), ("out_dtype", _i32), ("gout", _p), ("ldgo", _i64), ("gin", _p),
-                ("ldgi", _i64), ("gout_dtype", _i32), ("gin_dtype", _i32)]
+                ("ldgi", _i64), ("gout_dtype", _i32), ("gin_dtype", _i32), ("idx", _p)]
 
 
 class Upsample(C.Structure):
