@@ -139,10 +139,10 @@ int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
 size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks);
 
 /* WIN8 variant: grad[co][ci][0][dh][dw] = dwp[(dh*64 + dw*8 + ci)*lddw + co] */
-int vinet_unpack_wgrad_win8(const float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+int vinet_unpack_wgrad_win8(float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
                             vinet_stream_t stream);
 /* grad[co][ci][tap] = dwp[(tap*cs + ci)*lddw + co]  (taps in natural (dt,dh,dw) order) */
-int vinet_unpack_wgrad(const float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
+int vinet_unpack_wgrad(float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
                        int32_t ntaps, vinet_stream_t stream);
 
 /* (B,C,T,H,W) strided fp32 clip (train.py:205 hands a permuted view) -> NDHWC with C padded to cpad. */
@@ -165,12 +165,12 @@ typedef struct vinet_bn_stats {
   int32_t dtype;
   int64_t rows;
   int32_t C;
-  double* sums; /* [2][C]: sum, sum of squares; caller zeroes */
+  double* sums; /* [2][C]: sum, sum of squares; must be zero on entry (vinet_bn_finalize re-zeroes it after reading) */
 } vinet_bn_stats_t;
 int vinet_bn_stats(const vinet_bn_stats_t* d, vinet_stream_t stream);
 
 typedef struct vinet_bn_finalize {
-  const double* sums;
+  double* sums; /* training: consumed AND cleared, so the next step's vinet_bn_stats needs no memset */
   int64_t rows;
   int32_t C;
   const float* gamma;
@@ -218,7 +218,7 @@ typedef struct vinet_bn_bwd {
   const float* mean;
   const float* invstd;
   const float* gamma;
-  double* sums; /* [2][C]: sum(g*m), sum(g*m*y_norm); caller zeroes */
+  double* sums; /* [2][C]: sum(g*m), sum(g*m*y_norm); zero on entry, cleared again by vinet_bn_bwd_reduce on exit */
   float* dgamma;
   float* dbeta;
   void* dy;
@@ -387,7 +387,8 @@ const char* vinet_version(void);
 int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* sizeof() of every struct above, in declaration order (host-only; lets a binding check its layout) */
 int vinet_abi_sizes(int64_t* out, int32_t n);
-/* development switch (key 0: tcgen05 descriptor-encoding experiments, see csrc/conv_tc.cu); 0 in production */
+/* development switches (key 0: tcgen05 descriptor-encoding experiments, csrc/conv_tc.cu, 0 in production;
+ * key 1: paired 256-row work items of the TMA conv kernel, 1 in production) */
 int vinet_debug_set(int32_t key, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vinet_launch_count(void);

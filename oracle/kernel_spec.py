@@ -192,6 +192,7 @@ class Spec:
             s = _arr(d.sums, 2 * c, np.float64)
             mean = s[:c] / d.rows
             var = np.maximum(s[c:] / d.rows - mean * mean, 0)
+            s[:] = 0                                   # consumed and cleared
             invstd = 1 / np.sqrt(var + d.eps)
             if d.running_mean:
                 unb = var * d.rows / (d.rows - 1) if d.rows > 1 else var

@@ -23,6 +23,7 @@ int conv_wgrad_tc(const vinet_wgrad_t* d, cudaStream_t stream);
 int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream);
 int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream);
 int tc_debug_set(unsigned int v);
+int tma_pair_set(int v);
 
 // the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
 static bool dense_sources(const vinet_gather_t& g) {
@@ -110,6 +111,7 @@ extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
 }
 
 extern "C" int vinet_debug_set(int32_t key, int32_t value) {
+  if (key == 1) return tma_pair_set(value);
   VINET_CHECK(key == 0, "debug_set: unknown key %d", key);
   VINET_CHECK(tc_debug_set((unsigned int)value) == 0, "debug_set: cudaMemcpyToSymbol failed");
   return 0;

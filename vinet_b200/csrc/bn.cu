@@ -71,6 +71,8 @@ __global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d
     const double n = (double)d.rows;
     const double m = d.sums[c] / n;
     double var = d.sums[d.C + c] / n - m * m;
+    d.sums[c] = 0.0;  // leave the accumulators clean for the next step
+    d.sums[d.C + c] = 0.0;
     if (var < 0.0) var = 0.0;
     mean = (float)m;
     invstd = (float)(1.0 / sqrt(var + (double)d.eps));
@@ -119,11 +121,13 @@ __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, i
   });
 }
 
-__global__ void bn_bwd_finish_kernel(const double* sums, float* dgamma, float* dbeta, int C) {
+__global__ void bn_bwd_finish_kernel(double* sums, float* dgamma, float* dbeta, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     dbeta[c] = (float)sums[c];
     dgamma[c] = (float)sums[C + c];
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
   }
 }
 

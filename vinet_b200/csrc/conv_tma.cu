@@ -33,6 +33,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// pull a box into L2 only (no shared-memory destination, no barrier): hides DRAM latency behind the smem ring
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -40,26 +46,29 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 struct ConvTmaParams {
   CUtensorMap tmA[2];  // the two sources of the virtual T-concat (tmA[1] == tmA[0] without a concat)
   vinet_conv_t d;
-  int32_t bw, bh, tiles_w, tiles_h, ncb, stages, num_tiles;
-  int32_t wres;  // 1: the whole packed weight (one N tile) stays resident in shared memory for the CTA's lifetime
-  uint32_t acc_cols, idesc, a_bytes, b_bytes;
+  int32_t bw, bh, tiles_w, tiles_h, ncb, stages, num_items;
+  int32_t wres;   // 1: the whole packed weight (one N tile) stays resident in shared memory for the CTA's lifetime
+  int32_t halves; // position tiles per work item: 2 = "paired" 256-row item, both tiles share every weight block
+  int32_t tpf, ipf;  // tiles per frame, items per frame (= ceil(tpf / halves))
+  int32_t nbuf;   // TMEM accumulator sets: 2 = epilogue of item i overlaps the main loop of item i+1
+  uint32_t acc_stride, tmem_cols, idesc, a_bytes, b_bytes, a_stage;
 };
 
-struct TileCoord {
-  int nt, b, t, h0, w0;
+// One work item = `halves` position tiles of ONE frame (same taps, same source frame) x one N tile.
+struct ItemCoord {
+  int nt, b, t, tile0, nh;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvTmaParams& p, int tile) {
-  TileCoord c;
-  c.nt = tile % p.d.n_tiles;
-  int m = tile / p.d.n_tiles;
-  const int tw = m % p.tiles_w; m /= p.tiles_w;
-  const int th = m % p.tiles_h; m /= p.tiles_h;
+__device__ __forceinline__ ItemCoord decode_item(const ConvTmaParams& p, int item) {
+  ItemCoord c;
+  c.nt = item % p.d.n_tiles;
+  int m = item / p.d.n_tiles;
+  const int ip = m % p.ipf; m /= p.ipf;
   const int tr = m % p.d.g.Tr;
   c.b = m / p.d.g.Tr;
   c.t = tr * p.d.g.row_tstep + p.d.g.row_toff;
-  c.h0 = th * p.bh;
-  c.w0 = tw * p.bw;
+  c.tile0 = ip * p.halves;
+  c.nh = min(p.halves, p.tpf - c.tile0);
   return c;
 }
 
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = p.stages;
   uint8_t* sA = base;
-  uint8_t* sB = sA + (size_t)stages * TC_A_BYTES;  // per-stage weight blocks, or all k_blocks of them when resident
+  uint8_t* sB = sA + (size_t)stages * p.a_stage;  // per-stage weight blocks, or all k_blocks of them when resident
   const int nb_slots = p.wres ? p.d.k_blocks : stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_slots * p.b_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
@@ -103,6 +112,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const vinet_gather_t& g = p.d.g;
+  const uint32_t nbuf = (uint32_t)p.nbuf;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), 2 * p.acc_cols);
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   }
   tc_fence_before();
   __syncthreads();
@@ -140,20 +150,31 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         mbar_arrive_expect_tx(wbar, (uint32_t)KB * p.b_bytes);
         for (int kb = 0; kb < KB; ++kb) bulk_copy_g2s(sB0 + (uint32_t)kb * p.b_bytes, wbase + (size_t)kb * p.b_bytes, p.b_bytes, wbar);
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const ItemCoord ic = decode_item(p, item);
+        int h0[2], w0[2];
+        for (int hf = 0; hf < ic.nh; ++hf) {
+          const int tif = ic.tile0 + hf;
+          const int th = tif / p.tiles_w;
+          h0[hf] = th * p.bh;
+          w0[hf] = (tif - th * p.tiles_w) * p.bw;
+        }
+        const uint32_t tx = (uint32_t)ic.nh * p.a_bytes + (p.wres ? 0u : p.b_bytes);
         for (int tap = 0; tap < g.ntaps; ++tap) {
           int si, tl;
-          if (!tap_frame(g, tc.t, g.tap[tap][0], si, tl)) continue;
+          if (!tap_frame(g, ic.t, g.tap[tap][0], si, tl)) continue;
           const int dh = g.tap[tap][1], dw = g.tap[tap][2];
-          // FPROP boxes step through the source with the conv's spatial stride (tensor-map element strides)
-          const int hc = (g.mode == VINET_GATHER_FPROP) ? tc.h0 * g.sh - g.ph + dh : tc.h0 + g.ph - dh;
-          const int wc = (g.mode == VINET_GATHER_FPROP) ? tc.w0 * g.sw - g.pw + dw : tc.w0 + g.pw - dw;
-          const uint8_t* wtap = wbase + ((size_t)tc.nt * KB + (size_t)tap * p.ncb) * p.b_bytes;
+          const uint8_t* wtap = wbase + ((size_t)ic.nt * KB + (size_t)tap * p.ncb) * p.b_bytes;
           for (int cb = 0; cb < p.ncb; ++cb) {
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(full0 + 8 * s, p.wres ? p.a_bytes : p.a_bytes + p.b_bytes);
-            tma_load_5d(sA0 + (uint32_t)s * TC_A_BYTES, &p.tmA[si], full0 + 8 * s, cb * 64, wc, hc, tl, tc.b);
+            mbar_arrive_expect_tx(full0 + 8 * s, tx);
+            for (int hf = 0; hf < ic.nh; ++hf) {
+              // FPROP boxes step through the source with the conv's spatial stride (tensor-map element strides)
+              const int hc = (g.mode == VINET_GATHER_FPROP) ? h0[hf] * g.sh - g.ph + dh : h0[hf] + g.ph - dh;
+              const int wc = (g.mode == VINET_GATHER_FPROP) ? w0[hf] * g.sw - g.pw + dw : w0[hf] + g.pw - dw;
+              tma_load_5d(sA0 + (uint32_t)s * p.a_stage + (uint32_t)hf * TC_A_BYTES, &p.tmA[si], full0 + 8 * s, cb * 64, wc, hc,
+                          tl, ic.b);
+            }
             if (!p.wres) bulk_copy_g2s(sB0 + (uint32_t)s * p.b_bytes, wtap + (size_t)cb * p.b_bytes, p.b_bytes, full0 + 8 * s);
             if (++s == stages) { s = 0; ph ^= 1u; }
           }
@@ -165,29 +186,31 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     int s = 0;
     uint32_t ph = 0, lt = 0;
     if (p.wres) mbar_wait(wbar, 0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      if (!tile_has_work(g, tc.t)) continue;
-      const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const ItemCoord ic = decode_item(p, item);
+      if (!tile_has_work(g, ic.t)) continue;
+      const uint32_t as = lt % nbuf, aph = (lt / nbuf) & 1u;
       mbar_wait(tempty0 + 8 * as, aph ^ 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + as * p.acc_cols;
+      const uint32_t tacc = tmem_base + as * (uint32_t)p.halves * p.acc_stride;
       uint32_t acc = 0;
       for (int tap = 0; tap < g.ntaps; ++tap) {
         int si, tl;
-        if (!tap_frame(g, tc.t, g.tap[tap][0], si, tl)) continue;
+        if (!tap_frame(g, ic.t, g.tap[tap][0], si, tl)) continue;
         for (int cb = 0; cb < p.ncb; ++cb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           if (lane == 0) {
             const int rem = g.Cs - cb * 64;
             const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
-            const uint32_t a_stage = sA0 + (uint32_t)s * TC_A_BYTES;
             const uint32_t b_stage = sB0 + (uint32_t)(p.wres ? tap * p.ncb + cb : s) * p.b_bytes;
-            for (int kk = 0; kk < nk; ++kk) {
-              umma_bf16(tacc, desc_kmajor_sw128(a_stage + kk * 32, 0), desc_kmajor_sw128(b_stage + kk * 32, 0), p.idesc, acc);
-              acc = 1;
+            for (int hf = 0; hf < ic.nh; ++hf) {
+              const uint32_t a_stage = sA0 + (uint32_t)s * p.a_stage + (uint32_t)hf * TC_A_BYTES;
+              for (int kk = 0; kk < nk; ++kk)
+                umma_bf16(tacc + (uint32_t)hf * p.acc_stride, desc_kmajor_sw128(a_stage + kk * 32, 0),
+                          desc_kmajor_sw128(b_stage + kk * 32, 0), p.idesc, acc | (uint32_t)(kk != 0));
             }
+            acc = 1;
             umma_commit(empty0 + 8 * s);
           }
           __syncwarp();
@@ -206,38 +229,42 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     const int rh = row / p.bw, rw = row - rh * p.bw;
     const int BN = p.d.block_n;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      const bool any = tile_has_work(g, tc.t);
-      const int h = tc.h0 + rh, w = tc.w0 + rw;
-      const bool valid = row < p.bw * p.bh && h < g.Hr && w < g.Wr;
-      TO* orow = nullptr;
-      bool accum = false;
-      if (valid) {
-        RowCoord rc;
-        rc.b = tc.b; rc.t = tc.t; rc.h = h; rc.w = w;
-        orow = out_row_ptr<TO>(p.d, rc) + tc.nt * BN;
-        accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
-      }
-      const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const ItemCoord ic = decode_item(p, item);
+      const bool any = tile_has_work(g, ic.t);
+      const uint32_t as = lt % nbuf, aph = (lt / nbuf) & 1u;
       if (any) {
         mbar_wait(tfull0 + 8 * as, aph);
         tc_fence_after();
       }
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.acc_cols;
-      const int nlim = p.d.N - tc.nt * BN;  // columns of this tile that exist
-      for (int gi = half; gi < BN / 16; gi += 2) {
-        uint32_t r[16];
-        if (any) {
-          tmem_ld16(tacc + (uint32_t)(gi * 16), r);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] = 0u;
+      const int nlim = p.d.N - ic.nt * BN;  // columns of this tile that exist
+      for (int hf = 0; hf < ic.nh; ++hf) {
+        const int tif = ic.tile0 + hf;
+        const int th = tif / p.tiles_w;
+        const int h = th * p.bh + rh, w = (tif - th * p.tiles_w) * p.bw + rw;
+        const bool valid = row < p.bw * p.bh && h < g.Hr && w < g.Wr;
+        TO* orow = nullptr;
+        bool accum = false;
+        if (valid) {
+          RowCoord rc;
+          rc.b = ic.b; rc.t = ic.t; rc.h = h; rc.w = w;
+          orow = out_row_ptr<TO>(p.d, rc) + ic.nt * BN;
+          accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
         }
-        if (!valid) continue;
-        const int c0 = gi * 16;
-        if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, tc.nt * BN + c0, accum);
-        if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, tc.nt * BN + c0 + 8, accum);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.halves + (uint32_t)hf) * p.acc_stride;
+        for (int gi = half; gi < BN / 16; gi += 2) {
+          uint32_t r[16];
+          if (any) {
+            tmem_ld16(tacc + (uint32_t)(gi * 16), r);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = 0u;
+          }
+          if (!valid) continue;
+          const int c0 = gi * 16;
+          if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
+          if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
+        }
       }
       if (any) {
         tc_fence_before();
@@ -251,7 +278,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * p.acc_cols);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -512,6 +539,10 @@ static int sm_count() {
   return n;
 }
 
+// development switch (vinet_debug_set key 1): 0 disables the paired 256-row work items
+int g_tma_pair = 1;
+int tma_pair_set(int v) { g_tma_pair = v; return 0; }
+
 static int check_tma_gather(const vinet_gather_t& g, const char* what) {
   VINET_CHECK(g.dtype == VINET_BF16, "%s: the TMA kernel needs bf16 sources", what);
   VINET_CHECK((g.sh == 1 && g.sw == 1) || g.mode == VINET_GATHER_FPROP,
@@ -536,26 +567,41 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   pick_box(g.Hr, g.Wr, TC_BM, 1, true, &p.bw, &p.bh);
   p.tiles_w = (int)cdiv(g.Wr, p.bw);
   p.tiles_h = (int)cdiv(g.Hr, p.bh);
-  const int64_t tiles = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w * d->n_tiles;
-  VINET_CHECK(tiles < (1ll << 31), "conv_gemm_tma: too many tiles");
-  p.num_tiles = (int)tiles;
+  p.tpf = p.tiles_w * p.tiles_h;
   p.a_bytes = (uint32_t)(p.bw * p.bh * 128);
   p.b_bytes = (uint32_t)d->block_n * 128u;
-  p.acc_cols = tmem_cols_for(d->block_n);
   p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
+  p.acc_stride = (uint32_t)round_up(d->block_n, 32);
+  // These kernels run at the L2->SM bandwidth roof (~9.4 TB/s chip-wide), so what matters is bytes per FLOP.
+  // Pairing two position tiles of a frame per work item re-uses every weight block for 256 rows.
+  const int64_t frames = (int64_t)g.B * g.Tr;
+  const int64_t single_items = frames * p.tpf * d->n_tiles;
+  // Measured on B200 (tools/diag_tma.py): pairing wins whenever the four accumulators (2 tiles x 2 buffers) still fit
+  // the 512 TMEM columns (block_n <= 128); above that the lost epilogue overlap and the shallower ring cost more.
+  p.halves = (p.tpf >= 2 && g_tma_pair && 4u * p.acc_stride <= 512u && frames * cdiv(p.tpf, 2) * d->n_tiles >= 64) ? 2 : 1;
+  (void)single_items;
+  p.ipf = (int)cdiv(p.tpf, p.halves);
+  const int64_t items = frames * p.ipf * d->n_tiles;
+  VINET_CHECK(items < (1ll << 31), "conv_gemm_tma: too many tiles");
+  p.num_items = (int)items;
+  p.nbuf = (2u * p.halves * p.acc_stride <= 512u) ? 2 : 1;
+  const uint32_t need_cols = (uint32_t)p.nbuf * p.halves * p.acc_stride;
+  p.tmem_cols = tmem_cols_for((int)need_cols);
+  p.a_stage = (uint32_t)p.halves * TC_A_BYTES;
   const size_t wbytes = (size_t)d->k_blocks * p.b_bytes;
-  p.wres = (d->n_tiles == 1 && wbytes <= 96 * 1024 && tiles > 2 * (int64_t)sm_count()) ? 1 : 0;
-  const size_t stage_bytes = p.wres ? TC_A_BYTES : TC_A_BYTES + p.b_bytes;
+  p.wres = (d->n_tiles == 1 && wbytes <= 96 * 1024 && items > 2 * (int64_t)sm_count()) ? 1 : 0;
+  const size_t stage_bytes = p.wres ? p.a_stage : p.a_stage + p.b_bytes;
   int stages = (int)((200 * 1024 - (p.wres ? wbytes : 0)) / stage_bytes);
-  if (stages > 8) stages = 8;
+  if (stages > 12) stages = 12;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64;
+  VINET_CHECK(smem <= 227 * 1024, "conv_gemm_tma: %zu bytes of shared memory", smem);
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
   }
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
+  const unsigned grid = (unsigned)std::min<int64_t>(items, sm_count());
 #define LAUNCH_TMA(TO)                                                                                  \
   do {                                                                                                  \
     auto kern = conv_has_epilogue(*d) ? conv_gemm_tma_kernel<TO, true> : conv_gemm_tma_kernel<TO, false>; \

@@ -76,7 +76,7 @@ __global__ void pack_weights_simt_kernel(const __grid_constant__ vinet_pack_t d,
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int lddw, int cs, float* __restrict__ grad, int Cout,
+__global__ void unpack_wgrad_kernel(float* __restrict__ dwp, int lddw, int cs, float* __restrict__ grad, int Cout,
                                     int Cin, int ntaps) {
   const int64_t total = (int64_t)Cout * Cin * ntaps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -88,7 +88,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int lddw, int
   }
 }
 
-__global__ void unpack_wgrad_win8_kernel(const float* __restrict__ dwp, int lddw, float* __restrict__ grad, int Cout, int Cin,
+__global__ void unpack_wgrad_win8_kernel(float* __restrict__ dwp, int lddw, float* __restrict__ grad, int Cout, int Cin,
                                          int kh, int kw) {
   const int64_t total = (int64_t)Cout * Cin * kh * kw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -145,7 +145,7 @@ extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) 
   return 0;
 }
 
-extern "C" int vinet_unpack_wgrad_win8(const float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh,
+extern "C" int vinet_unpack_wgrad_win8(float* dwp, int32_t lddw, float* grad, int32_t Cout, int32_t Cin, int32_t kh,
                                        int32_t kw, vinet_stream_t stream) {
   VINET_CHECK(Cin <= 8 && kw <= 8, "unpack_wgrad_win8: Cin %d kw %d", Cin, kw);
   const int64_t total = (int64_t)Cout * Cin * kh * kw;
@@ -154,7 +154,7 @@ extern "C" int vinet_unpack_wgrad_win8(const float* dwp, int32_t lddw, float* gr
   return 0;
 }
 
-extern "C" int vinet_unpack_wgrad(const float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
+extern "C" int vinet_unpack_wgrad(float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
                                   int32_t ntaps, vinet_stream_t stream) {
   const int64_t total = (int64_t)Cout * Cin * ntaps;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dwp, lddw, cs, grad, Cout, Cin, ntaps);

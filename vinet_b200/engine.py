@@ -131,9 +131,15 @@ class Engine:
     def call(self, name, desc):
         self.lib.call(name, C.byref(desc), self.stream())
 
-    def buf(self, name, shape, dtype):
+    def buf(self, name, shape, dtype, zero=False):
+        """Pooled scratch tensor.  zero=True: allocated zero-filled ONCE; its consumer kernel clears what it reads
+        (BN statistics, packed weight gradients), so accumulate-into buffers need no per-step memset."""
         t = self.pool.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device:
+            if zero:
+                t = torch.zeros(shape, dtype=dtype, device=self.device)
+                self.pool[name] = t
+                return t
             t = torch.empty(shape, dtype=dtype, device=self.device)
             if _POISON and t.is_floating_point():
                 t.fill_(float("nan"))       # debug aid: reads of never-written scratch surface as NaN
@@ -160,6 +166,13 @@ class Engine:
         self.device, self.training, self.record = device, training, record
         self.tape, self.grad_bufs, self.zero_list, self.param_grads = [], [], [], {}
         self.gwritten = set()
+        self.bn_counters = []
+
+    def end_forward(self):
+        """nn.BatchNorm's num_batches_tracked counters of every layer touched by this forward, one launch."""
+        if self.bn_counters:
+            torch._foreach_add_(self.bn_counters, 1)
+            self.bn_counters = []
 
     def new_act(self, name, B, T, H, W, C_, xform=L.XF_IDENT, affine=False, dtype=None, gdtype=None):
         buf = self.buf(name, (B, T, H, W, C_), dtype or self.tdtype)
@@ -416,15 +429,14 @@ class Engine:
         fin.training = 1 if self.training else 0
         fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
         if self.training:
-            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64)
-            self.memset(sums)
+            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64, zero=True)
             sd = L.BnStats()
             sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
             self.call("vinet_bn_stats", sd)
             fin.sums = sums.data_ptr()
         self.call("vinet_bn_finalize", fin)
         if self.training:
-            bn.num_batches_tracked += 1          # host-side counter buffer (nn.BatchNorm semantics)
+            self.bn_counters.append(bn.num_batches_tracked)   # += 1 for all layers in one launch (end_forward)
         return st, ss
 
     def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot):
@@ -442,8 +454,7 @@ class Engine:
         training = self.training
 
         def backward():
-            bsums = self.buf(name_bn + ".bsums", (2, Cn), torch.float64)
-            self.memset(bsums)
+            bsums = self.buf(name_bn + ".bsums", (2, Cn), torch.float64, zero=True)
             dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
             if dy_slot is None:
                 dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
@@ -592,4 +603,5 @@ class Engine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
-        return self.param_grads
+        grads, self.param_grads = self.param_grads, {}     # hand over the only references: autograd can adopt the tensors
+        return grads

@@ -231,7 +231,7 @@ class _PlanFunction(torch.autograd.Function):
         if ctx.gen != e.generation:
             raise RuntimeError("vinet_b200: backward() of a stale forward (one outstanding forward per model)")
         grads = e.backward(gout.contiguous().float())
-        return (None, None, None, None) + (None,) * ctx.n_extra + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None) + (None,) * ctx.n_extra + tuple(grads.pop(n, None) for n in ctx.names)
 
 
 class _PlanModule(nn.Module):
@@ -288,7 +288,9 @@ class VideoSaliencyModel(_PlanModule):
         e.begin(x.device, self.training, record)
         xin = pack_input(e, x)
         ys = backbone_plan(e, prefix + "backbone.", self.backbone, xin)
-        return decoder_plan(e, prefix + "decoder.", self.decoder, *ys)
+        out = decoder_plan(e, prefix + "decoder.", self.decoder, *ys)
+        e.end_forward()
+        return out
 
 
 def pack_input(e, x):
