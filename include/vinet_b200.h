@@ -104,6 +104,9 @@ typedef struct vinet_conv {
   int32_t kernel;        /* VINET_KERNEL_* (TC engine); TMA expects w packed with VINET_KLAYOUT_TAP64 */
 } vinet_conv_t;
 int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stream_t stream);
+/* N tiling (block_n, n_tiles) this library wants for the convolution described by d (every field but w / block_n /
+ * n_tiles filled in): the caller packs the weights with it (vinet_pack_weights) and passes it back in d.  Host only. */
+int vinet_conv_tiling(const vinet_conv_t* d, int32_t engine, int32_t* block_n, int32_t* n_tiles);
 
 /*
  * dwp[(tap,c), n] += sum_rows gather(row,(tap,c)) * dy[row, n]   (fp32 atomics; caller zeroes dwp)
@@ -388,7 +391,8 @@ int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* sizeof() of every struct above, in declaration order (host-only; lets a binding check its layout) */
 int vinet_abi_sizes(int64_t* out, int32_t n);
 /* development switches (key 0: tcgen05 descriptor-encoding experiments, csrc/conv_tc.cu, 0 in production;
- * key 1: paired 256-row work items of the TMA conv kernel, 1 in production) */
+ * key 1: paired 256-row work items of the TMA conv kernel, 1 in production;
+ * key 2: the streaming (halo / frame re-use) conv kernel of csrc/conv_stream.cu, 1 in production) */
 int vinet_debug_set(int32_t key, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vinet_launch_count(void);

@@ -156,19 +156,27 @@ def test_full_size_clip_fp32_engine_vs_oracle_on_the_same_gpu():
         d = O.make_inputs(B, T, H, W, 21)
         x, gt = d["x"].cuda(), d["gt"].cuda()
         ref = ref.cuda().train()
+        ref64 = copy.deepcopy(ref).double()
         pr = ref(x); lr = O.kldiv(pr, gt); lr.backward()
+        p64 = ref64(x.double()); O.kldiv(p64, gt.double()).backward()
         m.train()
         pm = m(x); lm = kldiv(pm, gt); lm.backward()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     assert torch.allclose(pm, pr, rtol=1e-3, atol=1e-6), (pm - pr).abs().max().item()
     assert abs(lm.item() - lr.item()) <= 1e-5 * abs(lr.item()), (lm.item(), lr.item())
-    rp = dict(ref.named_parameters())
+    rp, r64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
     errs = sorted((float((q.grad - rp[n].grad).norm() / (rp[n].grad.norm() + 1e-30)), n) for n, q in m.named_parameters())
-    # decoder gradients (before the chaotic BatchNorm stack can amplify rounding) agree tightly; the median everywhere
+    # decoder gradients (before the chaotic BatchNorm stack can amplify rounding) agree tightly with the fp32 oracle
     assert all(e < 2e-3 for e, n in errs if n.startswith("decoder.convtsp4")), [x for x in errs if x[1].startswith("decoder.")][-3:]
     assert all(e < 2e-2 for e, n in errs if n.startswith("decoder.")), [x for x in errs if x[1].startswith("decoder.")][-3:]
-    assert errs[len(errs) // 2][0] < 2e-2, errs[len(errs) // 2]
+    # backbone: two correct fp32 implementations drift apart through 60 train-mode BatchNorm layers (tests/test_plan_cpu.py),
+    # so the yardstick is the fp64 oracle: this engine must sit as close to it as stock fp32 PyTorch does
+    e_mine = sorted(float((q.grad.double() - r64[n].grad).norm() / (r64[n].grad.norm() + 1e-30)) for n, q in m.named_parameters())
+    e_ref = sorted(float((rp[n].grad.double() - r64[n].grad).norm() / (r64[n].grad.norm() + 1e-30)) for n, _ in m.named_parameters())
+    print("full-size fp32 grad rel-L2 vs fp64: engine median %.3e max %.3e ; torch fp32 median %.3e max %.3e"
+          % (e_mine[len(e_mine) // 2], e_mine[-1], e_ref[len(e_ref) // 2], e_ref[-1]))
+    assert e_mine[len(e_mine) // 2] <= 2 * e_ref[len(e_ref) // 2] + 2e-3, (e_mine[len(e_mine) // 2], e_ref[len(e_ref) // 2])
     # running statistics follow nn.BatchNorm3d (momentum 1e-3, unbiased variance)
     sm, sr = m.state_dict(), ref.state_dict()
     for k in sr:

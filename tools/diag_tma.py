@@ -66,6 +66,10 @@ CASES = [  # B, T0, T1, H, W, Cin, Cout, k, stride_t, pad
     (1, 4, 16, 28, 48, 64, 64, (5, 3, 3), 5, (0, 1, 1)),     # convtsp4.0-like
     (1, 2, 0, 56, 96, 64, 192, (1, 3, 3), 1, (0, 1, 1)),     # base1.3.conv_s geometry (32x4 boxes)
     (1, 2, 0, 32, 64, 32, 32, (2, 1, 1), 2, (0, 0, 0)),      # convtsp4.6-like
+    (2, 5, 0, 12, 20, 32, 48, (3, 3, 3), 1, (1, 1, 1)),      # full 3x3x3 stride 1: halo + 3 live output frames
+    (2, 16, 0, 28, 48, 128, 192, (1, 3, 3), 1, (0, 1, 1)),   # 3c.b1.conv_s: streamed weights, 2 N tiles, many items per CTA
+    (2, 16, 0, 28, 48, 192, 192, (3, 1, 1), 1, (1, 0, 0)),   # 3c.b1.conv_t: resident weights, runs of output frames
+    (3, 9, 0, 20, 40, 64, 64, (7, 1, 1), 2, (3, 0, 0)),      # stem conv_t with an odd frame count
 ]
 
 
@@ -129,15 +133,18 @@ def child_perf():
     import torch
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     print("%-16s %8s | %21s | %21s | %21s" % ("layer", "GFLOP", "fprop ms (TF/s)", "dgrad ms (TF/s)", "wgrad ms (TF/s)"))
+    from vinet_b200 import lib as L
     for name, c in PERF:
-        for use_tma in (True, False):
-            e, srcs, w, geom, out, g = build_stem(use_tma) if c is None else build("bf16", use_tma, *c)
+        for use_tma in (True, False):      # True: streaming kernel where eligible; False: conv_tma.cu's per-tap boxes
+            L.get().call("vinet_debug_set", 2, 1 if use_tma else 0)
+            e, srcs, w, geom, out, g = build_stem(True) if c is None else build("bf16", True, *c)
             e.profile = []
             e.l2_flush = flush
             dy = torch.randn(out.buf.shape, device="cuda").to(e.tdtype)
             for it in range(3):
                 e.profile = []
                 bwd = e.conv("c", srcs, w, geom, out, cin_real=3 if c is None else None)
+                e.gwritten = set()          # data gradients as first writers (plain stores), like most layers of the model
                 bwd(dy.data_ptr(), out.C)
             torch.cuda.synchronize()
             agg = {}
@@ -149,7 +156,7 @@ def child_perf():
             for kind in ("fprop", "dgrad", "wgrad"):
                 ms, fl = agg.get(kind, (0.0, 0.0))
                 cells.append("%8.3f (%7.1f)" % (ms, fl / 1e9 / ms if ms > 0 else 0.0))
-            print("%-16s %8.1f | %s  [%s]" % (name, gf, " | ".join(cells), "tma" if use_tma else "gather"), flush=True)
+            print("%-16s %8.1f | %s  [%s]" % (name, gf, " | ".join(cells), "stream" if use_tma else "per-tap"), flush=True)
             del e
             torch.cuda.empty_cache()
 

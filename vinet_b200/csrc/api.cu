@@ -24,6 +24,8 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream);
 int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream);
 int tc_debug_set(unsigned int v);
 int tma_pair_set(int v);
+int stream_enable_set(int v);
+int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles);
 
 // the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
 static bool dense_sources(const vinet_gather_t& g) {
@@ -54,6 +56,22 @@ extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stre
   if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);
   set_error("conv_gemm: unknown engine %d", engine);
   return -1;
+}
+
+extern "C" int vinet_conv_tiling(const vinet_conv_t* d, int32_t engine, int32_t* block_n, int32_t* n_tiles) {
+  VINET_CHECK(d && block_n && n_tiles, "conv_tiling: null argument");
+  VINET_CHECK(d->N >= 1, "conv_tiling: N %d", d->N);
+  int bn = 0, nt = 0;
+  if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS &&
+      conv_stream_tiling(d, &bn, &nt)) {
+    *block_n = bn;
+    *n_tiles = nt;
+    return 0;
+  }
+  const int n16 = (int)round_up(d->N, 16);   // default: the fewest tiles of at most 256 columns
+  *n_tiles = (int)cdiv(n16, 256);
+  *block_n = (int)round_up(cdiv(n16, *n_tiles), 16);
+  return 0;
 }
 
 extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream) {
@@ -112,6 +130,7 @@ extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
 
 extern "C" int vinet_debug_set(int32_t key, int32_t value) {
   if (key == 1) return tma_pair_set(value);
+  if (key == 2) return stream_enable_set(value);
   VINET_CHECK(key == 0, "debug_set: unknown key %d", key);
   VINET_CHECK(tc_debug_set((unsigned int)value) == 0, "debug_set: cudaMemcpyToSymbol failed");
   return 0;

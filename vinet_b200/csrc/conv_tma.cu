@@ -539,6 +539,17 @@ static int sm_count() {
   return n;
 }
 
+// shared with conv_stream.cu
+int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
+                 int esw, int esh) {
+  return make_map(m, ptr, C, W, H, T, B, ld, ldh, bw, bh, esw, esh);
+}
+void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out) {
+  pick_box(H, W, max_rows, mult, full_tile_cost, bw_out, bh_out);
+}
+int tma_sm_count() { return sm_count(); }
+int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream);
+
 // development switch (vinet_debug_set key 1): 0 disables the paired 256-row work items
 int g_tma_pair = 1;
 int tma_pair_set(int v) { g_tma_pair = v; return 0; }
@@ -557,6 +568,10 @@ static int check_tma_gather(const vinet_gather_t& g, const char* what) {
 int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
   if (check_tma_gather(g, "conv_gemm_tma")) return -1;
+  {  // convolutions with tap re-use (spatial halo / temporal frame sharing) go to the streaming kernel, conv_stream.cu
+    const int r = conv_gemm_stream(d, stream);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   VINET_CHECK(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "conv_gemm_tma: bad block_n %d", d->block_n);
   VINET_CHECK(d->N % 8 == 0, "conv_gemm_tma: N %d must be a multiple of 8", d->N);
   ConvTmaParams p;

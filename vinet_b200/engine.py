@@ -238,10 +238,20 @@ class Engine:
         n_tiles = cdiv(n16, 256)
         return round_up(cdiv(n16, n_tiles), 16), n_tiles
 
-    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE):
+    def conv_tiling(self, d, n):
+        """(block_n, n_tiles) for the conv described by `d` (gather / outputs / kernel filled in).  The TMA-fed tensor-core
+        kernels pick their own N tiling per layer (csrc/conv_stream.cu); everything else uses the default."""
+        if self.eng == L.ENGINE_TC and d.kernel == L.KERNEL_TMA and "vinet_conv_tiling" in self.lib.fn:
+            bn, nt = C.c_int32(0), C.c_int32(0)
+            d.N = n
+            self.lib.call("vinet_conv_tiling", C.byref(d), self.eng, C.byref(bn), C.byref(nt))
+            return bn.value, nt.value
+        return self.tiling(n)
+
+    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE, tiling=None):
         """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version."""
-        ck = (key, mode, tuple(taps), self.eng, layout)
-        block_n, n_tiles = self.tiling(n)
+        block_n, n_tiles = tiling if tiling is not None else self.tiling(n)
+        ck = (key, mode, tuple(taps), self.eng, layout, block_n, n_tiles)
         if layout != L.KLAYOUT_DENSE:
             k_blocks = len(taps) * cdiv(cs, L.TC_BLOCK_K)
         else:
@@ -305,11 +315,9 @@ class Engine:
             s0.ldh = a0.Wp * 8
             g.src[1].ptr, g.src[1].T = None, 0
 
-        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout)
         d = L.Conv()
         d.kernel = kern
         fill_gather(d.g)
-        d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
         d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
         d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
         d.out_dtype, d.accumulate = self.dt, 0
@@ -317,6 +325,9 @@ class Engine:
         if ep is not None:
             assert bias is None
             d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
+        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout,
+                                                            tiling=self.conv_tiling(d, Cout))
+        d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
         self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
@@ -377,8 +388,6 @@ class Engine:
                 ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
                 n = w.shape[1]
                 dtma = self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
-                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
-                                                        L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE)
                 dd = L.Conv()
                 dd.kernel = L.KERNEL_TMA if dtma else L.KERNEL_GATHER
                 g = dd.g
@@ -390,13 +399,16 @@ class Engine:
                 g.src[0].ptr, g.src[0].scale, g.src[0].shift = dy, None, None
                 g.src[0].ld, g.src[0].T, g.src[0].xform = lddy, To, L.XF_IDENT
                 g.src[1].ptr, g.src[1].T = None, 0
-                dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
                 for i, s in enumerate(srcs):
                     dd.out[i], dd.ldo[i], dd.out_T[i] = s.gptr(), s.ldg, s.T
                 if len(srcs) == 1:
                     dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
                 dd.out_dtype, dd.accumulate = gdt, accmask
                 dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
+                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
+                                                        L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE,
+                                                        tiling=self.conv_tiling(dd, n))
+                dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
                 dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
                 self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
         return backward

@@ -130,6 +130,7 @@ class AvFuse(C.Structure):
 _S = C.c_void_p  # stream
 SIGNATURES = {
     "vinet_conv_gemm": (C.c_int, [C.POINTER(Conv), _i32, _S]),
+    "vinet_conv_tiling": (C.c_int, [C.POINTER(Conv), _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), _i32, _S]),
     "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
     "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
