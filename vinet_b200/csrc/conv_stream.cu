@@ -49,6 +49,7 @@ struct StreamParams {
   int32_t sp_kb[VINET_MAX_TAPS];   // first weight k-block of the tap (tap * ncb)
   int32_t sp_aoff16[VINET_MAX_TAPS], sp_boff16[VINET_MAX_TAPS];  // sp_aoff and sp_kb * b_bytes in 16-byte descriptor units
   int32_t nacc, a_stages, b_slots, wres, items_per_nt, ni;
+  int32_t tt, pos, tstep, toff, walk_Ts, walk_Tr;  // temporal-halo tiles: tt output frames x pos positions per sub-tile (tt = 1: off)
   uint32_t acc_stride, tmem_cols, idesc, a_stage_bytes, a_tx_sub, sub_stride, sbo, b_bytes;
 };
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ StItem st_decode(const StreamParams& p, int item) {
   const int r = m % p.nruns;
   c.b = m / p.nruns;
   c.i0 = r * p.run;
-  c.i1 = min(p.d.g.Tr, c.i0 + p.run);
+  c.i1 = min(p.walk_Tr, c.i0 + p.run);
   return c;
 }
 
@@ -74,7 +75,7 @@ struct StWalk {
   __device__ __forceinline__ void init(const StreamParams& p, const StItem& c) {
     const int f_lo = c.i0 * p.S + p.e_min;
     f = max(f_lo, 0);
-    f_end = min((c.i1 - 1) * p.S + p.e_max, p.d.g.Ts - 1);
+    f_end = min((c.i1 - 1) * p.S + p.e_max, p.walk_Ts - 1);
     q = f / p.S;
     r = f - q * p.S;
     i0 = c.i0;
@@ -189,8 +190,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
         StWalk wk;
         for (wk.init(p, c); wk.f <= wk.f_end; wk.next(p)) {
           if (!wk.used(p)) continue;
-          const int si = (wk.f >= g.src[0].T) ? 1 : 0;
-          const int tl = wk.f - (si ? g.src[0].T : 0);
+          const int fr = wk.f * p.tstep + p.toff;   // first source frame of the box (may lie in the temporal padding)
+          const int si = (fr >= g.src[0].T && g.src[1].ptr != nullptr) ? 1 : 0;
+          const int tl = fr - (si ? g.src[0].T : 0);
           for (int cb = 0; cb < p.ncb; ++cb) {
             mbar_wait(empty_a + 8 * s, ph ^ 1u);
             const uint32_t dst = sA0 + (uint32_t)s * p.a_stage_bytes;
@@ -346,7 +348,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
     const int q = warp & 3;
     const int half = (warp - 2 - ST_MAX_ISSUERS) >> 2;
     const int row = q * 32 + lane;
-    const int rh = row / p.tw, rw = row - rh * p.tw;
+    const int rt = row / p.pos, rrem = row - rt * p.pos;   // temporal-halo tiles stack tt frames of pos positions
+    const int rh = rrem / p.tw, rw = rrem - rh * p.tw;
     const int BN = p.d.block_n;
     const int nlim = p.d.N - nt * BN;
     const uint32_t nacc = (uint32_t)p.nacc;
@@ -357,7 +360,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
       for (int i = c.i0; i < c.i1; ++i) {
         mbar_wait(full_acc + 8 * slot, ph);
         tc_fence_after();
-        const int t = i * g.row_tstep + g.row_toff;
+        const int ti = i * p.tt + rt;
+        const int t = ti * g.row_tstep + g.row_toff;
         for (int sub = 0; sub < ns; ++sub) {
           int h, w;
           if (p.halo) {
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
             h = ty * p.th + rh;
             w = (tif - ty * p.tiles_w) * p.tw + rw;
           }
-          const bool valid = row < p.tw * p.th && h < g.Hr && w < g.Wr;
+          const bool valid = row < p.pos * p.tt && ti < g.Tr && h < g.Hr && w < g.Wr;
           TO* orow = nullptr;
           bool accum = false;
           if (valid) {
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
 
 // ------------------------------------------------------------------ host side
 int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
-                 int esw, int esh);
+                 int esw, int esh, int bt);
 void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out);
 int tma_sm_count();
 
@@ -502,7 +506,7 @@ struct Plan {
   bool ok = false;
   double cost = 1e300;
   int block_n = 0, n_tiles = 0, nsub = 0, nacc = 0, run = 0, a_stages = 0, b_slots = 0, wres = 0;
-  int halo = 0, tw = 0, th = 0, items_w = 0, items_h = 0, tiles_w = 0, tpf = 0, PW = 0, PH = 0;
+  int halo = 0, tw = 0, th = 0, items_w = 0, items_h = 0, tiles_w = 0, tpf = 0, PW = 0, PH = 0, tt = 1, PT = 1;
   uint32_t a_stage_bytes = 0, a_tx_sub = 0, sub_stride = 0, sbo = 0;
 };
 
@@ -534,77 +538,91 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
     const int acc_stride = (int)round_up(block_n, 32);
     const uint32_t b_bytes = (uint32_t)block_n * 128u;
     const int ctas = std::max(1, sms / n_tiles);
-    for (int nsub = 1; nsub <= 8; ++nsub) {
-      const int slots = 512 / (nsub * acc_stride);
-      if (slots < tm.L) break;
-      const int nacc = std::min(tm.L + 1, slots);
-      Plan c;
-      c.block_n = block_n; c.n_tiles = n_tiles; c.nsub = nsub; c.nacc = nacc;
-      double util;
-      if (spatial) {
-        c.halo = 1; c.tw = 8; c.th = 16;
-        c.PW = 8 * nsub + (tm.ew1 - tm.ew0);
-        c.PH = 16 + (tm.eh1 - tm.eh0);
-        if (c.PW > 256 || c.PH > 256) break;
-        c.items_w = (int)cdiv(g.Wr, 8 * nsub);
-        c.items_h = (int)cdiv(g.Hr, 16);
-        c.a_tx_sub = (uint32_t)(c.PW * c.PH * 128);
-        c.a_stage_bytes = (uint32_t)round_up(c.a_tx_sub, 1024);
-        c.sub_stride = 8 * 128;
-        c.sbo = (uint32_t)c.PW * 128u;
-        util = (double)cdiv(g.Wr, 8) / (double)(c.items_w * nsub);   // sub-tiles past the right edge are skipped
-      } else {
-        c.halo = 0; c.tw = fbw; c.th = fbh;
-        c.tiles_w = (int)cdiv(g.Wr, fbw);
-        c.tpf = c.tiles_w * (int)cdiv(g.Hr, fbh);
-        if (nsub > c.tpf) break;
-        c.items_w = (int)cdiv(c.tpf, nsub);
-        c.items_h = 1;
-        c.a_tx_sub = (uint32_t)(fbw * fbh * 128);
-        c.a_stage_bytes = (uint32_t)nsub * TC_A_BYTES;
-        c.sub_stride = TC_A_BYTES;
-        c.sbo = 1024;
-        util = (double)c.tpf / (double)(c.items_w * nsub);
-      }
-      // shared memory: resident weights when they fit beside two activation stages, else a ring of weight blocks
-      const size_t bar_bytes = 1024 + 1536;
-      const size_t wbytes = (size_t)KB * b_bytes;
-      if (wbytes + 2 * (size_t)c.a_stage_bytes + bar_bytes <= ST_SMEM_BUDGET) {
-        c.wres = 1;
-        c.b_slots = 1;
-        c.a_stages = (int)std::min<size_t>(6, (ST_SMEM_BUDGET - bar_bytes - wbytes) / c.a_stage_bytes);
-      } else {
-        c.wres = 0;
-        if (2 * (size_t)c.a_stage_bytes + 3 * (size_t)b_bytes + bar_bytes > ST_SMEM_BUDGET) continue;
-        c.a_stages = 2;
-        size_t left = ST_SMEM_BUDGET - bar_bytes - 2 * (size_t)c.a_stage_bytes;
-        c.b_slots = (int)std::min<size_t>(12, left / b_bytes);
-        // spend what is left beyond 6 weight slots on a third activation stage
-        if (c.b_slots > 6 && left - 6 * (size_t)b_bytes >= c.a_stage_bytes) {
-          c.a_stages = 3;
-          c.b_slots = (int)std::min<size_t>(12, (left - c.a_stage_bytes) / b_bytes);
+    // temporal-halo tiles (tt > 1): stride-1 temporal taps of a single source read ONE box of tt + kt - 1 frames
+    const bool thalo_ok = !spatial && tm.S == 1 && tm.ntg > 1 && g.src[1].ptr == nullptr;
+    for (int tt = 1; tt <= (thalo_ok ? 16 : 1); tt *= 2) {
+      if (tt > 1 && tt / 2 >= g.Tr) break;
+      const int L = tt > 1 ? 1 : tm.L;
+      const int walk_Tr = tt > 1 ? (int)cdiv(g.Tr, tt) : g.Tr;
+      int tbw = fbw, tbh = fbh;
+      if (tt > 1) pick_tma_box(g.Hr, g.Wr, TC_BM / tt, 8, true, &tbw, &tbh);
+      const int pos = tbw * tbh;
+      if (tt > 1 && pos * tt != TC_BM) continue;   // only full 128-row tiles keep the 8-row groups contiguous
+      for (int nsub = 1; nsub <= 8; ++nsub) {
+        const int slots = 512 / (nsub * acc_stride);
+        if (slots < L) break;
+        const int nacc = std::min(L + 1, slots);
+        Plan c;
+        c.block_n = block_n; c.n_tiles = n_tiles; c.nsub = nsub; c.nacc = nacc; c.tt = tt;
+        double util;
+        if (spatial) {
+          c.halo = 1; c.tw = 8; c.th = 16;
+          c.PW = 8 * nsub + (tm.ew1 - tm.ew0);
+          c.PH = 16 + (tm.eh1 - tm.eh0);
+          if (c.PW > 256 || c.PH > 256) break;
+          c.items_w = (int)cdiv(g.Wr, 8 * nsub);
+          c.items_h = (int)cdiv(g.Hr, 16);
+          c.a_tx_sub = (uint32_t)(c.PW * c.PH * 128);
+          c.a_stage_bytes = (uint32_t)round_up(c.a_tx_sub, 1024);
+          c.sub_stride = 8 * 128;
+          c.sbo = (uint32_t)c.PW * 128u;
+          util = (double)cdiv(g.Wr, 8) / (double)(c.items_w * nsub);   // sub-tiles past the right edge are skipped
+        } else {
+          c.halo = 0; c.tw = tbw; c.th = tbh;
+          c.PT = tt > 1 ? tt + (tm.e_max - tm.e_min) : 1;
+          c.tiles_w = (int)cdiv(g.Wr, tbw);
+          c.tpf = c.tiles_w * (int)cdiv(g.Hr, tbh);
+          if (nsub > c.tpf) break;
+          c.items_w = (int)cdiv(c.tpf, nsub);
+          c.items_h = 1;
+          c.a_tx_sub = (uint32_t)(pos * c.PT * 128);
+          c.sub_stride = (uint32_t)round_up(std::max<uint32_t>(c.a_tx_sub, TC_A_BYTES), 1024);
+          c.a_stage_bytes = (uint32_t)nsub * c.sub_stride;
+          c.sbo = 1024;
+          util = (double)c.tpf / (double)(c.items_w * nsub);
         }
-      }
-      for (int run = 1; run <= g.Tr; run = (run * 2 > g.Tr && run != g.Tr) ? g.Tr : run * 2) {
-        const int nruns = (int)cdiv(g.Tr, run);
-        const double frames = (double)(run - 1) * tm.S + (tm.e_max - tm.e_min) + 1;   // source frames walked per item
-        const double used = std::min(frames, (double)run * tm.ntg);
-        const double taps_per_out = (double)tm.nsp;
-        const double mma = run * taps_per_out * nk_sum * nsub * util * mma_clk16(block_n, std::min(ST_MAX_ISSUERS, nsub));
-        const double bytes = used * ncb * c.a_tx_sub * (c.halo ? 1.0 : nsub * util) +
-                             (c.wres ? 0.0 : run * taps_per_out * ncb * (double)b_bytes);
-        const double load = bytes / ST_LOAD_BPC;
-        const double epi = run * nsub * util * 128.0 * block_n * (d.accumulate ? 6.0 : 2.0) / 32.0 + 300.0 * run;
-        const double t_item = (nacc > tm.L ? std::max(std::max(mma, load), epi) : std::max(mma, load) + epi) + 1500.0;
-        const int64_t items = (int64_t)g.B * nruns * c.items_w * c.items_h;
-        const double total = (double)cdiv(items, ctas) * t_item + (c.wres ? wbytes / ST_LOAD_BPC : 0.0);
-        if (total < best.cost) {
-          best = c;
-          best.ok = true;
-          best.cost = total;
-          best.run = run;
+        // shared memory: resident weights when they fit beside two activation stages, else a ring of weight blocks
+        const size_t bar_bytes = 1024 + 1536;
+        const size_t wbytes = (size_t)KB * b_bytes;
+        if (wbytes + 2 * (size_t)c.a_stage_bytes + bar_bytes <= ST_SMEM_BUDGET) {
+          c.wres = 1;
+          c.b_slots = 1;
+          c.a_stages = (int)std::min<size_t>(6, (ST_SMEM_BUDGET - bar_bytes - wbytes) / c.a_stage_bytes);
+        } else {
+          c.wres = 0;
+          if (2 * (size_t)c.a_stage_bytes + 3 * (size_t)b_bytes + bar_bytes > ST_SMEM_BUDGET) continue;
+          c.a_stages = 2;
+          size_t left = ST_SMEM_BUDGET - bar_bytes - 2 * (size_t)c.a_stage_bytes;
+          c.b_slots = (int)std::min<size_t>(12, left / b_bytes);
+          // spend what is left beyond 6 weight slots on a third activation stage
+          if (c.b_slots > 6 && left - 6 * (size_t)b_bytes >= c.a_stage_bytes) {
+            c.a_stages = 3;
+            c.b_slots = (int)std::min<size_t>(12, (left - c.a_stage_bytes) / b_bytes);
+          }
         }
-        if (run == g.Tr) break;
+        const int issuers = std::min(ST_MAX_ISSUERS, nsub);
+        for (int run = 1; run <= walk_Tr; run = (run * 2 > walk_Tr && run != walk_Tr) ? walk_Tr : run * 2) {
+          const int nruns = (int)cdiv(walk_Tr, run);
+          // source stages walked per item and taps issued per output (a temporal-halo stage holds every tap)
+          const double frames = tt > 1 ? run : (double)(run - 1) * tm.S + (tm.e_max - tm.e_min) + 1;
+          const double used = tt > 1 ? run : std::min(frames, (double)run * tm.ntg);
+          const double taps_per_out = (double)tm.nsp;
+          const double mma = run * taps_per_out * nk_sum * nsub * util * mma_clk16(block_n, issuers);
+          const double bytes = used * ncb * c.a_tx_sub * (c.halo ? 1.0 : nsub * util) +
+                               (c.wres ? 0.0 : run * taps_per_out * ncb * (double)b_bytes);
+          const double load = bytes / ST_LOAD_BPC;
+          const double epi = run * nsub * util * 128.0 * block_n * (d.accumulate ? 6.0 : 2.0) / 32.0 + 300.0 * run;
+          const double t_item = (nacc > L ? std::max(std::max(mma, load), epi) : std::max(mma, load) + epi) + 1500.0;
+          const int64_t items = (int64_t)g.B * nruns * c.items_w * c.items_h;
+          const double total = (double)cdiv(items, ctas) * t_item + (c.wres ? wbytes / ST_LOAD_BPC : 0.0);
+          if (total < best.cost) {
+            best = c;
+            best.ok = true;
+            best.cost = total;
+            best.run = run;
+          }
+          if (run == walk_Tr) break;
+        }
       }
     }
   }
@@ -636,8 +654,8 @@ int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles) {
   const Plan pl = plan_stream(*d, tm, 0, 0, tma_sm_count());
   if (getenv("VINET_STREAM_DEBUG"))
     fprintf(stderr, "stream plan: mode %d rows %dx%dx%dx%d Cs %d N %d taps %d S %d L %d -> ok %d block_n %d x %d nsub %d nacc %d run %d "
-            "halo %d box %dx%d a_stages %d b_slots %d wres %d est %.0f kclk\n", d->g.mode, d->g.B, d->g.Tr, d->g.Hr, d->g.Wr, d->g.Cs,
-            d->N, d->g.ntaps, tm.S, tm.L, (int)pl.ok, pl.block_n, pl.n_tiles, pl.nsub, pl.nacc, pl.run, pl.halo,
+            "halo %d tt %d box %dx%d a_stages %d b_slots %d wres %d est %.0f kclk\n", d->g.mode, d->g.B, d->g.Tr, d->g.Hr, d->g.Wr, d->g.Cs,
+            d->N, d->g.ntaps, tm.S, tm.L, (int)pl.ok, pl.block_n, pl.n_tiles, pl.nsub, pl.nacc, pl.run, pl.halo, pl.tt,
             pl.halo ? pl.PW : pl.tw, pl.halo ? pl.PH : pl.th, pl.a_stages, pl.b_slots, pl.wres, pl.cost / 1e3);
   if (!pl.ok) return 0;
   *block_n = pl.block_n;
@@ -664,17 +682,27 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   p.halo = pl.halo; p.nsub = pl.nsub; p.tw = pl.tw; p.th = pl.th;
   p.items_w = pl.items_w; p.items_h = pl.items_h; p.tiles_w = pl.tiles_w; p.tpf = pl.tpf;
   p.PW = pl.PW; p.PH = pl.PH; p.ew0 = tm.ew0; p.eh0 = tm.eh0;
-  p.run = pl.run; p.nruns = (int)cdiv(g.Tr, pl.run); p.S = tm.S; p.ntg = tm.ntg;
-  p.e_min = tm.e_min; p.e_max = tm.e_max;
+  const bool thalo = pl.tt > 1;
+  p.tt = pl.tt; p.pos = pl.tw * pl.th;
+  p.tstep = thalo ? pl.tt : 1; p.toff = thalo ? tm.e_min : 0;
+  p.walk_Tr = thalo ? (int)cdiv(g.Tr, pl.tt) : g.Tr;
+  p.walk_Ts = thalo ? p.walk_Tr : g.Ts;
+  p.run = pl.run; p.nruns = (int)cdiv(p.walk_Tr, pl.run);
+  // temporal-halo tiles: every tap reads the same box, i.e. ONE tap group at offset 0 in units of whole tiles
+  p.S = thalo ? 1 : tm.S; p.ntg = thalo ? 1 : tm.ntg;
+  p.e_min = thalo ? 0 : tm.e_min; p.e_max = thalo ? 0 : tm.e_max;
   for (int k = 0; k < ST_MAX_TG; ++k) {
-    const int e = k < tm.ntg ? tm.tg_e[k] : 0;
-    p.tg_er[k] = ((e % tm.S) + tm.S) % tm.S;
-    p.tg_eq[k] = (e - p.tg_er[k]) / tm.S;
+    const int e = (k < tm.ntg && !thalo) ? tm.tg_e[k] : 0;
+    p.tg_er[k] = ((e % p.S) + p.S) % p.S;
+    p.tg_eq[k] = (e - p.tg_er[k]) / p.S;
   }
-  for (int k = 0; k <= ST_MAX_TG; ++k) p.tg_first[k] = k <= tm.ntg ? tm.tg_first[k] : tm.nsp;
+  for (int k = 0; k <= ST_MAX_TG; ++k) p.tg_first[k] = thalo ? (k == 0 ? 0 : tm.nsp) : (k <= tm.ntg ? tm.tg_first[k] : tm.nsp);
   for (int j = 0; j < VINET_MAX_TAPS; ++j) {
     if (j < tm.nsp) {
-      p.sp_aoff[j] = pl.halo ? ((tm.sp_eh[j] - tm.eh0) * pl.PW + (tm.sp_ew[j] - tm.ew0)) * 128 : 0;
+      int grp = 0;
+      while (j >= tm.tg_first[grp + 1]) ++grp;
+      p.sp_aoff[j] = pl.halo ? ((tm.sp_eh[j] - tm.eh0) * pl.PW + (tm.sp_ew[j] - tm.ew0)) * 128
+                             : (thalo ? (tm.tg_e[grp] - tm.e_min) * p.pos * 128 : 0);
       p.sp_kb[j] = tm.sp_tap[j] * p.ncb;
     } else {
       p.sp_aoff[j] = p.sp_kb[j] = 0;
@@ -703,7 +731,7 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     const int bw = pl.halo ? pl.PW : pl.tw, bh = pl.halo ? pl.PH : pl.th;
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1)) return -1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT)) return -1;
   }
   const int ctas = (int)std::min<int64_t>(items, std::max(1, sms / d->n_tiles));
   dim3 grid((unsigned)ctas, (unsigned)d->n_tiles);
