@@ -97,12 +97,14 @@ int main() {
   CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int iters = 4096;
   printf("%4s %4s %5s %5s | %10s %10s | %8s\n", "N", "nacc", "sbo", "shift", "issue clk", "total clk", "clk/MMA");
-  for (int variant = 0; variant < 3; ++variant) {
+  for (int variant = 0; variant < 6; ++variant) {
+    if (variant == 3) printf("MN-major A and B (wgrad): variant 3 canonical, 4 halo SBO/shift, 5 A K-major + B MN-major\n");
     for (int n : {32, 64, 96, 128, 192, 256}) {
       int nacc = variant == 1 ? std::min(4, 512 / ((n + 31) / 32 * 32)) : 1;
-      uint32_t sbo = variant == 2 ? 1280 : 1024;
-      int shift = variant == 2 ? 11 : 0;
-      rate_kernel<<<148, 128, smem>>>(n, make_idesc(128, n, 0, 0), iters, nacc, sbo, shift, d);
+      uint32_t sbo = (variant == 2 || variant == 4) ? 1280 : 1024;
+      int shift = (variant == 2 || variant == 4) ? 11 : 0;
+      const uint32_t idesc = variant >= 3 ? make_idesc(128, n, variant == 5 ? 0 : 1, 1) : make_idesc(128, n, 0, 0);
+      rate_kernel<<<148, 128, smem>>>(n, idesc, iters, nacc, sbo, shift, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       long long h[2];

@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
         const int rows = min(32, p.nunits * 64 - m0);
         for (int rr = 0; rr < rows; ++rr) {
           float* drow = p.d.dwp + (int64_t)(m0 + rr) * p.d.lddw + n0;
-          for (int col = lane; col < ncols; col += 32) atomicAdd(drow + col, stile[rr * P + col]);
+          const float* srow = stile + rr * P;
+          for (int col = lane * 4; col < ncols; col += 128) red_add_v4(drow + col, srow[col], srow[col + 1], srow[col + 2], srow[col + 3]);
         }
         __syncwarp();
       }
@@ -549,6 +550,7 @@ void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int
 }
 int tma_sm_count() { return sm_count(); }
 int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream);
+int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream);
 
 // development switch (vinet_debug_set key 1): 0 disables the paired 256-row work items
 int g_tma_pair = 1;
@@ -633,6 +635,10 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
   if (check_tma_gather(g, "conv_wgrad_tma")) return -1;
   VINET_CHECK(g.mode == VINET_GATHER_FPROP, "conv_wgrad_tma: needs an FPROP gather");
+  {  // spatial convolutions: all kh*kw taps of a channel block share one halo tile per chunk (conv_wgrad_halo.cu)
+    const int r = conv_wgrad_halo(d, stream);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   VINET_CHECK(d->dy_dtype == VINET_BF16 && d->N % 8 == 0 && d->lddy % 8 == 0, "conv_wgrad_tma: dy must be bf16, N %d lddy %lld",
               d->N, (long long)d->lddy);
   WgradTmaParams p;

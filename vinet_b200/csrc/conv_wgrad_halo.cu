@@ -1,0 +1,306 @@
+// Weight gradient of spatial (kh x kw > 1, stride 1) convolutions with ONE halo tile per position chunk (sm_100a).
+//
+//   dW[(dt,dh,dw,c), n] += sum over positions  A[b, t*st-pt+dt, h-ph+dh, w-pw+dw, c] * dY[b,t,h,w,n]
+//
+// conv_tma.cu's wgrad kernel fetches one activation box per (tap, 64-channel block) unit and keeps at most 4 units per CTA,
+// so a 3x3 conv pulls every activation through L2->SM nine times and every dY tile once per 4 units: those launches sit on
+// the L2->SM bandwidth roof (convtsp4.0: 360 TFLOP/s).  Here a CTA owns ALL kh*kw spatial taps of one (temporal tap,
+// 64-channel block) group against one N block of dY:
+//   * per chunk of 8 x 16 output positions it fetches ONE halo box {64 ch, 8+kw-1, 16+kh-1} and the dY box(es);
+//   * the A operand of tap (dh,dw) is the MN-major SWIZZLE_128B descriptor {start = box + (dh*PW + dw)*128, SBO = PW*128}
+//     (8-position atoms are rows of the tile); two taps are stacked into one M=128 accumulator through LBO = the byte
+//     distance between their windows (profiles/r1_umma_shift_test.txt: shifted MN-major descriptors read what they should);
+//   * ceil(kh*kw/2) fp32 accumulators of block_n <= 96 columns live in TMEM for the whole CTA lifetime (split over position
+//     chunks across CTAs, fp32 red.add into the packed TAP64 gradient at the end);
+//   * up to 4 warps issue the MMAs (one accumulator each; a single warp cannot feed the tensor pipe with N <= 96 MMAs).
+// Roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator, warps 2..5 MMA issuers, warps 6..9 epilogue.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+namespace vinet {
+
+constexpr int WH_THREADS = 320;
+constexpr int WH_MAX_ISSUERS = 4;
+constexpr int WH_MAX_SP = 16;       // spatial taps per group (<= 8 accumulators)
+constexpr uint32_t WH_UNIT = 16384;  // one 8 x 16 x 64-channel box
+
+int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
+                 int esw, int esh, int bt);
+int tma_sm_count();
+extern int g_stream_enable;
+
+struct WgHaloParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmDy;
+  vinet_wgrad_t d;
+  int32_t PW, PH, ncb, nsp, naccs, nblk, block_n, splits, stages, ni, tiles_w, tiles_h, kw;
+  uint32_t acc_cols, tmem_cols, idesc, a_bytes, a_tx, stage_bytes;
+};
+
+__device__ __forceinline__ void wh_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ bool wh_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void wh_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  const vinet_gather_t& g = p.d.g;
+  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
+  const int64_t per = cdiv(nchunks, p.splits);
+  const int64_t c_begin = (int64_t)blockIdx.z * per;
+  const int64_t c_end = min(nchunks, c_begin + per);
+  if (c_end <= c_begin) return;  // uniform for the CTA
+  const int KB = (int)(c_end - c_begin);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * p.stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, accum_bar = empty0 + 8 * stages;
+  const uint32_t s0 = smem_u32(base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.block_n;
+  const int n0 = blockIdx.y * BN;
+  const int dt = blockIdx.x / p.ncb, cb = blockIdx.x - dt * p.ncb;   // this CTA's (temporal tap, channel block) group
+  const int nblk_eff = min(p.nblk, (min(BN, p.d.N - n0) + 63) / 64);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA[0])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA[1])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmDy)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, p.ni);
+      }
+      mbar_init(accum_bar, p.ni);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: one halo box + the dY box(es) per chunk
+    if (lane == 0) {
+      int64_t m = c_begin;
+      int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
+      int th = (int)(m % p.tiles_h); m /= p.tiles_h;
+      int tr = (int)(m % g.Tr);
+      int b = (int)(m / g.Tr);
+      const bool cat = g.src[1].ptr != nullptr;
+      const int T0 = g.src[0].T;
+      const int dtv = g.tap[dt * p.nsp][0];
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = p.a_tx + (uint32_t)nblk_eff * WH_UNIT;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int t = tr * g.row_tstep + g.row_toff;
+        const int h0 = th * 16, w0 = tw * 8;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(full0 + 8 * s, tx);
+        const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
+        const int ts = t * g.st - g.pt + dtv;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
+        const int si = (cat && ts >= T0) ? 1 : 0;
+        wh_tma_load_5d(stage, &p.tmA[si], full0 + 8 * s, cb * 64, w0 - g.pw, h0 - g.ph, ts - (si ? T0 : 0), b);
+        for (int nb = 0; nb < nblk_eff; ++nb)
+          wh_tma_load_5d(stage + p.a_bytes + (uint32_t)nb * WH_UNIT, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            if (++tr == g.Tr) { tr = 0; ++b; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + WH_MAX_ISSUERS) {
+    // ---------------------------------------------------------------- MMA issuers: issuer k owns accumulators k, k+ni, ...
+    const int k = warp - 2;
+    if (k < p.ni) {
+      const uint32_t hi_common = (1u << 14) | (2u << 29);
+      const uint32_t a_hi = ((uint32_t)(p.PW * 128) >> 4) | hi_common;   // SBO = one tile row of the halo
+      const uint32_t b_hi = (1024u >> 4) | hi_common;
+      const uint32_t b_lbo = (WH_UNIT >> 4) << 16;
+      const uint32_t kstep_a = (uint32_t)(2 * p.PW * 128) >> 4;           // 16 positions = two tile rows
+      const uint32_t stage16 = p.stage_bytes >> 4;
+      const uint32_t s0_16 = (s0 & 0x3FFFFu) >> 4;
+      int s = 0;
+      uint32_t ph = 0, st16 = s0_16;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t b_lo0 = (st16 + (p.a_bytes >> 4)) | b_lbo;
+        for (int a = k; a < p.naccs; a += p.ni) {
+          const int j0 = 2 * a, j1 = min(2 * a + 1, p.nsp - 1);
+          const int o0 = ((j0 / p.kw) * p.PW + (j0 % p.kw)) * 8, o1 = ((j1 / p.kw) * p.PW + (j1 % p.kw)) * 8;   // 16-byte units
+          const uint32_t a_lo0 = (st16 + (uint32_t)o0) | ((uint32_t)(o1 - o0) << 16);   // LBO = distance between the two taps
+          const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
+          if (wh_elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              wh_umma(tacc, a_lo0 + (uint32_t)kk * kstep_a, a_hi, b_lo0 + (uint32_t)kk * 128u, b_hi, p.idesc, (uint32_t)((kb | kk) != 0));
+          }
+        }
+        if (wh_elect_one()) {
+          umma_commit(empty0 + 8 * s);
+          if (kb == KB - 1) umma_commit(accum_bar);
+        }
+        st16 += stage16;
+        if (++s == stages) { s = 0; ph ^= 1u; st16 = s0_16; }
+      }
+    }
+  } else if (warp >= 2 + WH_MAX_ISSUERS) {
+    // ---------------------------------------------------------------- epilogue: TMEM -> smem transpose -> coalesced red.add
+    mbar_wait(accum_bar, 0);  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
+    tc_fence_after();
+    fence_proxy_async();
+    const int q = warp & 3;
+    const int P = BN + 1;  // odd pitch: conflict-free column-wise writes
+    float* stile = reinterpret_cast<float*>(base) + (size_t)(q * 32) * P;
+    const int ncols = min(BN, p.d.N - n0);
+    for (int a = 0; a < p.naccs; ++a) {
+      // rows 32q..32q+31 of accumulator a belong to spatial tap 2a + (q >> 1), channels (q & 1)*32 ..
+      const int j = 2 * a + (q >> 1);
+      for (int gi = 0; gi < BN / 16; ++gi) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * p.acc_cols + (uint32_t)(gi * 16), r);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) stile[lane * P + gi * 16 + e] = __uint_as_float(r[e]);
+      }
+      __syncwarp();
+      if (j < p.nsp) {
+        const int unit = (dt * p.nsp + j) * p.ncb + cb;
+        const int c0 = (q & 1) * 32;
+        const int rows = min(32, g.Cs - cb * 64 - c0);   // channels that exist
+        for (int rr = 0; rr < rows; ++rr) {
+          float* drow = p.d.dwp + ((int64_t)unit * 64 + c0 + rr) * p.d.lddw + n0;
+          const float* srow = stile + rr * P;
+          for (int col = lane * 4; col < ncols; col += 128) red_add_v4(drow + col, srow[col], srow[col + 1], srow[col + 2], srow[col + 3]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// returns 1 when the launch was handled here, 0 when the caller should use its own kernel, <0 on error
+int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
+  const vinet_gather_t& g = d->g;
+  if (!g_stream_enable) return 0;
+  if (g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16 || d->dy_dtype != VINET_BF16) return 0;
+  if (g.sh != 1 || g.sw != 1 || g.Cs % 8 != 0 || d->N % 8 != 0 || d->lddy % 8 != 0) return 0;
+  if (g.Hr < 10) return 0;
+  for (int i = 0; i < 2; ++i) {
+    const vinet_src_t& s = g.src[i];
+    if (s.ptr == nullptr) continue;
+    if (s.xform != VINET_XF_IDENT || (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) || s.ld < g.Cs) return 0;
+  }
+  // taps must be the natural (dt, dh, dw) enumeration of a kt x kh x kw kernel with kh*kw > 1
+  int kt = 0, kh = 0, kw = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    kt = std::max(kt, g.tap[t][0] + 1);
+    kh = std::max(kh, g.tap[t][1] + 1);
+    kw = std::max(kw, g.tap[t][2] + 1);
+  }
+  const int nsp = kh * kw;
+  if (nsp < 2 || nsp > WH_MAX_SP || kt * nsp != g.ntaps) return 0;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.tap[t][0] != t / nsp || g.tap[t][1] != (t / kw) % kh || g.tap[t][2] != t % kw) return 0;
+  WgHaloParams p;
+  p.d = *d;
+  p.kw = kw;
+  p.nsp = nsp;
+  p.ncb = (g.Cs + 63) / 64;
+  p.naccs = (nsp + 1) / 2;
+  const int n16 = (int)round_up(d->N, 16);
+  const int bn_max = std::min(256, (512 / p.naccs) / 16 * 16);
+  const int n_tiles = (int)cdiv(n16, bn_max);
+  p.block_n = (int)round_up(cdiv(n16, n_tiles), 16);
+  p.acc_cols = (uint32_t)round_up(p.block_n, 32);
+  if ((int)p.acc_cols * p.naccs > 512) p.acc_cols = (uint32_t)p.block_n;   // e.g. 5 x 96
+  if ((int)p.acc_cols * p.naccs > 512) return 0;
+  p.tmem_cols = tmem_cols_for(p.naccs * (int)p.acc_cols);
+  p.nblk = (p.block_n + 63) / 64;
+  p.PW = 8 + kw - 1;
+  p.PH = 16 + kh - 1;
+  p.a_tx = (uint32_t)(p.PW * p.PH * 128);
+  p.a_bytes = (uint32_t)round_up(p.a_tx, 1024);
+  p.stage_bytes = p.a_bytes + (uint32_t)p.nblk * WH_UNIT;
+  p.tiles_w = (int)cdiv(g.Wr, 8);
+  p.tiles_h = (int)cdiv(g.Hr, 16);
+  p.idesc = make_idesc(TC_BM, p.block_n, 1, 1);
+  p.ni = std::min(WH_MAX_ISSUERS, p.naccs);
+  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
+  const int64_t base_ctas = (int64_t)kt * p.ncb * n_tiles;
+  const int sms = tma_sm_count();
+  // split the position chunks so that the CTA count fills whole waves of the machine (1 CTA per SM)
+  const int64_t smax = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nchunks / 2, 256), 65535));
+  int64_t splits = 1;
+  double best = 1e30;
+  for (int64_t sp = 1; sp <= smax; ++sp) {
+    // time in chunk units: waves x (main loop + prologue / transposing red.add epilogue, ~2.5 chunks per 96-column accumulator)
+    const double t = (double)cdiv(base_ctas * sp, sms) * ((double)cdiv(nchunks, sp) + 2.0 + 2.5 * p.naccs * p.block_n / 96.0);
+    if (t < best * 0.999) { best = t; splits = sp; }
+  }
+  p.splits = (int)splits;
+  int stages = (int)((200 * 1024) / p.stage_bytes);
+  stages = std::max(2, std::min(stages, 6));
+  p.stages = stages;
+  const size_t ring = (size_t)stages * p.stage_bytes;
+  if (ring < (size_t)128 * (p.block_n + 1) * sizeof(float)) return 0;   // the epilogue transposes through the ring
+  const size_t smem = std::max<size_t>(1024 + ring + 8 * (2 * stages + 1) + 64, 120 * 1024);
+  if (smem > 227 * 1024) return 0;
+  for (int i = 0; i < 2; ++i) {
+    const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.PW, p.PH, 1, 1, 1)) return -1;
+  }
+  if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, 8, 16, 1, 1, 1)) return -1;
+  dim3 grid((unsigned)(kt * p.ncb), (unsigned)n_tiles, (unsigned)splits);
+  cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  conv_wgrad_halo_kernel<<<grid, WH_THREADS, smem, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("conv_wgrad_halo: launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 1;
+}
+
+}  // namespace vinet

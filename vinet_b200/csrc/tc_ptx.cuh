@@ -85,6 +85,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 128-bit fp32 reduction to global memory (sm_90+): one L2 atomic transaction for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout; version=1, SWIZZLE_128B=2).
 // K-major: rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused for swizzled K-major.
 // g_tc_debug: descriptor-encoding experiments selectable at run time (vinet_debug_set), 0 in production:
