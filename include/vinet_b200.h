@@ -188,6 +188,9 @@ typedef struct vinet_bn_finalize {
   float* invstd;
 } vinet_bn_finalize_t;
 int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream);
+/* vinet_bn_stats + vinet_bn_finalize (training) in ONE launch: the last block to finish finalises.  Both descriptors must
+ * name the same sums buffer, which here holds [2][C] doubles FOLLOWED BY one 8-byte ticket (zero on entry, left zero). */
+int vinet_bn_stats_finalize(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, vinet_stream_t stream);
 
 /* out = relu?(scale*y + shift): materialises BatchNorm(+ReLU) of a raw conv output (possibly into a channel
  * slice of a concat buffer, model_utils.py:187), so that consumers read it untransformed (TMA-fed kernels). */
@@ -221,7 +224,8 @@ typedef struct vinet_bn_bwd {
   const float* mean;
   const float* invstd;
   const float* gamma;
-  double* sums; /* [2][C]: sum(g*m), sum(g*m*y_norm); zero on entry, cleared again by vinet_bn_bwd_reduce on exit */
+  double* sums; /* [2][C] sum(g*m), sum(g*m*y_norm) followed by one 8-byte ticket; zero on entry, cleared again by
+                   vinet_bn_bwd_reduce on exit (its last block also writes dgamma / dbeta) */
   float* dgamma;
   float* dbeta;
   void* dy;
@@ -392,7 +396,8 @@ int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 int vinet_abi_sizes(int64_t* out, int32_t n);
 /* development switches (key 0: tcgen05 descriptor-encoding experiments, csrc/conv_tc.cu, 0 in production;
  * key 1: paired 256-row work items of the TMA conv kernel, 1 in production;
- * key 2: the streaming (halo / frame re-use) conv kernel of csrc/conv_stream.cu, 1 in production) */
+ * key 2: the streaming (halo / frame re-use) conv kernels of csrc/conv_stream.cu and conv_wgrad_halo.cu, 1 in production;
+ * key 3: the frame-walking 3x3x3 max-pool kernel, 1 in production) */
 int vinet_debug_set(int32_t key, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vinet_launch_count(void);

@@ -98,3 +98,35 @@ def test_loss_func_contract():
     assert out.shape == (1,) and out.is_cuda
     ref = O.kldiv(s, gt) - O.cc(s, gt) - O.similarity(s, gt)
     assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 9, 11, 24), (1, 1, 4, 6, 8), (2, 16, 28, 48, 64)])
+def test_maxpool333_frame_walking_kernel_matches_scan_order_kernel(shape):
+    """The 3x3x3/s1/p1 fast path (frame-walking, packed bf16) against the generic scan-order kernel: values AND the
+    recorded arg-max taps must agree bit for bit, including ties (post-ReLU activations are full of equal zeros)."""
+    import ctypes as C
+    from vinet_b200 import lib as L
+    lib = L.get()
+    B, T, H, W, Cn = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(-2, 3, (B, T, H, W, Cn), generator=g).float().clamp_min(0).to(torch.bfloat16).cuda()   # many ties
+    res = []
+    for fast in (1, 0):
+        lib.call("vinet_debug_set", 3, fast)
+        out = torch.full((B, T, H, W, Cn), float("nan"), dtype=torch.bfloat16, device="cuda")
+        idx = torch.full((B, T, H, W, Cn), 255, dtype=torch.uint8, device="cuda")
+        d = L.Pool()
+        d.x, d.ldx, d.dtype, d.xform = x.data_ptr(), Cn, L.BF16, L.XF_IDENT
+        d.B, d.Ti, d.Hi, d.Wi, d.C = B, T, H, W, Cn
+        d.kt = d.kh = d.kw = 3
+        d.st = d.sh = d.sw = 1
+        d.pt = d.ph = d.pw = 1
+        d.To, d.Ho, d.Wo, d.out, d.ldo, d.out_dtype, d.idx = T, H, W, out.data_ptr(), Cn, L.BF16, idx.data_ptr()
+        lib.call("vinet_maxpool_fwd", C.byref(d), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        res.append((out.float().cpu(), idx.cpu()))
+    lib.call("vinet_debug_set", 3, 1)
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    ref = torch.nn.functional.max_pool3d(x.float().permute(0, 4, 1, 2, 3), 3, 1, 1).permute(0, 2, 3, 4, 1).cpu()
+    assert torch.equal(res[0][0], ref)

@@ -25,6 +25,7 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream);
 int tc_debug_set(unsigned int v);
 int tma_pair_set(int v);
 int stream_enable_set(int v);
+int pool_fast_set(int v);
 int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles);
 
 // the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
@@ -131,6 +132,7 @@ extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
 extern "C" int vinet_debug_set(int32_t key, int32_t value) {
   if (key == 1) return tma_pair_set(value);
   if (key == 2) return stream_enable_set(value);
+  if (key == 3) return pool_fast_set(value);
   VINET_CHECK(key == 0, "debug_set: unknown key %d", key);
   VINET_CHECK(tc_debug_set((unsigned int)value) == 0, "debug_set: cudaMemcpyToSymbol failed");
   return 0;

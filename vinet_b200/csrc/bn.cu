@@ -1,5 +1,7 @@
 // BatchNorm3d statistics / finalize / backward on NDHWC views (model_utils.py:132,145,149).
 // The normalisation itself is never a kernel: consumers apply scale/shift(+ReLU) when they read.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vinet {
@@ -7,8 +9,10 @@ namespace vinet {
 // Column reduction skeleton: blockDim = (G = C/8 channel groups, Ry rows in flight).
 // Each thread accumulates NV fp32 partial vectors of 8 channels over its rows, the block combines
 // them in shared memory and issues one double atomicAdd per channel.
-template <int NV, typename F>
-__device__ __forceinline__ void column_reduce(int64_t rows, int C, int64_t rows_per_block, double* sums, F&& body) {
+// Returns true in every thread of the LAST block to finish (ticket counter at sums[NV*C], left at zero): that block may read
+// the completed sums and run the layer's finalisation, which saves a dependent tiny launch per BatchNorm layer.
+template <int NV, bool TICKET, typename F>
+__device__ __forceinline__ bool column_reduce(int64_t rows, int C, int64_t rows_per_block, double* sums, F&& body) {
   extern __shared__ float red[];  // [Ry][NV][C]
   const int gx = threadIdx.x, ry = threadIdx.y, Ry = blockDim.y;
   float acc[NV][8];
@@ -31,12 +35,25 @@ __device__ __forceinline__ void column_reduce(int64_t rows, int C, int64_t rows_
     for (int y = 0; y < Ry; ++y) s += (double)red[(size_t)y * NV * C + i];
     atomicAdd(sums + i, s);
   }
+  if constexpr (!TICKET) return false;
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(sums + NV * C);
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    is_last = (t == (unsigned long long)gridDim.x - 1);
+    if (is_last) *ticket = 0ull;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
 }
 
 template <typename T>
 __global__ void bn_stats_kernel(const __grid_constant__ vinet_bn_stats_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
-  column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+  column_reduce<2, false>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
     float v[8];
     load8(y + r * d.ld + c, v);
 #pragma unroll
@@ -50,7 +67,7 @@ __global__ void bn_stats_kernel(const __grid_constant__ vinet_bn_stats_t d, int6
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int C, double* sums,
                               int64_t rows_per_block) {
-  column_reduce<1>(rows, C, rows_per_block, sums, [&](int64_t r, int c, float (&acc)[1][8]) {
+  column_reduce<1, false>(rows, C, rows_per_block, sums, [&](int64_t r, int c, float (&acc)[1][8]) {
     float v[8];
     load8(x + r * ld + c, v);
 #pragma unroll
@@ -63,14 +80,13 @@ __global__ void colsum_finish_kernel(const double* sums, float* out, int C) {
   if (c < C) out[c] = (float)sums[c];
 }
 
-__global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d.C) return;
+__device__ __forceinline__ void bn_finalize_channel(const vinet_bn_finalize_t& d, int c) {
   float mean, invstd;
   if (d.training) {
     const double n = (double)d.rows;
-    const double m = d.sums[c] / n;
-    double var = d.sums[d.C + c] / n - m * m;
+    volatile double* vs = d.sums;   // written by other blocks' atomics
+    const double m = vs[c] / n;
+    double var = vs[d.C + c] / n - m * m;
     d.sums[c] = 0.0;  // leave the accumulators clean for the next step
     d.sums[d.C + c] = 0.0;
     if (var < 0.0) var = 0.0;
@@ -92,6 +108,29 @@ __global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d
   d.invstd[c] = invstd;
 }
 
+__global__ void bn_finalize_kernel(const __grid_constant__ vinet_bn_finalize_t d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d.C) bn_finalize_channel(d, c);
+}
+
+// statistics + finalisation in one launch: the last block to finish turns the sums into scale/shift/mean/invstd
+template <typename T>
+__global__ void bn_stats_finalize_kernel(const __grid_constant__ vinet_bn_stats_t d, const __grid_constant__ vinet_bn_finalize_t f,
+                                         int64_t rows_per_block) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const bool last = column_reduce<2, true>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8];
+    load8(y + r * d.ld + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += v[e];
+      acc[1][e] = fmaf(v[e], v[e], acc[1][e]);
+    }
+  });
+  if (last)
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < f.C; c += blockDim.x * blockDim.y) bn_finalize_channel(f, c);
+}
+
 template <typename T, typename TG>
 __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
   const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
@@ -106,7 +145,7 @@ __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, i
     }
   }
   const bool relu = d.relu != 0;
-  column_reduce<2>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+  const bool last = column_reduce<2, true>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
     float v[8], g[8];
     load8(y + r * d.ldy + c, v);
     load8(gp + r * d.ldg + c, g);
@@ -119,15 +158,14 @@ __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, i
       acc[1][e] = fmaf(gm, yn, acc[1][e]);
     }
   });
-}
-
-__global__ void bn_bwd_finish_kernel(double* sums, float* dgamma, float* dbeta, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    dbeta[c] = (float)sums[c];
-    dgamma[c] = (float)sums[C + c];
-    sums[c] = 0.0;
-    sums[C + c] = 0.0;
+  if (last) {  // the last block to finish publishes dbeta / dgamma and clears the accumulators for the next step
+    volatile double* vs = d.sums;
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < d.C; c += blockDim.x * blockDim.y) {
+      d.dbeta[c] = (float)vs[c];
+      d.dgamma[c] = (float)vs[d.C + c];
+      d.sums[c] = 0.0;
+      d.sums[d.C + c] = 0.0;
+    }
   }
 }
 
@@ -197,20 +235,24 @@ struct ColGrid {
   int64_t rows_per_block;
   size_t smem;
 };
-static ColGrid col_grid(int64_t rows, int C, int nv) {
+// reduce: column reductions pay 2C fp64 atomics per block, so they stop at two blocks per SM; element-wise passes take as
+// many blocks as leave every thread at least two rows.  Either way small tensors (most of the 77 BatchNorm layers of this
+// model) get enough blocks to cover the machine instead of a few blocks walking 16+ rows per thread.
+static ColGrid col_grid(int64_t rows, int C, int nv, bool reduce) {
   ColGrid g;
   const int G = C / 8;
   int Ry = 256 / G;
   if (Ry < 1) Ry = 1;
   if (Ry > 128) Ry = 128;
   g.block = dim3(G, Ry);
-  int64_t rpb = (int64_t)Ry * 16;  // >= 16 rows per thread when the tensor is large enough
+  // 8 blocks per SM keep enough loads in flight to saturate HBM; a reduction also pays 2C fp64 atomics per block, so wide
+  // layers stop earlier.  Every thread keeps >= 4 rows: its per-channel constants (up to 48 loads) are set up once.
+  int64_t max_blocks = 148 * 8;
+  if (reduce) max_blocks = std::min<int64_t>(max_blocks, std::max<int64_t>(148, 160000 / (2 * C)));
+  int64_t rpt = cdiv(rows, (int64_t)Ry * max_blocks);   // rows per thread
+  if (rpt < 4) rpt = 4;
+  int64_t rpb = (int64_t)Ry * rpt;
   int64_t nb = cdiv(rows, rpb);
-  if (nb > 148 * 8) {
-    nb = 148 * 8;
-    rpb = round_up(cdiv(rows, nb), Ry);
-    nb = cdiv(rows, rpb);
-  }
   g.grid = (unsigned)(nb < 1 ? 1 : nb);
   g.rows_per_block = rpb;
   g.smem = (size_t)Ry * nv * C * sizeof(float);
@@ -223,7 +265,7 @@ using namespace vinet;
 
 extern "C" int vinet_bn_stats(const vinet_bn_stats_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_stats: C %d", d->C);
-  ColGrid g = col_grid(d->rows, d->C, 2);
+  ColGrid g = col_grid(d->rows, d->C, 2, true);
   VINET_DISPATCH_DTYPE(d->dtype, T, {
     if (g.smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     bn_stats_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
@@ -232,11 +274,23 @@ extern "C" int vinet_bn_stats(const vinet_bn_stats_t* d, vinet_stream_t stream) 
   return 0;
 }
 
+extern "C" int vinet_bn_stats_finalize(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024 && f->C == d->C && f->sums == d->sums && f->training, "bn_stats_finalize: C %d / %d", d->C, f->C);
+  ColGrid g = col_grid(d->rows, d->C, 2, true);
+  VINET_DISPATCH_DTYPE(d->dtype, T, {
+    if (g.smem > 48 * 1024)
+      cudaFuncSetAttribute(bn_stats_finalize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    bn_stats_finalize_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, *f, g.rows_per_block);
+  });
+  VINET_LAUNCH_OK("bn_stats_finalize");
+  return 0;
+}
+
 extern "C" int vinet_colsum(const void* x, int64_t ld, int32_t dtype, int64_t rows, int32_t C, double* ws, float* out,
                             vinet_stream_t stream) {
   VINET_CHECK(C % 8 == 0 && C <= 1024, "colsum: C %d", C);
   cudaMemsetAsync(ws, 0, sizeof(double) * C, (cudaStream_t)stream);
-  ColGrid g = col_grid(rows, C, 1);
+  ColGrid g = col_grid(rows, C, 1, true);
   VINET_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(
                                      reinterpret_cast<const T*>(x), ld, rows, C, ws, g.rows_per_block)));
   VINET_LAUNCH_OK("colsum");
@@ -254,7 +308,7 @@ extern "C" int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t st
 extern "C" int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0, "bn_apply: C %d", d->C);
   VINET_CHECK(d->C <= 1024, "bn_apply: C %d", d->C);
-  ColGrid g = col_grid(d->rows, d->C, 0);
+  ColGrid g = col_grid(d->rows, d->C, 0, false);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
       (bn_apply_kernel<T, TO><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(*d, g.rows_per_block))));
   VINET_LAUNCH_OK("bn_apply");
@@ -263,21 +317,19 @@ extern "C" int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream) 
 
 extern "C" int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd: C %d", d->C);
-  ColGrid g = col_grid(d->rows, d->C, 2);
+  ColGrid g = col_grid(d->rows, d->C, 2, true);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->g_dtype, TG, {
     if (g.smem > 48 * 1024)
       cudaFuncSetAttribute(bn_bwd_reduce_kernel<T, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     bn_bwd_reduce_kernel<T, TG><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, g.rows_per_block);
   }));
-  VINET_LAUNCH_OK("bn_bwd_reduce");
-  bn_bwd_finish_kernel<<<(unsigned)cdiv(d->C, 128), 128, 0, (cudaStream_t)stream>>>(d->sums, d->dgamma, d->dbeta, d->C);
-  VINET_LAUNCH_OK("bn_bwd_finish");
+  VINET_LAUNCH_OK("bn_bwd_reduce");   // the last block to finish writes dgamma / dbeta and clears the sums (no finish launch)
   return 0;
 }
 
 extern "C" int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd_apply: C %d", d->C);
-  ColGrid g = col_grid(d->rows, d->C, 0);
+  ColGrid g = col_grid(d->rows, d->C, 0, false);
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, VINET_DISPATCH_DTYPE(d->g_dtype, TG,
       (bn_bwd_apply_kernel<T, TD, TG><<<g.grid, g.block, 0, (cudaStream_t)stream>>>(*d, g.rows_per_block)))));
   VINET_LAUNCH_OK("bn_bwd_apply");

@@ -441,12 +441,17 @@ class Engine:
         fin.training = 1 if self.training else 0
         fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
         if self.training:
-            sums = self.buf(name_bn + ".sums", (2, Cn), torch.float64, zero=True)
+            sums = self.buf(name_bn + ".sums", (2 * Cn + 1,), torch.float64, zero=True)    # [2][C] sums + one ticket
             sd = L.BnStats()
             sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
-            self.call("vinet_bn_stats", sd)
             fin.sums = sums.data_ptr()
-        self.call("vinet_bn_finalize", fin)
+            if "vinet_bn_stats_finalize" in self.lib.fn:        # one launch: the last block finalises
+                self.lib.call("vinet_bn_stats_finalize", C.byref(sd), C.byref(fin), self.stream())
+            else:
+                self.call("vinet_bn_stats", sd)
+                self.call("vinet_bn_finalize", fin)
+        else:
+            self.call("vinet_bn_finalize", fin)
         if self.training:
             self.bn_counters.append(bn.num_batches_tracked)   # += 1 for all layers in one launch (end_forward)
         return st, ss
@@ -466,7 +471,7 @@ class Engine:
         training = self.training
 
         def backward():
-            bsums = self.buf(name_bn + ".bsums", (2, Cn), torch.float64, zero=True)
+            bsums = self.buf(name_bn + ".bsums", (2 * Cn + 1,), torch.float64, zero=True)        # [2][C] sums + one ticket
             dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
             if dy_slot is None:
                 dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)

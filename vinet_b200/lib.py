@@ -139,6 +139,7 @@ SIGNATURES = {
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
+    "vinet_bn_stats_finalize": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _S]),
     "vinet_bn_apply": (C.c_int, [C.POINTER(BnApply), _S]),
     "vinet_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
