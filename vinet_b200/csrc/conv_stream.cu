@@ -517,6 +517,7 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
   const bool spatial = tm.eh0 != 0 || tm.eh1 != 0 || tm.ew0 != 0 || tm.ew1 != 0;
   if (!spatial && tm.ntg <= 1) return best;   // a 1x1x1 conv has nothing to re-use: conv_tma.cu's kernel is the right one
   if (spatial && g.Hr < 10) return best;      // 16-row halo tiles waste most of a 7-row map
+  if (!spatial && tm.S > 1) return best;      // temporally strided frame walks (stem conv_t fprop) measured slower than per-tap boxes
   const int ncb = (g.Cs + 63) / 64;
   int nk_sum = 0;
   for (int cb = 0; cb < ncb; ++cb) {

@@ -43,6 +43,24 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+__device__ __forceinline__ bool tma_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with both shared-memory descriptors given as (low, high) 32-bit words
+__device__ __forceinline__ void tma_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 struct ConvTmaParams {
   CUtensorMap tmA[2];  // the two sources of the virtual T-concat (tmA[1] == tmA[0] without a concat)
   vinet_conv_t d;
@@ -182,7 +200,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+    // ---------------------------------------------------------------- MMA issuer: warp-uniform loop, one elected lane issues;
+    // 32-bit descriptor words (the high words are loop constants) keep the issue sequence short enough for N <= 128 MMAs
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, descriptor version 1, SWIZZLE_128B
+    const uint32_t sA_lo = ((sA0 & 0x3FFFFu) >> 4) | (1u << 16), sB_lo = ((sB0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_stage16 = p.a_stage >> 4, b16 = p.b_bytes >> 4, idesc = p.idesc;
     int s = 0;
     uint32_t ph = 0, lt = 0;
     if (p.wres) mbar_wait(wbar, 0);
@@ -200,25 +222,30 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         for (int cb = 0; cb < p.ncb; ++cb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          if (lane == 0) {
-            const int rem = g.Cs - cb * 64;
-            const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
-            const uint32_t b_stage = sB0 + (uint32_t)(p.wres ? tap * p.ncb + cb : s) * p.b_bytes;
-            for (int hf = 0; hf < ic.nh; ++hf) {
-              const uint32_t a_stage = sA0 + (uint32_t)s * p.a_stage + (uint32_t)hf * TC_A_BYTES;
-              for (int kk = 0; kk < nk; ++kk)
-                umma_bf16(tacc + (uint32_t)hf * p.acc_stride, desc_kmajor_sw128(a_stage + kk * 32, 0),
-                          desc_kmajor_sw128(b_stage + kk * 32, 0), p.idesc, acc | (uint32_t)(kk != 0));
+          const int rem = g.Cs - cb * 64;
+          const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+          const uint32_t b_lo = sB_lo + (uint32_t)(p.wres ? tap * p.ncb + cb : s) * b16;
+          uint32_t a_lo = sA_lo + (uint32_t)s * a_stage16;
+          uint32_t td = tacc;
+          for (int hf = 0; hf < ic.nh; ++hf, a_lo += (TC_A_BYTES >> 4), td += p.acc_stride) {
+            if (tma_elect_one()) {
+              tma_umma(td, a_lo, hi, b_lo, hi, idesc, acc);
+              if (nk == 4) {
+                tma_umma(td, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+                tma_umma(td, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+                tma_umma(td, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+              } else {
+                if (nk > 1) tma_umma(td, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+                if (nk > 2) tma_umma(td, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+              }
             }
-            acc = 1;
-            umma_commit(empty0 + 8 * s);
           }
-          __syncwarp();
+          acc = 1;
+          if (tma_elect_one()) umma_commit(empty0 + 8 * s);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
-      if (lane == 0) umma_commit(tfull0 + 8 * as);
-      __syncwarp();
+      if (tma_elect_one()) umma_commit(tfull0 + 8 * as);
       ++lt;
     }
   } else {
@@ -391,28 +418,33 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
       }
     }
   } else if (warp == 1) {
+    // MMA issuer: warp-uniform loop, elected lane, 32-bit descriptor words (MN-major: LBO = unit_bytes between 64-wide blocks)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t lbo = (p.unit_bytes >> 4) << 16;
+    const uint32_t unit16 = p.unit_bytes >> 4, stage16 = p.stage_bytes >> 4, idesc = p.idesc;
+    const uint32_t s0_16 = (s0 & 0x3FFFFu) >> 4;
+    const int ksteps = p.R / 16;
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, st16 = s0_16;
     for (int kb = 0; kb < KB; ++kb) {
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_stage = s0 + (uint32_t)s * p.stage_bytes;
-        const uint32_t b_stage = a_stage + (uint32_t)upc * p.unit_bytes;
-        for (int mbi = 0; mbi < nmb; ++mbi) {
-          const uint32_t a_mb = a_stage + (uint32_t)(2 * mbi) * p.unit_bytes;
-          const uint32_t tacc = tmem_base + (uint32_t)mbi * p.acc_cols;
-          for (int kk = 0; kk < p.R / 16; ++kk) {
-            // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B; 64-wide MN blocks unit_bytes apart
-            umma_bf16(tacc, desc_mnmajor_sw128(a_mb + kk * 2048, p.unit_bytes, 0),
-                      desc_mnmajor_sw128(b_stage + kk * 2048, p.unit_bytes, 0), p.idesc, (uint32_t)((kb | kk) != 0));
-          }
+      const uint32_t b_lo0 = (st16 + (uint32_t)upc * unit16) | lbo;
+      for (int mbi = 0; mbi < nmb; ++mbi) {
+        const uint32_t a_lo0 = (st16 + (uint32_t)(2 * mbi) * unit16) | lbo;
+        const uint32_t tacc = tmem_base + (uint32_t)mbi * p.acc_cols;
+        if (tma_elect_one()) {
+          // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B
+          for (int kk = 0; kk < ksteps; ++kk)
+            tma_umma(tacc, a_lo0 + (uint32_t)kk * 128u, hi, b_lo0 + (uint32_t)kk * 128u, hi, idesc, (uint32_t)((kb | kk) != 0));
         }
+      }
+      if (tma_elect_one()) {
         umma_commit(empty0 + 8 * s);
         if (kb == KB - 1) umma_commit(accum_bar);
       }
-      __syncwarp();
-      if (++s == stages) { s = 0; ph ^= 1u; }
+      st16 += stage16;
+      if (++s == stages) { s = 0; ph ^= 1u; st16 = s0_16; }
     }
   } else {
     mbar_wait(accum_bar, 0);  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
