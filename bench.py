@@ -112,8 +112,8 @@ def kernel_roofline(model, x, gt, kldiv, torch):
     loss.backward()
     torch.cuda.synchronize()
     rows = []
-    for name, kind, flops, e0, e1 in eng.profile:
-        rows.append({"name": name, "kind": kind, "gflop": flops / 1e9, "ms": e0.elapsed_time(e1)})
+    for name, kind, flops, e0, e1, kern in eng.profile:
+        rows.append({"name": name, "kind": kind, "gflop": flops / 1e9, "ms": e0.elapsed_time(e1), "kernel": kern})
     eng.profile, eng.l2_flush = None, None
     for p in model.parameters():
         p.grad = None
@@ -225,20 +225,27 @@ def main():
     table = kernel_roofline(model, dx.permute(0, 2, 1, 3, 4), dgt, kldiv, torch) if world == 1 else []
     roof = None
     if table:
-        dom = max(table, key=lambda r: (r["gflop"], -r["ms"]))
+        # dominant kernel = the CUDA kernel with the largest total time over the step's conv launches; its roofline entry
+        # is that kernel's largest launch, timed alone (L2 flushed) with CUDA events on the launching stream
+        by_kernel = {}
+        for r in table:
+            by_kernel[r["kernel"]] = by_kernel.get(r["kernel"], 0.0) + r["ms"]
+        dom_kernel = max(by_kernel, key=by_kernel.get)
+        dom = max((r for r in table if r["kernel"] == dom_kernel), key=lambda r: (r["gflop"], -r["ms"]))
         tot_ms = sum(r["ms"] for r in table)
-        traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        key = "%s/%s:%s" % (dom_kernel, dom["kind"], dom["name"])
+        traffic = None          # DRAM bytes per launch of that kernel from the committed ncu --set full capture (B=8)
         tk = os.path.join(ROOT, "profiles", "r1_top_kernel.json")
-        if os.path.isfile(tk):
-            j = json.load(open(tk))
-            if j.get(dom["kind"]) and dom["name"].endswith("convtsp3.0") and B == 8:
-                traffic = j[dom["kind"]]["traffic_bytes"]
-        kname = {"fprop": "conv_gemm_tma_kernel", "dgrad": "conv_gemm_tma_kernel", "wgrad": "conv_wgrad_tma_kernel"}[dom["kind"]]
+        if os.path.isfile(tk) and B == 8:
+            traffic = (json.load(open(tk)).get("captures", {}).get(key) or {}).get("traffic_bytes")
         roof = {"bound": "tensor", "achieved": dom["gflop"] / dom["ms"], "peak": burst, "unit": "TFLOP/s",
-                "frac": dom["gflop"] / dom["ms"] / burst, "traffic": traffic, "kernel": "%s/%s:%s" % (kname, dom["kind"], dom["name"]),
+                "frac": dom["gflop"] / dom["ms"] / burst, "traffic": traffic, "kernel": key,
+                "kernel_share_of_conv_time": by_kernel[dom_kernel] / tot_ms,
                 "peak_source": src + " burst bf16 (kernel timed alone, L2 flushed)",
+                "algorithmic_gflop_per_launch": dom["gflop"], "launch_ms": dom["ms"],
                 "conv_kernels_gflop": sum(r["gflop"] for r in table), "conv_kernels_ms_isolated": tot_ms,
                 "conv_kernels_tflops": sum(r["gflop"] for r in table) / tot_ms,
+                "conv_ms_by_kernel": {k: round(v, 3) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
                 "step_tflops": value * FWD_BWD_GFLOP / 1e3, "step_frac_of_sustained": value * FWD_BWD_GFLOP / 1e3 / world / sustained}
         if args.kernel_table:
             json.dump(table, open(args.kernel_table, "w"), indent=0)

@@ -390,6 +390,8 @@ int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t accumulate, 
 int vinet_colsum(const void* x, int64_t ld, int32_t dtype, int64_t rows, int32_t C, double* ws, float* out,
                  vinet_stream_t stream);
 const char* vinet_last_error(void);
+/* name of the CUDA kernel the calling thread's last vinet_conv_gemm / vinet_conv_wgrad launched (measurement aid) */
+const char* vinet_last_kernel(void);
 const char* vinet_version(void);
 int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* sizeof() of every struct above, in declaration order (host-only; lets a binding check its layout) */

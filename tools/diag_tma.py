@@ -148,7 +148,7 @@ def child_perf():
                 bwd(dy.data_ptr(), out.C)
             torch.cuda.synchronize()
             agg = {}
-            for label, kind, flops, e0, e1 in e.profile:
+            for label, kind, flops, e0, e1, _kern in e.profile:
                 ms, fl = agg.get(kind, (0.0, 0.0))
                 agg[kind] = (ms + e0.elapsed_time(e1), fl + flops)
             gf = agg["fprop"][1] / 1e9

@@ -23,7 +23,7 @@ def launches():
         cnt[name] += 1
     s = sum(tot.values())
     out = ["# %s: ncu launch list of one training step (B=8 x 32x224x384, bf16), gpu__time_duration.sum" % R,
-           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 800 --csv python bench.py --steps 1 --warmup 3",
+           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
            "# per-launch times are cold-cache and serialised: compare SHARES. %d launches, %.2f ms" % (len(rows), s),
            "%-40s %7s %10s %7s" % ("kernel", "count", "ms", "share")]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
@@ -80,11 +80,21 @@ if __name__ == "__main__":
     s = launches()
     B = 8
     fl = 2.0 * B * 4 * 28 * 48 * (5 * 9 * 480) * 192          # decoder.convtsp3.0, SURVEY Appendix A x B
-    a = ncu_summary("prof_tsp3_fprop.ncu-rep", "dominant conv launch: decoder.convtsp3.0 fprop (conv_gemm_tma_kernel), B=8", fl)
-    b = ncu_summary("prof_tsp3_wgrad.ncu-rep", "decoder.convtsp3.0 wgrad (conv_wgrad_tma_kernel), B=8", fl)
-    json.dump({"round": R, "dominant_kernel": "conv_gemm_tma_kernel/fprop:decoder.convtsp3.0", "fprop": a, "wgrad": b},
+    fl13 = 2.0 * B * 16 * 56 * 96 * (9 * 64) * 192            # backbone.base1.3.conv_s
+    caps = {}
+    for rep, key, title, flops in [
+            ("prof_tsp3_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp3.0",
+             "dominant kernel, largest launch: decoder.convtsp3.0 fprop (conv_stream_kernel: halo tiles, 3 sub-tiles, 3 issuing warps), B=8", fl),
+            ("prof_tsp3_wgrad.ncu-rep", "conv_wgrad_halo_kernel/wgrad:decoder.convtsp3.0",
+             "decoder.convtsp3.0 wgrad (conv_wgrad_halo_kernel), B=8", fl),
+            ("prof_b13s_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.3.conv_s",
+             "SepConv3d stack: backbone.base1.3.conv_s fprop (conv_stream_kernel), B=8", fl13)]:
+        r = ncu_summary(rep, title, flops)
+        if r:
+            caps[key] = r
+    json.dump({"round": R, "dominant_kernel": "conv_stream_kernel/fprop:decoder.convtsp3.0", "captures": caps},
               open(os.path.join(P, "%s_top_kernel.json" % R), "w"), indent=1)
     for f in ("profile_step.log", "diag_tma.log"):
         if os.path.isfile(os.path.join(G, f)):
             open(os.path.join(P, "%s_%s" % (R, f.replace(".log", ".txt"))), "w").write(open(os.path.join(G, f)).read())
-    print("launch list total %.2f ms; top kernel" % s, a)
+    print("launch list total %.2f ms; captures" % s, caps)

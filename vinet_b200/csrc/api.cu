@@ -8,6 +8,8 @@ namespace vinet {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+static thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -103,6 +105,7 @@ extern "C" int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t a
 }
 
 extern "C" const char* vinet_last_error(void) { return g_err; }
+extern "C" const char* vinet_last_kernel(void) { return g_last_kernel; }
 extern "C" const char* vinet_version(void) { return "vinet_b200 0.2 (sm_100a; TMA-fed persistent tcgen05+TMEM conv, fp32 SIMT parity engine)"; }
 extern "C" int64_t vinet_launch_count(void) { return (int64_t)g_launches.load(); }
 

@@ -131,6 +131,7 @@ int conv_gemm_simt(const vinet_conv_t* d, cudaStream_t stream) {
   dim3 grid((unsigned)cdiv(M, SM_BM), (unsigned)(npad / SM_BN));
   VINET_DISPATCH_DTYPE(d->g.dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO,
       (conv_gemm_simt_kernel<T, TO><<<grid, 256, 0, stream>>>(*d, npad))));
+  note_kernel("conv_gemm_simt_kernel");
   VINET_LAUNCH_OK("conv_gemm_simt");
   return 0;
 }
@@ -140,6 +141,7 @@ int conv_wgrad_simt(const vinet_wgrad_t* d, cudaStream_t stream) {
   dim3 grid((unsigned)cdiv(mw, SM_BM), (unsigned)cdiv(d->N, SM_BN), (unsigned)d->splits);
   VINET_DISPATCH_DTYPE(d->g.dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD,
       (conv_wgrad_simt_kernel<T, TD><<<grid, 256, 0, stream>>>(*d))));
+  note_kernel("conv_wgrad_simt_kernel");
   VINET_LAUNCH_OK("conv_wgrad_simt");
   return 0;
 }

@@ -744,6 +744,7 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   } while (0)
   VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_STREAM(TO));
 #undef LAUNCH_STREAM
+  note_kernel("conv_stream_kernel");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -404,6 +404,7 @@ int conv_gemm_tc(const vinet_conv_t* d, cudaStream_t stream) {
   } while (0)
   VINET_DISPATCH_DTYPE(d->g.dtype, T, VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_GEMM(T, TO)));
 #undef LAUNCH_GEMM
+  note_kernel("conv_gemm_tc_kernel");
   VINET_LAUNCH_OK("conv_gemm_tc");
   return 0;
 }
@@ -431,6 +432,7 @@ int conv_wgrad_tc(const vinet_wgrad_t* d, cudaStream_t stream) {
   } while (0)
   VINET_DISPATCH_DTYPE(d->g.dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, LAUNCH_WGRAD(T, TD)));
 #undef LAUNCH_WGRAD
+  note_kernel("conv_wgrad_tc_kernel");
   VINET_LAUNCH_OK("conv_wgrad_tc");
   return 0;
 }

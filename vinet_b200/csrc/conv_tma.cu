@@ -659,6 +659,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   } while (0)
   VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_TMA(TO));
 #undef LAUNCH_TMA
+  note_kernel("conv_gemm_tma_kernel");
   VINET_LAUNCH_OK("conv_gemm_tma");
   return 0;
 }
@@ -722,6 +723,7 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   conv_wgrad_tma_kernel<<<grid, TMA_WGRAD_THREADS, smem, stream>>>(p);
+  note_kernel("conv_wgrad_tma_kernel");
   VINET_LAUNCH_OK("conv_wgrad_tma");
   return 0;
 }

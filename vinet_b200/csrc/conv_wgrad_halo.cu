@@ -294,6 +294,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   dim3 grid((unsigned)(kt * p.ncb), (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   conv_wgrad_halo_kernel<<<grid, WH_THREADS, smem, stream>>>(p);
+  note_kernel("conv_wgrad_halo_kernel");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -157,7 +157,8 @@ class Engine:
         e0.record()
         fn()
         e1.record()
-        self.profile.append((label, kind, flops, e0, e1))
+        kern = self.lib.fn["vinet_last_kernel"]().decode() if "vinet_last_kernel" in self.lib.fn else ""
+        self.profile.append((label, kind, flops, e0, e1, kern))
 
     def memset(self, t):
         self.lib.call("vinet_memset_async", t.data_ptr(), 0, t.numel() * t.element_size(), self.stream())

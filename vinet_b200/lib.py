@@ -161,6 +161,7 @@ SIGNATURES = {
     "vinet_axpy_f32": (C.c_int, [_p, _p, _i64, _i32, _S]),
     "vinet_colsum": (C.c_int, [_p, _i64, _i32, _i64, _i32, _p, _p, _S]),
     "vinet_last_error": (C.c_char_p, []),
+    "vinet_last_kernel": (C.c_char_p, []),
     "vinet_version": (C.c_char_p, []),
     "vinet_device_info": (C.c_int, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_launch_count": (_i64, []),
