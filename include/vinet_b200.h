@@ -236,6 +236,11 @@ typedef struct vinet_bn_bwd {
 } vinet_bn_bwd_t;
 int vinet_bn_bwd_reduce(const vinet_bn_bwd_t* d, vinet_stream_t stream);
 int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream);
+/* Whole-layer variants (one cooperative launch each): training forward = stats + finalize + apply, backward = reduce + apply.
+ * The blocks reduce, the last one finalises and raises a flag, all of them then apply to the rows they have just read.
+ * The sums buffers hold [2][C] doubles followed by THREE 8-byte words (ticket, flag, departures), zero between launches. */
+int vinet_bn_fwd_fused(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, const vinet_bn_apply_t* a, vinet_stream_t stream);
+int vinet_bn_bwd_fused(const vinet_bn_bwd_t* d, vinet_stream_t stream);
 
 /* ---- nn.MaxPool3d (model.py:696-714, model_utils.py:178...; model.py:229) ---- */
 typedef struct vinet_pool {
@@ -257,7 +262,9 @@ typedef struct vinet_pool {
   int64_t ldgi;
   int32_t gout_dtype, gin_dtype;
   uint8_t* idx; /* optional [B,To,Ho,Wo,C] bytes: forward records the winning tap ((dt*kh+dh)*kw+dw, first maximum in
-                   scan order), backward scatters with it; NULL: backward recomputes the arg-max */
+                   scan order) and backward scatters with it (or gathers per input element, vinet_debug_set key 3);
+                   NULL: backward recomputes the arg-max */
+  int32_t gin_overwrite; /* backward: 1 = gin is written (the pool is the first writer of that gradient), 0 = gin += */
 } vinet_pool_t;
 int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream);
 int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream);
@@ -399,7 +406,7 @@ int vinet_abi_sizes(int64_t* out, int32_t n);
 /* development switches (key 0: tcgen05 descriptor-encoding experiments, csrc/conv_tc.cu, 0 in production;
  * key 1: paired 256-row work items of the TMA conv kernel, 1 in production;
  * key 2: the streaming (halo / frame re-use) conv kernels of csrc/conv_stream.cu and conv_wgrad_halo.cu, 1 in production;
- * key 3: the frame-walking 3x3x3 max-pool kernel, 1 in production) */
+ * key 3: max-pool kernels, bit 0 = frame-walking 3x3x3 forward, bit 1 = gather (atomic-free) backward; 1 in production) */
 int vinet_debug_set(int32_t key, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vinet_launch_count(void);

@@ -273,6 +273,8 @@ class Spec:
         n_out = d.B * d.To * d.Ho * d.Wo
         g = _rows_view(d.gout, n_out, d.ldgo, d.C)
         gin = _rows_view(d.gin, d.B * d.Ti * d.Hi * d.Wi, d.ldgi, d.C)
+        if d.gin_overwrite:
+            gin[:] = 0
         arg = arg.reshape(n_out, d.C)
         cc = np.broadcast_to(np.arange(d.C), arg.shape)
         ok = arg >= 0

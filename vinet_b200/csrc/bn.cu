@@ -169,6 +169,144 @@ __global__ void bn_bwd_reduce_kernel(const __grid_constant__ vinet_bn_bwd_t d, i
   }
 }
 
+// ---- whole-layer kernels (cooperative launch: every block is resident) ------------------------------------------------------------
+// A BatchNorm layer is reduce -> (tiny) finalise -> element-wise apply.  Most of the 77 layers of this model are small (a few
+// MB), so three dependent launches cost more in latency than in bandwidth.  Here one launch does all three: every block reduces
+// its rows, the last block to arrive finalises and raises a flag, every block waits for the flag and applies to the SAME rows
+// (which it has just pulled through L2).  Flag protocol after the sums: [ticket][flag][departures], all zero between launches.
+__device__ __forceinline__ void grid_wait_flag(double* sums, int nv_c, bool last) {
+  unsigned long long* flag = reinterpret_cast<unsigned long long*>(sums + nv_c + 1);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (last) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(flag, 1ull);
+  }
+  if (tid == 0) {
+    unsigned ns = 32;
+    while (atomicAdd(flag, 0ull) == 0ull) {
+      __nanosleep(ns);
+      if (ns < 1024) ns *= 2;
+    }
+  }
+  __syncthreads();
+  __threadfence();
+}
+__device__ __forceinline__ void grid_depart(double* sums, int nv_c) {
+  unsigned long long* flag = reinterpret_cast<unsigned long long*>(sums + nv_c + 1);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long t = atomicAdd(flag + 1, 1ull);
+    if (t == (unsigned long long)gridDim.x - 1) {   // everyone has seen the flag: leave the words clean for the next launch
+      flag[1] = 0ull;
+      __threadfence();
+      atomicExch(flag, 0ull);
+    }
+  }
+}
+
+template <typename T, typename TO>
+__global__ void bn_fwd_fused_kernel(const __grid_constant__ vinet_bn_stats_t d, const __grid_constant__ vinet_bn_finalize_t f,
+                                    const __grid_constant__ vinet_bn_apply_t a, int64_t rows_per_block) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const bool last = column_reduce<2, true>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8];
+    load8(y + r * d.ld + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += v[e];
+      acc[1][e] = fmaf(v[e], v[e], acc[1][e]);
+    }
+  });
+  if (last)
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < f.C; c += blockDim.x * blockDim.y) bn_finalize_channel(f, c);
+  grid_wait_flag(d.sums, 2 * d.C, last);
+  // ---- apply to this block's rows
+  TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
+  const int c = threadIdx.x * 8, Ry = blockDim.y;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = __ldcg(a.scale + c + e); sh[e] = __ldcg(a.shift + c + e); }
+  const bool relu = a.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(a.rows, r_begin + rows_per_block);
+#pragma unroll 4
+  for (int64_t r = r_begin + threadIdx.y; r < r_end; r += Ry) {
+    float v[8];
+    load8(y + r * a.ldy + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = fmaf(v[e], sc[e], sh[e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
+    store8(out + r * a.ldo + c, v);
+  }
+  grid_depart(d.sums, 2 * d.C);
+}
+
+template <typename T, typename TD, typename TG>
+__global__ void bn_bwd_fused_kernel(const __grid_constant__ vinet_bn_bwd_t d, int64_t rows_per_block) {
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
+  TD* __restrict__ dy = reinterpret_cast<TD*>(d.dy);
+  const int c = threadIdx.x * 8, Ry = blockDim.y;
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e);
+    mu[e] = __ldg(d.mean + c + e); is[e] = __ldg(d.invstd + c + e);
+  }
+  const bool relu = d.relu != 0;
+  const bool last = column_reduce<2, true>(d.rows, d.C, rows_per_block, d.sums, [&](int64_t r, int cc, float (&acc)[2][8]) {
+    float v[8], g[8];
+    load8(y + r * d.ldy + cc, v);
+    load8(gp + r * d.ldg + cc, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
+      acc[0][e] += gm;
+      acc[1][e] = fmaf(gm, yn, acc[1][e]);
+    }
+  });
+  if (last) {
+    volatile double* vs = d.sums;
+    for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < d.C; ch += blockDim.x * blockDim.y) {
+      d.dbeta[ch] = (float)vs[ch];
+      d.dgamma[ch] = (float)vs[d.C + ch];
+      d.sums[ch] = 0.0;
+      d.sums[d.C + ch] = 0.0;
+    }
+  }
+  grid_wait_flag(d.sums, 2 * d.C, last);
+  const float inv_n = 1.0f / (float)d.rows;
+  float k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    k1[e] = d.training ? __ldcg(d.dbeta + c + e) * inv_n : 0.f;
+    k2[e] = d.training ? __ldcg(d.dgamma + c + e) * inv_n : 0.f;
+  }
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(d.rows, r_begin + rows_per_block);
+#pragma unroll 4
+  for (int64_t r = r_begin + threadIdx.y; r < r_end; r += Ry) {
+    float v[8], g[8], o[8];
+    load8(y + r * d.ldy + c, v);
+    load8(gp + r * d.ldg + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
+      o[e] = sc[e] * (gm - k1[e] - yn * k2[e]);
+    }
+    store8(dy + r * d.lddy + c, o);
+  }
+  grid_depart(d.sums, 2 * d.C);
+}
+
 // Elementwise passes use the same (channel group, row) thread layout as the reductions: a thread owns 8 channels,
 // keeps their per-channel constants in registers and walks rows with several 128-bit loads in flight.
 template <typename T, typename TD, typename TG>
@@ -283,6 +421,64 @@ extern "C" int vinet_bn_stats_finalize(const vinet_bn_stats_t* d, const vinet_bn
     bn_stats_finalize_kernel<T><<<g.grid, g.block, g.smem, (cudaStream_t)stream>>>(*d, *f, g.rows_per_block);
   });
   VINET_LAUNCH_OK("bn_stats_finalize");
+  return 0;
+}
+
+// grid of a cooperative whole-layer kernel: col_grid capped at what can be resident at once
+template <typename K>
+static int coop_grid(K kernel, ColGrid* g, int64_t rows, const char* what) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g->smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(g->block.x * g->block.y), g->smem);
+  VINET_CHECK(e == cudaSuccess && per_sm >= 1 && sms >= 1, "%s: occupancy query failed", what);
+  const int64_t cap = (int64_t)per_sm * sms;
+  if ((int64_t)g->grid > cap) {
+    const int64_t Ry = g->block.y;
+    g->rows_per_block = round_up(cdiv(rows, cap), Ry);
+    g->grid = (unsigned)cdiv(rows, g->rows_per_block);
+  }
+  return 0;
+}
+
+extern "C" int vinet_bn_fwd_fused(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, const vinet_bn_apply_t* a,
+                                  vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024 && f->C == d->C && a->C == d->C && f->sums == d->sums && f->training &&
+              a->y == d->y && a->ldy == d->ld && a->rows == d->rows && a->dtype == d->dtype, "bn_fwd_fused: inconsistent descriptors");
+  ColGrid g = col_grid(d->rows, d->C, 2, true);
+  int64_t rpb = 0;
+#define LAUNCH_FWD(T, TO)                                                                             \
+  do {                                                                                                \
+    if (coop_grid(bn_fwd_fused_kernel<T, TO>, &g, d->rows, "bn_fwd_fused")) return -1;                \
+    rpb = g.rows_per_block;                                                                           \
+    void* args[] = {(void*)d, (void*)f, (void*)a, (void*)&rpb};                                       \
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_kernel<T, TO>, dim3(g.grid), g.block, args, g.smem, \
+                                                (cudaStream_t)stream);                                \
+    VINET_CHECK(e == cudaSuccess, "bn_fwd_fused: cooperative launch failed: %s", cudaGetErrorString(e)); \
+  } while (0)
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(a->out_dtype, TO, LAUNCH_FWD(T, TO)));
+#undef LAUNCH_FWD
+  VINET_LAUNCH_OK("bn_fwd_fused");
+  return 0;
+}
+
+extern "C" int vinet_bn_bwd_fused(const vinet_bn_bwd_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->C % 8 == 0 && d->C <= 1024, "bn_bwd_fused: C %d", d->C);
+  ColGrid g = col_grid(d->rows, d->C, 2, true);
+  int64_t rpb = 0;
+#define LAUNCH_BWD(T, TD, TG)                                                                         \
+  do {                                                                                                \
+    if (coop_grid(bn_bwd_fused_kernel<T, TD, TG>, &g, d->rows, "bn_bwd_fused")) return -1;            \
+    rpb = g.rows_per_block;                                                                           \
+    void* args[] = {(void*)d, (void*)&rpb};                                                           \
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<T, TD, TG>, dim3(g.grid), g.block, args, g.smem, \
+                                                (cudaStream_t)stream);                                \
+    VINET_CHECK(e == cudaSuccess, "bn_bwd_fused: cooperative launch failed: %s", cudaGetErrorString(e)); \
+  } while (0)
+  VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, VINET_DISPATCH_DTYPE(d->g_dtype, TG, LAUNCH_BWD(T, TD, TG))));
+#undef LAUNCH_BWD
+  VINET_LAUNCH_OK("bn_bwd_fused");
   return 0;
 }
 

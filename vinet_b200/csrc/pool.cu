@@ -293,6 +293,62 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __grid_constant_
   }
 }
 
+// Backward as a GATHER over the recorded arg-max taps: one thread = one INPUT position x 8 channels.  It visits the (at most
+// ceil(k/s)^3) windows that contain the position, compares their recorded tap bytes with the tap this position would be in
+// that window, and sums the matching output gradients.  No atomics (deterministic), no zero-initialised gradient buffer.
+template <typename TGO, typename TGI>
+__global__ void __launch_bounds__(256) maxpool_bwd_gather_kernel(const __grid_constant__ vinet_pool_t d) {
+  const int G = d.C / 8;
+  const int64_t total = (int64_t)d.B * d.Ti * d.Hi * d.Wi * G;
+  const TGO* __restrict__ gout = reinterpret_cast<const TGO*>(d.gout);
+  TGI* __restrict__ gin = reinterpret_cast<TGI*>(d.gin);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % G) * 8; r /= G;
+    const int w = (int)(r % d.Wi); r /= d.Wi;
+    const int h = (int)(r % d.Hi); r /= d.Hi;
+    const int t = (int)(r % d.Ti);
+    const int b = (int)(r / d.Ti);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // windows (to, ho, wo) containing (t, h, w): to*st - pt <= t < to*st - pt + kt
+    const int to_hi = min(d.To - 1, (t + d.pt) / d.st), to_lo = max(0, (t + d.pt - d.kt + d.st) / d.st);
+    const int ho_hi = min(d.Ho - 1, (h + d.ph) / d.sh), ho_lo = max(0, (h + d.ph - d.kh + d.sh) / d.sh);
+    const int wo_hi = min(d.Wo - 1, (w + d.pw) / d.sw), wo_lo = max(0, (w + d.pw - d.kw + d.sw) / d.sw);
+    for (int to = to_lo; to <= to_hi; ++to) {
+      const int dt = t + d.pt - to * d.st;
+      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        const int dh = h + d.ph - ho * d.sh;
+        const int64_t orow = (((int64_t)b * d.To + to) * d.Ho + ho) * d.Wo;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          const int dw = w + d.pw - wo * d.sw;
+          const unsigned tap = (unsigned)((dt * d.kh + dh) * d.kw + dw);
+          const unsigned tap4 = tap * 0x01010101u;
+          const uint2 pk = __ldg(reinterpret_cast<const uint2*>(d.idx + (orow + wo) * d.C + c));
+          const unsigned m0 = __vcmpeq4(pk.x, tap4), m1 = __vcmpeq4(pk.y, tap4);
+          if ((m0 | m1) == 0u) continue;
+          float g[8];
+          load8(gout + (orow + wo) * d.ldgo + c, g);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((m0 >> (8 * e)) & 1u) acc[e] += g[e];
+            if ((m1 >> (8 * e)) & 1u) acc[4 + e] += g[4 + e];
+          }
+        }
+      }
+    }
+    TGI* dst = gin + ((((int64_t)b * d.Ti + t) * d.Hi + h) * d.Wi + w) * d.ldgi + c;
+    if (!d.gin_overwrite) {
+      float o[8];
+      load8(dst, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += o[e];
+    }
+    store8(dst, acc);
+  }
+}
+
 }  // namespace vinet
 using namespace vinet;
 
@@ -310,12 +366,13 @@ static int pool_check(const vinet_pool_t* d) {
 }
 
 namespace vinet {
-int g_pool_fast = 1;   // vinet_debug_set key 3: 0 forces the generic scan-order kernels (tests compare the two bit for bit)
+int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = gather backward
+                       // (deterministic, no atomics; measured slower than the atomic scatter on B200, so off by default)
 int pool_fast_set(int v) { g_pool_fast = v; return 0; }
 }  // namespace vinet
 
 static bool pool_is_333(const vinet_pool_t* d) {
-  return g_pool_fast && d->dtype == VINET_BF16 && d->out_dtype == VINET_BF16 && d->xform == VINET_XF_IDENT && d->kt == 3 && d->kh == 3 &&
+  return (g_pool_fast & 1) && d->dtype == VINET_BF16 && d->out_dtype == VINET_BF16 && d->xform == VINET_XF_IDENT && d->kt == 3 && d->kh == 3 &&
          d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 && d->pt == 1 && d->ph == 1 && d->pw == 1 && d->Hi >= 2 && d->Wi >= 2 &&
          (int64_t)d->B * d->Hi * d->Wi * (d->C / 8) < (int64_t)0x7fffffff;
 }
@@ -343,6 +400,19 @@ extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
 
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
   if (pool_check(d)) return -1;
+  if (d->idx && (g_pool_fast & 2)) {   // gather over the recorded taps: no atomics, writes or accumulates every input element once
+    const int64_t total = (int64_t)d->B * d->Ti * d->Hi * d->Wi * (d->C / 8);
+    const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 148 * 64));
+    VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
+        (maxpool_bwd_gather_kernel<TGO, TGI><<<nb, 256, 0, (cudaStream_t)stream>>>(*d))));
+    VINET_LAUNCH_OK("maxpool_bwd_gather");
+    return 0;
+  }
+  if (d->gin_overwrite) {        // the scatter kernels accumulate: start from zero
+    const size_t esz = d->gin_dtype == VINET_BF16 ? 2 : 4;
+    VINET_CHECK(d->ldgi == d->C, "maxpool_bwd: gin_overwrite needs a dense gradient buffer for the scatter kernels");
+    cudaMemsetAsync(d->gin, 0, (size_t)d->B * d->Ti * d->Hi * d->Wi * d->C * esz, (cudaStream_t)stream);
+  }
   if (d->idx) {
     VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
         (maxpool_bwd_kernel<T, TGO, TGI, true><<<pool_grid(d), 256, 0, (cudaStream_t)stream>>>(*d)))));

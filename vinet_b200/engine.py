@@ -431,8 +431,10 @@ class Engine:
         conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real)
         self._bn_tail(name_bn, bn, raw, out, conv_bwd, None)
 
-    def _bn_finalize(self, name_bn, bn, rows, Cn, raw):
-        """Batch statistics of `raw` (training) or the running statistics -> (mean/invstd, scale/shift) buffers."""
+    def _bn_finalize(self, name_bn, bn, rows, Cn, raw, apply=None):
+        """Batch statistics of `raw` (training) or the running statistics -> (mean/invstd, scale/shift) buffers.
+        apply = a filled BnApply descriptor: also materialise relu(scale*y+shift); training mode does all three steps in ONE
+        cooperative launch (vinet_bn_fwd_fused)."""
         st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)      # mean, invstd
         ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)        # scale, shift
         fin = L.BnFinalize()
@@ -441,18 +443,26 @@ class Engine:
         fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
         fin.training = 1 if self.training else 0
         fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+        if apply is not None:
+            apply.scale, apply.shift = ss[0].data_ptr(), ss[1].data_ptr()
+        done = False
         if self.training:
-            sums = self.buf(name_bn + ".sums", (2 * Cn + 1,), torch.float64, zero=True)    # [2][C] sums + one ticket
+            sums = self.buf(name_bn + ".sums", (2 * Cn + 4,), torch.float64, zero=True)    # [2][C] sums + ticket / flag / departures
             sd = L.BnStats()
             sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
             fin.sums = sums.data_ptr()
-            if "vinet_bn_stats_finalize" in self.lib.fn:        # one launch: the last block finalises
+            if apply is not None and "vinet_bn_fwd_fused" in self.lib.fn:
+                self.lib.call("vinet_bn_fwd_fused", C.byref(sd), C.byref(fin), C.byref(apply), self.stream())
+                done = True
+            elif "vinet_bn_stats_finalize" in self.lib.fn:      # one launch: the last block finalises
                 self.lib.call("vinet_bn_stats_finalize", C.byref(sd), C.byref(fin), self.stream())
             else:
                 self.call("vinet_bn_stats", sd)
                 self.call("vinet_bn_finalize", fin)
         else:
             self.call("vinet_bn_finalize", fin)
+        if apply is not None and not done:
+            self.call("vinet_bn_apply", apply)
         if self.training:
             self.bn_counters.append(bn.num_batches_tracked)   # += 1 for all layers in one launch (end_forward)
         return st, ss
@@ -461,18 +471,17 @@ class Engine:
         """BatchNorm + ReLU of the raw conv output `raw` into `out`, and its backward.  The backward either
         hands dY to `conv_bwd` (own conv) or writes it into `dy_slot` = (ptr, ld) of a fused group's dY buffer."""
         Cn, rows = out.C, out.rows
-        st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw)
         out.xform, out.scale, out.shift = L.XF_IDENT, None, None
         ap = L.BnApply()
         ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
-        ap.scale, ap.shift, ap.out, ap.ldo, ap.out_dtype = ss[0].data_ptr(), ss[1].data_ptr(), out.ptr(), out.ld, self.dt
-        self.call("vinet_bn_apply", ap)
+        ap.out, ap.ldo, ap.out_dtype = out.ptr(), out.ld, self.dt
+        st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw, apply=ap)
         if not self.record:
             return
         training = self.training
 
         def backward():
-            bsums = self.buf(name_bn + ".bsums", (2 * Cn + 1,), torch.float64, zero=True)        # [2][C] sums + one ticket
+            bsums = self.buf(name_bn + ".bsums", (2 * Cn + 4,), torch.float64, zero=True)        # [2][C] sums + ticket / flag / departures
             dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
             if dy_slot is None:
                 dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
@@ -485,8 +494,11 @@ class Engine:
             b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
             b.dy, b.lddy, b.dy_dtype, b.training = dy_ptr, lddy, self.dt, 1 if training else 0
             b.g_dtype = out.gdt
-            self.call("vinet_bn_bwd_reduce", b)
-            self.call("vinet_bn_bwd_apply", b)
+            if "vinet_bn_bwd_fused" in self.lib.fn:      # reduce + apply in one cooperative launch
+                self.call("vinet_bn_bwd_fused", b)
+            else:
+                self.call("vinet_bn_bwd_reduce", b)
+                self.call("vinet_bn_bwd_apply", b)
             self.param_grads[name_bn + ".weight"] = dgamma
             self.param_grads[name_bn + ".bias"] = dbeta
             if conv_bwd is not None:
@@ -547,7 +559,13 @@ class Engine:
         self.call("vinet_maxpool_fwd", d)
         if self.record and a.needs_grad:
             def backward():
-                self.ensure_init(a)
+                # first writer of a's gradient: the gather kernel stores every element; otherwise it accumulates
+                key = a.grad.data_ptr()
+                d.gin_overwrite = 1 if (key not in self.gwritten and a.gchoff == 0 and a.C == a.ldg) else 0
+                if d.gin_overwrite:
+                    self.gwritten.add(key)
+                else:
+                    self.ensure_init(a)
                 d.gout, d.ldgo, d.gin, d.ldgi = out.gptr(), out.ldg, a.gptr(), a.ldg
                 d.gout_dtype, d.gin_dtype = out.gdt, a.gdt
                 self.call("vinet_maxpool_bwd", d)

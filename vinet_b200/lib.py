@@ -87,7 +87,7 @@ class Pool(C.Structure):
                 ("kt", _i32), ("kh", _i32), ("kw", _i32), ("st", _i32), ("sh", _i32), ("sw", _i32),
                 ("pt", _i32), ("ph", _i32), ("pw", _i32), ("To", _i32), ("Ho", _i32), ("Wo", _i32),
                 ("out", _p), ("ldo", _i64), ("out_dtype", _i32), ("gout", _p), ("ldgo", _i64), ("gin", _p),
-                ("ldgi", _i64), ("gout_dtype", _i32), ("gin_dtype", _i32), ("idx", _p)]
+                ("ldgi", _i64), ("gout_dtype", _i32), ("gin_dtype", _i32), ("idx", _p), ("gin_overwrite", _i32)]
 
 
 class Upsample(C.Structure):
@@ -143,6 +143,8 @@ SIGNATURES = {
     "vinet_bn_apply": (C.c_int, [C.POINTER(BnApply), _S]),
     "vinet_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
+    "vinet_bn_fwd_fused": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), C.POINTER(BnApply), _S]),
+    "vinet_bn_bwd_fused": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_maxpool_fwd": (C.c_int, [C.POINTER(Pool), _S]),
     "vinet_maxpool_bwd": (C.c_int, [C.POINTER(Pool), _S]),
     "vinet_upsample_fwd": (C.c_int, [C.POINTER(Upsample), _S]),
