@@ -1,6 +1,7 @@
 // BatchNorm3d statistics / finalize / backward on NDHWC views (model_utils.py:132,145,149).
 // The normalisation itself is never a kernel: consumers apply scale/shift(+ReLU) when they read.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -384,11 +385,15 @@ static ColGrid col_grid(int64_t rows, int C, int nv, bool reduce) {
   if (Ry > 128) Ry = 128;
   g.block = dim3(G, Ry);
   // 8 blocks per SM keep enough loads in flight to saturate HBM; a reduction also pays 2C fp64 atomics per block, so wide
-  // layers stop earlier.  Every thread keeps >= 4 rows: its per-channel constants (up to 48 loads) are set up once.
-  int64_t max_blocks = 148 * 8;
-  if (reduce) max_blocks = std::min<int64_t>(max_blocks, std::max<int64_t>(148, 160000 / (2 * C)));
+  // layers stop earlier.  Every thread keeps >= 8 rows: its per-channel constants (up to 48 loads) are set up once.
+  static const int env_maxb = getenv("VINET_BN_MAXB") ? atoi(getenv("VINET_BN_MAXB")) : 0;        // tuning knobs (tools/bn_bench.py)
+  static const int env_minrpt = getenv("VINET_BN_MINRPT") ? atoi(getenv("VINET_BN_MINRPT")) : 0;
+  static const int env_atom = getenv("VINET_BN_ATOM") ? atoi(getenv("VINET_BN_ATOM")) : 160000;
+  int64_t max_blocks = env_maxb ? env_maxb : 148 * 8;
+  if (reduce) max_blocks = std::min<int64_t>(max_blocks, std::max<int64_t>(148, env_atom / (2 * C)));
   int64_t rpt = cdiv(rows, (int64_t)Ry * max_blocks);   // rows per thread
-  if (rpt < 4) rpt = 4;
+  const int64_t min_rpt = env_minrpt ? env_minrpt : 8;
+  if (rpt < min_rpt) rpt = min_rpt;
   int64_t rpb = (int64_t)Ry * rpt;
   int64_t nb = cdiv(rows, rpb);
   g.grid = (unsigned)(nb < 1 ? 1 : nb);

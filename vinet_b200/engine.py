@@ -451,7 +451,9 @@ class Engine:
             sd = L.BnStats()
             sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
             fin.sums = sums.data_ptr()
-            if apply is not None and "vinet_bn_fwd_fused" in self.lib.fn:
+            # one cooperative launch pays off for very large tensors only (measured, tools/bn_bench.py): small layers are
+            # latency-bound and two plain launches pipeline better than one launch with a grid-wide wait
+            if apply is not None and "vinet_bn_fwd_fused" in self.lib.fn and rows * Cn * raw.buf.element_size() >= (400 << 20):
                 self.lib.call("vinet_bn_fwd_fused", C.byref(sd), C.byref(fin), C.byref(apply), self.stream())
                 done = True
             elif "vinet_bn_stats_finalize" in self.lib.fn:      # one launch: the last block finalises
@@ -494,7 +496,7 @@ class Engine:
             b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
             b.dy, b.lddy, b.dy_dtype, b.training = dy_ptr, lddy, self.dt, 1 if training else 0
             b.g_dtype = out.gdt
-            if "vinet_bn_bwd_fused" in self.lib.fn:      # reduce + apply in one cooperative launch
+            if "vinet_bn_bwd_fused" in self.lib.fn and rows * Cn * raw.buf.element_size() >= (24 << 20):   # reduce + apply in one cooperative launch
                 self.call("vinet_bn_bwd_fused", b)
             else:
                 self.call("vinet_bn_bwd_reduce", b)
