@@ -70,10 +70,10 @@ def soundnet_plan(e, pfx, net, audio):
             g = ga
             for i, d, b, xin, y, out, conv, bn in reversed(layers):
                 dy = e.buf("%sdy%d" % (pfx, i), tuple(y.shape), torch.float32)
-                dgam, dbet = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+                dgam, dbet = e.grad_tensor("%sbatchnorm%d.weight" % (pfx, i), bn.weight), e.grad_tensor("%sbatchnorm%d.bias" % (pfx, i), bn.bias)
                 b.gout, b.dy, b.dgamma, b.dbeta = g.data_ptr(), dy.data_ptr(), dgam.data_ptr(), dbet.data_ptr()
                 e.lib.call("vinet_bn1d_bwd", C.byref(b), e.stream())
-                gw, gb = torch.empty_like(conv.weight), torch.empty_like(conv.bias)
+                gw, gb = e.grad_tensor("%sconv%d.weight" % (pfx, i), conv.weight), e.grad_tensor("%sconv%d.bias" % (pfx, i), conv.bias)
                 dx = e.buf("%sdx%d" % (pfx, i), tuple(xin.shape), torch.float32) if i > 1 else None
                 d.dy, d.dx, d.dw, d.dbias = dy.data_ptr(), (dx.data_ptr() if dx is not None else None), gw.data_ptr(), gb.data_ptr()
                 e.lib.call("vinet_conv1d_bwd", C.byref(d), e.stream())
@@ -101,7 +101,7 @@ def avfuse_plan(e, name, y0, a, ga, bil):
     e.lib.call("vinet_avfuse_fwd", C.byref(d), e.stream())
     if e.record:
         def backward():
-            gw, gb = torch.empty_like(bil.weight), torch.empty_like(bil.bias)
+            gw, gb = e.grad_tensor(name + ".weight", bil.weight), e.grad_tensor(name + ".bias", bil.bias)
             assert out.gdt == L.F32 and y0.gdt == L.F32, "the AV fusion kernel keeps fp32 gradients"
             e.ensure_init(y0)
             d.gout, d.ldgo, d.gy0, d.ldgy0 = out.gptr(), out.ldg, y0.gptr(), y0.ldg

@@ -119,6 +119,7 @@ class Engine:
         self.training = False
         self.record = False
         self.use_tma = True     # False: force the register-gather tcgen05 kernels (tests / A-B timing)
+        self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)})
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
 
@@ -145,6 +146,16 @@ class Engine:
                 t.fill_(float("nan"))       # debug aid: reads of never-written scratch surface as NaN
             self.pool[name] = t
         return t
+
+    def grad_tensor(self, name, like, zero=False):
+        """Where the gradient of parameter `name` is written: its slice of the flat arena when one is installed (all
+        gradients then live in ONE buffer: a single NCCL all-reduce, no per-tensor bucket copies), else a fresh tensor."""
+        if self.arena is not None:
+            hit = self.arena[1].get(name)
+            if hit is not None and self.arena[0].device == like.device:
+                t = self.arena[0][hit[0]:hit[0] + hit[1]].view(like.shape)
+                return t.zero_() if zero else t
+        return torch.zeros_like(like) if zero else torch.empty_like(like)
 
     def timed(self, label, kind, flops, fn):
         """Run one kernel call; when profiling, bracket it with CUDA events on the launching stream (after
@@ -281,9 +292,11 @@ class Engine:
         return (self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
                 and all(s.xform == L.XF_IDENT for s in srcs))
 
-    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None):
+    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None, wgrad_split=None):
         """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY.
-        ep = (scale, shift, act): fused per-channel epilogue (inference-mode BatchNorm folding)."""
+        ep = (scale, shift, act): fused per-channel epilogue (inference-mode BatchNorm folding).
+        wgrad_split = [(parameter name, out channels)]: `w` is a concatenation of several parameters along Cout; the
+        weight gradient is unpacked straight into each member's gradient tensor."""
         a0 = srcs[0]
         cs = a0.C
         Cout = w.shape[0]
@@ -355,16 +368,25 @@ class Engine:
                 chunks = cdiv(rows, 16)
             wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
             self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
-            gw = torch.empty_like(w)
-            if win:
-                self.lib.call("vinet_unpack_wgrad_win8", dwp.data_ptr(), lddw, gw.data_ptr(), Cout, w.shape[1], geom.kh,
-                              geom.kw, self.stream())
+            if wgrad_split is not None:
+                off = 0
+                for pname, c in wgrad_split:      # member columns [off, off+c) of the packed gradient
+                    gwm = self.grad_tensor(pname, w[off:off + c])
+                    self.lib.call("vinet_unpack_wgrad", dwp.data_ptr() + 4 * off, lddw, csk, gwm.data_ptr(), c, w.shape[1],
+                                  len(taps), self.stream())
+                    self.param_grads[pname] = gwm
+                    off += c
             else:
-                self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
-                              self.stream())
-            self.param_grads[name + ".weight"] = gw
+                gw = self.grad_tensor(name + ".weight", w)
+                if win:
+                    self.lib.call("vinet_unpack_wgrad_win8", dwp.data_ptr(), lddw, gw.data_ptr(), Cout, w.shape[1], geom.kh,
+                                  geom.kw, self.stream())
+                else:
+                    self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
+                                  self.stream())
+                self.param_grads[name + ".weight"] = gw
             if bias is not None:
-                gb = torch.empty_like(bias)
+                gb = self.grad_tensor(name + ".bias", bias)
                 ws = self.buf("colsum.ws", (1024,), torch.float64)
                 self.lib.call("vinet_colsum", dy, lddy, self.dt, rows, Cout, ws.data_ptr(), gb.data_ptr(), self.stream())
                 self.param_grads[name + ".bias"] = gb
@@ -484,7 +506,7 @@ class Engine:
 
         def backward():
             bsums = self.buf(name_bn + ".bsums", (2 * Cn + 4,), torch.float64, zero=True)        # [2][C] sums + ticket / flag / departures
-            dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+            dgamma, dbeta = self.grad_tensor(name_bn + ".weight", bn.weight), self.grad_tensor(name_bn + ".bias", bn.bias)
             if dy_slot is None:
                 dy = self.buf("dy.%d" % (rows * Cn), (rows, Cn), self.tdtype)
                 dy_ptr, lddy = dy.data_ptr(), Cn
@@ -528,18 +550,14 @@ class Engine:
             self.wcache[key] = (vers, wcat, [w for _, _, w, _, _ in members])
         wcat = self.wcache[key][1]
         rawcat = Act(self.buf(gname + ".raw", (x.B, x.T, x.H, x.W, tot), self.tdtype), x.B, x.T, x.H, x.W, tot)
-        conv_bwd = self.conv(gname, [x], wcat, _G1, rawcat)
+        conv_bwd = self.conv(gname, [x], wcat, _G1, rawcat,
+                             wgrad_split=[(nc + ".weight", c) for (nc, _, _, _, _), c in zip(members, couts)])
         dycat = None
         if self.record:
             dycat = self.buf(gname + ".dy", (rawcat.rows, tot), self.tdtype)
 
             def group_backward():
-                conv_bwd(dycat.data_ptr(), tot)
-                gw = self.param_grads.pop(gname + ".weight")
-                off = 0
-                for (nc, _, _, _, _), c in zip(members, couts):
-                    self.param_grads[nc + ".weight"] = gw[off:off + c]
-                    off += c
+                conv_bwd(dycat.data_ptr(), tot)      # unpacks the weight gradient straight into the members' tensors
             self.tape.append(group_backward)      # appended first => runs after every member's BatchNorm backward
         off = 0
         for (nc, nb, w, bn, out), c in zip(members, couts):
@@ -617,7 +635,7 @@ class Engine:
         self.call("vinet_head_fwd", d)
         if self.record:
             def backward(gout, _keep=out):       # the descriptor holds a raw pointer to `out` (sigmoid output): keep it alive
-                gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+                gw, gb = self.grad_tensor(name + ".weight", w, zero=True), self.grad_tensor(name + ".bias", b, zero=True)
                 d.gout, d.dw, d.db = gout.data_ptr(), gw.data_ptr(), gb.data_ptr()
                 if conv_bwd is not None:        # input is a raw conv output: dx is that conv's dY
                     dx = self.buf("dy.%d" % (a.rows * a.C), (a.rows, a.C), self.tdtype)

@@ -254,12 +254,53 @@ class _PlanModule(nn.Module):
             engines[key].generation = 0
         return engines[key]
 
+    # ---- flat gradient arena (multi-GPU: ONE all-reduce on one buffer instead of DDP's per-tensor bucket copies) ----
+    def enable_grad_arena(self, on=True):
+        """Write every parameter gradient into one flat fp32 buffer; ``param.grad`` tensors become views of it."""
+        self.__dict__["_use_arena"] = bool(on)
+        self.__dict__.pop("_arenas", None)
+        return self
+
+    def _arena_for(self, device, named):
+        arenas = self.__dict__.setdefault("_arenas", {})
+        key = (str(device), tuple(n for n, _ in named))
+        if key not in arenas:
+            layout, off = {}, 0
+            for n, p in named:
+                layout[n] = (off, p.numel())
+                off += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
+            arenas[key] = (torch.zeros(off, dtype=torch.float32, device=device), layout)
+        return arenas[key]
+
+    def sync_gradients(self, group=None):
+        """Average the gradients of the last backward over the process group: one NCCL all-reduce of the flat arena
+        (124.4 MB for ViNet).  BatchNorm statistics stay per replica (the reference's nn.DataParallel semantics)."""
+        import torch.distributed as dist
+        arenas = self.__dict__.get("_arenas")
+        assert arenas, "sync_gradients() needs enable_grad_arena() and a backward pass"
+        world = dist.get_world_size(group)
+        for flat, _ in arenas.values():
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(flat, group=group)
+                flat.div_(world)
+
+    def broadcast_parameters(self, src=0, group=None):
+        """Rank `src`'s parameters and buffers to every rank (what DistributedDataParallel does at construction)."""
+        import torch.distributed as dist
+        for t in list(self.parameters()) + list(self.buffers()):
+            dist.broadcast(t.data, src, group=group)
+        return self
+
     def _call_plan(self, x, *extra):
         if x.device.type != "cuda" and self.__dict__.get("_backend") is None:
             raise RuntimeError("vinet_b200 has no CPU path: move the model and inputs to a CUDA device")
         named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and self._plan_uses(n)]
         names = tuple(n for n, _ in named)
         record = torch.is_grad_enabled() and len(named) > 0
+        e = self._engine_for(x.device)
+        e.arena = self._arena_for(x.device, named) if (record and self.__dict__.get("_use_arena")) else None
         return _PlanFunction.apply(self, record, names, x, *extra, *[p for _, p in named])
 
     def _plan_uses(self, name):
