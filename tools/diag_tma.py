@@ -70,6 +70,8 @@ CASES = [  # B, T0, T1, H, W, Cin, Cout, k, stride_t, pad
     (2, 16, 0, 28, 48, 128, 192, (1, 3, 3), 1, (0, 1, 1)),   # 3c.b1.conv_s: streamed weights, 2 N tiles, many items per CTA
     (2, 16, 0, 28, 48, 192, 192, (3, 1, 1), 1, (1, 0, 0)),   # 3c.b1.conv_t: resident weights, runs of output frames
     (3, 9, 0, 20, 40, 64, 64, (7, 1, 1), 2, (3, 0, 0)),      # stem conv_t with an odd frame count
+    (1, 24, 0, 16, 36, 64, 64, (7, 1, 1), 2, (3, 0, 0)),     # stem conv_t, 12 output frames: strided temporal-halo tiles (partial)
+    (2, 32, 0, 8, 16, 64, 64, (7, 1, 1), 2, (3, 0, 0)),      # stem conv_t, 16 output frames: one full temporal-halo tile
 ]
 
 

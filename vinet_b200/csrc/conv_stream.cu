@@ -517,7 +517,6 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
   const bool spatial = tm.eh0 != 0 || tm.eh1 != 0 || tm.ew0 != 0 || tm.ew1 != 0;
   if (!spatial && tm.ntg <= 1) return best;   // a 1x1x1 conv has nothing to re-use: conv_tma.cu's kernel is the right one
   if (spatial && g.Hr < 10) return best;      // 16-row halo tiles waste most of a 7-row map
-  if (!spatial && tm.S > 1) return best;      // temporally strided frame walks (stem conv_t fprop) measured slower than per-tap boxes
   const int ncb = (g.Cs + 63) / 64;
   int nk_sum = 0;
   for (int cb = 0; cb < ncb; ++cb) {
@@ -540,9 +539,11 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
     const uint32_t b_bytes = (uint32_t)block_n * 128u;
     const int ctas = std::max(1, sms / n_tiles);
     // temporal-halo tiles (tt > 1): stride-1 temporal taps of a single source read ONE box of tt + kt - 1 frames
-    const bool thalo_ok = !spatial && tm.S == 1 && tm.ntg > 1 && g.src[1].ptr == nullptr;
+    // (temporally strided convs, S > 1: 8 positions per frame so that every 8-row group is one source frame, SBO = S frames)
+    const bool thalo_ok = !spatial && tm.ntg > 1 && g.src[1].ptr == nullptr;
     for (int tt = 1; tt <= (thalo_ok ? 16 : 1); tt *= 2) {
       if (tt > 1 && tt / 2 >= g.Tr) break;
+      if (tm.S > 1 && tt != 16) continue;        // strided frame walks measured slower than per-tap boxes: temporal halo or nothing
       const int L = tt > 1 ? 1 : tm.L;
       const int walk_Tr = tt > 1 ? (int)cdiv(g.Tr, tt) : g.Tr;
       int tbw = fbw, tbh = fbh;
@@ -570,7 +571,8 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
           util = (double)cdiv(g.Wr, 8) / (double)(c.items_w * nsub);   // sub-tiles past the right edge are skipped
         } else {
           c.halo = 0; c.tw = tbw; c.th = tbh;
-          c.PT = tt > 1 ? tt + (tm.e_max - tm.e_min) : 1;
+          c.PT = tt > 1 ? (tt - 1) * tm.S + (tm.e_max - tm.e_min) + 1 : 1;
+          if (c.PT > 256) continue;
           c.tiles_w = (int)cdiv(g.Wr, tbw);
           c.tpf = c.tiles_w * (int)cdiv(g.Hr, tbh);
           if (nsub > c.tpf) break;
@@ -579,7 +581,7 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
           c.a_tx_sub = (uint32_t)(pos * c.PT * 128);
           c.sub_stride = (uint32_t)round_up(std::max<uint32_t>(c.a_tx_sub, TC_A_BYTES), 1024);
           c.a_stage_bytes = (uint32_t)nsub * c.sub_stride;
-          c.sbo = 1024;
+          c.sbo = (tt > 1 && tm.S > 1) ? (uint32_t)(tm.S * pos * 128) : 1024u;
           util = (double)c.tpf / (double)(c.items_w * nsub);
         }
         // shared memory: resident weights when they fit beside two activation stages, else a ring of weight blocks
@@ -685,7 +687,7 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   p.PW = pl.PW; p.PH = pl.PH; p.ew0 = tm.ew0; p.eh0 = tm.eh0;
   const bool thalo = pl.tt > 1;
   p.tt = pl.tt; p.pos = pl.tw * pl.th;
-  p.tstep = thalo ? pl.tt : 1; p.toff = thalo ? tm.e_min : 0;
+  p.tstep = thalo ? pl.tt * tm.S : 1; p.toff = thalo ? tm.e_min : 0;
   p.walk_Tr = thalo ? (int)cdiv(g.Tr, pl.tt) : g.Tr;
   p.walk_Ts = thalo ? p.walk_Tr : g.Ts;
   p.run = pl.run; p.nruns = (int)cdiv(p.walk_Tr, pl.run);
