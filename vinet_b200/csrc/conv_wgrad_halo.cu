@@ -36,8 +36,11 @@ struct WgHaloParams {
   CUtensorMap tmA[2];
   CUtensorMap tmDy;
   vinet_wgrad_t d;
-  int32_t PW, PH, ncb, nsp, naccs, nblk, block_n, splits, stages, ni, tiles_w, tiles_h, kw;
-  uint32_t acc_cols, tmem_cols, idesc, a_bytes, a_tx, stage_bytes;
+  int32_t ncb, nsp, naccs, nblk, block_n, splits, stages, ni, tiles_w, tiles_h, nT, temporal;
+  int32_t cw, ch, aw0, ah0, at_step, at0, dyt_step;   // chunk (tw, th, tr) -> TMA coordinates of the activation / dY boxes
+  int32_t uoff16[WH_MAX_SP];                          // window of unit j inside the activation box, in 16-byte units
+  uint32_t a_sbo, kstep_a16;                          // stride between 8-position atoms; 16 positions in 16-byte units
+  uint32_t acc_cols, tmem_cols, idesc, a_bytes, a_tx, dy_unit, stage_bytes;
 };
 
 __device__ __forceinline__ void wh_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
@@ -66,7 +69,7 @@ __device__ __forceinline__ void wh_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t
 
 __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
   const vinet_gather_t& g = p.d.g;
-  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
+  const int64_t nchunks = (int64_t)g.B * p.nT * p.tiles_h * p.tiles_w;
   const int64_t per = cdiv(nchunks, p.splits);
   const int64_t c_begin = (int64_t)blockIdx.z * per;
   const int64_t c_end = min(nchunks, c_begin + per);
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.block_n;
   const int n0 = blockIdx.y * BN;
-  const int dt = blockIdx.x / p.ncb, cb = blockIdx.x - dt * p.ncb;   // this CTA's (temporal tap, channel block) group
+  // this CTA's group: (temporal tap, channel block) with all spatial taps, or (channel block) with all temporal taps
+  const int dt = p.temporal ? 0 : blockIdx.x / p.ncb, cb = blockIdx.x - dt * p.ncb;
   const int nblk_eff = min(p.nblk, (min(BN, p.d.N - n0) + 63) / 64);
 
   if (warp == 0 && lane == 0) {
@@ -114,31 +118,30 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
       int64_t m = c_begin;
       int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
       int th = (int)(m % p.tiles_h); m /= p.tiles_h;
-      int tr = (int)(m % g.Tr);
-      int b = (int)(m / g.Tr);
+      int tr = (int)(m % p.nT);
+      int b = (int)(m / p.nT);
       const bool cat = g.src[1].ptr != nullptr;
       const int T0 = g.src[0].T;
-      const int dtv = g.tap[dt * p.nsp][0];
+      const int at0 = p.at0 + (p.temporal ? 0 : g.tap[dt * p.nsp][0]);
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = p.a_tx + (uint32_t)nblk_eff * WH_UNIT;
+      const uint32_t tx = p.a_tx + (uint32_t)nblk_eff * p.dy_unit;
       for (int kb = 0; kb < KB; ++kb) {
-        const int t = tr * g.row_tstep + g.row_toff;
-        const int h0 = th * 16, w0 = tw * 8;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(full0 + 8 * s, tx);
         const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
-        const int ts = t * g.st - g.pt + dtv;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
+        const int ts = tr * p.at_step + at0;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
         const int si = (cat && ts >= T0) ? 1 : 0;
-        wh_tma_load_5d(stage, &p.tmA[si], full0 + 8 * s, cb * 64, w0 - g.pw, h0 - g.ph, ts - (si ? T0 : 0), b);
+        wh_tma_load_5d(stage, &p.tmA[si], full0 + 8 * s, cb * 64, tw * p.cw + p.aw0, th * p.ch + p.ah0, ts - (si ? T0 : 0), b);
         for (int nb = 0; nb < nblk_eff; ++nb)
-          wh_tma_load_5d(stage + p.a_bytes + (uint32_t)nb * WH_UNIT, &p.tmDy, full0 + 8 * s, n0 + nb * 64, w0, h0, tr, b);
+          wh_tma_load_5d(stage + p.a_bytes + (uint32_t)nb * p.dy_unit, &p.tmDy, full0 + 8 * s, n0 + nb * 64, tw * p.cw, th * p.ch,
+                         tr * p.dyt_step, b);
         if (++s == stages) { s = 0; ph ^= 1u; }
         if (++tw == p.tiles_w) {
           tw = 0;
           if (++th == p.tiles_h) {
             th = 0;
-            if (++tr == g.Tr) { tr = 0; ++b; }
+            if (++tr == p.nT) { tr = 0; ++b; }
           }
         }
       }
@@ -148,10 +151,10 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
     const int k = warp - 2;
     if (k < p.ni) {
       const uint32_t hi_common = (1u << 14) | (2u << 29);
-      const uint32_t a_hi = ((uint32_t)(p.PW * 128) >> 4) | hi_common;   // SBO = one tile row of the halo
+      const uint32_t a_hi = (p.a_sbo >> 4) | hi_common;   // SBO = distance between 8-position atoms (a halo tile row / S frames)
       const uint32_t b_hi = (1024u >> 4) | hi_common;
-      const uint32_t b_lbo = (WH_UNIT >> 4) << 16;
-      const uint32_t kstep_a = (uint32_t)(2 * p.PW * 128) >> 4;           // 16 positions = two tile rows
+      const uint32_t b_lbo = (p.dy_unit >> 4) << 16;
+      const uint32_t kstep_a = p.kstep_a16;               // 16 positions = two atoms
       const uint32_t stage16 = p.stage_bytes >> 4;
       const uint32_t s0_16 = (s0 & 0x3FFFFu) >> 4;
       int s = 0;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
         const uint32_t b_lo0 = (st16 + (p.a_bytes >> 4)) | b_lbo;
         for (int a = k; a < p.naccs; a += p.ni) {
           const int j0 = 2 * a, j1 = min(2 * a + 1, p.nsp - 1);
-          const int o0 = ((j0 / p.kw) * p.PW + (j0 % p.kw)) * 8, o1 = ((j1 / p.kw) * p.PW + (j1 % p.kw)) * 8;   // 16-byte units
+          const int o0 = p.uoff16[j0], o1 = p.uoff16[j1];
           const uint32_t a_lo0 = (st16 + (uint32_t)o0) | ((uint32_t)(o1 - o0) << 16);   // LBO = distance between the two taps
           const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
           if (wh_elect_one()) {
@@ -219,35 +222,41 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
   }
 }
 
+void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out);
+
 // returns 1 when the launch was handled here, 0 when the caller should use its own kernel, <0 on error
 int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
   if (!g_stream_enable) return 0;
   if (g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16 || d->dy_dtype != VINET_BF16) return 0;
   if (g.sh != 1 || g.sw != 1 || g.Cs % 8 != 0 || d->N % 8 != 0 || d->lddy % 8 != 0) return 0;
-  if (g.Hr < 10) return 0;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[i];
     if (s.ptr == nullptr) continue;
     if (s.xform != VINET_XF_IDENT || (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) || s.ld < g.Cs) return 0;
   }
-  // taps must be the natural (dt, dh, dw) enumeration of a kt x kh x kw kernel with kh*kw > 1
+  // taps must be the natural (dt, dh, dw) enumeration of a kt x kh x kw kernel
   int kt = 0, kh = 0, kw = 0;
   for (int t = 0; t < g.ntaps; ++t) {
     kt = std::max(kt, g.tap[t][0] + 1);
     kh = std::max(kh, g.tap[t][1] + 1);
     kw = std::max(kw, g.tap[t][2] + 1);
   }
-  const int nsp = kh * kw;
-  if (nsp < 2 || nsp > WH_MAX_SP || kt * nsp != g.ntaps) return 0;
+  const int nspat = kh * kw;
+  if (kt * nspat != g.ntaps) return 0;
   for (int t = 0; t < g.ntaps; ++t)
-    if (g.tap[t][0] != t / nsp || g.tap[t][1] != (t / kw) % kh || g.tap[t][2] != t % kw) return 0;
+    if (g.tap[t][0] != t / nspat || g.tap[t][1] != (t / kw) % kh || g.tap[t][2] != t % kw) return 0;
+  // spatial mode: kh*kw > 1 taps share a spatial halo box.  temporal mode: kh = kw = 1, the kt temporal taps of a single
+  // source share a box of (tt-1)*st + kt frames x pos positions (tt*pos = 128 output positions per chunk).
+  const bool temporal = nspat == 1 && kt > 1 && g.src[1].ptr == nullptr && g.row_tstep == 1 && g.row_toff == 0;
+  if (!temporal && (nspat < 2 || g.Hr < 10)) return 0;
   WgHaloParams p;
   p.d = *d;
-  p.kw = kw;
-  p.nsp = nsp;
+  p.temporal = temporal ? 1 : 0;
+  p.nsp = temporal ? kt : nspat;
+  if (p.nsp > WH_MAX_SP) return 0;
   p.ncb = (g.Cs + 63) / 64;
-  p.naccs = (nsp + 1) / 2;
+  p.naccs = (p.nsp + 1) / 2;
   const int n16 = (int)round_up(d->N, 16);
   const int bn_max = std::min(256, (512 / p.naccs) / 16 * 16);
   const int n_tiles = (int)cdiv(n16, bn_max);
@@ -257,17 +266,48 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   if ((int)p.acc_cols * p.naccs > 512) return 0;
   p.tmem_cols = tmem_cols_for(p.naccs * (int)p.acc_cols);
   p.nblk = (p.block_n + 63) / 64;
-  p.PW = 8 + kw - 1;
-  p.PH = 16 + kh - 1;
-  p.a_tx = (uint32_t)(p.PW * p.PH * 128);
+  p.dy_unit = WH_UNIT;
+  int abw, abh, abt = 1, dbw, dbh, dbt = 1;   // activation / dY box extents
+  if (!temporal) {
+    const int PW = 8 + kw - 1, PH = 16 + kh - 1;
+    abw = PW; abh = PH; dbw = 8; dbh = 16;
+    p.cw = 8; p.ch = 16; p.aw0 = -g.pw; p.ah0 = -g.ph;
+    p.at_step = g.row_tstep * g.st; p.at0 = g.row_toff * g.st - g.pt; p.dyt_step = 1;
+    p.nT = g.Tr;
+    p.tiles_w = (int)cdiv(g.Wr, 8);
+    p.tiles_h = (int)cdiv(g.Hr, 16);
+    for (int j = 0; j < WH_MAX_SP; ++j) p.uoff16[j] = j < nspat ? ((j / kw) * PW + (j % kw)) * 8 : 0;
+    p.a_sbo = (uint32_t)PW * 128u;
+    p.kstep_a16 = (uint32_t)(2 * PW * 128) >> 4;
+  } else {
+    // tt output frames x pos positions per chunk; a temporally strided conv needs pos = 8 (one atom = one source frame)
+    int tt = g.st > 1 ? 16 : 8;
+    while (tt > 1 && tt / 2 >= g.Tr) tt /= 2;
+    if (g.st > 1 && tt != 16) return 0;
+    const int pos = TC_BM / tt;
+    pick_tma_box(g.Hr, g.Wr, pos, 8, true, &dbw, &dbh);
+    if (dbw * dbh != pos) return 0;
+    abw = dbw; abh = dbh;
+    abt = (tt - 1) * g.st + kt;
+    dbt = tt;
+    if (abt > 256) return 0;
+    p.cw = dbw; p.ch = dbh; p.aw0 = 0; p.ah0 = 0;
+    p.at_step = tt * g.st; p.at0 = -g.pt; p.dyt_step = tt;
+    p.nT = (int)cdiv(g.Tr, tt);
+    p.tiles_w = (int)cdiv(g.Wr, dbw);
+    p.tiles_h = (int)cdiv(g.Hr, dbh);
+    for (int j = 0; j < WH_MAX_SP; ++j) p.uoff16[j] = j < kt ? j * pos * 8 : 0;   // tap dt = the box shifted by dt frames
+    p.a_sbo = g.st > 1 ? (uint32_t)(g.st * pos * 128) : 1024u;
+    p.kstep_a16 = (2u * p.a_sbo) >> 4;
+  }
+  p.a_tx = (uint32_t)(abw * abh * abt * 128);
   p.a_bytes = (uint32_t)round_up(p.a_tx, 1024);
-  p.stage_bytes = p.a_bytes + (uint32_t)p.nblk * WH_UNIT;
-  p.tiles_w = (int)cdiv(g.Wr, 8);
-  p.tiles_h = (int)cdiv(g.Hr, 16);
+  p.stage_bytes = p.a_bytes + (uint32_t)p.nblk * p.dy_unit;
   p.idesc = make_idesc(TC_BM, p.block_n, 1, 1);
   p.ni = std::min(WH_MAX_ISSUERS, p.naccs);
-  const int64_t nchunks = (int64_t)g.B * g.Tr * p.tiles_h * p.tiles_w;
-  const int64_t base_ctas = (int64_t)kt * p.ncb * n_tiles;
+  const int64_t nchunks = (int64_t)g.B * p.nT * p.tiles_h * p.tiles_w;
+  const int groups = (temporal ? 1 : kt) * p.ncb;
+  const int64_t base_ctas = (int64_t)groups * n_tiles;
   const int sms = tma_sm_count();
   // split the position chunks so that the CTA count fills whole waves of the machine (1 CTA per SM)
   const int64_t smax = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nchunks / 2, 256), 65535));
@@ -288,10 +328,10 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   if (smem > 227 * 1024) return 0;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.PW, p.PH, 1, 1, 1)) return -1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, 1, abt)) return -1;
   }
-  if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, 8, 16, 1, 1, 1)) return -1;
-  dim3 grid((unsigned)(kt * p.ncb), (unsigned)n_tiles, (unsigned)splits);
+  if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, dbw, dbh, 1, 1, dbt)) return -1;
+  dim3 grid((unsigned)groups, (unsigned)n_tiles, (unsigned)splits);
   cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   conv_wgrad_halo_kernel<<<grid, WH_THREADS, smem, stream>>>(p);
   note_kernel("conv_wgrad_halo_kernel");
