@@ -50,6 +50,7 @@ struct StreamParams {
   int32_t sp_aoff16[VINET_MAX_TAPS], sp_boff16[VINET_MAX_TAPS];  // sp_aoff and sp_kb * b_bytes in 16-byte descriptor units
   int32_t nacc, a_stages, b_slots, wres, items_per_nt, ni;
   int32_t tt, pos, tstep, toff, walk_Ts, walk_Tr;  // temporal-halo tiles: tt output frames x pos positions per sub-tile (tt = 1: off)
+  int32_t par_h0[2], par_off[2], par_sh;           // halo == 2 (row-strided conv): one box per source-row parity, see conv_gemm_stream_strided
   uint32_t acc_stride, tmem_cols, idesc, a_stage_bytes, a_tx_sub, sub_stride, sbo, b_bytes;
 };
 
@@ -196,7 +197,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
           for (int cb = 0; cb < p.ncb; ++cb) {
             mbar_wait(empty_a + 8 * s, ph ^ 1u);
             const uint32_t dst = sA0 + (uint32_t)s * p.a_stage_bytes;
-            if (p.halo) {
+            if (p.halo == 2) {   // spatially strided conv: the rows a tile needs form par_sh lattices, one box per lattice
+              mbar_arrive_expect_tx(full_a + 8 * s, (uint32_t)p.par_sh * p.a_tx_sub);
+              for (int par = 0; par < p.par_sh; ++par)
+                st_tma_load_5d(dst + (uint32_t)p.par_off[par], &p.tmA[0], full_a + 8 * s, cb * 64, c.tx * 8 * p.nsub + p.ew0,
+                               c.ty * p.th * p.par_sh + p.par_h0[par], tl, c.b);
+            } else if (p.halo) {
               mbar_arrive_expect_tx(full_a + 8 * s, p.a_tx_sub);
               st_tma_load_5d(dst, &p.tmA[si], full_a + 8 * s, cb * 64, c.tx * 8 * p.nsub + p.ew0, c.ty * p.th + p.eh0, tl, c.b);
             } else {
@@ -666,9 +672,108 @@ int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles) {
   return 1;
 }
 
+static int stream_launch(StreamParams& p, const vinet_conv_t* d, int sms, cudaStream_t stream) {
+  const int nb_slots = p.wres ? d->k_blocks : p.b_slots;
+  size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)nb_slots * p.b_bytes +
+                8 * (size_t)(2 * p.a_stages + 2 * p.b_slots + 2 * p.nacc + 1) + 64 + 8 * VINET_MAX_TAPS;
+  if (smem > 227 * 1024) {
+    set_error("conv_gemm_stream: %zu bytes of shared memory", smem);
+    return -1;
+  }
+  smem = std::max<size_t>(smem, 120 * 1024);   // one CTA per SM: two co-resident CTAs would fight over the 512 TMEM columns
+  const int ctas = (int)std::min<int64_t>(p.items_per_nt, std::max(1, sms / d->n_tiles));
+  dim3 grid((unsigned)ctas, (unsigned)d->n_tiles);
+#define LAUNCH_STREAM(TO)                                                                             \
+  do {                                                                                                \
+    auto kern = conv_has_epilogue(*d) ? conv_stream_kernel<TO, true> : conv_stream_kernel<TO, false>; \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    kern<<<grid, ST_THREADS, smem, stream>>>(p);                                                      \
+  } while (0)
+  VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_STREAM(TO));
+#undef LAUNCH_STREAM
+  note_kernel("conv_stream_kernel");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("conv_gemm_stream: launch failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 1;
+}
+
+// Row-strided convolution over sliding-window rows (the stem conv_s: (1,7,7)/(1,2,2) on the WIN8 input, one K block per kernel
+// row dh).  Output row h reads source rows h*sh - ph + dh: for a 16-row tile these form `sh` lattices (row parities for sh = 2),
+// each fetched as ONE box with a row element-stride of sh; tap dh is then a plain row offset inside its lattice's box, i.e. a
+// canonical (SBO = row pitch) descriptor.  7 boxes of 16 rows per tile become 2 boxes of 19: 3x less L2->SM traffic.
+static int conv_gemm_stream_strided(const vinet_conv_t* d, cudaStream_t stream) {
+  const vinet_gather_t& g = d->g;
+  if (!g_stream_enable || g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16) return 0;
+  if (g.src[1].ptr != nullptr || g.src[0].xform != VINET_XF_IDENT) return 0;
+  if (g.Cs != 64 || g.sw != 1 || g.sh < 2 || g.sh > 2 || g.st != 1 || g.row_tstep != 1 || g.row_toff != 0 || g.pt != 0) return 0;
+  if (d->n_tiles != 1 || d->block_n > 128 || d->N % 8 != 0 || g.ntaps > 16 || d->k_blocks != g.ntaps) return 0;
+  if (g.Hr < 10) return 0;
+  int q[VINET_MAX_TAPS], par[VINET_MAX_TAPS], qmin[2] = {1 << 20, 1 << 20}, qmax[2] = {-(1 << 20), -(1 << 20)};
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.tap[t][0] != 0 || g.tap[t][2] != 0) return 0;
+    const int o = g.tap[t][1] - g.ph;
+    par[t] = ((o % 2) + 2) % 2;
+    q[t] = (o - par[t]) / 2;
+    qmin[par[t]] = std::min(qmin[par[t]], q[t]);
+    qmax[par[t]] = std::max(qmax[par[t]], q[t]);
+  }
+  if (qmax[0] < qmin[0] || qmax[1] < qmin[1]) return 0;
+  const int PHm = 16 + std::max(qmax[0] - qmin[0], qmax[1] - qmin[1]);
+  const int sms = tma_sm_count();
+  StreamParams p;
+  p.d = *d;
+  p.ncb = 1;
+  p.acc_stride = (uint32_t)round_up(d->block_n, 32);
+  p.b_bytes = (uint32_t)d->block_n * 128u;
+  const size_t wbytes = (size_t)d->k_blocks * p.b_bytes;
+  int nsub = 0;
+  for (int ns = 4; ns >= 1; --ns) {   // widest item whose two stages fit beside the resident weights and whose accumulators double-buffer
+    const size_t stage = (size_t)2 * PHm * 8 * ns * 128;
+    if (2 * stage + wbytes + 4096 <= ST_SMEM_BUDGET && 2 * ns * (int)p.acc_stride <= 512) { nsub = ns; break; }
+  }
+  if (nsub == 0) return 0;
+  p.halo = 2; p.nsub = nsub; p.tw = 8; p.th = 16;
+  p.items_w = (int)cdiv(g.Wr, 8 * nsub); p.items_h = (int)cdiv(g.Hr, 16); p.tiles_w = 0; p.tpf = 0;
+  p.PW = 8 * nsub; p.PH = PHm; p.ew0 = 0; p.eh0 = 0;
+  p.par_sh = 2;
+  p.a_tx_sub = (uint32_t)(PHm * 8 * nsub * 128);
+  for (int k = 0; k < 2; ++k) {
+    p.par_h0[k] = 2 * qmin[k] + k;               // source row of the box's first row, relative to 2 * (tile's first output row)
+    p.par_off[k] = k * (int)p.a_tx_sub;
+  }
+  p.a_stage_bytes = 2 * p.a_tx_sub;
+  p.tt = 1; p.pos = 128; p.tstep = 1; p.toff = 0; p.walk_Tr = g.Tr; p.walk_Ts = g.Ts;
+  p.run = 1; p.nruns = g.Tr; p.S = 1; p.ntg = 1; p.e_min = 0; p.e_max = 0;
+  for (int k = 0; k < ST_MAX_TG; ++k) { p.tg_er[k] = 0; p.tg_eq[k] = 0; }
+  for (int k = 0; k <= ST_MAX_TG; ++k) p.tg_first[k] = k == 0 ? 0 : g.ntaps;
+  for (int j = 0; j < VINET_MAX_TAPS; ++j) {
+    p.sp_aoff[j] = j < g.ntaps ? p.par_off[par[j]] + (q[j] - qmin[par[j]]) * p.PW * 128 : 0;
+    p.sp_kb[j] = j < g.ntaps ? j : 0;
+    p.sp_aoff16[j] = p.sp_aoff[j] >> 4;
+    p.sp_boff16[j] = (int32_t)(((int64_t)p.sp_kb[j] * d->block_n * 128) >> 4);
+  }
+  p.nacc = 2; p.a_stages = 2; p.b_slots = 1; p.wres = 1; p.ni = std::min(ST_MAX_ISSUERS, nsub);
+  const int64_t items = (int64_t)g.B * g.Tr * p.items_w * p.items_h;
+  if (items >= (1ll << 31)) return 0;
+  p.items_per_nt = (int)items;
+  p.tmem_cols = tmem_cols_for(p.nacc * nsub * (int)p.acc_stride);
+  p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
+  p.sub_stride = 8 * 128;
+  p.sbo = (uint32_t)p.PW * 128u;
+  const vinet_src_t& s = g.src[0];
+  if (make_tma_map(&p.tmA[0], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.PW, PHm, 1, 2, 1)) return -1;
+  p.tmA[1] = p.tmA[0];
+  return stream_launch(p, d, sms, stream);
+}
+
 // returns 1 when the launch was handled here, 0 when the caller should use its own kernel, <0 on error
 int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
+  if (g.sh != 1 && g.src[0].ptr != nullptr && g.src[0].ld < g.Cs) return conv_gemm_stream_strided(d, stream);
   if (!stream_eligible(*d)) return 0;
   TapMap tm;
   if (!build_tap_map(g, &tm)) return 0;
@@ -723,37 +828,13 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
   p.a_stage_bytes = pl.a_stage_bytes; p.a_tx_sub = pl.a_tx_sub; p.sub_stride = pl.sub_stride; p.sbo = pl.sbo;
   p.b_bytes = (uint32_t)d->block_n * 128u;
-  const int nb_slots = p.wres ? d->k_blocks : p.b_slots;
-  size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)nb_slots * p.b_bytes +
-                8 * (size_t)(2 * p.a_stages + 2 * p.b_slots + 2 * p.nacc + 1) + 64 + 8 * VINET_MAX_TAPS;
-  if (smem > 227 * 1024) {
-    set_error("conv_gemm_stream: %zu bytes of shared memory", smem);
-    return -1;
-  }
-  smem = std::max<size_t>(smem, 120 * 1024);   // one CTA per SM: two co-resident CTAs would fight over the 512 TMEM columns
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     const int bw = pl.halo ? pl.PW : pl.tw, bh = pl.halo ? pl.PH : pl.th;
     if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT)) return -1;
   }
-  const int ctas = (int)std::min<int64_t>(items, std::max(1, sms / d->n_tiles));
-  dim3 grid((unsigned)ctas, (unsigned)d->n_tiles);
-#define LAUNCH_STREAM(TO)                                                                             \
-  do {                                                                                                \
-    auto kern = conv_has_epilogue(*d) ? conv_stream_kernel<TO, true> : conv_stream_kernel<TO, false>; \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-    kern<<<grid, ST_THREADS, smem, stream>>>(p);                                                      \
-  } while (0)
-  VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_STREAM(TO));
-#undef LAUNCH_STREAM
-  note_kernel("conv_stream_kernel");
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) {
-    set_error("conv_gemm_stream: launch failed: %s", cudaGetErrorString(e));
-    return -2;
-  }
-  return 1;
+  p.par_sh = 1; p.par_h0[0] = p.par_h0[1] = 0; p.par_off[0] = p.par_off[1] = 0;
+  return stream_launch(p, d, sms, stream);
 }
 
 }  // namespace vinet
