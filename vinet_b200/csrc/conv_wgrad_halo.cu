@@ -38,6 +38,7 @@ struct WgHaloParams {
   vinet_wgrad_t d;
   int32_t ncb, nsp, naccs, nblk, block_n, splits, stages, ni, tiles_w, tiles_h, nT, temporal;
   int32_t cw, ch, aw0, ah0, at_step, at0, dyt_step;   // chunk (tw, th, tr) -> TMA coordinates of the activation / dY boxes
+  int32_t nbox, ah_mul, box_h0[2], box_off[2];        // row-strided convs: one activation box per source-row lattice
   int32_t uoff16[WH_MAX_SP];                          // window of unit j inside the activation box, in 16-byte units
   uint32_t a_sbo, kstep_a16;                          // stride between 8-position atoms; 16 positions in 16-byte units
   uint32_t acc_cols, tmem_cols, idesc, a_bytes, a_tx, dy_unit, stage_bytes;
@@ -132,7 +133,9 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
         const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
         const int ts = tr * p.at_step + at0;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
         const int si = (cat && ts >= T0) ? 1 : 0;
-        wh_tma_load_5d(stage, &p.tmA[si], full0 + 8 * s, cb * 64, tw * p.cw + p.aw0, th * p.ch + p.ah0, ts - (si ? T0 : 0), b);
+        for (int k = 0; k < p.nbox; ++k)
+          wh_tma_load_5d(stage + (uint32_t)p.box_off[k], &p.tmA[si], full0 + 8 * s, cb * 64, tw * p.cw + p.aw0,
+                         th * p.ch * p.ah_mul + p.ah0 + p.box_h0[k], ts - (si ? T0 : 0), b);
         for (int nb = 0; nb < nblk_eff; ++nb)
           wh_tma_load_5d(stage + p.a_bytes + (uint32_t)nb * p.dy_unit, &p.tmDy, full0 + 8 * s, n0 + nb * 64, tw * p.cw, th * p.ch,
                          tr * p.dyt_step, b);
@@ -229,8 +232,12 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
   if (!g_stream_enable) return 0;
   if (g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16 || d->dy_dtype != VINET_BF16) return 0;
-  if (g.sh != 1 || g.sw != 1 || g.Cs % 8 != 0 || d->N % 8 != 0 || d->lddy % 8 != 0) return 0;
-  for (int i = 0; i < 2; ++i) {
+  if (g.sw != 1 || g.Cs % 8 != 0 || d->N % 8 != 0 || d->lddy % 8 != 0) return 0;
+  // row-strided conv over sliding-window rows (stem conv_s on the WIN8 input): see conv_gemm_stream_strided
+  const bool rowstride = g.sh == 2 && g.src[1].ptr == nullptr && g.src[0].ld < g.Cs && g.Cs == 64 && g.st == 1 && g.pt == 0 &&
+                         g.row_tstep == 1 && g.row_toff == 0 && g.src[0].xform == VINET_XF_IDENT;
+  if (g.sh != 1 && !rowstride) return 0;
+  for (int i = 0; i < 2 && !rowstride; ++i) {
     const vinet_src_t& s = g.src[i];
     if (s.ptr == nullptr) continue;
     if (s.xform != VINET_XF_IDENT || (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) || s.ld < g.Cs) return 0;
@@ -248,7 +255,8 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
     if (g.tap[t][0] != t / nspat || g.tap[t][1] != (t / kw) % kh || g.tap[t][2] != t % kw) return 0;
   // spatial mode: kh*kw > 1 taps share a spatial halo box.  temporal mode: kh = kw = 1, the kt temporal taps of a single
   // source share a box of (tt-1)*st + kt frames x pos positions (tt*pos = 128 output positions per chunk).
-  const bool temporal = nspat == 1 && kt > 1 && g.src[1].ptr == nullptr && g.row_tstep == 1 && g.row_toff == 0;
+  const bool temporal = !rowstride && nspat == 1 && kt > 1 && g.src[1].ptr == nullptr && g.row_tstep == 1 && g.row_toff == 0;
+  if (rowstride && (kt != 1 || kw != 1 || kh < 2)) return 0;
   if (!temporal && (nspat < 2 || g.Hr < 10)) return 0;
   WgHaloParams p;
   p.d = *d;
@@ -267,8 +275,38 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   p.tmem_cols = tmem_cols_for(p.naccs * (int)p.acc_cols);
   p.nblk = (p.block_n + 63) / 64;
   p.dy_unit = WH_UNIT;
-  int abw, abh, abt = 1, dbw, dbh, dbt = 1;   // activation / dY box extents
-  if (!temporal) {
+  int abw, abh, abt = 1, dbw, dbh, dbt = 1, aesh = 1;   // activation / dY box extents, row element stride of the activation box
+  p.nbox = 1; p.ah_mul = 1; p.box_h0[0] = p.box_h0[1] = 0; p.box_off[0] = p.box_off[1] = 0;
+  if (rowstride) {
+    // tap dh reads source row 2h + (dh - ph): lattice par = (dh - ph) mod 2, row q = (dh - ph - par) / 2 inside its box
+    int q[WH_MAX_SP], par[WH_MAX_SP], qmin[2] = {1 << 20, 1 << 20}, qmax[2] = {-(1 << 20), -(1 << 20)};
+    for (int j = 0; j < kh; ++j) {
+      const int o = j - g.ph;
+      par[j] = ((o % 2) + 2) % 2;
+      q[j] = (o - par[j]) / 2;
+      qmin[par[j]] = std::min(qmin[par[j]], q[j]);
+      qmax[par[j]] = std::max(qmax[par[j]], q[j]);
+    }
+    if (qmax[0] < qmin[0] || qmax[1] < qmin[1]) return 0;
+    const int PHm = 16 + std::max(qmax[0] - qmin[0], qmax[1] - qmin[1]);
+    abw = 8; abh = PHm; dbw = 8; dbh = 16; aesh = 2;
+    p.cw = 8; p.ch = 16; p.aw0 = 0; p.ah0 = 0; p.ah_mul = 2;
+    p.at_step = 1; p.at0 = 0; p.dyt_step = 1;
+    p.nT = g.Tr;
+    p.tiles_w = (int)cdiv(g.Wr, 8);
+    p.tiles_h = (int)cdiv(g.Hr, 16);
+    p.nbox = 2;
+    const int first = par[0];                    // the lattice of tap 0 goes first so that stacked pairs have LBO >= 0
+    for (int k = 0; k < 2; ++k) {
+      p.box_h0[k] = 2 * qmin[k] + k;
+      p.box_off[k] = (k == first ? 0 : PHm * 8 * 128);
+    }
+    for (int j = 0; j < WH_MAX_SP; ++j) p.uoff16[j] = j < kh ? (p.box_off[par[j]] + (q[j] - qmin[par[j]]) * 8 * 128) >> 4 : 0;
+    for (int a2 = 0; 2 * a2 + 1 < kh; ++a2)
+      if (p.uoff16[2 * a2 + 1] < p.uoff16[2 * a2]) return 0;
+    p.a_sbo = 1024u;
+    p.kstep_a16 = 2048u >> 4;
+  } else if (!temporal) {
     const int PW = 8 + kw - 1, PH = 16 + kh - 1;
     abw = PW; abh = PH; dbw = 8; dbh = 16;
     p.cw = 8; p.ch = 16; p.aw0 = -g.pw; p.ah0 = -g.ph;
@@ -300,7 +338,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
     p.a_sbo = g.st > 1 ? (uint32_t)(g.st * pos * 128) : 1024u;
     p.kstep_a16 = (2u * p.a_sbo) >> 4;
   }
-  p.a_tx = (uint32_t)(abw * abh * abt * 128);
+  p.a_tx = (uint32_t)(abw * abh * abt * 128) * (uint32_t)p.nbox;
   p.a_bytes = (uint32_t)round_up(p.a_tx, 1024);
   p.stage_bytes = p.a_bytes + (uint32_t)p.nblk * p.dy_unit;
   p.idesc = make_idesc(TC_BM, p.block_n, 1, 1);
@@ -328,7 +366,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   if (smem > 227 * 1024) return 0;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, 1, abt)) return -1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, aesh, abt)) return -1;
   }
   if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, dbw, dbh, 1, 1, dbt)) return -1;
   dim3 grid((unsigned)groups, (unsigned)n_tiles, (unsigned)splits);
