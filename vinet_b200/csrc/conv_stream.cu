@@ -549,7 +549,7 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
     const bool thalo_ok = !spatial && tm.ntg > 1 && g.src[1].ptr == nullptr;
     for (int tt = 1; tt <= (thalo_ok ? 16 : 1); tt *= 2) {
       if (tt > 1 && tt / 2 >= g.Tr) break;
-      if (tm.S > 1 && tt != 16) continue;        // strided frame walks measured slower than per-tap boxes: temporal halo or nothing
+      if (!spatial && tm.S > 1 && tt != 16) continue;   // strided frame walks measured slower than per-tap boxes: temporal halo or nothing
       const int L = tt > 1 ? 1 : tm.L;
       const int walk_Tr = tt > 1 ? (int)cdiv(g.Tr, tt) : g.Tr;
       int tbw = fbw, tbh = fbh;
