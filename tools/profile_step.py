@@ -42,7 +42,7 @@ tot = collections.defaultdict(float)
 cnt = collections.Counter()
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", ev.name))
+        name = ev.name if os.environ.get("VINET_PROFILE_FULLNAMES") and ev.name.startswith("void at::") else re.sub(r"<.*", "", re.sub(r"\(.*", "", ev.name))
         tot[name] += ev.device_time / 1e3 if hasattr(ev, "device_time") else ev.cuda_time / 1e3
         cnt[name] += 1
 s = sum(tot.values())

@@ -4,6 +4,7 @@
 // order, like ATen) as one byte; backward then scatters the gradient without re-scanning the window.  Without a
 // recorded index (inference-only forward / legacy callers) backward recomputes the arg-max.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -400,7 +401,10 @@ extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
 
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
   if (pool_check(d)) return -1;
-  if (d->idx && (g_pool_fast & 2)) {   // gather over the recorded taps: no atomics, writes or accumulates every input element once
+  // windows that can contain one input element: the gather visits all of them, so it only pays for strided pools
+  const int cand = (int)(cdiv(d->kt, d->st) * cdiv(d->kh, d->sh) * cdiv(d->kw, d->sw));
+  static const int gather_max = getenv("VINET_POOL_GATHER_MAX") ? atoi(getenv("VINET_POOL_GATHER_MAX")) : 0;
+  if (d->idx && ((g_pool_fast & 2) || cand <= gather_max)) {   // gather over the recorded taps: no atomics, writes or accumulates every input element once
     const int64_t total = (int64_t)d->B * d->Ti * d->Hi * d->Wi * (d->C / 8);
     const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 148 * 64));
     VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
