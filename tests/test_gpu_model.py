@@ -182,3 +182,32 @@ def test_full_size_clip_fp32_engine_vs_oracle_on_the_same_gpu():
     for k in sr:
         if "running_" in k:
             assert torch.allclose(sm[k], sr[k], rtol=1e-3, atol=1e-5), k
+
+
+@pytest.mark.parametrize("shape", [(8, 2, 128, 192), (16, 1, 448, 768), (48, 1, 224, 384), (32, 3, 160, 224)])
+def test_sweep_shapes_tcgen05_engine_runs_and_tracks_the_ffma_engine(shape):
+    """BASELINE.json config 5 (resolution / clip-length sweep, restated per SURVEY §8d to what the reference supports): every
+    shape makes the streaming kernels pick different tilings.  Whole-model runs of two engines only track each other loosely
+    (bf16 rounding noise is amplified through 60 train-mode BatchNorm layers with tiny batches - the per-tap and streaming
+    kernels differ from each other by as much as either differs from the FFMA engine), so this is the smoke half of the
+    sweep; the exact half is tests/test_gpu_kernels.py::test_conv_kernels_match_ffma_engine_on_sweep_geometries."""
+    T, B, H, W = shape
+    meta = {"T": T, "seed": 31, "keys": list(VideoSaliencyModel(num_clips=T).state_dict().keys())}
+    d = O.make_inputs(B, T, H, W, 31)
+    x, gt = d["x"].cuda(), d["gt"].cuda()
+    res = {}
+    for prec in ("bf16", "bf16_simt"):
+        _, m = _build(meta, prec)
+        m.train()
+        pred = m(x)
+        loss = kldiv(pred, gt)
+        loss.backward()
+        gn = sum(float(p.grad.float().norm()) for p in m.parameters())
+        res[prec] = (pred.detach().float().cpu(), float(loss.detach()), gn)
+        del m
+        torch.cuda.empty_cache()
+    pa, la, ga = res["bf16"]
+    pb, lb, gb = res["bf16_simt"]
+    assert torch.isfinite(pa).all() and pa.shape == (B, H, W) and np.isfinite(ga)
+    assert (pa - pb).abs().mean().item() <= 5e-2, (pa - pb).abs().mean().item()
+    assert abs(la - lb) <= 5e-2 * abs(lb), (la, lb)
