@@ -240,6 +240,12 @@ int vinet_bn_bwd_apply(const vinet_bn_bwd_t* d, vinet_stream_t stream);
  * The blocks reduce, the last one finalises and raises a flag, all of them then apply to the rows they have just read.
  * The sums buffers hold [2][C] doubles followed by THREE 8-byte words (ticket, flag, departures), zero between launches. */
 int vinet_bn_fwd_fused(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, const vinet_bn_apply_t* a, vinet_stream_t stream);
+/* Multi-layer variants: n <= 4 independent BatchNorm layers (arrays of n descriptors, same storage types) in ONE launch per
+ * pass - small layers cost ~6 us per launch whatever they do.  stats_finalize_multi = batch statistics + finalisation
+ * (sums buffers as for vinet_bn_stats_finalize), apply_multi = materialisation, bwd_multi = reduce launch + apply launch. */
+int vinet_bn_stats_finalize_multi(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, int32_t n, vinet_stream_t stream);
+int vinet_bn_apply_multi(const vinet_bn_apply_t* a, int32_t n, vinet_stream_t stream);
+int vinet_bn_bwd_multi(const vinet_bn_bwd_t* b, int32_t n, vinet_stream_t stream);
 int vinet_bn_bwd_fused(const vinet_bn_bwd_t* d, vinet_stream_t stream);
 
 /* ---- nn.MaxPool3d (model.py:696-714, model_utils.py:178...; model.py:229) ---- */

@@ -368,6 +368,216 @@ __global__ void bn_apply_kernel(const __grid_constant__ vinet_bn_apply_t d, int6
   }
 }
 
+// ---- multi-layer launches ---------------------------------------------------------------------------------------------------------
+// Most BatchNorm layers of this model are small (a Mixed block has seven, a few MB each) and cost ~6 us per launch whatever
+// they do.  Layers that are ready at the same time (the three fused 1x1 branches + the pool branch, the two conv_s, the two
+// conv_t of a Mixed block) are therefore processed by ONE launch: blockIdx.y selects the layer ("segment"), every segment
+// brings its own descriptor, block count and sums / ticket buffer.  Blocks are 1-D (256 threads) and derive the
+// (channel group, row lane) mapping from their segment's channel count.
+constexpr int BN_MAX_SEG = 4;
+constexpr int BN_MT = 256;
+
+struct SegMap {
+  int gx, ry, Ry;
+  bool active;
+};
+__device__ __forceinline__ SegMap seg_map(int C) {
+  SegMap m;
+  const int G = C / 8;
+  m.Ry = BN_MT / G;
+  m.gx = threadIdx.x % G;
+  m.ry = threadIdx.x / G;
+  m.active = m.ry < m.Ry;
+  return m;
+}
+
+template <int NV, typename F>
+__device__ __forceinline__ bool column_reduce_1d(const SegMap& m, int64_t rows, int C, int64_t rows_per_block, int nblocks, double* sums,
+                                                 F&& body) {
+  extern __shared__ float red[];  // [Ry][NV][C]
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  if (m.active) {
+#pragma unroll 4
+    for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) body(r, m.gx * 8, acc);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[((size_t)m.ry * NV + v) * C + m.gx * 8 + e] = acc[v][e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV * C; i += BN_MT) {
+    double s = 0.0;
+    for (int y = 0; y < m.Ry; ++y) s += (double)red[(size_t)y * NV * C + i];
+    atomicAdd(sums + i, s);
+  }
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(sums + NV * C);
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    is_last = (t == (unsigned long long)nblocks - 1);
+    if (is_last) *ticket = 0ull;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
+}
+
+struct BnFwdMulti {
+  vinet_bn_stats_t s[BN_MAX_SEG];
+  vinet_bn_finalize_t f[BN_MAX_SEG];
+  int64_t rpb[BN_MAX_SEG];
+  int32_t nb[BN_MAX_SEG];
+};
+struct BnApplyMulti {
+  vinet_bn_apply_t a[BN_MAX_SEG];
+  int64_t rpb[BN_MAX_SEG];
+  int32_t nb[BN_MAX_SEG];
+};
+struct BnBwdMulti {
+  vinet_bn_bwd_t b[BN_MAX_SEG];
+  int64_t rpb[BN_MAX_SEG];
+  int32_t nb[BN_MAX_SEG];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BN_MT) bn_stats_finalize_multi_kernel(const __grid_constant__ BnFwdMulti p) {
+  const int seg = blockIdx.y;
+  if ((int)blockIdx.x >= p.nb[seg]) return;
+  const vinet_bn_stats_t& d = p.s[seg];
+  const vinet_bn_finalize_t& f = p.f[seg];
+  const SegMap m = seg_map(d.C);
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const bool last = column_reduce_1d<2>(m, d.rows, d.C, p.rpb[seg], p.nb[seg], d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8];
+    load8(y + r * d.ld + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += v[e];
+      acc[1][e] = fmaf(v[e], v[e], acc[1][e]);
+    }
+  });
+  if (last)
+    for (int c = threadIdx.x; c < f.C; c += BN_MT) bn_finalize_channel(f, c);
+}
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(BN_MT) bn_apply_multi_kernel(const __grid_constant__ BnApplyMulti p) {
+  const int seg = blockIdx.y;
+  if ((int)blockIdx.x >= p.nb[seg]) return;
+  const vinet_bn_apply_t& d = p.a[seg];
+  const SegMap m = seg_map(d.C);
+  if (!m.active) return;
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  TO* __restrict__ out = reinterpret_cast<TO*>(d.out);
+  const int c = m.gx * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e); }
+  const bool relu = d.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rpb[seg];
+  const int64_t r_end = min(d.rows, r_begin + p.rpb[seg]);
+#pragma unroll 4
+  for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) {
+    float v[8];
+    load8(y + r * d.ldy + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = fmaf(v[e], sc[e], sh[e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
+    store8(out + r * d.ldo + c, v);
+  }
+}
+
+template <typename T, typename TG>
+__global__ void __launch_bounds__(BN_MT) bn_bwd_reduce_multi_kernel(const __grid_constant__ BnBwdMulti p) {
+  const int seg = blockIdx.y;
+  if ((int)blockIdx.x >= p.nb[seg]) return;
+  const vinet_bn_bwd_t& d = p.b[seg];
+  const SegMap m = seg_map(d.C);
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
+  float sc[8], sh[8], mu[8], is[8];
+  {
+    const int c = m.gx * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e);
+      mu[e] = __ldg(d.mean + c + e); is[e] = __ldg(d.invstd + c + e);
+    }
+  }
+  const bool relu = d.relu != 0;
+  const bool last = column_reduce_1d<2>(m, d.rows, d.C, p.rpb[seg], p.nb[seg], d.sums, [&](int64_t r, int c, float (&acc)[2][8]) {
+    float v[8], g[8];
+    load8(y + r * d.ldy + c, v);
+    load8(gp + r * d.ldg + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
+      acc[0][e] += gm;
+      acc[1][e] = fmaf(gm, yn, acc[1][e]);
+    }
+  });
+  if (last) {
+    volatile double* vs = d.sums;
+    for (int c = threadIdx.x; c < d.C; c += BN_MT) {
+      d.dbeta[c] = (float)vs[c];
+      d.dgamma[c] = (float)vs[d.C + c];
+      d.sums[c] = 0.0;
+      d.sums[d.C + c] = 0.0;
+    }
+  }
+}
+
+template <typename T, typename TD, typename TG>
+__global__ void __launch_bounds__(BN_MT) bn_bwd_apply_multi_kernel(const __grid_constant__ BnBwdMulti p) {
+  const int seg = blockIdx.y;
+  if ((int)blockIdx.x >= p.nb[seg]) return;
+  const vinet_bn_bwd_t& d = p.b[seg];
+  const SegMap m = seg_map(d.C);
+  if (!m.active) return;
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  const TG* __restrict__ gp = reinterpret_cast<const TG*>(d.g);
+  TD* __restrict__ dy = reinterpret_cast<TD*>(d.dy);
+  const int c = m.gx * 8;
+  const float inv_n = 1.0f / (float)d.rows;
+  float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e);
+    mu[e] = __ldg(d.mean + c + e); is[e] = __ldg(d.invstd + c + e);
+    k1[e] = d.training ? __ldg(d.dbeta + c + e) * inv_n : 0.f;
+    k2[e] = d.training ? __ldg(d.dgamma + c + e) * inv_n : 0.f;
+  }
+  const bool relu = d.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rpb[seg];
+  const int64_t r_end = min(d.rows, r_begin + p.rpb[seg]);
+#pragma unroll 4
+  for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) {
+    float v[8], g[8], o[8];
+    load8(y + r * d.ldy + c, v);
+    load8(gp + r * d.ldg + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float yh = fmaf(v[e], sc[e], sh[e]);
+      const float gm = (relu && !(yh > 0.f)) ? 0.f : g[e];
+      const float yn = (v[e] - mu[e]) * is[e];
+      o[e] = sc[e] * (gm - k1[e] - yn * k2[e]);
+    }
+    store8(dy + r * d.lddy + c, o);
+  }
+}
+
 struct ColGrid {
   dim3 block;
   unsigned grid;
@@ -484,6 +694,85 @@ extern "C" int vinet_bn_bwd_fused(const vinet_bn_bwd_t* d, vinet_stream_t stream
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dy_dtype, TD, VINET_DISPATCH_DTYPE(d->g_dtype, TG, LAUNCH_BWD(T, TD, TG))));
 #undef LAUNCH_BWD
   VINET_LAUNCH_OK("bn_bwd_fused");
+  return 0;
+}
+
+// per-segment block count / rows per block of a multi-layer launch (1-D blocks of BN_MT threads)
+static void seg_grid(int64_t rows, int C, bool reduce, int64_t* rpb, int32_t* nb, size_t* smem, int nv) {
+  const int G = C / 8, Ry = BN_MT / G;
+  int64_t max_blocks = 148 * 8;
+  if (reduce) max_blocks = std::min<int64_t>(max_blocks, std::max<int64_t>(148, 160000 / (2 * C)));
+  int64_t rpt = cdiv(rows, (int64_t)Ry * max_blocks);
+  if (rpt < 8) rpt = 8;
+  *rpb = (int64_t)Ry * rpt;
+  *nb = (int32_t)std::max<int64_t>(1, cdiv(rows, *rpb));
+  *smem = std::max(*smem, (size_t)Ry * nv * C * sizeof(float));
+}
+
+extern "C" int vinet_bn_stats_finalize_multi(const vinet_bn_stats_t* d, const vinet_bn_finalize_t* f, int32_t n, vinet_stream_t stream) {
+  VINET_CHECK(n >= 1 && n <= BN_MAX_SEG, "bn_stats_finalize_multi: %d segments", n);
+  BnFwdMulti p;
+  size_t smem = 0;
+  int32_t gx = 1;
+  for (int i = 0; i < n; ++i) {
+    VINET_CHECK(d[i].C % 8 == 0 && d[i].C <= 1024 && f[i].C == d[i].C && f[i].sums == d[i].sums && f[i].training &&
+                d[i].dtype == d[0].dtype, "bn_stats_finalize_multi: segment %d", i);
+    p.s[i] = d[i];
+    p.f[i] = f[i];
+    seg_grid(d[i].rows, d[i].C, true, &p.rpb[i], &p.nb[i], &smem, 2);
+    gx = std::max(gx, p.nb[i]);
+  }
+  for (int i = n; i < BN_MAX_SEG; ++i) p.nb[i] = 0;
+  VINET_DISPATCH_DTYPE(d[0].dtype, T, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_finalize_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bn_stats_finalize_multi_kernel<T><<<dim3((unsigned)gx, (unsigned)n), BN_MT, smem, (cudaStream_t)stream>>>(p);
+  });
+  VINET_LAUNCH_OK("bn_stats_finalize_multi");
+  return 0;
+}
+
+extern "C" int vinet_bn_apply_multi(const vinet_bn_apply_t* a, int32_t n, vinet_stream_t stream) {
+  VINET_CHECK(n >= 1 && n <= BN_MAX_SEG, "bn_apply_multi: %d segments", n);
+  BnApplyMulti p;
+  size_t smem = 0;
+  int32_t gx = 1;
+  for (int i = 0; i < n; ++i) {
+    VINET_CHECK(a[i].C % 8 == 0 && a[i].C <= 1024 && a[i].dtype == a[0].dtype && a[i].out_dtype == a[0].out_dtype, "bn_apply_multi: segment %d", i);
+    p.a[i] = a[i];
+    seg_grid(a[i].rows, a[i].C, false, &p.rpb[i], &p.nb[i], &smem, 0);
+    gx = std::max(gx, p.nb[i]);
+  }
+  for (int i = n; i < BN_MAX_SEG; ++i) p.nb[i] = 0;
+  VINET_DISPATCH_DTYPE(a[0].dtype, T, VINET_DISPATCH_DTYPE(a[0].out_dtype, TO,
+      (bn_apply_multi_kernel<T, TO><<<dim3((unsigned)gx, (unsigned)n), BN_MT, 0, (cudaStream_t)stream>>>(p))));
+  VINET_LAUNCH_OK("bn_apply_multi");
+  return 0;
+}
+
+extern "C" int vinet_bn_bwd_multi(const vinet_bn_bwd_t* b, int32_t n, vinet_stream_t stream) {
+  VINET_CHECK(n >= 1 && n <= BN_MAX_SEG, "bn_bwd_multi: %d segments", n);
+  BnBwdMulti pr, pa;
+  size_t smem = 0, none = 0;
+  int32_t gr = 1, ga = 1;
+  for (int i = 0; i < n; ++i) {
+    VINET_CHECK(b[i].C % 8 == 0 && b[i].C <= 1024 && b[i].dtype == b[0].dtype && b[i].g_dtype == b[0].g_dtype &&
+                b[i].dy_dtype == b[0].dy_dtype, "bn_bwd_multi: segment %d", i);
+    pr.b[i] = b[i];
+    pa.b[i] = b[i];
+    seg_grid(b[i].rows, b[i].C, true, &pr.rpb[i], &pr.nb[i], &smem, 2);
+    seg_grid(b[i].rows, b[i].C, false, &pa.rpb[i], &pa.nb[i], &none, 0);
+    gr = std::max(gr, pr.nb[i]);
+    ga = std::max(ga, pa.nb[i]);
+  }
+  for (int i = n; i < BN_MAX_SEG; ++i) pr.nb[i] = pa.nb[i] = 0;
+  VINET_DISPATCH_DTYPE(b[0].dtype, T, VINET_DISPATCH_DTYPE(b[0].g_dtype, TG, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_multi_kernel<T, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bn_bwd_reduce_multi_kernel<T, TG><<<dim3((unsigned)gr, (unsigned)n), BN_MT, smem, (cudaStream_t)stream>>>(pr);
+  }));
+  VINET_LAUNCH_OK("bn_bwd_reduce_multi");
+  VINET_DISPATCH_DTYPE(b[0].dtype, T, VINET_DISPATCH_DTYPE(b[0].dy_dtype, TD, VINET_DISPATCH_DTYPE(b[0].g_dtype, TG,
+      (bn_bwd_apply_multi_kernel<T, TD, TG><<<dim3((unsigned)ga, (unsigned)n), BN_MT, 0, (cudaStream_t)stream>>>(pa)))));
+  VINET_LAUNCH_OK("bn_bwd_apply_multi");
   return 0;
 }
 

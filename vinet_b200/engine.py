@@ -119,6 +119,7 @@ class Engine:
         self.training = False
         self.record = False
         self.use_tma = True     # False: force the register-gather tcgen05 kernels (tests / A-B timing)
+        self._bn_pending = None  # deferred BatchNorm tails of layers that are ready together (bn_begin / bn_flush)
         self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)})
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
@@ -179,6 +180,7 @@ class Engine:
         self.tape, self.grad_bufs, self.zero_list, self.param_grads = [], [], [], {}
         self.gwritten = set()
         self.bn_counters = []
+        self._bn_pending = None
 
     def end_forward(self):
         """nn.BatchNorm's num_batches_tracked counters of every layer touched by this forward, one launch."""
@@ -491,10 +493,84 @@ class Engine:
             self.bn_counters.append(bn.num_batches_tracked)   # += 1 for all layers in one launch (end_forward)
         return st, ss
 
+    # ---- multi-layer BatchNorm launches: layers that are ready at the same time share ONE launch per pass ----
+    def bn_begin(self):
+        if self.training and "vinet_bn_stats_finalize_multi" in self.lib.fn:
+            self._bn_pending = []
+
+    def bn_end(self):
+        self.bn_flush()
+        self._bn_pending = None
+
+    def bn_flush(self):
+        pend = self._bn_pending
+        if not pend:
+            return
+        self._bn_pending = []
+        for i in range(0, len(pend), 4):
+            self._bn_batch(pend[i:i + 4])
+
+    def _bn_batch(self, members):
+        """members: [(name_bn, bn, raw, out, conv_bwd, dy_slot)] - small train-mode layers: one stats+finalise launch, one
+        apply launch; backward one reduce launch + one apply launch, then each member's convolution backward."""
+        n = len(members)
+        sds, fins, aps, keep = (L.BnStats * n)(), (L.BnFinalize * n)(), (L.BnApply * n)(), []
+        for i, (name_bn, bn, raw, out, conv_bwd, dy_slot) in enumerate(members):
+            Cn, rows = out.C, out.rows
+            st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)
+            ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)
+            sums = self.buf(name_bn + ".sums", (2 * Cn + 4,), torch.float64, zero=True)
+            sd, fin, ap = sds[i], fins[i], aps[i]
+            sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
+            fin.sums, fin.rows, fin.C, fin.gamma, fin.beta = sums.data_ptr(), rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
+            fin.eps, fin.momentum, fin.training = bn.eps, bn.momentum, 1
+            fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+            ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
+            ap.scale, ap.shift, ap.out, ap.ldo, ap.out_dtype = ss[0].data_ptr(), ss[1].data_ptr(), out.ptr(), out.ld, self.dt
+            out.xform, out.scale, out.shift = L.XF_IDENT, None, None
+            self.bn_counters.append(bn.num_batches_tracked)
+            keep.append((st, ss))
+        self.lib.call("vinet_bn_stats_finalize_multi", sds, fins, n, self.stream())
+        self.lib.call("vinet_bn_apply_multi", aps, n, self.stream())
+        if not self.record:
+            return
+
+        def backward():
+            bs, outs = (L.BnBwd * n)(), []
+            for i, (name_bn, bn, raw, out, conv_bwd, dy_slot) in enumerate(members):
+                Cn, rows = out.C, out.rows
+                st, ss = keep[i]
+                bsums = self.buf(name_bn + ".bsums", (2 * Cn + 4,), torch.float64, zero=True)
+                dgamma, dbeta = self.grad_tensor(name_bn + ".weight", bn.weight), self.grad_tensor(name_bn + ".bias", bn.bias)
+                if dy_slot is None:
+                    # members of one launch need distinct dY buffers
+                    dy = self.buf("dy.%d.%d" % (rows * Cn, i), (rows, Cn), self.tdtype)
+                    dy_ptr, lddy = dy.data_ptr(), Cn
+                else:
+                    dy_ptr, lddy = dy_slot
+                b = bs[i]
+                b.g, b.ldg, b.y, b.ldy, b.dtype, b.rows, b.C, b.relu = out.gptr(), out.ldg, raw.ptr(), raw.ld, self.dt, rows, Cn, 1
+                b.scale, b.shift, b.mean, b.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+                b.gamma, b.sums, b.dgamma, b.dbeta = bn.weight.data_ptr(), bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr()
+                b.dy, b.lddy, b.dy_dtype, b.training, b.g_dtype = dy_ptr, lddy, self.dt, 1, out.gdt
+                self.param_grads[name_bn + ".weight"] = dgamma
+                self.param_grads[name_bn + ".bias"] = dbeta
+                outs.append((conv_bwd, dy_ptr, lddy))
+            assert len({o.gdt for _, _, _, o, _, _ in members}) == 1
+            self.lib.call("vinet_bn_bwd_multi", bs, n, self.stream())
+            for conv_bwd, dy_ptr, lddy in reversed(outs):
+                if conv_bwd is not None:
+                    conv_bwd(dy_ptr, lddy)
+        self.tape.append(backward)
+
     def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot):
         """BatchNorm + ReLU of the raw conv output `raw` into `out`, and its backward.  The backward either
         hands dY to `conv_bwd` (own conv) or writes it into `dy_slot` = (ptr, ld) of a fused group's dY buffer."""
         Cn, rows = out.C, out.rows
+        if self._bn_pending is not None and self.training and rows * Cn * raw.buf.element_size() < (24 << 20):
+            self._bn_pending.append((name_bn, bn, raw, out, conv_bwd, dy_slot))      # small layer: wait for its launch mates
+            return
         out.xform, out.scale, out.shift = L.XF_IDENT, None, None
         ap = L.BnApply()
         ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1

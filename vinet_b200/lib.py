@@ -145,6 +145,9 @@ SIGNATURES = {
     "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_fwd_fused": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), C.POINTER(BnApply), _S]),
     "vinet_bn_bwd_fused": (C.c_int, [C.POINTER(BnBwd), _S]),
+    "vinet_bn_stats_finalize_multi": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _i32, _S]),
+    "vinet_bn_apply_multi": (C.c_int, [C.POINTER(BnApply), _i32, _S]),
+    "vinet_bn_bwd_multi": (C.c_int, [C.POINTER(BnBwd), _i32, _S]),
     "vinet_maxpool_fwd": (C.c_int, [C.POINTER(Pool), _S]),
     "vinet_maxpool_bwd": (C.c_int, [C.POINTER(Pool), _S]),
     "vinet_upsample_fwd": (C.c_int, [C.POINTER(Upsample), _S]),

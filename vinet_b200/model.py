@@ -124,7 +124,8 @@ class DecoderConvUp(nn.Module):
 
 
 # ----------------------------------------------------------------------------- the fused plan
-def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
+def _sepconv_s(e, pfx, srcs, m, cin_real=None):
+    """First half of SepConv3d (model_utils.py:144-146): (1,k,k) conv + BN + ReLU -> the intermediate activation."""
     a0 = srcs[0]
     k, s, p = m.k, m.stride, m.padding
     gs = ConvGeom((1, k, k), (1, s, s), (0, p, p))
@@ -132,12 +133,22 @@ def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
     cout = m.conv_s.weight.shape[0]
     mid = e.new_act(pfx + ".s", a0.B, To, Ho, Wo, cout)
     e.conv_bn(pfx + ".conv_s", pfx + ".bn_s", srcs, m.conv_s.weight, m.bn_s, gs, mid, cin_real=cin_real)
+    return mid
+
+
+def _sepconv_t(e, pfx, mid, m, out=None):
+    """Second half of SepConv3d (model_utils.py:148-150): (k,1,1) conv + BN + ReLU."""
+    k, s, p = m.k, m.stride, m.padding
     gt = ConvGeom((k, 1, 1), (s, 1, 1), (p, 0, 0))
-    To2, _, _ = gt.out_dims(To, Ho, Wo)
+    To2, _, _ = gt.out_dims(mid.T, mid.H, mid.W)
     if out is None:
-        out = e.new_act(pfx + ".t", a0.B, To2, Ho, Wo, cout)
+        out = e.new_act(pfx + ".t", mid.B, To2, mid.H, mid.W, m.conv_t.weight.shape[0])
     e.conv_bn(pfx + ".conv_t", pfx + ".bn_t", [mid], m.conv_t.weight, m.bn_t, gt, out)
     return out
+
+
+def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
+    return _sepconv_t(e, pfx, _sepconv_s(e, pfx, srcs, m, cin_real=cin_real), m, out)
 
 
 _G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
@@ -155,6 +166,9 @@ def _mixed(e, pfx, x, m, gdtype=None):
     branch first, the three 1x1 convs on x fused into one GEMM); the arithmetic per branch is unchanged."""
     cin, b0, b1r, b1, b2r, b2, b3 = arch.MIXED[m.name]
     out = e.new_act(pfx + ".cat", x.B, x.T, x.H, x.W, b0 + b1 + b2 + b3, gdtype=gdtype)
+    # The BatchNorm layers that are ready together run as ONE multi-layer launch per pass (Engine.bn_begin / bn_flush):
+    # {branch0, branch1.0, branch2.0, branch3.1}, then both conv_s, then both conv_t - 3 launch groups instead of 7 layers.
+    e.bn_begin()
     # pool branch first: its backward (a scatter-add) then runs after the convs' data gradients have written x.grad
     p = e.maxpool(pfx + ".branch3.pool", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     _basic(e, pfx + ".branch3.1", p, m.branch3[1], out.slice(b0 + b1 + b2, b3))
@@ -164,8 +178,13 @@ def _mixed(e, pfx, x, m, gdtype=None):
         (pfx + ".branch0.0.conv", pfx + ".branch0.0.bn", m.branch0[0].conv.weight, m.branch0[0].bn, out.slice(0, b0)),
         (pfx + ".branch1.0.conv", pfx + ".branch1.0.bn", m.branch1[0].conv.weight, m.branch1[0].bn, t1),
         (pfx + ".branch2.0.conv", pfx + ".branch2.0.bn", m.branch2[0].conv.weight, m.branch2[0].bn, t2)])
-    _sepconv(e, pfx + ".branch1.1", [t1], m.branch1[1], out.slice(b0, b1))
-    _sepconv(e, pfx + ".branch2.1", [t2], m.branch2[1], out.slice(b0 + b1, b2))
+    e.bn_flush()
+    m1 = _sepconv_s(e, pfx + ".branch1.1", [t1], m.branch1[1])
+    m2 = _sepconv_s(e, pfx + ".branch2.1", [t2], m.branch2[1])
+    e.bn_flush()
+    _sepconv_t(e, pfx + ".branch1.1", m1, m.branch1[1], out.slice(b0, b1))
+    _sepconv_t(e, pfx + ".branch2.1", m2, m.branch2[1], out.slice(b0 + b1, b2))
+    e.bn_end()
     return out
 
 
