@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--no-adam", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N>1: wrap in DistributedDataParallel instead of the flat-arena all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--kernel-table", default="", help="write the per-conv-launch timing table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -157,7 +158,8 @@ def main():
         # with a single NCCL all-reduce per step (model.sync_gradients) - no per-tensor bucket copies
         model.broadcast_parameters(0)
         model.enable_grad_arena()
-    opt = None if args.no_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    use_graph = world == 1 and not args.no_graph and not args.no_adam
+    opt = None if args.no_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     # caller layout: (B,T,3,H,W) memory viewed as (B,3,T,H,W)  (train.py:204-205)
@@ -201,6 +203,20 @@ def main():
             ms = t.item()
         return ms
 
+    graphed = None
+    if use_graph:
+        # the public GraphedTrainStep API: the whole step (forward, kldiv, backward, fused Adam) captured once as a CUDA
+        # graph and replayed; falls back to eager launches if the capture is refused
+        try:
+            from vinet_b200 import GraphedTrainStep
+            graphed = GraphedTrainStep(model, kldiv, opt, dx.permute(0, 2, 1, 3, 4), dgt)
+            eager_step = step
+
+            def step(x_btchw, gt):          # noqa: F811
+                return graphed(x_btchw.permute(0, 2, 1, 3, 4), gt)
+        except Exception as ex:          # pragma: no cover
+            sys.stderr.write("bench: CUDA graph capture failed (%s); running eagerly\n" % str(ex)[:200])
+            graphed = None
     for _ in range(max(args.warmup, 3)):
         step(dx, dgt)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -209,6 +225,8 @@ def main():
     n0 = lib.launch_count()
     ms = timed(lambda: step(dx, dgt), args.steps)
     launches = lib.launch_count() - n0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps
     # end-to-end: pinned host -> device every step, loss read back every step
     sink = []
 
@@ -285,7 +303,7 @@ def main():
             "config": {"workload": "ViNet (VideoSaliencyModel) fwd + kldiv + bwd%s, batch %d x 32x224x384 clips per GPU, %s"
                                    % ("" if args.no_adam else " + fused Adam", B, args.precision),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "grad_sync": "none" if world == 1 else ("DistributedDataParallel" if args.ddp else "flat arena, one NCCL all-reduce"),
+                       "cuda_graph": graphed is not None, "grad_sync": "none" if world == 1 else ("DistributedDataParallel" if args.ddp else "flat arena, one NCCL all-reduce"),
                        "l2": "inputs (264 MB/clip-batch) and activations (GBs) exceed the 126 MB L2; no explicit flush",
                        "e2e_pipeline": "H2D of step i+1 (pinned host, copy stream) overlaps the kernels of step i; loss.item() every step"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": hx.numel() * 4 + hgt.numel() * 4, "d2h_bytes_per_step": 4,

@@ -139,6 +139,10 @@ typedef struct vinet_pack {
   int32_t layout; /* VINET_KLAYOUT_* */
 } vinet_pack_t;
 int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
+/* n TC-engine packs in ONE launch.  table_dev: n descriptors in DEVICE memory (each as for vinet_pack_weights, already
+ * validated once through it); chunk_begin_dev[e] = sum over entries < e of n_tiles*k_blocks*block_n*8 (16-byte chunks). */
+int vinet_pack_weights_multi(const vinet_pack_t* table_dev, const int64_t* chunk_begin_dev, int32_t n, int64_t total_chunks,
+                             vinet_stream_t stream);
 size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks);
 
 /* WIN8 variant: grad[co][ci][0][dh][dw] = dwp[(dh*64 + dw*8 + ci)*lddw + co] */

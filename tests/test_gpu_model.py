@@ -211,3 +211,42 @@ def test_sweep_shapes_tcgen05_engine_runs_and_tracks_the_ffma_engine(shape):
     assert torch.isfinite(pa).all() and pa.shape == (B, H, W) and np.isfinite(ga)
     assert (pa - pb).abs().mean().item() <= 5e-2, (pa - pb).abs().mean().item()
     assert abs(la - lb) <= 5e-2 * abs(lb), (la, lb)
+
+
+def test_graphed_train_step_replays_the_eager_step():
+    """vinet_b200.GraphedTrainStep: capture leaves parameters / buffers / optimizer state untouched, and replays follow the
+    eager training trajectory (fp32 engine; atomics make the two runs differ in summation order only)."""
+    from vinet_b200 import GraphedTrainStep
+    T, B, H, W = 8, 2, 64, 96
+    meta = {"T": T, "seed": 5, "keys": list(VideoSaliencyModel(num_clips=T).state_dict().keys())}
+    d = O.make_inputs(B, T, H, W, 5)
+    x, gt = d["x"].cuda(), d["gt"].cuda()
+    losses = {}
+    finals = {}
+    for mode in ("eager", "graph"):
+        _, m = _build(meta, "fp32")
+        m.train()
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True, capturable=True)
+        if mode == "graph":
+            step = GraphedTrainStep(m, kldiv, opt, x, gt)
+            after = m.state_dict()
+            assert all(torch.equal(before[k], after[k]) for k in before), "capture must not change the training state"
+            assert step.launches_per_replay > 100
+            run = lambda: float(step(x, gt))
+        else:
+            def run():
+                opt.zero_grad(set_to_none=True)
+                loss = kldiv(m(x), gt)
+                loss.backward()
+                opt.step()
+                return float(loss.detach())
+        losses[mode] = [run() for _ in range(3)]
+        m.eval()
+        with torch.no_grad():
+            finals[mode] = m(x).float().cpu()          # eager forward after replays: packed weights must have been refreshed
+        del m
+    assert losses["eager"][0] != losses["eager"][2]
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 1e-3 * abs(a), (losses["eager"], losses["graph"])
+    assert (finals["eager"] - finals["graph"]).abs().max().item() <= 2e-3

@@ -109,3 +109,27 @@ def test_loss_wrappers_shapes_and_values():
         assert abs(out.item() - (O.kldiv(s, gt) - O.cc(s, gt)).item()) < 1e-5
     finally:
         PL._backend = None
+
+
+def test_packed_weights_follow_a_fused_optimizer_step():
+    """torch.optim.Adam(fused=True) updates parameters WITHOUT bumping Tensor._version, so the engine's cache of packed conv
+    weights must not key on the version alone: after an optimizer step the same engine has to compute with the NEW weights
+    (what a fresh engine computes), both in the next training forward and in an eval forward."""
+    T = 8
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, 3)
+    m = _spec_model(T, ref).train()
+    d = O.make_inputs(1, T, 64, 64, 3)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=True)
+    v0 = m.decoder.convtsp1[0].weight._version
+    loss = O.kldiv(m(d["x"]), d["gt"])
+    loss.backward()
+    opt.step()
+    assert m.decoder.convtsp1[0].weight._version == v0, "this torch bumps versions in fused Adam: the test no longer bites"
+    m.eval()
+    with torch.no_grad():
+        same_engine = m(d["x"])
+    fresh = _spec_model(T, m).eval()          # same (updated) parameters, empty caches
+    with torch.no_grad():
+        want = fresh(d["x"])
+    assert torch.allclose(same_engine, want, rtol=1e-5, atol=1e-7), (same_engine - want).abs().max()

@@ -1,4 +1,6 @@
 // Layout conversion kernels: clip -> NDHWC, PyTorch conv weights -> GEMM B operand, packed wgrad -> PyTorch.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vinet {
@@ -59,6 +61,34 @@ __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = weight_elem(d, n, kb * 64 + j * 8 + e);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
+    uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
+  }
+}
+
+// Every cached packed weight of a model in ONE launch: weights change at every optimizer step, and ~150 separate pack
+// launches of a few microseconds each would cost more than the bytes they move.  tab / begin live in device memory;
+// begin[e] is the first 16-byte chunk of entry e in the concatenated chunk space.
+__global__ void pack_weights_tc_multi_kernel(const vinet_pack_t* __restrict__ tab, const int64_t* __restrict__ begin, int n,
+                                             int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(begin + mid) <= i) lo = mid; else hi = mid - 1;
+    }
+    const vinet_pack_t& d = tab[lo];
+    const int64_t li = i - __ldg(begin + lo);
+    const int j = (int)(li & 7);
+    int64_t r = li >> 3;
+    const int nl = (int)(r % d.block_n); r /= d.block_n;
+    const int kb = (int)(r % d.k_blocks);
+    const int nt = (int)(r / d.k_blocks);
+    const int nn = nt * d.block_n + nl;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = weight_elem(d, nn, kb * 64 + j * 8 + e);
     uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
     uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
@@ -142,6 +172,15 @@ extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) 
     pack_weights_simt_kernel<<<grid_for((int64_t)d->k_blocks * 64 * npad, 256), 256, 0, (cudaStream_t)stream>>>(*d, npad);
   }
   VINET_LAUNCH_OK("pack_weights");
+  return 0;
+}
+
+extern "C" int vinet_pack_weights_multi(const vinet_pack_t* table_dev, const int64_t* chunk_begin_dev, int32_t n, int64_t total_chunks,
+                                        vinet_stream_t stream) {
+  VINET_CHECK(table_dev && chunk_begin_dev && n >= 1 && total_chunks >= 1, "pack_weights_multi: empty table");
+  unsigned nb = (unsigned)std::min<int64_t>(cdiv(total_chunks, 256), 148 * 16);
+  pack_weights_tc_multi_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk_begin_dev, n, total_chunks);
+  VINET_LAUNCH_OK("pack_weights_multi");
   return 0;
 }
 

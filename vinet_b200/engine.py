@@ -25,6 +25,27 @@ from . import lib as L
 
 _POISON = bool(os.environ.get("VINET_POISON"))
 
+# Packed (bf16, swizzled) copies of the conv weights are cached per parameter.  Tensor._version alone cannot tell when a
+# parameter changed: fused optimizers (torch.optim.Adam(fused=True), the fast path every trainer uses) update parameters
+# WITHOUT bumping it.  Every optimizer step therefore also advances this epoch (global post-step hook), and a cache entry
+# is valid only for the (version, epoch) it was packed at.
+_WEIGHT_EPOCH = [0]
+
+
+def _on_optimizer_step(*_args, **_kwargs):
+    _WEIGHT_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_on_optimizer_step)
+except Exception:      # pragma: no cover - very old torch: fall back to re-packing on every recorded forward
+    _WEIGHT_EPOCH = None
+
+
+def _wstamp(w):
+    return (w._version, _WEIGHT_EPOCH[0]) if _WEIGHT_EPOCH is not None else None
+
 
 def cdiv(a, b):
     return -(-a // b)
@@ -120,6 +141,10 @@ class Engine:
         self.record = False
         self.use_tma = True     # False: force the register-gather tcgen05 kernels (tests / A-B timing)
         self._bn_pending = None  # deferred BatchNorm tails of layers that are ready together (bn_begin / bn_flush)
+        self.pack_descs = {}     # cache key -> (vinet_pack_t, 16-byte chunks): everything refresh_packed_weights() re-packs
+        self._pack_table = None
+        self.weights_dirty = False   # set by GraphedTrainStep: parameters changed without a Tensor._version bump
+        self._repack_all = False
         self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)})
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
@@ -181,6 +206,9 @@ class Engine:
         self.gwritten = set()
         self.bn_counters = []
         self._bn_pending = None
+        self._repack_all, self.weights_dirty = self.weights_dirty, False
+        if self.eng == L.ENGINE_TC:
+            self.refresh_packed_weights()
 
     def end_forward(self):
         """nn.BatchNorm's num_batches_tracked counters of every layer touched by this forward, one launch."""
@@ -271,7 +299,7 @@ class Engine:
         else:
             k_blocks = cdiv(len(taps) * cs, L.TC_BLOCK_K)
         hit = self.wcache.get(ck)
-        if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] is w:
+        if hit is not None and hit[0] is not None and hit[0] == _wstamp(w) and hit[1].device == w.device and hit[3] is w and not self._repack_all:
             return hit[1], block_n, n_tiles, k_blocks
         nbytes = self.lib.fn["vinet_packed_weight_bytes"](self.eng, n, block_n, n_tiles, k_blocks)
         out = hit[1] if hit is not None and hit[1].numel() == nbytes and hit[1].device == w.device else \
@@ -285,8 +313,43 @@ class Engine:
         d.engine, d.block_n, d.n_tiles, d.k_blocks, d.out = self.eng, block_n, n_tiles, k_blocks, out.data_ptr()
         d.layout = layout
         self.call("vinet_pack_weights", d)
-        self.wcache[ck] = (w._version, out, None, w)
+        self.wcache[ck] = (_wstamp(w), out, None, w)
+        if self.eng == L.ENGINE_TC and "vinet_pack_weights_multi" in self.lib.fn:
+            if ck not in self.pack_descs:
+                self._pack_table = None                       # a new entry: the device table must be rebuilt
+            self.pack_descs[ck] = (d, n_tiles * k_blocks * block_n * 8)
         return out, block_n, n_tiles, k_blocks
+
+    def refresh_packed_weights(self):
+        """Parameters changed (optimizer step): re-pack EVERY cached weight with one launch instead of one per conv call."""
+        if not self.pack_descs or self.device is None or self.device.type != "cuda":
+            return
+        stale = self._repack_all or any(self.wcache[ck][0] != _wstamp(self.wcache[ck][3]) for ck in self.pack_descs)
+        if not stale:
+            return
+        for key, hit in self.wcache.items():                   # fused 1x1 groups: refresh the concatenated weights in place
+            if isinstance(key, str) and key.endswith(".wcat"):
+                with torch.no_grad():
+                    torch.cat([w.detach() for w in hit[2]], 0, out=hit[1])
+                self.wcache[key] = (tuple(_wstamp(w) for w in hit[2]), hit[1], hit[2])
+        if self._pack_table is None:
+            keys = list(self.pack_descs)
+            n = len(keys)
+            tab = (L.Pack * n)()
+            begin, tot = [], 0
+            for i, ck in enumerate(keys):
+                C.memmove(C.byref(tab[i]), C.byref(self.pack_descs[ck][0]), C.sizeof(L.Pack))
+                begin.append(tot)
+                tot += self.pack_descs[ck][1]
+            tab_dev = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(self.device)
+            beg_dev = torch.tensor(begin, dtype=torch.int64, device=self.device)
+            self._pack_table = (keys, tab_dev, beg_dev, tot)
+        keys, tab_dev, beg_dev, tot = self._pack_table
+        self.lib.call("vinet_pack_weights_multi", tab_dev.data_ptr(), beg_dev.data_ptr(), len(keys), tot, self.stream())
+        for ck in keys:
+            hit = self.wcache[ck]
+            self.wcache[ck] = (_wstamp(hit[3]), hit[1], None, hit[3])
+        self._repack_all = False
 
     # ------------------------------------------------------------------ convolution
     def tma_ok(self, srcs, geom):
@@ -618,11 +681,14 @@ class Engine:
         couts = [w.shape[0] for _, _, w, _, _ in members]
         tot = sum(couts)
         key = gname + ".wcat"
-        vers = tuple(w._version for _, _, w, _, _ in members)
+        vers = tuple(_wstamp(w) for _, _, w, _, _ in members)
         hit = self.wcache.get(key)
-        if hit is None or hit[0] != vers or any(a is not b[2] for a, b in zip(hit[2], members)):
+        if hit is None or None in vers or hit[0] != vers or self._repack_all or any(a is not b[2] for a, b in zip(hit[2], members)):
             with torch.no_grad():
-                wcat = torch.cat([w.detach() for _, _, w, _, _ in members], 0).contiguous()
+                if hit is not None and all(a is b[2] for a, b in zip(hit[2], members)):
+                    wcat = torch.cat([w.detach() for _, _, w, _, _ in members], 0, out=hit[1])     # same storage: packs point at it
+                else:
+                    wcat = torch.cat([w.detach() for _, _, w, _, _ in members], 0).contiguous()
             self.wcache[key] = (vers, wcat, [w for _, _, w, _, _ in members])
         wcat = self.wcache[key][1]
         rawcat = Act(self.buf(gname + ".raw", (x.B, x.T, x.H, x.W, tot), self.tdtype), x.B, x.T, x.H, x.W, tot)

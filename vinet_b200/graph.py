@@ -1,0 +1,73 @@
+"""CUDA-graph capture of one whole training step (optimizer + step glue).
+
+A step of this path is ~550 kernel launches of a few microseconds each; replaying them as ONE CUDA graph removes the
+per-launch CPU work and shortens the gaps between dependent kernels.  Everything the step does is already stream-ordered
+C-ABI calls plus PyTorch's fused Adam, so the capture is plain ``torch.cuda.graph``:
+
+    step = GraphedTrainStep(model, vinet_b200.kldiv, optimizer, example_clip, example_gt)
+    for clip, gt in loader:
+        loss = step(clip, gt)          # device tensor, valid until the next call
+
+The optimizer must be capturable (``torch.optim.Adam(..., fused=True, capturable=True)``).  Shapes are fixed at capture.
+"""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3):
+        assert example_x.is_cuda, "GraphedTrainStep needs CUDA tensors"
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        # static inputs with the caller's memory layout (train.py:205 hands a permuted (B,3,T,H,W) view of BTCHW memory)
+        self.x = torch.empty_strided(example_x.shape, example_x.stride(), dtype=example_x.dtype, device=example_x.device)
+        self.gt = torch.empty_strided(example_gt.shape, example_gt.stride(), dtype=example_gt.dtype, device=example_gt.device)
+        self.x.copy_(example_x)
+        self.gt.copy_(example_gt)
+        # warm-up and capture must not change the training state: snapshot parameters, buffers and optimizer state
+        saved = [t.detach().clone() for t in list(model.parameters()) + list(model.buffers())]
+        fresh_opt = len(optimizer.state) == 0
+        saved_opt = None if fresh_opt else [[v.detach().clone() if torch.is_tensor(v) else v for v in st.values()]
+                                            for st in optimizer.state.values()]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=example_x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(example_x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        from . import lib as _lib
+        n0 = _lib.get().launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager_step(zero=False)
+        self.launches_per_replay = _lib.get().launch_count() - n0     # kernels of this library inside one replay
+        with torch.no_grad():
+            for t, s in zip(list(model.parameters()) + list(model.buffers()), saved):
+                t.copy_(s)
+            for i, st in enumerate(optimizer.state.values()):
+                for j, (k, v) in enumerate(st.items()):
+                    if torch.is_tensor(v):
+                        v.zero_() if fresh_opt else v.copy_(saved_opt[i][j])
+        self._mark_weights_dirty()
+
+    def _eager_step(self, zero=True):
+        if zero:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model(self.x), self.gt)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _mark_weights_dirty(self):
+        # replays update the parameters without bumping Tensor._version: tell the engines that their packed weight copies
+        # must be refreshed by the next eager forward (the captured step re-packs by itself)
+        for e in self.model.__dict__.get("_engines", {}).values():
+            e.weights_dirty = True
+
+    def __call__(self, x, gt):
+        self.x.copy_(x, non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        self.graph.replay()
+        self._mark_weights_dirty()
+        return self.loss

@@ -133,6 +133,7 @@ SIGNATURES = {
     "vinet_conv_tiling": (C.c_int, [C.POINTER(Conv), _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), _i32, _S]),
     "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
+    "vinet_pack_weights_multi": (C.c_int, [_p, _p, _i32, _i64, _S]),
     "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
     "vinet_unpack_wgrad": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _S]),
     "vinet_unpack_wgrad_win8": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _S]),
