@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--no-adam", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N>1: wrap in DistributedDataParallel instead of the flat-arena all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--kernel-table", default="", help="write the per-conv-launch timing table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -158,6 +158,7 @@ def main():
         # with a single NCCL all-reduce per step (model.sync_gradients) - no per-tensor bucket copies
         model.broadcast_parameters(0)
         model.enable_grad_arena()
+    # N>1 stays eager: capturing the NCCL all-reduce together with the step dead-locked at N=2 (round-1 experiment)
     use_graph = world == 1 and not args.no_graph and not args.no_adam
     opt = None if args.no_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     B = args.batch
@@ -209,7 +210,8 @@ def main():
         # graph and replayed; falls back to eager launches if the capture is refused
         try:
             from vinet_b200 import GraphedTrainStep
-            graphed = GraphedTrainStep(model, kldiv, opt, dx.permute(0, 2, 1, 3, 4), dgt)
+            graphed = GraphedTrainStep(model, kldiv, opt, dx.permute(0, 2, 1, 3, 4), dgt,
+                                       after_backward=model.sync_gradients if world > 1 else None)
             eager_step = step
 
             def step(x_btchw, gt):          # noqa: F811

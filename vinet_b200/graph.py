@@ -9,14 +9,16 @@ C-ABI calls plus PyTorch's fused Adam, so the capture is plain ``torch.cuda.grap
         loss = step(clip, gt)          # device tensor, valid until the next call
 
 The optimizer must be capturable (``torch.optim.Adam(..., fused=True, capturable=True)``).  Shapes are fixed at capture.
+Multi-GPU: pass ``after_backward=model.sync_gradients`` (flat gradient arena) and the NCCL all-reduce is part of the graph.
 """
 import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3):
+    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None):
         assert example_x.is_cuda, "GraphedTrainStep needs CUDA tensors"
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.after_backward = after_backward      # e.g. model.sync_gradients: the NCCL all-reduce is captured with the step
         # static inputs with the caller's memory layout (train.py:205 hands a permuted (B,3,T,H,W) view of BTCHW memory)
         self.x = torch.empty_strided(example_x.shape, example_x.stride(), dtype=example_x.dtype, device=example_x.device)
         self.gt = torch.empty_strided(example_gt.shape, example_gt.stride(), dtype=example_gt.dtype, device=example_gt.device)
@@ -56,6 +58,8 @@ class GraphedTrainStep:
             self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model(self.x), self.gt)
         loss.backward()
+        if self.after_backward is not None:
+            self.after_backward()
         self.optimizer.step()
         return loss
 
