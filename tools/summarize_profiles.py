@@ -22,9 +22,10 @@ def launches():
         tot[name] += float(x["Metric Value"].replace(",", "")) / 1e6
         cnt[name] += 1
     s = sum(tot.values())
-    out = ["# %s: ncu launch list of one training step (B=8 x 32x224x384, bf16), gpu__time_duration.sum" % R,
-           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
-           "# per-launch times are cold-cache and serialised: compare SHARES. %d launches, %.2f ms" % (len(rows), s),
+    out = ["# %s: ncu launch list of the training step (B=8 x 32x224x384, bf16, eager launches), gpu__time_duration.sum" % R,
+           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 650 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph",
+           "# a window of %d consecutive launches (about 1.15 steps: ~565 launches per step), %.2f ms; per-launch times are" % (len(rows), s),
+           "# cold-cache and serialised: compare SHARES with profiles/%s_profile_step.txt (CUPTI, one step, warm)" % R,
            "%-40s %7s %10s %7s" % ("kernel", "count", "ms", "share")]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         out.append("%-40s %7d %10.3f %6.1f%%" % (k[:40], cnt[k], v, 100 * v / s))
