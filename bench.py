@@ -158,9 +158,10 @@ def main():
         # with a single NCCL all-reduce per step (model.sync_gradients) - no per-tensor bucket copies
         model.broadcast_parameters(0)
         model.enable_grad_arena()
-    # N>1 stays eager: capturing the NCCL all-reduce together with the step dead-locked at N=2 (round-1 experiment)
-    use_graph = world == 1 and not args.no_graph and not args.no_adam
-    opt = None if args.no_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
+    # N=1: the whole step is one CUDA graph.  N>1 (flat arena): forward + loss + backward are the graph, the NCCL all-reduce
+    # and the optimizer run eagerly after each replay (capturing NCCL inside the step dead-locked at N=2 in round 1).
+    use_graph = not args.no_graph and not args.no_adam and not (world > 1 and args.ddp)
+    opt = None if args.no_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph and world == 1)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     # caller layout: (B,T,3,H,W) memory viewed as (B,3,T,H,W)  (train.py:204-205)
@@ -211,7 +212,7 @@ def main():
         try:
             from vinet_b200 import GraphedTrainStep
             graphed = GraphedTrainStep(model, kldiv, opt, dx.permute(0, 2, 1, 3, 4), dgt,
-                                       after_backward=model.sync_gradients if world > 1 else None)
+                                       after_backward=model.sync_gradients if world > 1 else None, capture_optimizer=world == 1)
             eager_step = step
 
             def step(x_btchw, gt):          # noqa: F811

@@ -213,7 +213,8 @@ def test_sweep_shapes_tcgen05_engine_runs_and_tracks_the_ffma_engine(shape):
     assert abs(la - lb) <= 5e-2 * abs(lb), (la, lb)
 
 
-def test_graphed_train_step_replays_the_eager_step():
+@pytest.mark.parametrize("capture_optimizer", [True, False])
+def test_graphed_train_step_replays_the_eager_step(capture_optimizer):
     """vinet_b200.GraphedTrainStep: capture leaves parameters / buffers / optimizer state untouched, and replays follow the
     eager training trajectory (fp32 engine; atomics make the two runs differ in summation order only)."""
     from vinet_b200 import GraphedTrainStep
@@ -227,9 +228,11 @@ def test_graphed_train_step_replays_the_eager_step():
         _, m = _build(meta, "fp32")
         m.train()
         before = {k: v.clone() for k, v in m.state_dict().items()}
-        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True, capturable=True)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True, capturable=capture_optimizer)
         if mode == "graph":
-            step = GraphedTrainStep(m, kldiv, opt, x, gt)
+            # capture_optimizer=False: forward + loss + backward are the graph, the optimizer runs eagerly after each replay
+            # (bench.py's N>1 mode, where the NCCL all-reduce sits between the two)
+            step = GraphedTrainStep(m, kldiv, opt, x, gt, capture_optimizer=capture_optimizer)
             after = m.state_dict()
             assert all(torch.equal(before[k], after[k]) for k in before), "capture must not change the training state"
             assert step.launches_per_replay > 100

@@ -15,10 +15,12 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None):
+    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None, capture_optimizer=True):
         assert example_x.is_cuda, "GraphedTrainStep needs CUDA tensors"
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
-        self.after_backward = after_backward      # e.g. model.sync_gradients: the NCCL all-reduce is captured with the step
+        # after_backward: e.g. model.sync_gradients.  capture_optimizer=False captures forward + loss + backward only and runs
+        # after_backward() and optimizer.step() eagerly after every replay (multi-GPU: NCCL stays outside the graph)
+        self.after_backward, self.capture_optimizer = after_backward, capture_optimizer
         # static inputs with the caller's memory layout (train.py:205 hands a permuted (B,3,T,H,W) view of BTCHW memory)
         self.x = torch.empty_strided(example_x.shape, example_x.stride(), dtype=example_x.dtype, device=example_x.device)
         self.gt = torch.empty_strided(example_gt.shape, example_gt.stride(), dtype=example_gt.dtype, device=example_gt.device)
@@ -42,7 +44,7 @@ class GraphedTrainStep:
         from . import lib as _lib
         n0 = _lib.get().launch_count()
         with torch.cuda.graph(self.graph):
-            self.loss = self._eager_step(zero=False)
+            self.loss = self._eager_step(zero=False) if capture_optimizer else self._fwd_bwd()
         self.launches_per_replay = _lib.get().launch_count() - n0     # kernels of this library inside one replay
         with torch.no_grad():
             for t, s in zip(list(model.parameters()) + list(model.buffers()), saved):
@@ -53,11 +55,15 @@ class GraphedTrainStep:
                         v.zero_() if fresh_opt else v.copy_(saved_opt[i][j])
         self._mark_weights_dirty()
 
+    def _fwd_bwd(self):
+        loss = self.loss_fn(self.model(self.x), self.gt)
+        loss.backward()
+        return loss
+
     def _eager_step(self, zero=True):
         if zero:
             self.optimizer.zero_grad(set_to_none=True)
-        loss = self.loss_fn(self.model(self.x), self.gt)
-        loss.backward()
+        loss = self._fwd_bwd()
         if self.after_backward is not None:
             self.after_backward()
         self.optimizer.step()
@@ -73,5 +79,9 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
         self.graph.replay()
+        if not self.capture_optimizer:       # gradients live in static tensors (param.grad) that every replay overwrites
+            if self.after_backward is not None:
+                self.after_backward()
+            self.optimizer.step()
         self._mark_weights_dirty()
         return self.loss
