@@ -29,6 +29,36 @@ __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) 
   }
 }
 
+// Fast path of the common case (C = 3 -> 8 channels, unit stride along W, W % 4 == 0, bf16 output): one thread converts FOUR
+// consecutive pixels - three 128-bit loads (one per colour plane) and four 128-bit stores - instead of 3 scalar loads per pixel;
+// the first / last group of a row also writes the zero columns on its side.
+__global__ void __launch_bounds__(256) pack_input_vec4_kernel(const __grid_constant__ vinet_pack_input_t d) {
+  const int Wp = d.Wp > 0 ? d.Wp : d.W;
+  const int G = d.W / 4;
+  const int64_t total = (int64_t)d.B * d.T * d.H * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int gq = (int)(r % G); r /= G;
+    const int h = (int)(r % d.H); r /= d.H;
+    const int t = (int)(r % d.T);
+    const int b = (int)(r / d.T);
+    const float* src = d.x + b * d.sb + t * d.st + h * d.sh + gq * 4;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(src + d.sc));
+    const float4 c2 = __ldg(reinterpret_cast<const float4*>(src + 2 * d.sc));
+    uint4* row = reinterpret_cast<uint4*>(d.out) + (((int64_t)b * d.T + t) * d.H + h) * Wp;   // one uint4 = one 8-channel pixel
+    uint4* dst = row + d.wl + gq * 4;
+    dst[0] = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), 0u, 0u);
+    dst[1] = make_uint4(pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f), 0u, 0u);
+    dst[2] = make_uint4(pack_bf16x2(c0.z, c1.z), pack_bf16x2(c2.z, 0.f), 0u, 0u);
+    dst[3] = make_uint4(pack_bf16x2(c0.w, c1.w), pack_bf16x2(c2.w, 0.f), 0u, 0u);
+    if (gq == 0)
+      for (int k = 0; k < d.wl; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (gq == G - 1)
+      for (int k = d.wl + d.W; k < Wp; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------ weights
 // element (n, k) of the GEMM B operand; DENSE: k = tap_idx*cs + c, TAP64: k = tap_idx*round_up(cs,64) + c
 __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k) {
@@ -146,6 +176,13 @@ extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stre
   VINET_CHECK(d->cpad % 8 == 0 && d->cpad >= d->C, "pack_input: cpad %d", d->cpad);
   VINET_CHECK(d->Wp == 0 || d->Wp >= d->wl + d->W, "pack_input: Wp %d < wl %d + W %d", d->Wp, d->wl, d->W);
   const int64_t total = (int64_t)d->B * d->T * d->H * (d->Wp > 0 ? d->Wp : d->W);
+  const bool vec4 = d->out_dtype == VINET_BF16 && d->C == 3 && d->cpad == 8 && d->sw == 1 && d->W % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && d->sb % 4 == 0 && d->sc % 4 == 0 && d->st % 4 == 0 && d->sh % 4 == 0;
+  if (vec4) {
+    pack_input_vec4_kernel<<<grid_for((int64_t)d->B * d->T * d->H * (d->W / 4), 256), 256, 0, (cudaStream_t)stream>>>(*d);
+    VINET_LAUNCH_OK("pack_input_vec4");
+    return 0;
+  }
   VINET_DISPATCH_DTYPE(d->out_dtype, TO, (pack_input_kernel<TO><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d)));
   VINET_LAUNCH_OK("pack_input");
   return 0;
