@@ -11,7 +11,9 @@
 //   * temporal taps share the source FRAME: a CTA walks the source frames of a run of output frames in order and
 //     issues, for each frame, the MMAs of every (tap, output frame) pair it feeds into a ring of TMEM accumulators;
 //     an accumulator is committed to the epilogue warps when its last source frame has been consumed;
-//   * weights stay resident in shared memory when one N tile of them fits, else stream through their own ring.
+//   * weights stay resident in shared memory when one N tile of them fits, else stream through their own ring;
+//   * row-strided convs over sliding-window rows (the stem conv_s) fetch one box per source-row lattice (parity) with a row
+//     element-stride, so a kernel row is again a plain row offset inside its lattice's box (conv_gemm_stream_strided).
 //
 // Roles (448 threads): warp 0 activation producer (TMA), warp 1 TMEM allocator + weight producer (bulk copies), warps 2..5 MMA
 // issuers, warps 6..13 epilogue (two per TMEM lane quarter).  grid = (CTAs per N tile, N tiles).
