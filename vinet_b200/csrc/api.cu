@@ -106,7 +106,7 @@ extern "C" int vinet_axpy_f32(float* dst, const float* src, int64_t n, int32_t a
 
 extern "C" const char* vinet_last_error(void) { return g_err; }
 extern "C" const char* vinet_last_kernel(void) { return g_last_kernel; }
-extern "C" const char* vinet_version(void) { return "vinet_b200 0.2 (sm_100a; TMA-fed persistent tcgen05+TMEM conv, fp32 SIMT parity engine)"; }
+extern "C" const char* vinet_version(void) { return "vinet_b200 0.3 (sm_100a; streaming halo-tile tcgen05+TMEM conv with multi-warp MMA issue, per-tap TMA conv, fp32 SIMT parity engine)"; }
 extern "C" int64_t vinet_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
