@@ -85,7 +85,11 @@ class Spec:
     """Drop-in for vinet_b200.lib.Library on host memory."""
 
     def __init__(self):
-        self.fn = {"vinet_packed_weight_bytes": self._packed_bytes}
+        # names the engine probes with `in lib.fn` to pick its fused / multi-layer BatchNorm paths: the spec implements them by
+        # composition of the single-layer specs, so the CPU plan tests walk the same host logic (batching, tape order)
+        self.fn = {"vinet_packed_weight_bytes": self._packed_bytes, "vinet_bn_stats_finalize": None, "vinet_bn_fwd_fused": None,
+                   "vinet_bn_bwd_fused": None, "vinet_bn_stats_finalize_multi": None, "vinet_bn_apply_multi": None,
+                   "vinet_bn_bwd_multi": None}
         self.launches = 0
 
     def launch_count(self):
@@ -207,6 +211,30 @@ class Spec:
         _arr(d.shift, c)[:] = _arr(d.beta, c) - mean * sc
         _arr(d.mean, c)[:] = mean
         _arr(d.invstd, c)[:] = invstd
+
+    def bn_stats_finalize(self, d, f, stream):
+        self.bn_stats(d, stream)
+        self.bn_finalize(f, stream)
+
+    def bn_fwd_fused(self, d, f, a, stream):
+        self.bn_stats_finalize(d, f, stream)
+        self.bn_apply(a, stream)
+
+    def bn_bwd_fused(self, d, stream):
+        self.bn_bwd_reduce(d, stream)
+        self.bn_bwd_apply(d, stream)
+
+    def bn_stats_finalize_multi(self, ds, fs, n, stream):
+        for i in range(n):
+            self.bn_stats_finalize(ds[i], fs[i], stream)
+
+    def bn_apply_multi(self, aps, n, stream):
+        for i in range(n):
+            self.bn_apply(aps[i], stream)
+
+    def bn_bwd_multi(self, bs, n, stream):
+        for i in range(n):
+            self.bn_bwd_fused(bs[i], stream)
 
     def bn_apply(self, d, stream):
         assert d.dtype == L.F32 and d.out_dtype == L.F32
