@@ -253,3 +253,31 @@ def test_graphed_train_step_replays_the_eager_step(capture_optimizer):
     for a, b in zip(losses["eager"], losses["graph"]):
         assert abs(a - b) <= 1e-3 * abs(a), (losses["eager"], losses["graph"])
     assert (finals["eager"] - finals["graph"]).abs().max().item() <= 2e-3
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: the multi-layer BatchNorm launch grouped layers with "
+                                        "fp32 and bf16 incoming gradients (AViNet's last Mixed block) into one launch and asserted; the "
+                                        "grouping fix (Engine.bn_flush) is CPU-reviewed only and this test has not run on hardware yet")
+def test_avinet_bf16_engine_trains():
+    """AViNet in the throughput mode (bf16 storage, tcgen05): forward + kldiv + backward run, every trained parameter gets a
+    finite gradient and the loss stays near the reference's fp32 value (golden vector)."""
+    from vinet_b200 import VideoAudioSaliencyModel
+    name = "avinet_t32_train"
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    ref = O.AViNetOracle(meta["T"])
+    O.randomize_(ref, meta["seed"])
+    m = VideoAudioSaliencyModel(num_clips=meta["T"], soundnet_weights=False)
+    m.load_state_dict(ref.state_dict())
+    m = m.cuda().set_precision("bf16").train()
+    d = O.make_inputs(meta["B"], meta["T"], meta["H"], meta["W"], meta["seed"], audio=True)
+    pred = m(d["x"].cuda(), d["audio"].cuda())
+    loss = kldiv(pred, d["gt"].cuda())
+    loss.backward()
+    assert torch.isfinite(pred).all() and pred.shape == (meta["B"], meta["H"], meta["W"])
+    want = float(z["loss_kldiv"])
+    assert abs(loss.item() - want) <= 0.1 * abs(want), (loss.item(), want)
+    for n, q in m.named_parameters():
+        if "conv8_" in n:
+            continue
+        assert q.grad is not None and torch.isfinite(q.grad).all(), n

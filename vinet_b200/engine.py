@@ -570,8 +570,14 @@ class Engine:
         if not pend:
             return
         self._bn_pending = []
-        for i in range(0, len(pend), 4):
-            self._bn_batch(pend[i:i + 4])
+        # one launch handles layers whose incoming gradients share a storage type (AViNet keeps the gradient of the last
+        # Mixed block's output in fp32 for the audio-visual fusion while its inner activations use bf16 gradients)
+        groups = {}
+        for mbr in pend:
+            groups.setdefault(mbr[3].gdt, []).append(mbr)
+        for members in groups.values():
+            for i in range(0, len(members), 4):
+                self._bn_batch(members[i:i + 4])
 
     def _bn_batch(self, members):
         """members: [(name_bn, bn, raw, out, conv_bwd, dy_slot)] - small train-mode layers: one stats+finalise launch, one
