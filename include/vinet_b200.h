@@ -137,6 +137,8 @@ typedef struct vinet_pack {
   int32_t engine, block_n, n_tiles, k_blocks;
   void* out; /* TC: bf16 [n_tiles][k_blocks][block_n][64] 128B-swizzled; SIMT: fp32 [k_blocks*64][round_up(N,64)] */
   int32_t layout; /* VINET_KLAYOUT_* */
+  int32_t part;   /* TC engine: which bf16 term of the weight is packed: 0 = bf16(w), 1 = bf16(w - part0), 2 = bf16(w - part0 - part1)
+                     (split-precision "bf16x3" parity mode, see vinet_split_bf16); 0 everywhere else */
 } vinet_pack_t;
 int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
 /* n TC-engine packs in ONE launch.  table_dev: n descriptors in DEVICE memory (each as for vinet_pack_weights, already
@@ -164,6 +166,29 @@ typedef struct vinet_pack_input {
                      With explicit zero columns the stem conv can address a row as overlapping windows (WIN8). */
 } vinet_pack_input_t;
 int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream);
+
+/*
+ * Split-precision operands for the tensor-core PARITY mode ("bf16x3"): an fp32 view x[rows, C] (after its pending
+ * transform) is written as nparts bf16 planes with x ~= part[0] + part[1] (+ part[2]): part[0] = bf16(x),
+ * part[1] = bf16(x - part[0]), part[2] = bf16(x - part[0] - part[1]).  A convolution is then the sum of the tcgen05 launches
+ * A_i x W_j with i + j < nparts (3 launches for 2 parts: the dropped A_1 x W_1 term is 2^-16 relative), accumulated in fp32
+ * through vinet_conv_t.accumulate / the wgrad atomics: the same kernels as the bf16 throughput mode reach fp32-class
+ * accuracy, which is how the north-star tolerances (maps 1e-3, losses 1e-5) are gated on the measured tcgen05 path.
+ */
+typedef struct vinet_split {
+  const void* x;
+  int64_t ld;
+  int32_t dtype; /* storage type of x (VINET_F32 in the parity mode) */
+  int64_t rows;
+  int32_t C;     /* multiple of 8 */
+  const float* scale; /* pending transform of x, as for vinet_src_t */
+  const float* shift;
+  int32_t xform;
+  int32_t nparts; /* 2 or 3 */
+  void* part[3];  /* bf16 [rows, ldo] each */
+  int64_t ldo;
+} vinet_split_t;
+int vinet_split_bf16(const vinet_split_t* d, vinet_stream_t stream);
 
 /* ---- BatchNorm3d / BatchNorm2d (model_utils.py:132,145,149; model.py:752...) ---- */
 typedef struct vinet_bn_stats {

@@ -20,14 +20,28 @@ EPS = np.float32(2.2204e-16)
 def _arr(ptr, n, dtype=np.float32):
     if not ptr or n == 0:
         return None
-    ct = {np.float32: C.c_float, np.float64: C.c_double, np.int32: C.c_int32, np.uint8: C.c_uint8}[dtype]
+    ct = {np.float32: C.c_float, np.float64: C.c_double, np.int32: C.c_int32, np.uint8: C.c_uint8, np.uint16: C.c_uint16}[dtype]
     return np.ctypeslib.as_array((ct * int(n)).from_address(int(ptr)))
 
 
-def _rows_view(ptr, rows, ld, c):
-    """[rows, c] strided view of a channel slice whose row stride is ld."""
+def _rows_view(ptr, rows, ld, c, dtype=L.F32):
+    """[rows, c] strided view of a channel slice whose row stride is ld (bf16 storage: a widened fp32 COPY, read-only use)."""
+    if dtype == L.BF16:
+        a = _arr(ptr, (rows - 1) * ld + c, np.uint16)
+        v = np.lib.stride_tricks.as_strided(a, shape=(rows, c), strides=(ld * 2, 2))
+        return (v.astype(np.uint32) << 16).view(np.float32)
     a = _arr(ptr, (rows - 1) * ld + c)
     return np.lib.stride_tricks.as_strided(a, shape=(rows, c), strides=(ld * 4, 4))
+
+
+def _bf16_bits(x):
+    """fp32 array -> bf16 bit patterns (round to nearest even), as uint16."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def _bf16_round(x):
+    return (_bf16_bits(x).astype(np.uint32) << 16).view(np.float32)
 
 
 def _xform(v, xf, scale, shift, c0, c):
@@ -53,7 +67,6 @@ def _row_coords(g):
 
 def gather_matrix(g):
     """A[rows, ntaps*Cs] of the implicit GEMM described by a vinet_gather_t."""
-    assert g.dtype == L.F32, "the spec handles fp32 storage only"
     b, t, h, w = _row_coords(g)
     rows = b.shape[0]
     A = np.zeros((rows, g.ntaps * g.Cs), np.float32)
@@ -76,7 +89,7 @@ def gather_matrix(g):
                 continue
             tl = ts[sel] - (T0 if si else 0)
             pos = ((b[sel] * s.T + tl) * g.Hs + hs[sel]) * g.Ws + ws[sel]
-            src = _rows_view(s.ptr, g.B * s.T * g.Hs * g.Ws, s.ld, g.Cs)
+            src = _rows_view(s.ptr, g.B * s.T * g.Hs * g.Ws, s.ld, g.Cs, g.dtype)
             A[np.nonzero(sel)[0], ti * g.Cs:(ti + 1) * g.Cs] = _xform(src[pos], s.xform, s.scale, s.shift, 0, g.Cs)
     return A
 
@@ -126,8 +139,15 @@ class Spec:
         out[..., :d.C] = np.transpose(x, (0, 2, 3, 4, 1))
 
     def pack_weights(self, d, stream):
-        assert d.engine == L.ENGINE_SIMT and d.layout == L.KLAYOUT_DENSE
+        # the spec keeps ONE packed format (fp32 [k][npad]) for both engines; a TC-engine pack holds term `part` of the
+        # weight's bf16 expansion (split-precision parity mode), exactly what the tcgen05 kernels multiply with
+        assert d.layout == L.KLAYOUT_DENSE and (d.part == 0 or d.engine == L.ENGINE_TC)
         w = _arr(d.w, d.Cout * d.Cin * d.kt * d.kh * d.kw).reshape(d.Cout, d.Cin, d.kt, d.kh, d.kw)
+        if d.engine == L.ENGINE_TC:
+            w = w.copy()
+            for _ in range(d.part):
+                w = w - _bf16_round(w)
+            w = _bf16_round(w)
         n = d.Cout if d.mode == L.GATHER_FPROP else d.Cin
         npad = -(-n // 64) * 64
         out = _arr(d.out, d.k_blocks * 64 * npad).reshape(d.k_blocks * 64, npad)
@@ -138,6 +158,14 @@ class Spec:
                 out[ti * d.cs:ti * d.cs + d.Cin, :d.Cout] = w[:, :, dt, dh, dw].T
             else:
                 out[ti * d.cs:ti * d.cs + d.Cout, :d.Cin] = w[:, :, dt, dh, dw]
+
+    def split_bf16(self, d, stream):
+        v = _xform(_rows_view(d.x, d.rows, d.ld, d.C, d.dtype), d.xform, d.scale, d.shift, 0, d.C)
+        for p in range(d.nparts):
+            bits = _bf16_bits(v)
+            out = _arr(d.part[p], (d.rows - 1) * d.ldo + d.C, np.uint16)
+            np.lib.stride_tricks.as_strided(out, shape=(d.rows, d.C), strides=(d.ldo * 2, 2))[:] = bits
+            v = v - (bits.astype(np.uint32) << 16).view(np.float32)
 
     def unpack_wgrad(self, dwp, lddw, cs, grad, cout, cin, ntaps, stream):
         rows = -(-(ntaps * cs) // 128) * 128
@@ -177,7 +205,7 @@ class Spec:
     def conv_wgrad(self, d, engine, stream):
         A = gather_matrix(d.g)
         rows = A.shape[0]
-        dy = _rows_view(d.dy, rows, d.lddy, d.N)
+        dy = _rows_view(d.dy, rows, d.lddy, d.N, d.dy_dtype)
         k = A.shape[1]
         kp = -(-k // 128) * 128
         dwp = _arr(d.dwp, kp * d.lddw).reshape(kp, d.lddw)

@@ -255,9 +255,6 @@ def test_graphed_train_step_replays_the_eager_step(capture_optimizer):
     assert (finals["eager"] - finals["graph"]).abs().max().item() <= 2e-3
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: the multi-layer BatchNorm launch grouped layers with "
-                                        "fp32 and bf16 incoming gradients (AViNet's last Mixed block) into one launch and asserted; the "
-                                        "grouping fix (Engine.bn_flush) is CPU-reviewed only and this test has not run on hardware yet")
 def test_avinet_bf16_engine_trains():
     """AViNet in the throughput mode (bf16 storage, tcgen05): forward + kldiv + backward run, every trained parameter gets a
     finite gradient and the loss stays near the reference's fp32 value (golden vector)."""

@@ -133,3 +133,87 @@ def test_packed_weights_follow_a_fused_optimizer_step():
     with torch.no_grad():
         want = fresh(d["x"])
     assert torch.allclose(same_engine, want, rtol=1e-5, atol=1e-7), (same_engine - want).abs().max()
+
+
+def test_weight_cache_follows_writes_behind_autograd():
+    """`p.data.copy_()` bumps neither Tensor._version nor the optimizer epoch; `invalidate_weight_cache()` (called by
+    broadcast_parameters) must make the next forward use the new weights, and `param.data = new` (moved storage) is detected
+    by the cache stamp itself."""
+    T = 8
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, 4)
+    m = _spec_model(T, ref).eval()
+    d = O.make_inputs(1, T, 64, 64, 4)
+    other = O.ViNetOracle(T)
+    O.randomize_(other, 9)
+    with torch.no_grad():
+        first = m(d["x"])
+        for (n, p), (_, q) in zip(m.named_parameters(), other.named_parameters()):
+            p.data.copy_(q)
+        for (n, p), (_, q) in zip(m.named_buffers(), other.named_buffers()):
+            p.data.copy_(q)
+        m.invalidate_weight_cache()
+        second = m(d["x"])
+        want = _spec_model(T, other).eval()(d["x"])
+    assert (first - second).abs().max() > 1e-3
+    assert torch.allclose(second, want, rtol=1e-5, atol=1e-7), (second - want).abs().max()
+    # moved storage: no explicit invalidation needed
+    with torch.no_grad():
+        for p, q in zip(m.parameters(), ref.parameters()):
+            p.data = q.detach().clone()
+        for p, q in zip(m.buffers(), ref.buffers()):
+            p.data = q.detach().clone()
+        third = m(d["x"])
+    assert torch.allclose(third, first, rtol=1e-5, atol=1e-7), (third - first).abs().max()
+
+
+def test_grad_arena_accumulates_and_second_backward_raises():
+    """with the flat gradient arena, param.grad aliases the arena after the first backward; a second forward/backward
+    without zero_grad must ACCUMULATE (g1 + g2) exactly like plain autograd, and a second backward through the same forward
+    must raise instead of returning partial gradients."""
+    T = 8
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, 6)
+    d1, d2 = O.make_inputs(1, T, 64, 64, 6), O.make_inputs(1, T, 64, 64, 7)
+    grads = {}
+    for arena in (False, True):
+        m = _spec_model(T, ref).train()
+        if arena:
+            m.enable_grad_arena()
+        for d in (d1, d2):
+            loss = O.kldiv(m(d["x"]), d["gt"])
+            loss.backward()
+        grads[arena] = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for n in grads[False]:
+        a, b = grads[False][n], grads[True][n]
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()) + 1e-12), n
+    m = _spec_model(T, ref).train()
+    out = m(d1["x"])
+    loss = O.kldiv(out, d1["gt"])
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        loss.backward()
+
+
+def test_split_precision_plan_tracks_fp64():
+    """Host logic of the tensor-core parity mode ("bf16x6": operand splitting, term order, accumulate masks of the data gradient,
+    shared packed weight gradient) on the numpy kernel spec: forward and gradients sit as close to an fp64 oracle run as the
+    fp32 plan does."""
+    T, B, H, W = 8, 1, 64, 64
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, 0)
+    ref.train()
+    ref64 = copy.deepcopy(ref).double()
+    d = O.make_inputs(B, T, H, W, 0)
+    p64 = ref64(d["x"].double()); O.kldiv(p64, d["gt"].double()).backward()
+    r64 = dict(ref64.named_parameters())
+    errs = {}
+    for prec in ("fp32", "bf16x6"):
+        m = _spec_model(T, ref).set_precision(prec)
+        m.__dict__["_backend"] = Spec()
+        m.train()
+        pm = m(d["x"]); O.kldiv(pm, d["gt"]).backward()
+        eg = [float((q.grad - r64[n].grad).norm() / (r64[n].grad.norm() + 1e-30)) for n, q in m.named_parameters()]
+        errs[prec] = (float(((pm.detach() - p64.detach()).abs() / p64.detach().abs()).max()), float(np.median(eg)))
+    assert errs["bf16x6"][0] <= 3 * errs["fp32"][0] + 1e-5, errs
+    assert errs["bf16x6"][1] <= 3 * errs["fp32"][1] + 1e-3, errs

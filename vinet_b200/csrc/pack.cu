@@ -78,6 +78,12 @@ __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k
   return __ldg(d.w + ((((int64_t)co * d.Cin + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
 }
 
+// term `part` of the bf16 expansion w ~= p0 + p1 + p2 (split-precision parity mode): the value left after removing the leading terms
+__device__ __forceinline__ float weight_part(float v, int part) {
+  for (int q = 0; q < part; ++q) v -= __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+
 // TC: one thread per 16-byte chunk (8 consecutive k) of [n_tiles][k_blocks][block_n][64], 128B-swizzled.
 __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
   const int64_t chunks = (int64_t)d.n_tiles * d.k_blocks * d.block_n * 8;
@@ -90,7 +96,7 @@ __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
     const int n = nt * d.block_n + nl;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = weight_elem(d, n, kb * 64 + j * 8 + e);
+    for (int e = 0; e < 8; ++e) v[e] = weight_part(weight_elem(d, n, kb * 64 + j * 8 + e), d.part);
     uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
     uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
@@ -118,7 +124,7 @@ __global__ void pack_weights_tc_multi_kernel(const vinet_pack_t* __restrict__ ta
     const int nn = nt * d.block_n + nl;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = weight_elem(d, nn, kb * 64 + j * 8 + e);
+    for (int e = 0; e < 8; ++e) v[e] = weight_part(weight_elem(d, nn, kb * 64 + j * 8 + e), d.part);
     uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
     uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
@@ -161,6 +167,31 @@ __global__ void unpack_wgrad_win8_kernel(float* __restrict__ dwp, int lddw, floa
   }
 }
 
+// ------------------------------------------------------------------ split-precision operands (parity mode)
+// One thread per 8 channels of one row: x -> (pending transform) -> bf16 expansion planes.
+template <typename T>
+__global__ void __launch_bounds__(256) split_bf16_kernel(const __grid_constant__ vinet_split_t d) {
+  const T* __restrict__ x = reinterpret_cast<const T*>(d.x);
+  const int G = d.C / 8;
+  const int64_t total = d.rows * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float v[8];
+    load8(x + r * d.ld + c, v);
+    apply_xform<8>(v, d.xform, d.scale, d.shift, c);
+    for (int p = 0; p < d.nparts; ++p) {
+      float h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        v[e] -= h[e];
+      }
+      store8(reinterpret_cast<__nv_bfloat16*>(d.part[p]) + r * d.ldo + c, h);
+    }
+  }
+}
+
 static inline unsigned grid_for(int64_t n, int block) {
   int64_t g = cdiv(n, block);
   if (g > 148 * 16) g = 148 * 16;
@@ -188,6 +219,17 @@ extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stre
   return 0;
 }
 
+extern "C" int vinet_split_bf16(const vinet_split_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d && d->C % 8 == 0 && d->C >= 8 && d->rows >= 1, "split_bf16: C %d rows %lld", d ? d->C : -1, d ? (long long)d->rows : -1ll);
+  VINET_CHECK(d->nparts >= 1 && d->nparts <= 3 && d->ldo >= d->C && d->ldo % 8 == 0, "split_bf16: nparts %d ldo %lld", d->nparts,
+              (long long)d->ldo);
+  for (int p = 0; p < d->nparts; ++p) VINET_CHECK(d->part[p] != nullptr, "split_bf16: part %d is null", p);
+  const int64_t total = d->rows * (d->C / 8);
+  VINET_DISPATCH_DTYPE(d->dtype, T, (split_bf16_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d)));
+  VINET_LAUNCH_OK("split_bf16");
+  return 0;
+}
+
 extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t block_n, int32_t n_tiles, int32_t k_blocks) {
   if (engine == VINET_ENGINE_TC) return (size_t)n_tiles * k_blocks * block_n * 128;
   return (size_t)k_blocks * 64 * round_up(N, 64) * sizeof(float);
@@ -196,6 +238,7 @@ extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t b
 extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
   VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN8, "pack_weights: layout %d", d->layout);
+  VINET_CHECK(d->part >= 0 && d->part <= 2 && (d->part == 0 || d->engine == VINET_ENGINE_TC), "pack_weights: part %d", d->part);
   VINET_CHECK(d->layout != VINET_KLAYOUT_WIN8 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 8 && d->kw <= 8 && d->cs == 64),
               "pack_weights: WIN8 needs an FPROP pack with Cin <= 8, kw <= 8, cs == 64");
   const int64_t csk = d->layout == VINET_KLAYOUT_DENSE ? d->cs : round_up(d->cs, 64);

@@ -12,8 +12,11 @@ Data model
     upsample, head and loss backward are all explicit kernels.
 
 Precision modes
-  * ``bf16`` : bf16 storage, tcgen05 tensor-core GEMMs (fp32 accumulation in TMEM)   — throughput mode
-  * ``fp32`` : fp32 storage, fp32 FFMA GEMMs                                          — parity mode
+  * ``bf16``   : bf16 storage, tcgen05 tensor-core GEMMs (fp32 accumulation in TMEM)   — throughput mode
+  * ``bf16x3`` : fp32 storage; every conv operand is split into bf16 terms (x = x0 + x1) and the convolution is the sum of
+                 the three tcgen05 launches x0*w0 + x0*w1 + x1*w0 accumulated in fp32     — tensor-core PARITY mode: the very
+                 kernels of the throughput mode gated at the north-star tolerances (``bf16x6``: three terms, six launches)
+  * ``fp32``   : fp32 storage, fp32 FFMA GEMMs                                          — reference parity mode
 """
 import ctypes as C
 import os
@@ -44,7 +47,8 @@ except Exception:      # pragma: no cover - very old torch: fall back to re-pack
 
 
 def _wstamp(w):
-    return (w._version, _WEIGHT_EPOCH[0]) if _WEIGHT_EPOCH is not None else None
+    # the storage address is part of the stamp: `param.data = new` / `.to()` keep the Parameter object but move its memory
+    return (w._version, _WEIGHT_EPOCH[0], w.data_ptr()) if _WEIGHT_EPOCH is not None else None
 
 
 def cdiv(a, b):
@@ -122,13 +126,20 @@ _G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
 
 
 class Engine:
+    PRECISIONS = ("bf16", "fp32", "bf16_simt", "bf16x3", "bf16x6")
+
     def __init__(self, precision="bf16", backend=None):
         # "bf16_simt": bf16 storage with the fp32 FFMA engine — the on-device cross-check of the tcgen05 path
-        assert precision in ("bf16", "fp32", "bf16_simt")
+        assert precision in self.PRECISIONS
         self.precision = precision
-        self.eng = L.ENGINE_TC if precision == "bf16" else L.ENGINE_SIMT
-        self.dt = L.F32 if precision == "fp32" else L.BF16
-        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        # split-precision parity mode: activations / gradients stay fp32, conv operands are bf16 expansions (vinet_split_bf16)
+        self.split = {"bf16x3": 2, "bf16x6": 3}.get(precision, 0)
+        self.eng = L.ENGINE_TC if (precision == "bf16" or self.split) else L.ENGINE_SIMT
+        self.dt = L.F32 if (precision == "fp32" or self.split) else L.BF16
+        self.tdtype = torch.float32 if self.dt == L.F32 else torch.bfloat16
+        self.opdt = L.BF16 if self.split else self.dt      # storage type of the conv operands (sources and dY)
+        # (operand part, weight part) of every launch of one convolution; parts i + j < nparts
+        self.terms = [(i, j) for n in range(self.split) for i in range(n + 1) for j in [n - i]] if self.split else [(0, 0)]
         self.lib = backend if backend is not None else L.get()   # tests may inject the numpy kernel spec
         self.pool = {}
         self.wcache = {}
@@ -139,13 +150,15 @@ class Engine:
         self.device = None
         self.training = False
         self.record = False
-        self.use_tma = True     # False: force the register-gather tcgen05 kernels (tests / A-B timing)
+        self.use_tma = backend is None   # False: force the register-gather tcgen05 kernels (tests / A-B timing / numpy spec)
         self._bn_pending = None  # deferred BatchNorm tails of layers that are ready together (bn_begin / bn_flush)
         self.pack_descs = {}     # cache key -> (vinet_pack_t, 16-byte chunks): everything refresh_packed_weights() re-packs
         self._pack_table = None
         self.weights_dirty = False   # set by GraphedTrainStep: parameters changed without a Tensor._version bump
         self._repack_all = False
-        self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)})
+        self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)}, {name: parameter})
+        self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
+        self.consumed_gen = -1  # generation whose tape has been run: a second backward through it must fail loudly
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
 
@@ -180,7 +193,12 @@ class Engine:
             hit = self.arena[1].get(name)
             if hit is not None and self.arena[0].device == like.device:
                 t = self.arena[0][hit[0]:hit[0] + hit[1]].view(like.shape)
-                return t.zero_() if zero else t
+                # autograd adopted the arena view as param.grad on the previous backward: if that gradient is still alive
+                # (gradient accumulation, zero_grad(set_to_none=False)), writing the slice would destroy it and AccumulateGrad
+                # would add the tensor to itself.  Hand out a scratch tensor instead: autograd then accumulates INTO the arena.
+                p = self.arena[2].get(name) if len(self.arena) > 2 else None
+                if p is None or p.grad is None or p.grad.data_ptr() != t.data_ptr():
+                    return t.zero_() if zero else t
         return torch.zeros_like(like) if zero else torch.empty_like(like)
 
     def timed(self, label, kind, flops, fn):
@@ -207,7 +225,7 @@ class Engine:
         self.bn_counters = []
         self._bn_pending = None
         self._repack_all, self.weights_dirty = self.weights_dirty, False
-        if self.eng == L.ENGINE_TC:
+        if self.eng == L.ENGINE_TC and not self.replica:
             self.refresh_packed_weights()
 
     def end_forward(self):
@@ -261,7 +279,7 @@ class Engine:
 
     def _gather_fprop(self, g, srcs, geom, cs, To, Ho, Wo):
         a0 = srcs[0]
-        g.mode, g.dtype = L.GATHER_FPROP, self.dt
+        g.mode, g.dtype = L.GATHER_FPROP, self.opdt
         g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, To, Ho, Wo, 1, 0
         g.Ts, g.Hs, g.Ws, g.Cs = sum(s.T for s in srcs), a0.H, a0.W, cs
         taps = _taps(geom.kt, geom.kh, geom.kw)
@@ -290,10 +308,11 @@ class Engine:
             return bn.value, nt.value
         return self.tiling(n)
 
-    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE, tiling=None):
-        """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version."""
+    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE, tiling=None, part=0):
+        """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version.
+        part: which term of the weight's bf16 expansion (split-precision parity mode)."""
         block_n, n_tiles = tiling if tiling is not None else self.tiling(n)
-        ck = (key, mode, tuple(taps), self.eng, layout, block_n, n_tiles)
+        ck = (key, mode, tuple(taps), self.eng, layout, block_n, n_tiles, part)
         if layout != L.KLAYOUT_DENSE:
             k_blocks = len(taps) * cdiv(cs, L.TC_BLOCK_K)
         else:
@@ -311,12 +330,13 @@ class Engine:
         d.cs, d.mode, d.ntaps = cs, mode, len(taps)
         _fill_taps(d.tap, taps)
         d.engine, d.block_n, d.n_tiles, d.k_blocks, d.out = self.eng, block_n, n_tiles, k_blocks, out.data_ptr()
-        d.layout = layout
+        d.layout, d.part = layout, part
         self.call("vinet_pack_weights", d)
         self.wcache[ck] = (_wstamp(w), out, None, w)
         if self.eng == L.ENGINE_TC and "vinet_pack_weights_multi" in self.lib.fn:
-            if ck not in self.pack_descs:
-                self._pack_table = None                       # a new entry: the device table must be rebuilt
+            old = self.pack_descs.get(ck)
+            if old is None or old[0].w != d.w or old[0].out != d.out:
+                self._pack_table = None                       # a new entry / moved storage: the device table must be rebuilt
             self.pack_descs[ck] = (d, n_tiles * k_blocks * block_n * 8)
         return out, block_n, n_tiles, k_blocks
 
@@ -332,6 +352,11 @@ class Engine:
                 with torch.no_grad():
                     torch.cat([w.detach() for w in hit[2]], 0, out=hit[1])
                 self.wcache[key] = (tuple(_wstamp(w) for w in hit[2]), hit[1], hit[2])
+        for ck, (dsc, _) in self.pack_descs.items():            # parameters whose storage moved (param.data = ..., .to())
+            ptr = self.wcache[ck][3].data_ptr()
+            if dsc.w != ptr:
+                dsc.w = ptr
+                self._pack_table = None
         if self._pack_table is None:
             keys = list(self.pack_descs)
             n = len(keys)
@@ -357,16 +382,51 @@ class Engine:
         return (self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
                 and all(s.xform == L.XF_IDENT for s in srcs))
 
+    # ---- split-precision operands (parity mode "bf16x3" / "bf16x6") ----
+    def split_view(self, name, ptr, ld, dtype, rows, C_, xform=L.XF_IDENT, scale=None, shift=None):
+        """bf16 expansion planes [rows, C] of an fp32 view (after its pending transform): x ~= part0 + part1 (+ part2)."""
+        parts = [self.buf("%s.%d" % (name, i), (rows, C_), torch.bfloat16) for i in range(self.split)]
+        d = L.Split()
+        d.x, d.ld, d.dtype, d.rows, d.C = ptr, ld, dtype, rows, C_
+        d.scale, d.shift, d.xform, d.nparts, d.ldo = _ptr(scale), _ptr(shift), xform, self.split, C_
+        for i, t in enumerate(parts):
+            d.part[i] = t.data_ptr()
+        self.call("vinet_split_bf16", d)
+        return parts
+
+    def split_sources(self, name, srcs):
+        """[part][source] operand Acts of a convolution: plain bf16 NDHWC tensors the TMA-fed kernels can fetch."""
+        out = [[] for _ in range(self.split)]
+        for si, a in enumerate(srcs):
+            if isinstance(a, WinAct):
+                rows, C_ = a.B * a.T * a.H * a.Wp, 8
+                planes = self.split_view("%s.sp%d" % (name, si), a.buf.data_ptr(), 8, self.dt, rows, C_)
+                for i, t in enumerate(planes):
+                    out[i].append(WinAct(t.view(a.B, a.T, a.H, a.Wp, 8), a.B, a.T, a.H, a.W, a.wl, a.Wp))
+            else:
+                planes = self.split_view("%s.sp%d" % (name, si), a.ptr(), a.ld, self.dt, a.rows, a.C, a.xform, a.scale, a.shift)
+                for i, t in enumerate(planes):
+                    out[i].append(Act(t.view(a.B, a.T, a.H, a.W, a.C), a.B, a.T, a.H, a.W, a.C))
+        return out
+
     def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None, wgrad_split=None):
         """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY.
         ep = (scale, shift, act): fused per-channel epilogue (inference-mode BatchNorm folding).
         wgrad_split = [(parameter name, out channels)]: `w` is a concatenation of several parameters along Cout; the
-        weight gradient is unpacked straight into each member's gradient tensor."""
-        a0 = srcs[0]
+        weight gradient is unpacked straight into each member's gradient tensor.
+        Split-precision parity mode: every GEMM below is issued once per (operand part, weight part) term into the same fp32
+        output (first term stores, the others accumulate); the kernels are the ones the bf16 mode runs."""
+        if self.split:
+            assert ep is None, "the split-precision mode accumulates raw terms: no non-linear epilogue"
+            psrcs = self.split_sources(name, srcs)
+        else:
+            psrcs = [srcs]
+        terms = self.terms
+        a0 = psrcs[0][0]
         cs = a0.C
         Cout = w.shape[0]
         win = isinstance(a0, WinAct)
-        tma = win or self.tma_ok(srcs, geom)
+        tma = win or self.tma_ok(psrcs[0], geom)
         kern = L.KERNEL_TMA if tma else L.KERNEL_GATHER
         layout = L.KLAYOUT_WIN8 if win else (L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE)
         To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
@@ -381,58 +441,67 @@ class Engine:
             assert (Wo - 1) * geom.sw + 8 <= a0.Wp
             taps, cs = [(0, dh, 0) for dh in range(geom.kh)], 64
 
-        def fill_gather(g):
+        def fill_gather(g, ss):
             if not win:
-                return self._gather_fprop(g, srcs, geom, cs, To, Ho, Wo)
-            g.mode, g.dtype = L.GATHER_FPROP, self.dt
-            g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, To, Ho, Wo, 1, 0
-            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = a0.T, a0.H, Wo, 64, len(taps)
+                return self._gather_fprop(g, ss, geom, cs, To, Ho, Wo)
+            aw = ss[0]
+            g.mode, g.dtype = L.GATHER_FPROP, self.opdt
+            g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = aw.B, To, Ho, Wo, 1, 0
+            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 64, len(taps)
             _fill_taps(g.tap, taps)
             g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
             s0 = g.src[0]
-            s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = a0.buf.data_ptr(), None, None, 8 * geom.sw, a0.T, L.XF_IDENT
-            s0.ldh = a0.Wp * 8
+            s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = aw.buf.data_ptr(), None, None, 8 * geom.sw, aw.T, L.XF_IDENT
+            s0.ldh = aw.Wp * 8
             g.src[1].ptr, g.src[1].T = None, 0
 
-        d = L.Conv()
-        d.kernel = kern
-        fill_gather(d.g)
-        d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
-        d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
-        d.out_dtype, d.accumulate = self.dt, 0
-        d.ep_scale, d.ep_shift, d.ep_act = None, _ptr(bias), L.ACT_NONE
-        if ep is not None:
-            assert bias is None
-            d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
-        wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout,
-                                                            tiling=self.conv_tiling(d, Cout))
-        d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
-        self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
+        for ti, (pa, pw) in enumerate(terms):
+            d = L.Conv()
+            d.kernel = kern
+            fill_gather(d.g, psrcs[pa])
+            d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
+            d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
+            d.out_dtype, d.accumulate = self.dt, (0 if ti == 0 else 1)
+            d.ep_scale, d.ep_shift, d.ep_act = None, (_ptr(bias) if ti == 0 else None), L.ACT_NONE
+            if ep is not None:
+                assert bias is None
+                d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
+            wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout,
+                                                                tiling=self.conv_tiling(d, Cout), part=pw)
+            d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
+            self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
         if not self.record:
             return None
 
         def backward(dy, lddy):
+            rows = a0.B * To * Ho * Wo
+            # operand form of dY: the tensor itself, or its bf16 expansion planes in the split-precision mode
+            if self.split:
+                planes = self.split_view("dyp.%d" % (rows * Cout), dy, lddy, self.dt, rows, Cout)
+                dyp = [(t.data_ptr(), Cout) for t in planes]
+            else:
+                dyp = [(dy, lddy)]
             # ---- weight gradient
             csk = round_up(cs, 64) if tma else cs          # TAP64 rows of the packed gradient
             ktot = len(taps) * csk
             lddw = round_up(Cout, 64)
             dwp = self.buf(name + ".dwp", (round_up(ktot, 128), lddw), torch.float32)
             self.memset(dwp)
-            wg = L.Wgrad()
-            wg.kernel = kern
-            fill_gather(wg.g)
-            wg.dy, wg.lddy, wg.dy_dtype, wg.N, wg.dwp, wg.lddw = dy, lddy, self.dt, Cout, dwp.data_ptr(), lddw
-            rows = a0.B * To * Ho * Wo
-            if self.eng == L.ENGINE_TC:
-                tiles = cdiv(ktot, 128) * self.tiling(Cout)[1]
-                chunks = cdiv(rows, 64)
-            else:
-                tiles = cdiv(ktot, 64) * cdiv(Cout, 64)
-                chunks = cdiv(rows, 16)
-            wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
-            self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
+            for pa, pd in terms:
+                wg = L.Wgrad()
+                wg.kernel = kern
+                fill_gather(wg.g, psrcs[pa])
+                wg.dy, wg.lddy, wg.dy_dtype, wg.N, wg.dwp, wg.lddw = dyp[pd][0], dyp[pd][1], self.opdt, Cout, dwp.data_ptr(), lddw
+                if self.eng == L.ENGINE_TC:
+                    tiles = cdiv(ktot, 128) * self.tiling(Cout)[1]
+                    chunks = cdiv(rows, 64)
+                else:
+                    tiles = cdiv(ktot, 64) * cdiv(Cout, 64)
+                    chunks = cdiv(rows, 16)
+                wg.splits = max(1, min(cdiv(2 * 148, tiles), cdiv(chunks, 4)))
+                self.timed(name, "wgrad", flops, lambda: self.lib.call("vinet_conv_wgrad", C.byref(wg), self.eng, self.stream()))
             if wgrad_split is not None:
                 off = 0
                 for pname, c in wgrad_split:      # member columns [off, off+c) of the packed gradient
@@ -472,33 +541,35 @@ class Engine:
                 for s in srcs:
                     self.ensure_init(s)
             accmask = sum((0 if self.first_write(s) else 1) << i for i, s in enumerate(srcs))
+            allmask = (1 << len(srcs)) - 1
             for dts, t0, frames in phases:
                 ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
                 n = w.shape[1]
                 dtma = self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
-                dd = L.Conv()
-                dd.kernel = L.KERNEL_TMA if dtma else L.KERNEL_GATHER
-                g = dd.g
-                g.mode, g.dtype = L.GATHER_DGRAD, self.dt
-                g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, frames, a0.H, a0.W, geom.st, t0
-                g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = To, Ho, Wo, Cout, len(ptaps)
-                _fill_taps(g.tap, ptaps)
-                g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
-                g.src[0].ptr, g.src[0].scale, g.src[0].shift = dy, None, None
-                g.src[0].ld, g.src[0].T, g.src[0].xform = lddy, To, L.XF_IDENT
-                g.src[1].ptr, g.src[1].T = None, 0
-                for i, s in enumerate(srcs):
-                    dd.out[i], dd.ldo[i], dd.out_T[i] = s.gptr(), s.ldg, s.T
-                if len(srcs) == 1:
-                    dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
-                dd.out_dtype, dd.accumulate = gdt, accmask
-                dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
-                wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
-                                                        L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE,
-                                                        tiling=self.conv_tiling(dd, n))
-                dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
-                dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
-                self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
+                for ti, (pd, pw) in enumerate(terms):
+                    dd = L.Conv()
+                    dd.kernel = L.KERNEL_TMA if dtma else L.KERNEL_GATHER
+                    g = dd.g
+                    g.mode, g.dtype = L.GATHER_DGRAD, self.opdt
+                    g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, frames, a0.H, a0.W, geom.st, t0
+                    g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = To, Ho, Wo, Cout, len(ptaps)
+                    _fill_taps(g.tap, ptaps)
+                    g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
+                    g.src[0].ptr, g.src[0].scale, g.src[0].shift = dyp[pd][0], None, None
+                    g.src[0].ld, g.src[0].T, g.src[0].xform = dyp[pd][1], To, L.XF_IDENT
+                    g.src[1].ptr, g.src[1].T = None, 0
+                    for i, s in enumerate(srcs):
+                        dd.out[i], dd.ldo[i], dd.out_T[i] = s.gptr(), s.ldg, s.T
+                    if len(srcs) == 1:
+                        dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
+                    dd.out_dtype, dd.accumulate = gdt, (accmask if ti == 0 else allmask)
+                    dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
+                    wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
+                                                            L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE,
+                                                            tiling=self.conv_tiling(dd, n), part=pw)
+                    dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
+                    dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
+                    self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
         return backward
 
     # ------------------------------------------------------------------ conv + BatchNorm (+ReLU pending)
@@ -509,7 +580,7 @@ class Engine:
         plain activations, which is what lets the TMA-fed kernels fetch them.  Pure inference (no tape, running
         statistics): scale/shift/ReLU are folded into the conv epilogue and nothing else is launched."""
         Cn = out.C
-        if not self.training and not self.record:
+        if not self.training and not self.record and not self.split:
             ss = self._bn_finalize(name_bn, bn, out.rows, Cn, None)[1]
             out.xform, out.scale, out.shift = L.XF_IDENT, None, None
             self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
@@ -680,7 +751,7 @@ class Engine:
         (x is read once instead of three times), each member keeps its own BatchNorm; backward runs ONE
         weight-gradient and ONE data-gradient GEMM over the concatenated dY.
         members: [(name_conv, name_bn, conv_weight, bn, out_act)]."""
-        if not self.training and not self.record:          # inference: per-member convs with folded BatchNorm
+        if not self.training and not self.record and not self.split:      # inference: per-member convs with folded BatchNorm
             for nc, nb, w, bn, out in members:
                 self.conv_bn(nc, nb, [x], w, bn, _G1, out)
             return
@@ -807,5 +878,6 @@ class Engine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        self.consumed_gen = getattr(self, "generation", -1)
         grads, self.param_grads = self.param_grads, {}     # hand over the only references: autograd can adopt the tensors
         return grads

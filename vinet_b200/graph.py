@@ -9,7 +9,9 @@ C-ABI calls plus PyTorch's fused Adam, so the capture is plain ``torch.cuda.grap
         loss = step(clip, gt)          # device tensor, valid until the next call
 
 The optimizer must be capturable (``torch.optim.Adam(..., fused=True, capturable=True)``).  Shapes are fixed at capture.
-Multi-GPU: pass ``after_backward=model.sync_gradients`` (flat gradient arena) and the NCCL all-reduce is part of the graph.
+Multi-GPU: ``after_backward=model.sync_gradients`` (flat gradient arena).  With ``capture_optimizer=True`` the all-reduce and
+the optimizer are captured with the step; with ``capture_optimizer=False`` the graph holds forward + loss + backward and the
+all-reduce + optimizer run eagerly after every replay.
 """
 import torch
 
@@ -17,6 +19,7 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None, capture_optimizer=True):
         assert example_x.is_cuda, "GraphedTrainStep needs CUDA tensors"
+        assert warmup >= 1, "at least one eager warm-up step (lazy initialisation must not happen during capture)"
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         # after_backward: e.g. model.sync_gradients.  capture_optimizer=False captures forward + loss + backward only and runs
         # after_backward() and optimizer.step() eagerly after every replay (multi-GPU: NCCL stays outside the graph)
@@ -42,6 +45,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
         from . import lib as _lib
+        self._mark_weights_dirty()        # the re-pack of the cached tensor-core weights must be part of the captured step
         n0 = _lib.get().launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._eager_step(zero=False) if capture_optimizer else self._fwd_bwd()

@@ -50,7 +50,7 @@ class Wgrad(C.Structure):
 class Pack(C.Structure):
     _fields_ = [("w", _p), ("Cout", _i32), ("Cin", _i32), ("kt", _i32), ("kh", _i32), ("kw", _i32), ("cs", _i32),
                 ("mode", _i32), ("ntaps", _i32), ("tap", (C.c_int8 * 4) * MAX_TAPS), ("engine", _i32),
-                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p), ("layout", _i32)]
+                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p), ("layout", _i32), ("part", _i32)]
 
 
 class PackInput(C.Structure):
@@ -126,6 +126,11 @@ class AvFuse(C.Structure):
                 ("gaudio", _p), ("dw", _p), ("dbias", _p)]
 
 
+class Split(C.Structure):
+    _fields_ = [("x", _p), ("ld", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32), ("scale", _p), ("shift", _p),
+                ("xform", _i32), ("nparts", _i32), ("part", _p * 3), ("ldo", _i64)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinet_b200.h
 _S = C.c_void_p  # stream
 SIGNATURES = {
@@ -138,6 +143,7 @@ SIGNATURES = {
     "vinet_unpack_wgrad": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _S]),
     "vinet_unpack_wgrad_win8": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _S]),
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
+    "vinet_split_bf16": (C.c_int, [C.POINTER(Split), _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
     "vinet_bn_stats_finalize": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _S]),
@@ -177,7 +183,7 @@ SIGNATURES = {
 
 # declaration order of the structs in the header (vinet_abi_sizes)
 ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
-               Conv1d, Bn1d, AvFuse]
+               Conv1d, Bn1d, AvFuse, Split]
 
 
 class VinetError(RuntimeError):

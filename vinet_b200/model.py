@@ -249,6 +249,9 @@ class _PlanFunction(torch.autograd.Function):
         e = ctx.engine
         if ctx.gen != e.generation:
             raise RuntimeError("vinet_b200: backward() of a stale forward (one outstanding forward per model)")
+        if ctx.gen == e.consumed_gen:
+            raise RuntimeError("vinet_b200: second backward() through the same forward: the activation tape is consumed by the "
+                               "first one (retain_graph is not supported; run the forward again)")
         grads = e.backward(gout.contiguous().float())
         return (None, None, None, None) + (None,) * ctx.n_extra + tuple(grads.pop(n, None) for n in ctx.names)
 
@@ -260,7 +263,9 @@ class _PlanModule(nn.Module):
     _n_extra = 0
 
     def set_precision(self, precision):
-        assert precision in ("bf16", "fp32", "bf16_simt")
+        """"bf16": throughput mode (bf16 storage, tcgen05).  "bf16x3": tensor-core parity mode (fp32 storage, every conv = three
+        tcgen05 launches over bf16-split operands; "bf16x6" adds a third term).  "fp32": FFMA reference parity mode."""
+        assert precision in Engine.PRECISIONS
         self.precision = precision
         self.__dict__.pop("_engines", None)
         return self
@@ -288,7 +293,7 @@ class _PlanModule(nn.Module):
             for n, p in named:
                 layout[n] = (off, p.numel())
                 off += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
-            arenas[key] = (torch.zeros(off, dtype=torch.float32, device=device), layout)
+            arenas[key] = (torch.zeros(off, dtype=torch.float32, device=device), layout, dict(named))
         return arenas[key]
 
     def sync_gradients(self, group=None):
@@ -298,7 +303,7 @@ class _PlanModule(nn.Module):
         arenas = self.__dict__.get("_arenas")
         assert arenas, "sync_gradients() needs enable_grad_arena() and a backward pass"
         world = dist.get_world_size(group)
-        for flat, _ in arenas.values():
+        for flat, *_ in arenas.values():
             if dist.get_backend(group) == "nccl":
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
             else:
@@ -309,17 +314,37 @@ class _PlanModule(nn.Module):
         """Rank `src`'s parameters and buffers to every rank (what DistributedDataParallel does at construction)."""
         import torch.distributed as dist
         for t in list(self.parameters()) + list(self.buffers()):
-            dist.broadcast(t.data, src, group=group)
+            dist.broadcast(t.detach(), src, group=group)      # detach() shares the version counter (t.data would not bump it)
+        return self.invalidate_weight_cache()
+
+    def invalidate_weight_cache(self):
+        """Parameters were written behind autograd's back (``p.data.copy_``, EMA updates, a custom in-place optimizer): make
+        every engine re-pack its cached tensor-core weight copies on the next forward."""
+        for e in self.__dict__.get("_engines", {}).values():
+            e.weights_dirty = True
         return self
+
+    def _replica_parameters(self):
+        """nn.DataParallel replica (train.py:182-184): ``_parameters`` is empty, the broadcast copies live in
+        ``_former_parameters`` of every sub-module and are plain attributes with a grad_fn."""
+        named = []
+        for prefix, mod in self.named_modules():
+            for k, t in getattr(mod, "_former_parameters", {}).items():
+                if t is not None:
+                    named.append(((prefix + "." if prefix else "") + k, t))
+        return named
 
     def _call_plan(self, x, *extra):
         if x.device.type != "cuda" and self.__dict__.get("_backend") is None:
             raise RuntimeError("vinet_b200 has no CPU path: move the model and inputs to a CUDA device")
-        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and self._plan_uses(n)]
+        replica = bool(getattr(self, "_is_replica", False))
+        params = self._replica_parameters() if replica else self.named_parameters()
+        named = [(n, p) for n, p in params if p.requires_grad and self._plan_uses(n)]
         names = tuple(n for n, _ in named)
         record = torch.is_grad_enabled() and len(named) > 0
         e = self._engine_for(x.device)
-        e.arena = self._arena_for(x.device, named) if (record and self.__dict__.get("_use_arena")) else None
+        e.replica = replica
+        e.arena = self._arena_for(x.device, named) if (record and self.__dict__.get("_use_arena") and not replica) else None
         return _PlanFunction.apply(self, record, names, x, *extra, *[p for _, p in named])
 
     def _plan_uses(self, name):
