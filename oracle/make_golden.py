@@ -28,6 +28,10 @@ CASES = [
     ("vinet_t32_eval", "vinet", 32, 2, 96, 64, False, 3),
     ("vinet_t48_eval", "vinet", 48, 1, 64, 64, False, 4),
     ("avinet_t32_train", "avinet", 32, 1, 224, 384, True, 5),
+    # ablation decoders (--num_hier 0/1/2, model.py:501,564,627): name, kind, T, B, H, W, train, seed, num_hier
+    ("vinet_hier0_train", "vinet", 32, 1, 64, 64, True, 6, 0),
+    ("vinet_hier1_eval", "vinet", 32, 1, 64, 96, False, 7, 1),
+    ("vinet_hier2_train", "vinet", 32, 1, 64, 64, True, 8, 2),
 ]
 
 
@@ -50,11 +54,11 @@ def grad_digest(model):
     return out
 
 
-def run_case(name, kind, T, B, H, W, train, seed):
+def run_case(name, kind, T, B, H, W, train, seed, num_hier=3):
     torch.manual_seed(0)
     if kind == "vinet":
-        ref = ref_loader.build_vinet(T)
-        mine = O.ViNetOracle(T)
+        ref = ref_loader.build_vinet(T, num_hier)
+        mine = O.ViNetOracle(T, num_hier)
     else:
         ref = ref_loader.build_avinet()
         mine = O.AViNetOracle(T)
@@ -68,7 +72,7 @@ def run_case(name, kind, T, B, H, W, train, seed):
     args = (d["x"],) if kind == "vinet" else (d["x"], d["audio"])
     _, ref_loss = ref_loader.load()
     rec = {}
-    meta = {"kind": kind, "T": T, "B": B, "H": H, "W": W, "train": train, "seed": seed,
+    meta = {"kind": kind, "T": T, "B": B, "H": H, "W": W, "train": train, "seed": seed, "num_hier": num_hier,
             "x_checksum": checksum(d["x"]), "gt_checksum": checksum(d["gt"]),
             "w_checksum": checksum(torch.cat([p.detach().flatten() for p in mine.parameters()])),
             "keys": list(rs.keys()), "shapes": [list(v.shape) for v in rs.values()]}

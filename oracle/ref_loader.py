@@ -52,9 +52,9 @@ def load():
     return m, l
 
 
-def build_vinet(num_clips=32):
+def build_vinet(num_clips=32, num_hier=3):
     m, _ = load()
-    return m.VideoSaliencyModel(num_clips=num_clips)
+    return m.VideoSaliencyModel(num_clips=num_clips, num_hier=num_hier)
 
 
 def build_avinet():

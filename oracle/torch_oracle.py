@@ -99,11 +99,14 @@ class Decoder(nn.Module):
     """conv -> ReLU -> 2x bilinear, T-concat with the skip tensor, time-collapsing convs, sigmoid
     (model.py:251-311 and the 8/16/48-frame variants)."""
 
-    def __init__(self, num_clips=32):
+    def __init__(self, num_clips=32, num_hier=3):
         super().__init__()
+        self.num_hier = num_hier
+        if num_hier != 3:
+            num_clips = 32       # the ablation decoders exist for 32-frame clips only (model.py:84-90 ignores num_clips)
         self.upsampling = nn.Upsample(scale_factor=(1, 2, 2), mode="trilinear")
         heads = []
-        for cin, cout, kt in arch.DECODER_HEAD:
+        for cin, cout, kt in arch.decoder_head(num_hier):
             heads.append([nn.Conv3d(cin, cout, (kt, 3, 3), (kt, 1, 1), (0, 1, 1), bias=False),
                           nn.ReLU(), self.upsampling])
         tail = []
@@ -122,22 +125,25 @@ class Decoder(nn.Module):
         self.convtsp3 = _Seq(*heads[2])
         self.convtsp4 = _Seq(*(heads[3] + tail))
 
-    def forward(self, y0, y1, y2, y3):
+    def forward(self, y0, y1=None, y2=None, y3=None):
+        h = self.num_hier
         z = self.convtsp1(y0)
-        z = self.convtsp2(torch.cat((z, y1), 2))
-        z = self.convtsp3(torch.cat((z, y2), 2))
-        z = self.convtsp4(torch.cat((z, y3), 2))
+        z = self.convtsp2(torch.cat((z, y1), 2) if h >= 1 else z)
+        z = self.convtsp3(torch.cat((z, y2), 2) if h >= 2 else z)
+        z = self.convtsp4(torch.cat((z, y3), 2) if h >= 3 else z)
         return z.view(z.size(0), z.size(3), z.size(4))
 
 
 class ViNetOracle(nn.Module):
-    def __init__(self, num_clips=32):
+    def __init__(self, num_clips=32, num_hier=3):
         super().__init__()
         self.backbone = Backbone()
-        self.decoder = Decoder(num_clips)
+        self.num_hier = num_hier
+        self.decoder = Decoder(num_clips, num_hier)
 
     def forward(self, x):
-        return self.decoder(*self.backbone(x))
+        ys = self.backbone(x)
+        return self.decoder(*ys[:self.num_hier + 1])
 
 
 class SoundNetOracle(nn.Module):

@@ -18,9 +18,9 @@ CASES = sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLD, "v
 
 
 def _build(meta, precision):
-    ref = O.ViNetOracle(meta["T"])
+    ref = O.ViNetOracle(meta["T"], meta.get("num_hier", 3))
     O.randomize_(ref, meta["seed"])
-    m = VideoSaliencyModel(num_clips=meta["T"])
+    m = VideoSaliencyModel(num_clips=meta["T"], num_hier=meta.get("num_hier", 3))
     assert list(m.state_dict().keys()) == meta["keys"]
     m.load_state_dict(ref.state_dict())
     return ref, m.cuda().set_precision(precision)

@@ -27,9 +27,9 @@ TC_KERNELS = {"conv_stream_kernel", "conv_wgrad_halo_kernel", "conv_gemm_tma_ker
 
 
 def _build(meta, precision):
-    ref = O.ViNetOracle(meta["T"])
+    ref = O.ViNetOracle(meta["T"], meta.get("num_hier", 3))
     O.randomize_(ref, meta["seed"])
-    m = VideoSaliencyModel(num_clips=meta["T"])
+    m = VideoSaliencyModel(num_clips=meta["T"], num_hier=meta.get("num_hier", 3))
     m.load_state_dict(ref.state_dict())
     return ref, m.cuda().set_precision(precision)
 

@@ -25,6 +25,9 @@ def test_arch_tables_agree():
     assert oarch.DECODER_HEAD == parch.DECODER_HEAD and oarch.SOUNDNET == parch.SOUNDNET
     for t in (8, 16, 32, 48):
         assert oarch.decoder_tail(t) == parch.decoder_tail(t)
+    for h in (0, 1, 2, 3):
+        assert oarch.decoder_head(h) == parch.decoder_head(h)
+    assert parch.decoder_head(3) == parch.DECODER_HEAD
 
 
 def test_losses_golden():
@@ -52,7 +55,7 @@ def test_model_golden(name):
         pytest.skip("fast mode")
     z = np.load(os.path.join(GOLD, name + ".npz"))
     T, B, H, W, seed = meta["T"], meta["B"], meta["H"], meta["W"], meta["seed"]
-    model = O.ViNetOracle(T) if meta["kind"] == "vinet" else O.AViNetOracle(T)
+    model = O.ViNetOracle(T, meta.get("num_hier", 3)) if meta["kind"] == "vinet" else O.AViNetOracle(T)
     sd = model.state_dict()
     assert list(sd.keys()) == meta["keys"]
     assert [list(v.shape) for v in sd.values()] == meta["shapes"]

@@ -21,10 +21,35 @@ def test_conv_concat_relu_upsample_vs_torch():
 
 
 def test_model_state_dict_layout_matches_oracle():
-    for t in (8, 16, 32, 48):
-        a, b = VideoSaliencyModel(num_clips=t).state_dict(), O.ViNetOracle(t).state_dict()
+    for t, h in [(8, 3), (16, 3), (32, 3), (48, 3), (32, 0), (32, 1), (32, 2)]:
+        a, b = VideoSaliencyModel(num_clips=t, num_hier=h).state_dict(), O.ViNetOracle(t, h).state_dict()
         assert list(a.keys()) == list(b.keys())
         assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+
+
+@pytest.mark.parametrize("num_hier", [0, 1, 2])
+def test_ablation_decoders_plan(num_hier):
+    """--num_hier 0/1/2 (DecoderConvUpNoHier / 1Hier / 2Hier, /root/reference/model.py:501-688) from the same descriptor-driven
+    plan: forward and every parameter gradient against the oracle (skip tensors the decoder does not read still get their
+    gradient from the backbone chain)."""
+    T, B, H, W = 32, 1, 64, 64
+    ref = O.ViNetOracle(T, num_hier)
+    O.randomize_(ref, 40 + num_hier)
+    ref.train()
+    m = VideoSaliencyModel(num_clips=T, num_hier=num_hier)
+    m.load_state_dict(ref.state_dict())
+    m.set_precision("fp32")
+    m.__dict__["_backend"] = Spec()
+    m.train()
+    d = O.make_inputs(B, T, H, W, 40 + num_hier)
+    pr = ref(d["x"]); O.kldiv(pr, d["gt"]).backward()
+    pm = m(d["x"]); O.kldiv(pm, d["gt"]).backward()
+    assert torch.allclose(pm, pr, rtol=1e-3, atol=1e-6), (pm - pr).abs().max()
+    rp = dict(ref.named_parameters())
+    for n, q in m.named_parameters():
+        assert q.grad is not None, n
+        if n.startswith("decoder.convtsp4"):
+            assert float((q.grad - rp[n].grad).norm() / (rp[n].grad.norm() + 1e-30)) < 2e-2, n
 
 
 def _spec_model(T, ref):

@@ -57,6 +57,12 @@ def decoder_tail(num_clips):
 # Decoder head convs (shared by all clip lengths): (Cin, Cout, kt)        model.py:256-271
 DECODER_HEAD = [(1024, 832, 1), (832, 480, 3), (480, 192, 5), (192, 64, 5)]
 
+
+def decoder_head(num_hier=3):
+    """Head convs of the decoder that fuses `num_hier` skip levels (DecoderConvUpNoHier / 1Hier / 2Hier / DecoderConvUp,
+    model.py:501,564,627,251): stage i > num_hier has no skip tensor to collapse, so its kernel is (1,3,3)."""
+    return [(cin, cout, kt if i <= num_hier else 1) for i, (cin, cout, kt) in enumerate(DECODER_HEAD)]
+
 # SoundNet layers 1..7: (Cin, Cout, k, pad, pool)  stride is always 2     model.py:750-786
 SOUNDNET = [(1, 16, 64, 32, 8), (16, 32, 32, 16, 8), (32, 64, 16, 8, 1), (64, 128, 8, 4, 1),
             (128, 256, 4, 2, 4), (256, 512, 4, 2, 1), (512, 1024, 4, 2, 1)]

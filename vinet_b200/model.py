@@ -102,14 +102,17 @@ class BackBoneS3D(nn.Module):
 
 
 class DecoderConvUp(nn.Module):
-    """Parameter layout of DecoderConvUp / DecoderConvUp8 / 16 / 48 (model.py:251-499)."""
+    """Parameter layout of DecoderConvUp / DecoderConvUp8 / 16 / 48 (model.py:251-499) and of the ablation decoders
+    DecoderConvUpNoHier / 1Hier / 2Hier (model.py:501-688; num_hier < 3, 32-frame clips only like the reference)."""
 
-    def __init__(self, num_clips=32):
+    def __init__(self, num_clips=32, num_hier=3):
         super().__init__()
-        self.num_clips = num_clips
+        if num_hier != 3:
+            num_clips = 32       # model.py:84-90: the ablation decoders ignore num_clips
+        self.num_clips, self.num_hier = num_clips, num_hier
         self.upsampling = Marker("Upsample((1,2,2),trilinear)")
         heads = [[ConvParams(cin, cout, (kt, 3, 3)), Marker("ReLU"), self.upsampling]
-                 for cin, cout, kt in arch.DECODER_HEAD]
+                 for cin, cout, kt in arch.decoder_head(num_hier)]
         tail = []
         for item in arch.decoder_tail(num_clips):
             if isinstance(item, str):
@@ -210,10 +213,11 @@ def backbone_plan(e, pfx, bb, x, y0_gdtype=None):
 
 
 def decoder_plan(e, pfx, dec, y0, y1, y2, y3):
-    """DecoderConvUp*.forward (model.py:286-311): returns the (B,H,W) fp32 saliency map tensor."""
+    """DecoderConvUp*.forward (model.py:286-311; ablations :543-562, :606-625, :669-688): returns the (B,H,W) fp32 saliency
+    map tensor.  Stage i concatenates the skip tensor y_i along time only when i <= num_hier."""
     heads = [dec.convtsp1[0], dec.convtsp2[0], dec.convtsp3[0], dec.convtsp4[0]]
     names = ["convtsp1.0", "convtsp2.0", "convtsp3.0", "convtsp4.0"]
-    skips = [None, y1, y2, y3]
+    skips = [None] + [y if i < dec.num_hier else None for i, y in enumerate((y1, y2, y3))]
     z = y0
     for m, nm, skip in zip(heads, names, skips):
         kt = m.weight.shape[2]
@@ -352,18 +356,20 @@ class _PlanModule(nn.Module):
 
 
 class VideoSaliencyModel(_PlanModule):
-    """ViNet (model.py:72-112). Only the default ``use_upsample=True, num_hier=3`` family is on the hot
-    path; other settings raise, like the reference does for ``use_upsample=False``."""
+    """ViNet (model.py:72-112): ``num_hier`` 3 (default; clip lengths 8/16/32/48) and the ablation decoders 0/1/2
+    (model.py:501-688).  ``use_upsample=False`` raises like the reference does (its DecoderConvT does not exist)."""
 
     def __init__(self, transformer_in_channel=32, nhead=4, use_upsample=True, num_hier=3, num_clips=32):
         super().__init__()
         if not use_upsample:
             raise NameError("name 'DecoderConvT' is not defined")      # model.py:101 — same failure as the reference
-        if num_hier != 3:
-            raise NotImplementedError("num_hier=%r ablation decoders are out of the hot-path scope" % (num_hier,))
+        if num_hier not in (0, 1, 2, 3):
+            raise AttributeError("'VideoSaliencyModel' object has no attribute 'decoder'")   # model.py:84-99 builds none either
+        if num_hier == 3 and num_clips not in (8, 16, 32, 48):
+            raise AttributeError("'VideoSaliencyModel' object has no attribute 'decoder'")
         self.backbone = BackBoneS3D()
         self.num_hier = num_hier
-        self.decoder = DecoderConvUp(num_clips)
+        self.decoder = DecoderConvUp(num_clips, num_hier)
 
     def forward(self, x):
         return self._call_plan(x)
