@@ -139,6 +139,8 @@ typedef struct vinet_pack {
   int32_t layout; /* VINET_KLAYOUT_* */
   int32_t part;   /* TC engine: which bf16 term of the weight is packed: 0 = bf16(w), 1 = bf16(w - part0), 2 = bf16(w - part0 - part1)
                      (split-precision "bf16x3" parity mode, see vinet_split_bf16); 0 everywhere else */
+  int32_t ld_cin; /* input-channel extent of the tensor `w` points into when Cin names a channel SLICE of it (w already offset
+                     to the slice's first channel); 0 = Cin.  The parity mode packs K chunks of a convolution separately. */
 } vinet_pack_t;
 int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream);
 /* n TC-engine packs in ONE launch.  table_dev: n descriptors in DEVICE memory (each as for vinet_pack_weights, already

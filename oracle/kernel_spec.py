@@ -142,7 +142,10 @@ class Spec:
         # the spec keeps ONE packed format (fp32 [k][npad]) for both engines; a TC-engine pack holds term `part` of the
         # weight's bf16 expansion (split-precision parity mode), exactly what the tcgen05 kernels multiply with
         assert d.layout == L.KLAYOUT_DENSE and (d.part == 0 or d.engine == L.ENGINE_TC)
-        w = _arr(d.w, d.Cout * d.Cin * d.kt * d.kh * d.kw).reshape(d.Cout, d.Cin, d.kt, d.kh, d.kw)
+        ldc, kk = (d.ld_cin or d.Cin), d.kt * d.kh * d.kw
+        flat = _arr(d.w, ((d.Cout - 1) * ldc + d.Cin) * kk)           # Cin may name a channel slice of a wider tensor
+        w = np.lib.stride_tricks.as_strided(flat, shape=(d.Cout, d.Cin, d.kt, d.kh, d.kw),
+                                            strides=(ldc * kk * 4, kk * 4, d.kh * d.kw * 4, d.kw * 4, 4))
         if d.engine == L.ENGINE_TC:
             w = w.copy()
             for _ in range(d.part):

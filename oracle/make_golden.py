@@ -29,9 +29,9 @@ CASES = [
     ("vinet_t48_eval", "vinet", 48, 1, 64, 64, False, 4),
     ("avinet_t32_train", "avinet", 32, 1, 224, 384, True, 5),
     # ablation decoders (--num_hier 0/1/2, model.py:501,564,627): name, kind, T, B, H, W, train, seed, num_hier
-    ("vinet_hier0_train", "vinet", 32, 1, 64, 64, True, 6, 0),
+    ("vinet_hier0_train", "vinet", 32, 2, 64, 96, True, 6, 0),
     ("vinet_hier1_eval", "vinet", 32, 1, 64, 96, False, 7, 1),
-    ("vinet_hier2_train", "vinet", 32, 1, 64, 64, True, 8, 2),
+    ("vinet_hier2_train", "vinet", 32, 2, 96, 64, True, 8, 2),
 ]
 
 

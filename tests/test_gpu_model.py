@@ -61,7 +61,10 @@ def test_fp32_engine_matches_reference_golden(name):
         for k in z.files:
             if k.startswith("grad/decoder"):
                 g = named[k[5:]].grad.cpu().numpy()
-                assert np.allclose(g, z[k], rtol=5e-3, atol=5e-4 * np.abs(z[k]).max()), k
+                assert np.linalg.norm(g - z[k]) / np.linalg.norm(z[k]) < 1e-2, k
+            elif k.startswith("grad/backbone"):      # the committed backbone gradient goldens (two fp32 implementations through
+                g = named[k[5:]].grad.cpu().numpy()  # ~60 train-mode BatchNorm layers agree to a few percent, not bit-wise)
+                assert np.linalg.norm(g - z[k]) / (np.linalg.norm(z[k]) + 1e-30) < 1e-1, k
             if k.startswith("stat/"):
                 assert np.allclose(m.state_dict()[k[5:]].cpu().numpy(), z[k], rtol=1e-3, atol=1e-5), k
 

@@ -91,7 +91,7 @@ def test_tensorcore_parity_mode_matches_reference_golden(name):
         g = named[k[5:]].grad.cpu().numpy()
         rl2 = np.linalg.norm(g - z[k]) / (np.linalg.norm(z[k]) + 1e-30)
         if k.startswith("grad/decoder"):
-            assert np.allclose(g, z[k], rtol=5e-3, atol=5e-4 * np.abs(z[k]).max()), (k, rl2)
+            assert rl2 < 1e-2, (k, rl2)
         else:
             worst_bb = max(worst_bb, rl2)
             assert rl2 < 1e-1, (k, rl2)

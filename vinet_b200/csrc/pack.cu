@@ -62,11 +62,12 @@ __global__ void __launch_bounds__(256) pack_input_vec4_kernel(const __grid_const
 // ------------------------------------------------------------------ weights
 // element (n, k) of the GEMM B operand; DENSE: k = tap_idx*cs + c, TAP64: k = tap_idx*round_up(cs,64) + c
 __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k) {
+  const int ldc = d.ld_cin > 0 ? d.ld_cin : d.Cin;   // channel extent of the underlying tensor (Cin may name a slice of it)
   if (d.layout == VINET_KLAYOUT_WIN8) {  // k = dh_tap*64 + dw*8 + ci; FPROP only
     const int tap = k >> 6, dw = (k >> 3) & 7, ci = k & 7;
     if (tap >= d.ntaps || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
     const int dt = d.tap[tap][0], dh = d.tap[tap][1];
-    return __ldg(d.w + ((((int64_t)n * d.Cin + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
+    return __ldg(d.w + ((((int64_t)n * ldc + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
   }
   const int csk = (d.layout == VINET_KLAYOUT_TAP64) ? ((d.cs + 63) / 64) * 64 : d.cs;
   const int tap = k / csk, c = k - tap * csk;
@@ -75,7 +76,7 @@ __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k
   if (d.mode == VINET_GATHER_FPROP) { co = n; ci = c; } else { co = c; ci = n; }
   if (co >= d.Cout || ci >= d.Cin) return 0.f;
   const int dt = d.tap[tap][0], dh = d.tap[tap][1], dw = d.tap[tap][2];
-  return __ldg(d.w + ((((int64_t)co * d.Cin + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
+  return __ldg(d.w + ((((int64_t)co * ldc + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
 }
 
 // term `part` of the bf16 expansion w ~= p0 + p1 + p2 (split-precision parity mode): the value left after removing the leading terms
@@ -239,6 +240,7 @@ extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) 
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
   VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN8, "pack_weights: layout %d", d->layout);
   VINET_CHECK(d->part >= 0 && d->part <= 2 && (d->part == 0 || d->engine == VINET_ENGINE_TC), "pack_weights: part %d", d->part);
+  VINET_CHECK(d->ld_cin == 0 || d->ld_cin >= d->Cin, "pack_weights: ld_cin %d < Cin %d", d->ld_cin, d->Cin);
   VINET_CHECK(d->layout != VINET_KLAYOUT_WIN8 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 8 && d->kw <= 8 && d->cs == 64),
               "pack_weights: WIN8 needs an FPROP pack with Cin <= 8, kw <= 8, cs == 64");
   const int64_t csk = d->layout == VINET_KLAYOUT_DENSE ? d->cs : round_up(d->cs, 64);

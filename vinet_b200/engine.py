@@ -277,12 +277,13 @@ class Engine:
     def _src(self, s, a):
         s.ptr, s.scale, s.shift, s.ld, s.T, s.xform = a.ptr(), _ptr(a.scale), _ptr(a.shift), a.ld, a.T, a.xform
 
-    def _gather_fprop(self, g, srcs, geom, cs, To, Ho, Wo):
+    def _gather_fprop(self, g, srcs, geom, cs, To, Ho, Wo, taps=None):
         a0 = srcs[0]
         g.mode, g.dtype = L.GATHER_FPROP, self.opdt
         g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, To, Ho, Wo, 1, 0
         g.Ts, g.Hs, g.Ws, g.Cs = sum(s.T for s in srcs), a0.H, a0.W, cs
-        taps = _taps(geom.kt, geom.kh, geom.kw)
+        if taps is None:
+            taps = _taps(geom.kt, geom.kh, geom.kw)
         g.ntaps = len(taps)
         _fill_taps(g.tap, taps)
         g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
@@ -308,11 +309,12 @@ class Engine:
             return bn.value, nt.value
         return self.tiling(n)
 
-    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE, tiling=None, part=0):
+    def packed_weight(self, w, key, mode, taps, cs, n, layout=L.KLAYOUT_DENSE, tiling=None, part=0, cslice=None):
         """bf16-swizzled (TC) or fp32 (SIMT) GEMM B operand of a conv weight, cached per parameter version.
-        part: which term of the weight's bf16 expansion (split-precision parity mode)."""
+        part: which term of the weight's bf16 expansion (split-precision parity mode); cslice = (c0, c): only the reduction
+        channels [c0, c0+c) (input channels for FPROP, output channels for DGRAD) — `cs` is then c."""
         block_n, n_tiles = tiling if tiling is not None else self.tiling(n)
-        ck = (key, mode, tuple(taps), self.eng, layout, block_n, n_tiles, part)
+        ck = (key, mode, tuple(taps), self.eng, layout, block_n, n_tiles, part, cslice)
         if layout != L.KLAYOUT_DENSE:
             k_blocks = len(taps) * cdiv(cs, L.TC_BLOCK_K)
         else:
@@ -327,6 +329,15 @@ class Engine:
         wc = w.detach()
         assert wc.is_contiguous() and wc.dtype == torch.float32
         d.w, d.Cout, d.Cin, d.kt, d.kh, d.kw = wc.data_ptr(), *wc.shape
+        woff = 0
+        if cslice is not None:
+            c0, c = cslice
+            kk = wc.shape[2] * wc.shape[3] * wc.shape[4]
+            if mode == L.GATHER_FPROP:          # a range of input channels: same strides, shifted base
+                woff, d.ld_cin, d.Cin = 4 * c0 * kk, wc.shape[1], c
+            else:                               # a range of output channels (the outermost dimension)
+                woff, d.Cout = 4 * c0 * wc.shape[1] * kk, c
+            d.w = wc.data_ptr() + woff
         d.cs, d.mode, d.ntaps = cs, mode, len(taps)
         _fill_taps(d.tap, taps)
         d.engine, d.block_n, d.n_tiles, d.k_blocks, d.out = self.eng, block_n, n_tiles, k_blocks, out.data_ptr()
@@ -337,7 +348,7 @@ class Engine:
             old = self.pack_descs.get(ck)
             if old is None or old[0].w != d.w or old[0].out != d.out:
                 self._pack_table = None                       # a new entry / moved storage: the device table must be rebuilt
-            self.pack_descs[ck] = (d, n_tiles * k_blocks * block_n * 8)
+            self.pack_descs[ck] = (d, n_tiles * k_blocks * block_n * 8, woff)
         return out, block_n, n_tiles, k_blocks
 
     def refresh_packed_weights(self):
@@ -352,8 +363,8 @@ class Engine:
                 with torch.no_grad():
                     torch.cat([w.detach() for w in hit[2]], 0, out=hit[1])
                 self.wcache[key] = (tuple(_wstamp(w) for w in hit[2]), hit[1], hit[2])
-        for ck, (dsc, _) in self.pack_descs.items():            # parameters whose storage moved (param.data = ..., .to())
-            ptr = self.wcache[ck][3].data_ptr()
+        for ck, (dsc, _, woff) in self.pack_descs.items():      # parameters whose storage moved (param.data = ..., .to())
+            ptr = self.wcache[ck][3].data_ptr() + woff
             if dsc.w != ptr:
                 dsc.w = ptr
                 self._pack_table = None
@@ -393,6 +404,29 @@ class Engine:
             d.part[i] = t.data_ptr()
         self.call("vinet_split_bf16", d)
         return parts
+
+    # tcgen05.mma adds into its fp32 TMEM accumulator with truncation: a GEMM of K elements carries a bias of about
+    # (K/16) * 2^-24 relative (measured through the goldens: 1e-4 on the K = 22,464 decoder conv).  The parity mode therefore
+    # issues the leading (hi x hi) term in tap chunks of at most SPLIT_KCHUNK reduction elements, each starting from a zero
+    # accumulator and added to the fp32 output by the epilogue's round-to-nearest add.  The other terms are 2^-8 smaller.
+    SPLIT_KCHUNK = 256
+
+    def term_launches(self, taps, cs, chunk_channels=True):
+        """[(operand part, weight part, tap subset, first channel, channels)] of one GEMM, in issue order (the first launch
+        stores, the rest accumulate).  Chunks of the leading term are whole taps, or 64-aligned channel ranges of one tap."""
+        if not self.split:
+            return [(0, 0, taps, 0, cs)]
+        out = []
+        kc = self.SPLIT_KCHUNK
+        for pa, pw in self.terms:
+            if (pa, pw) != (0, 0) or len(taps) * cs <= kc:
+                out.append((pa, pw, taps, 0, cs))
+            elif cs <= kc or not chunk_channels:
+                per = max(1, kc // cs)
+                out += [(0, 0, taps[i:i + per], 0, cs) for i in range(0, len(taps), per)]
+            else:
+                out += [(0, 0, [t], c0, min(kc, cs - c0)) for t in taps for c0 in range(0, cs, kc)]
+        return out
 
     def split_sources(self, name, srcs):
         """[part][source] operand Acts of a convolution: plain bf16 NDHWC tensors the TMA-fed kernels can fetch."""
@@ -441,14 +475,17 @@ class Engine:
             assert (Wo - 1) * geom.sw + 8 <= a0.Wp
             taps, cs = [(0, dh, 0) for dh in range(geom.kh)], 64
 
-        def fill_gather(g, ss):
+        def fill_gather(g, ss, tp=None, c0=0, c=None):
+            tp = taps if tp is None else tp
             if not win:
-                return self._gather_fprop(g, ss, geom, cs, To, Ho, Wo)
+                if c is not None and c != cs:
+                    ss = [a.slice(c0, c) for a in ss]
+                return self._gather_fprop(g, ss, geom, cs if c is None else c, To, Ho, Wo, tp)
             aw = ss[0]
             g.mode, g.dtype = L.GATHER_FPROP, self.opdt
             g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = aw.B, To, Ho, Wo, 1, 0
-            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 64, len(taps)
-            _fill_taps(g.tap, taps)
+            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 64, len(tp)
+            _fill_taps(g.tap, tp)
             g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
             s0 = g.src[0]
             s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = aw.buf.data_ptr(), None, None, 8 * geom.sw, aw.T, L.XF_IDENT
@@ -457,10 +494,10 @@ class Engine:
 
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
-        for ti, (pa, pw) in enumerate(terms):
+        for ti, (pa, pw, tp, c0, cc) in enumerate(self.term_launches(taps, cs, chunk_channels=not win)):
             d = L.Conv()
             d.kernel = kern
-            fill_gather(d.g, psrcs[pa])
+            fill_gather(d.g, psrcs[pa], tp, c0, cc)
             d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
             d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
             d.out_dtype, d.accumulate = self.dt, (0 if ti == 0 else 1)
@@ -468,10 +505,12 @@ class Engine:
             if ep is not None:
                 assert bias is None
                 d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
-            wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, taps, cs, Cout, layout,
-                                                                tiling=self.conv_tiling(d, Cout), part=pw)
+            wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, tp, cc, Cout, layout,
+                                                                tiling=self.conv_tiling(d, Cout), part=pw,
+                                                                cslice=None if cc == cs else (c0, cc))
             d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
-            self.timed(name, "fprop", flops, lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
+            self.timed(name, "fprop", flops * len(tp) * cc / (len(taps) * cs),
+                       lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
         if not self.record:
             return None
 
@@ -546,16 +585,16 @@ class Engine:
                 ptaps = [(dt, b, c) for dt in dts for b in range(geom.kh) for c in range(geom.kw)]
                 n = w.shape[1]
                 dtma = self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
-                for ti, (pd, pw) in enumerate(terms):
+                for ti, (pd, pw, tp, c0, cc) in enumerate(self.term_launches(ptaps, Cout)):
                     dd = L.Conv()
                     dd.kernel = L.KERNEL_TMA if dtma else L.KERNEL_GATHER
                     g = dd.g
                     g.mode, g.dtype = L.GATHER_DGRAD, self.opdt
                     g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = a0.B, frames, a0.H, a0.W, geom.st, t0
-                    g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = To, Ho, Wo, Cout, len(ptaps)
-                    _fill_taps(g.tap, ptaps)
+                    g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = To, Ho, Wo, cc, len(tp)
+                    _fill_taps(g.tap, tp)
                     g.st, g.sh, g.sw, g.pt, g.ph, g.pw = geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw
-                    g.src[0].ptr, g.src[0].scale, g.src[0].shift = dyp[pd][0], None, None
+                    g.src[0].ptr, g.src[0].scale, g.src[0].shift = dyp[pd][0] + 2 * c0 * (1 if self.split else 0), None, None
                     g.src[0].ld, g.src[0].T, g.src[0].xform = dyp[pd][1], To, L.XF_IDENT
                     g.src[1].ptr, g.src[1].T = None, 0
                     for i, s in enumerate(srcs):
@@ -564,11 +603,12 @@ class Engine:
                         dd.out[1], dd.ldo[1], dd.out_T[1] = None, 0, 0
                     dd.out_dtype, dd.accumulate = gdt, (accmask if ti == 0 else allmask)
                     dd.ep_scale, dd.ep_shift, dd.ep_act = None, None, L.ACT_NONE
-                    wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, ptaps, Cout, n,
+                    wpd, bn_, nt_, kb_ = self.packed_weight(w, name, L.GATHER_DGRAD, tp, cc, n,
                                                             L.KLAYOUT_TAP64 if dtma else L.KLAYOUT_DENSE,
-                                                            tiling=self.conv_tiling(dd, n), part=pw)
+                                                            tiling=self.conv_tiling(dd, n), part=pw,
+                                                            cslice=None if cc == Cout else (c0, cc))
                     dd.w, dd.N, dd.block_n, dd.n_tiles, dd.k_blocks = wpd.data_ptr(), n, bn_, nt_, kb_
-                    dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(ptaps) * Cout * n
+                    dflops = 2.0 * a0.B * frames * a0.H * a0.W * len(tp) * cc * n
                     self.timed(name, "dgrad", dflops, lambda: self.lib.call("vinet_conv_gemm", C.byref(dd), self.eng, self.stream()))
         return backward
 

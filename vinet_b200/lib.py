@@ -50,7 +50,7 @@ class Wgrad(C.Structure):
 class Pack(C.Structure):
     _fields_ = [("w", _p), ("Cout", _i32), ("Cin", _i32), ("kt", _i32), ("kh", _i32), ("kw", _i32), ("cs", _i32),
                 ("mode", _i32), ("ntaps", _i32), ("tap", (C.c_int8 * 4) * MAX_TAPS), ("engine", _i32),
-                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p), ("layout", _i32), ("part", _i32)]
+                ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32), ("out", _p), ("layout", _i32), ("part", _i32), ("ld_cin", _i32)]
 
 
 class PackInput(C.Structure):
