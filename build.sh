@@ -4,6 +4,7 @@ set -e
 cd "$(dirname "$0")"
 SRC=vinet_b200/csrc
 OUT=vinet_b200/libvinet_b200.so
+if [ "$1" = "--clean" ]; then rm -rf build "$OUT"; fi      # full recompile (VINET_CLEAN_BUILD=1 python -c "import __graft_entry__ as g; g.build()")
 mkdir -p build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -I$SRC --expt-relaxed-constexpr ${VINET_NVCC_EXTRA}"

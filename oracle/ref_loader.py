@@ -11,10 +11,25 @@ import sys
 import types
 
 REF_DIR = os.environ.get("VINET_REFERENCE_DIR", "/root/reference")
+# build-time copy of the unmodified reference sources (git-ignored, made by __graft_entry__.build(); travels to the GPU box)
+VENDORED_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 def available():
     return os.path.isfile(os.path.join(REF_DIR, "model.py"))
+
+
+def use_dir(path):
+    """Import the reference from `path` (e.g. baseline/_ref on the GPU box) instead of /root/reference."""
+    global REF_DIR
+    if os.path.abspath(path) != os.path.abspath(REF_DIR):
+        REF_DIR = path
+        _cache.clear()
+        for name in ("model", "model_utils", "loss"):
+            sys.modules.pop(name, None)
+
+
+_cache = {}
 
 
 @contextlib.contextmanager
@@ -25,9 +40,6 @@ def _cwd(path):
         yield
     finally:
         os.chdir(old)
-
-
-_cache = {}
 
 
 def load():
@@ -57,7 +69,17 @@ def build_vinet(num_clips=32, num_hier=3):
     return m.VideoSaliencyModel(num_clips=num_clips, num_hier=num_hier)
 
 
-def build_avinet():
+def build_avinet(random_soundnet=False):
+    """random_soundnet: the 57 MB soundnet8_final.pth is not vendored; model.py:224 loads it relative to the cwd, so hand its
+    torch.load a freshly initialised SoundNet state_dict instead (synthetic benchmarks only need the shapes)."""
     m, _ = load()
+    import torch
     with _cwd(REF_DIR):
+        if random_soundnet and not os.path.isfile("soundnet8_final.pth"):
+            real_load = torch.load
+            torch.load = lambda *a, **k: m.SoundNet().state_dict()
+            try:
+                return m.VideoAudioSaliencyModel()
+            finally:
+                torch.load = real_load
         return m.VideoAudioSaliencyModel()

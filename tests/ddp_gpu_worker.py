@@ -1,0 +1,57 @@
+"""Worker of tests/test_gpu_multi.py (launched with torchrun, 2 ranks, NCCL): rank r trains on clip r; after the single all-reduce
+of the flat gradient arena every rank must hold the mean of the two shard gradients (computed here on rank 0 alone)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+
+from oracle import torch_oracle as O
+from vinet_b200 import VideoSaliencyModel, kldiv
+
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+T, H, W = 8, 64, 96
+
+
+def model(seed):
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, seed)
+    m = VideoSaliencyModel(num_clips=T)
+    m.load_state_dict(ref.state_dict())
+    return m.to(dev).set_precision(precision).train()
+
+
+d = O.make_inputs(2, T, H, W, 0)
+x, gt = d["x"].to(dev), d["gt"].to(dev)
+m = model(seed=rank)                 # different weights per rank: broadcast_parameters must make them rank 0's
+m.broadcast_parameters(0)
+m.enable_grad_arena()
+pred = m(x[rank:rank + 1])
+kldiv(pred, gt[rank:rank + 1]).backward()
+m.sync_gradients()
+torch.cuda.synchronize()
+if rank == 0:
+    shard = []
+    for i in range(2):
+        s = model(seed=0)
+        kldiv(s(x[i:i + 1]), gt[i:i + 1]).backward()
+        shard.append({n: p.grad.float().clone() for n, p in s.named_parameters()})
+    worst = 0.0
+    for n, p in m.named_parameters():
+        want = 0.5 * (shard[0][n] + shard[1][n])
+        err = float((p.grad.float() - want).norm() / (want.norm() + 1e-30))
+        worst = max(worst, err)
+    tol = 2e-3 if precision == "fp32" else 5e-2       # bf16: atomics / summation order on bf16-stored activations
+    print("worst rel-L2 of averaged gradient vs mean of shards: %.3e" % worst)
+    assert worst < tol, worst
+ok = torch.ones(1, device=dev)
+dist.all_reduce(ok)
+if rank == 0:
+    print("DDP_GPU_WORKER_OK")
+dist.destroy_process_group()

@@ -17,7 +17,8 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None, capture_optimizer=True):
+    def __init__(self, model, loss_fn, optimizer, example_x, example_gt, warmup=3, after_backward=None, capture_optimizer=True,
+                 example_extra=()):
         assert example_x.is_cuda, "GraphedTrainStep needs CUDA tensors"
         assert warmup >= 1, "at least one eager warm-up step (lazy initialisation must not happen during capture)"
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
@@ -29,6 +30,8 @@ class GraphedTrainStep:
         self.gt = torch.empty_strided(example_gt.shape, example_gt.stride(), dtype=example_gt.dtype, device=example_gt.device)
         self.x.copy_(example_x)
         self.gt.copy_(example_gt)
+        # further model inputs (AViNet: the audio excerpt), also static
+        self.extra = [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device).copy_(t) for t in example_extra]
         # warm-up and capture must not change the training state: snapshot parameters, buffers and optimizer state
         saved = [t.detach().clone() for t in list(model.parameters()) + list(model.buffers())]
         fresh_opt = len(optimizer.state) == 0
@@ -60,7 +63,7 @@ class GraphedTrainStep:
         self._mark_weights_dirty()
 
     def _fwd_bwd(self):
-        loss = self.loss_fn(self.model(self.x), self.gt)
+        loss = self.loss_fn(self.model(self.x, *self.extra), self.gt)
         loss.backward()
         return loss
 
@@ -79,9 +82,11 @@ class GraphedTrainStep:
         for e in self.model.__dict__.get("_engines", {}).values():
             e.weights_dirty = True
 
-    def __call__(self, x, gt):
+    def __call__(self, x, gt, *extra):
         self.x.copy_(x, non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
+        for dst, src in zip(self.extra, extra):
+            dst.copy_(src, non_blocking=True)
         self.graph.replay()
         if not self.capture_optimizer:       # gradients live in static tensors (param.grad) that every replay overwrites
             if self.after_backward is not None:
@@ -89,3 +94,47 @@ class GraphedTrainStep:
             self.optimizer.step()
         self._mark_weights_dirty()
         return self.loss
+
+
+class GraphedForward:
+    """Inference forward (``model.eval()``, no autograd) captured once as a CUDA graph and replayed: the ~150 launches of a folded
+    BatchNorm forward become one graph launch.  Shapes are fixed at capture; parameters are read at replay time through the
+    engine's packed copies, so call ``refresh()`` after loading new weights.
+
+        fwd = GraphedForward(model, example_clip)          # AViNet: GraphedForward(model, example_clip, example_audio)
+        saliency = fwd(clip)                               # (B,H,W) fp32, valid until the next call
+    """
+
+    def __init__(self, model, example_x, *example_extra, warmup=2):
+        assert example_x.is_cuda and not model.training, "GraphedForward needs CUDA tensors and model.eval()"
+        self.model = model
+        self.inputs = [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device).copy_(t)
+                       for t in (example_x,) + tuple(example_extra)]
+        self._capture(warmup)
+
+    def _capture(self, warmup):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.inputs[0].device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                self.model(*self.inputs)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.inputs[0].device)
+        from . import lib as _lib
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.get().launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self.model(*self.inputs)
+        self.launches_per_replay = _lib.get().launch_count() - n0
+
+    def refresh(self):
+        """Parameters changed (load_state_dict, training steps in between): re-pack and re-capture."""
+        self.model.invalidate_weight_cache()
+        self._capture(1)
+
+    def __call__(self, x, *extra):
+        for dst, src in zip(self.inputs, (x,) + extra):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
