@@ -102,6 +102,10 @@ typedef struct vinet_conv {
   const float* ep_shift; /* per-output-channel (bias), may be NULL */
   int32_t ep_act;        /* VINET_ACT_* */
   int32_t kernel;        /* VINET_KERNEL_* (TC engine); TMA expects w packed with VINET_KLAYOUT_TAP64 */
+  double* stats;         /* optional (TC engine + TMA kernels, no epilogue, accumulate == 0): BatchNorm batch statistics of the raw
+                            output taken from the fp32 accumulators in the epilogue: stats[n] += sum over rows, stats[N + n] += sum
+                            of squares (per-CTA partials, fp64 atomics across CTAs).  Caller zeroes; vinet_bn_apply_stats consumes.
+                            Replaces the read pass of vinet_bn_stats (model_utils.py:132-138,145-150). */
 } vinet_conv_t;
 int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stream_t stream);
 /* N tiling (block_n, n_tiles) this library wants for the convolution described by d (every field but w / block_n /
@@ -217,6 +221,8 @@ typedef struct vinet_bn_finalize {
   float* shift;     /* beta - mean * scale */
   float* mean;
   float* invstd;
+  int64_t sq_stride; /* doubles between sum[c] and sum-of-squares[c] in `sums`; 0 = C.  A layer that is a channel slice of a fused
+                        convolution (Mixed_* 1x1 group) reads its slice of the group's statistics with sq_stride = the group's N. */
 } vinet_bn_finalize_t;
 int vinet_bn_finalize(const vinet_bn_finalize_t* d, vinet_stream_t stream);
 /* vinet_bn_stats + vinet_bn_finalize (training) in ONE launch: the last block to finish finalises.  Both descriptors must
@@ -239,6 +245,11 @@ typedef struct vinet_bn_apply {
   int32_t out_dtype;
 } vinet_bn_apply_t;
 int vinet_bn_apply(const vinet_bn_apply_t* d, vinet_stream_t stream);
+/* Training-mode finalisation + materialisation in ONE launch for n <= 4 layers whose statistics were accumulated by the
+ * convolution epilogue (vinet_conv_t.stats): every thread derives scale / shift of its 8 channels from f[i].sums, the first block
+ * of a layer also publishes scale / shift / mean / invstd and updates the running statistics (momentum, unbiased variance);
+ * then out = relu?(scale*y + shift).  f[i].sums is only read (the caller zeroes its statistics arena once per step). */
+int vinet_bn_apply_stats_multi(const vinet_bn_finalize_t* f, const vinet_bn_apply_t* a, int32_t n, vinet_stream_t stream);
 
 /* Backward of y_hat = relu?(scale*y + shift) w.r.t. the raw conv output y. */
 typedef struct vinet_bn_bwd {

@@ -44,6 +44,14 @@ for rows, Cn in SHAPES:
         return e0.elapsed_time(e1) / n * 1e3
     t_f = timeit(lambda: lib.call("vinet_bn_fwd_fused", C.byref(sd), C.byref(f), C.byref(a), st))
     t_s = timeit(lambda: (lib.call("vinet_bn_stats_finalize", C.byref(sd), C.byref(f), st), lib.call("vinet_bn_apply", C.byref(a), st)))
+    fa, aa = (L.BnFinalize * 1)(), (L.BnApply * 1)()
+    C.memmove(C.byref(fa[0]), C.byref(f), C.sizeof(L.BnFinalize)); C.memmove(C.byref(aa[0]), C.byref(a), C.sizeof(L.BnApply))
+    sums.fill_(1.0)
+    t_as = timeit(lambda: lib.call("vinet_bn_apply_stats_multi", fa, aa, 1, st))
+    t_am = timeit(lambda: lib.call("vinet_bn_apply_multi", aa, 1, st))
+    t_a1 = timeit(lambda: lib.call("vinet_bn_apply", C.byref(a), st))
+    print("   apply only: bn_apply %7.1f us, apply_multi %7.1f us, apply_stats_multi %7.1f us" % (t_a1, t_am, t_as))
+    sums.zero_()
     t_b = timeit(lambda: lib.call("vinet_bn_bwd_fused", C.byref(b), st))
     t_b2 = timeit(lambda: (lib.call("vinet_bn_bwd_reduce", C.byref(b), st), lib.call("vinet_bn_bwd_apply", C.byref(b), st)))
     mb = rows * Cn * 2 / 1e6

@@ -54,6 +54,7 @@ extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stre
   VINET_CHECK(d->g.B > 0 && d->g.Tr > 0 && d->g.Hr > 0 && d->g.Wr > 0, "conv_gemm: empty row space");
   VINET_CHECK(d->g.st > 0 && d->g.sh > 0 && d->g.sw > 0 && d->g.row_tstep > 0, "conv_gemm: bad strides");
   if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA) return conv_gemm_tma(d, (cudaStream_t)stream);
+  VINET_CHECK(d->stats == nullptr, "conv_gemm: epilogue BatchNorm statistics are a feature of the TMA-fed tensor-core kernels");
   VINET_CHECK(dense_sources(d->g), "conv_gemm: only the TMA kernel reads pitched / sliding-window sources");
   if (engine == VINET_ENGINE_TC) return conv_gemm_tc(d, (cudaStream_t)stream);
   if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);

@@ -497,6 +497,80 @@ __global__ void __launch_bounds__(BN_MT) bn_apply_multi_kernel(const __grid_cons
   }
 }
 
+// Finalisation + materialisation for layers whose statistics were accumulated by the convolution epilogue (vinet_conv_t.stats):
+// every thread derives scale / shift of its 8 channels from the fp64 sums (same arithmetic as bn_finalize_channel); the first
+// block of a layer publishes scale / shift / mean / invstd for the backward pass and updates the running statistics.
+struct BnApplyStatsMulti {
+  vinet_bn_finalize_t f[BN_MAX_SEG];
+  vinet_bn_apply_t a[BN_MAX_SEG];
+  int64_t rpb[BN_MAX_SEG];
+  double inv_n[BN_MAX_SEG];   // 1 / rows, computed on the host (an fp64 division costs microseconds of latency on the device)
+  int32_t nb[BN_MAX_SEG];
+};
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(BN_MT) bn_apply_stats_multi_kernel(const __grid_constant__ BnApplyStatsMulti p) {
+  const int seg = blockIdx.y;
+  if ((int)blockIdx.x >= p.nb[seg]) return;
+  const vinet_bn_apply_t& d = p.a[seg];
+  const vinet_bn_finalize_t& f = p.f[seg];
+  const SegMap m = seg_map(d.C);
+  const T* __restrict__ y = reinterpret_cast<const T*>(d.y);
+  TO* __restrict__ out = reinterpret_cast<TO*>(d.out);
+  const int c = m.gx * 8;
+  const int64_t sqs = f.sq_stride > 0 ? f.sq_stride : f.C;
+  // B200 has few fp64 lanes: ONE thread per channel group (row lane 0) turns the fp64 sums into fp32 scale / shift and shares
+  // them through shared memory (measured: with every thread doing it a 33 MB layer took 64 us instead of 10)
+  __shared__ float s_sc[1024], s_sh[1024];
+  if (m.ry == 0) {
+    const bool publish = blockIdx.x == 0;
+    const double inv_n = p.inv_n[seg];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double mu = __ldcg(f.sums + c + e) * inv_n;
+      const double var_d = fma(-mu, mu, __ldcg(f.sums + sqs + c + e) * inv_n);
+      const float var = fmaxf((float)var_d, 0.f);
+      const float mean = (float)mu;
+      const float invstd = rsqrtf(var + f.eps);
+      const float scv = __ldg(f.gamma + c + e) * invstd;
+      const float shv = __ldg(f.beta + c + e) - mean * scv;
+      s_sc[c + e] = scv;
+      s_sh[c + e] = shv;
+      if (publish) {
+        f.scale[c + e] = scv;
+        f.shift[c + e] = shv;
+        f.mean[c + e] = mean;
+        f.invstd[c + e] = invstd;
+        if (f.running_mean) {
+          const float n = (float)f.rows;
+          const float unbiased = (f.rows > 1) ? var * (n / (n - 1.f)) : var;
+          f.running_mean[c + e] = (1.f - f.momentum) * f.running_mean[c + e] + f.momentum * mean;
+          f.running_var[c + e] = (1.f - f.momentum) * f.running_var[c + e] + f.momentum * unbiased;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!m.active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = s_sc[c + e]; sh[e] = s_sh[c + e]; }
+  const bool relu = d.relu != 0;
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rpb[seg];
+  const int64_t r_end = min(d.rows, r_begin + p.rpb[seg]);
+#pragma unroll 4
+  for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) {
+    float v[8];
+    load8(y + r * d.ldy + c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = fmaf(v[e], sc[e], sh[e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
+    store8(out + r * d.ldo + c, v);
+  }
+}
+
 template <typename T, typename TG>
 __global__ void __launch_bounds__(BN_MT) bn_bwd_reduce_multi_kernel(const __grid_constant__ BnBwdMulti p) {
   const int seg = blockIdx.y;
@@ -746,6 +820,27 @@ extern "C" int vinet_bn_apply_multi(const vinet_bn_apply_t* a, int32_t n, vinet_
   VINET_DISPATCH_DTYPE(a[0].dtype, T, VINET_DISPATCH_DTYPE(a[0].out_dtype, TO,
       (bn_apply_multi_kernel<T, TO><<<dim3((unsigned)gx, (unsigned)n), BN_MT, 0, (cudaStream_t)stream>>>(p))));
   VINET_LAUNCH_OK("bn_apply_multi");
+  return 0;
+}
+
+extern "C" int vinet_bn_apply_stats_multi(const vinet_bn_finalize_t* f, const vinet_bn_apply_t* a, int32_t n, vinet_stream_t stream) {
+  VINET_CHECK(n >= 1 && n <= BN_MAX_SEG, "bn_apply_stats_multi: %d segments", n);
+  BnApplyStatsMulti p;
+  size_t smem = 0;
+  int32_t gx = 1;
+  for (int i = 0; i < n; ++i) {
+    VINET_CHECK(a[i].C % 8 == 0 && a[i].C <= 1024 && f[i].C == a[i].C && f[i].rows == a[i].rows && f[i].training && f[i].sums != nullptr &&
+                a[i].dtype == a[0].dtype && a[i].out_dtype == a[0].out_dtype, "bn_apply_stats_multi: segment %d", i);
+    p.f[i] = f[i];
+    p.a[i] = a[i];
+    p.inv_n[i] = 1.0 / (double)f[i].rows;
+    seg_grid(a[i].rows, a[i].C, false, &p.rpb[i], &p.nb[i], &smem, 0);
+    gx = std::max(gx, p.nb[i]);
+  }
+  for (int i = n; i < BN_MAX_SEG; ++i) p.nb[i] = 0;
+  VINET_DISPATCH_DTYPE(a[0].dtype, T, VINET_DISPATCH_DTYPE(a[0].out_dtype, TO,
+      (bn_apply_stats_multi_kernel<T, TO><<<dim3((unsigned)gx, (unsigned)n), BN_MT, 0, (cudaStream_t)stream>>>(p))));
+  VINET_LAUNCH_OK("bn_apply_stats_multi");
   return 0;
 }
 

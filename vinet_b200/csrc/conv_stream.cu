@@ -33,6 +33,7 @@ namespace vinet {
 constexpr int ST_THREADS = 448;
 constexpr int ST_MAX_ISSUERS = 4;
 constexpr int ST_MAX_TG = 8;
+constexpr int ST_STATS_FLOATS = 2 * 256;   // per-CTA BatchNorm statistic partials: [sum | sum of squares][column of the N tile]
 
 struct StreamParams {
   CUtensorMap tmA[2];
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
   const uint32_t full_a = smem_u32(bars), empty_a = full_a + 8 * AS, full_b = empty_a + 8 * AS, empty_b = full_b + 8 * BS;
   const uint32_t full_acc = empty_b + 8 * BS, empty_acc = full_acc + 8 * p.nacc, wbar = empty_acc + 8 * p.nacc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 2 * p.nacc + 1);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // ST_STATS_FLOATS floats, used when p.d.stats != nullptr
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const vinet_gather_t& g = p.d.g;
@@ -361,6 +363,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
     const int BN = p.d.block_n;
     const int nlim = p.d.N - nt * BN;
     const uint32_t nacc = (uint32_t)p.nacc;
+    const bool stats = p.d.stats != nullptr;
+    const int etid = threadIdx.x - 32 * (2 + ST_MAX_ISSUERS);   // 0..255 among the epilogue warps
+    if (stats) {
+      for (int i = etid; i < ST_STATS_FLOATS; i += 256) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     uint32_t slot = 0, ph = 0;
     for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
       const StItem c = st_decode(p, item);
@@ -370,7 +378,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
         tc_fence_after();
         const int ti = i * p.tt + rt;
         const int t = ti * g.row_tstep + g.row_toff;
-        for (int sub = 0; sub < ns; ++sub) {
+        // output row of this lane in sub-tile `sub` (nullptr: the row lies outside the problem)
+        auto sub_row = [&](int sub, bool& accum) -> TO* {
           int h, w;
           if (p.halo) {
             h = c.ty * p.th + rh;
@@ -382,28 +391,67 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
             w = (tif - ty * p.tiles_w) * p.tw + rw;
           }
           const bool valid = row < p.pos * p.tt && ti < g.Tr && h < g.Hr && w < g.Wr;
-          TO* orow = nullptr;
-          bool accum = false;
-          if (valid) {
-            RowCoord rc;
-            rc.b = c.b; rc.t = t; rc.h = h; rc.w = w;
-            orow = out_row_ptr<TO>(p.d, rc) + nt * BN;
-            accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
+          if (!valid) return nullptr;
+          RowCoord rc;
+          rc.b = c.b; rc.t = t; rc.h = h; rc.w = w;
+          accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
+          return out_row_ptr<TO>(p.d, rc) + nt * BN;
+        };
+        if (!stats) {
+          for (int sub = 0; sub < ns; ++sub) {
+            bool accum = false;
+            TO* orow = sub_row(sub, accum);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (slot * (uint32_t)p.nsub + (uint32_t)sub) * p.acc_stride;
+            for (int gi = half; gi < BN / 16; gi += 2) {
+              uint32_t r[16];
+              tmem_ld16(tacc + (uint32_t)(gi * 16), r);
+              if (orow == nullptr) continue;
+              const int c0 = gi * 16;
+              if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum);
+              if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, nt * BN + c0 + 8, accum);
+            }
           }
-          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (slot * (uint32_t)p.nsub + (uint32_t)sub) * p.acc_stride;
+        } else {
+          // BatchNorm statistics of the raw output from the fp32 accumulators: column-group outermost, so that the lane-local
+          // partial sums run over every sub-tile of the item before ONE cross-lane reduction per 16 columns
           for (int gi = half; gi < BN / 16; gi += 2) {
-            uint32_t r[16];
-            tmem_ld16(tacc + (uint32_t)(gi * 16), r);
-            if (!valid) continue;
             const int c0 = gi * 16;
-            if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum);
-            if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, nt * BN + c0 + 8, accum);
+            float sv[16], sq[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sv[e] = sq[e] = 0.f;
+            for (int sub = 0; sub < ns; ++sub) {
+              bool accum = false;
+              TO* orow = sub_row(sub, accum);
+              const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (slot * (uint32_t)p.nsub + (uint32_t)sub) * p.acc_stride;
+              uint32_t r[16];
+              tmem_ld16(tacc + (uint32_t)c0, r);
+              if (orow == nullptr) continue;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float x = __uint_as_float(r[e]);
+                sv[e] += x;
+                sq[e] = fmaf(x, x, sq[e]);
+              }
+              if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum);
+              if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, nt * BN + c0 + 8, accum);
+            }
+            warp_colsum16(sv, lane);
+            warp_colsum16(sq, lane);
+            const int col = c0 + colsum16_col(lane);
+            if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (lane & 1) ? sq[0] : sv[0]);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_acc + 8 * slot);
         if (++slot == nacc) { slot = 0; ph ^= 1u; }
+      }
+    }
+    if (stats) {   // per-CTA partials -> fp64 atomics on the layer's statistics
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = etid; i < 2 * BN; i += 256) {
+        const int which = i / BN, col = i - which * BN;
+        if (col < nlim) atomicAdd(p.d.stats + (size_t)which * p.d.N + nt * BN + col, (double)s_stats[which * 256 + col]);
       }
     }
   }
@@ -427,7 +475,7 @@ int stream_enable_set(int v) { g_stream_enable = v; return 0; }
 namespace {
 
 constexpr double ST_LOAD_BPC = 30.0;      // sustained L2->SM bytes per clock per SM with every SM pulling (tools/tma_bench.cu)
-constexpr size_t ST_SMEM_BUDGET = 222 * 1024;
+constexpr size_t ST_SMEM_BUDGET = 220 * 1024;   // + barriers + the 2 KB of per-CTA BatchNorm statistic partials <= 227 KB
 
 // 128 x n x 16 MMA: tensor pipe vs shared-memory operand reads vs what one issuing warp sustains (~90 clk per MMA, measured)
 double mma_clk16(int n, int issuers) { return std::max(std::max(n / 2.0, 32.0 + n / 4.0), 90.0 / issuers); }
@@ -677,7 +725,7 @@ int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles) {
 static int stream_launch(StreamParams& p, const vinet_conv_t* d, int sms, cudaStream_t stream) {
   const int nb_slots = p.wres ? d->k_blocks : p.b_slots;
   size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)nb_slots * p.b_bytes +
-                8 * (size_t)(2 * p.a_stages + 2 * p.b_slots + 2 * p.nacc + 1) + 64 + 8 * VINET_MAX_TAPS;
+                8 * (size_t)(2 * p.a_stages + 2 * p.b_slots + 2 * p.nacc + 1) + 64 + 8 * VINET_MAX_TAPS + 4 * ST_STATS_FLOATS;
   if (smem > 227 * 1024) {
     set_error("conv_gemm_stream: %zu bytes of shared memory", smem);
     return -1;

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   const int nb_slots = p.wres ? p.d.k_blocks : stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_slots * p.b_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA BatchNorm statistic partials (p.d.stats != nullptr)
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, tfull0 = empty0 + 8 * stages, tempty0 = tfull0 + 16;
   const uint32_t wbar = tempty0 + 16;
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
@@ -255,6 +256,25 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     const int row = q * 32 + lane;
     const int rh = row / p.bw, rw = row - rh * p.bw;
     const int BN = p.d.block_n;
+    const bool stats = p.d.stats != nullptr;
+    const int etid = threadIdx.x - 64;   // 0..255 among the epilogue warps
+    if (stats) {
+      for (int i = etid; i < 512; i += 256) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    int stats_nt = -1;                   // N tile the partials in shared memory belong to
+    auto flush_stats = [&]() {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int nl = p.d.N - stats_nt * BN;
+      for (int i = etid; i < 2 * BN; i += 256) {
+        const int which = i / BN, col = i - which * BN;
+        if (col < nl) {
+          atomicAdd(p.d.stats + (size_t)which * p.d.N + stats_nt * BN + col, (double)s_stats[which * 256 + col]);
+          s_stats[which * 256 + col] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     uint32_t lt = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const ItemCoord ic = decode_item(p, item);
@@ -265,32 +285,73 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         tc_fence_after();
       }
       const int nlim = p.d.N - ic.nt * BN;  // columns of this tile that exist
-      for (int hf = 0; hf < ic.nh; ++hf) {
+      auto half_row = [&](int hf, bool& accum) -> TO* {
         const int tif = ic.tile0 + hf;
         const int th = tif / p.tiles_w;
         const int h = th * p.bh + rh, w = (tif - th * p.tiles_w) * p.bw + rw;
         const bool valid = row < p.bw * p.bh && h < g.Hr && w < g.Wr;
-        TO* orow = nullptr;
-        bool accum = false;
-        if (valid) {
-          RowCoord rc;
-          rc.b = ic.b; rc.t = ic.t; rc.h = h; rc.w = w;
-          orow = out_row_ptr<TO>(p.d, rc) + ic.nt * BN;
-          accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
-        }
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.halves + (uint32_t)hf) * p.acc_stride;
-        for (int gi = half; gi < BN / 16; gi += 2) {
-          uint32_t r[16];
-          if (any) {
-            tmem_ld16(tacc + (uint32_t)(gi * 16), r);
-          } else {
+        if (!valid) return nullptr;
+        RowCoord rc;
+        rc.b = ic.b; rc.t = ic.t; rc.h = h; rc.w = w;
+        accum = (p.d.accumulate >> out_index(p.d, rc)) & 1;
+        return out_row_ptr<TO>(p.d, rc) + ic.nt * BN;
+      };
+      if (!stats) {
+        for (int hf = 0; hf < ic.nh; ++hf) {
+          bool accum = false;
+          TO* orow = half_row(hf, accum);
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.halves + (uint32_t)hf) * p.acc_stride;
+          for (int gi = half; gi < BN / 16; gi += 2) {
+            uint32_t r[16];
+            if (any) {
+              tmem_ld16(tacc + (uint32_t)(gi * 16), r);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = 0u;
+              for (int e = 0; e < 16; ++e) r[e] = 0u;
+            }
+            if (orow == nullptr) continue;
+            const int c0 = gi * 16;
+            if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
+            if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
           }
-          if (!valid) continue;
+        }
+      } else {
+        // BatchNorm statistics from the fp32 accumulators (see conv_stream.cu): a CTA's items may belong to different N tiles
+        // (items enumerate nt fastest), so the partials are flushed whenever the N tile changes
+        if (stats_nt != ic.nt) {
+          if (stats_nt >= 0) flush_stats();
+          stats_nt = ic.nt;
+        }
+        for (int gi = half; gi < BN / 16; gi += 2) {
           const int c0 = gi * 16;
-          if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
-          if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
+          float sv[16], sq[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sv[e] = sq[e] = 0.f;
+          for (int hf = 0; hf < ic.nh; ++hf) {
+            bool accum = false;
+            TO* orow = half_row(hf, accum);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (as * (uint32_t)p.halves + (uint32_t)hf) * p.acc_stride;
+            uint32_t r[16];
+            if (any) {
+              tmem_ld16(tacc + (uint32_t)c0, r);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = 0u;
+            }
+            if (orow == nullptr) continue;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float x = __uint_as_float(r[e]);
+              sv[e] += x;
+              sq[e] = fmaf(x, x, sq[e]);
+            }
+            if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
+            if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
+          }
+          warp_colsum16(sv, lane);
+          warp_colsum16(sq, lane);
+          const int col = c0 + colsum16_col(lane);
+          if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (lane & 1) ? sq[0] : sv[0]);
         }
       }
       if (any) {
@@ -300,6 +361,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
         ++lt;
       }
     }
+    if (stats && stats_nt >= 0) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -602,6 +664,8 @@ static int check_tma_gather(const vinet_gather_t& g, const char* what) {
 int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
   if (check_tma_gather(g, "conv_gemm_tma")) return -1;
+  VINET_CHECK(d->stats == nullptr || (!conv_has_epilogue(*d) && d->accumulate == 0 && d->block_n <= 256),
+              "conv_gemm_tma: epilogue statistics need a raw (no epilogue, non-accumulating) output");
   {  // convolutions with tap re-use (spatial halo / temporal frame sharing) go to the streaming kernel, conv_stream.cu
     const int r = conv_gemm_stream(d, stream);
     if (r != 0) return r < 0 ? r : 0;
@@ -644,7 +708,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   if (stages > 12) stages = 12;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64;
+  const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64 + 2048;
   VINET_CHECK(smem <= 227 * 1024, "conv_gemm_tma: %zu bytes of shared memory", smem);
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];

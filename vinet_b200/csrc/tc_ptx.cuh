@@ -85,6 +85,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Column sums of 16 consecutive accumulator columns over the 32 rows (lanes) of a warp by a reduce-scatter butterfly (15 + 1
+// shuffles instead of 16 x 5).  On return v[0] of lane L holds the 32-lane total of column
+// ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1); lanes L and L^1 hold the same column.
+__device__ __forceinline__ int colsum16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+template <int W, int BIT>
+__device__ __forceinline__ void colsum_step(float (&v)[16], int lane) {
+  const bool up = (lane & BIT) != 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float send = up ? v[i] : v[i + W];
+    const float keep = up ? v[i + W] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+  }
+}
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+  colsum_step<8, 16>(v, lane);
+  colsum_step<4, 8>(v, lane);
+  colsum_step<2, 4>(v, lane);
+  colsum_step<1, 2>(v, lane);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // 128-bit fp32 reduction to global memory (sm_90+): one L2 atomic transaction for four consecutive floats
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -227,6 +227,22 @@ class Engine:
         self._repack_all, self.weights_dirty = self.weights_dirty, False
         if self.eng == L.ENGINE_TC and not self.replica:
             self.refresh_packed_weights()
+        # BatchNorm batch statistics taken in the convolution epilogue (bf16 tensor-core training): one fp64 arena for all
+        # layers of the step, bump-allocated in plan order and zeroed by ONE memset per step
+        self.epi_stats = (self.eng == L.ENGINE_TC and not self.split and training and self.use_tma
+                          and "vinet_bn_apply_stats_multi" in self.lib.fn and not os.environ.get("VINET_NO_EPI_STATS"))
+        self.stats_off = 0
+        self.epi_stats_1x1 = not os.environ.get("VINET_NO_EPI_STATS_1X1")
+        if self.epi_stats:
+            self.stats_arena = self.buf("bn.stats_arena", (1 << 16,), torch.float64)
+            self.memset(self.stats_arena)
+
+    def stats_slice(self, n):
+        """Device pointer of 2*n zeroed doubles ([sum | sum of squares][n channels]) for one convolution of this step."""
+        off = self.stats_off
+        self.stats_off += 2 * n
+        assert self.stats_off <= self.stats_arena.numel(), "BatchNorm statistics arena exhausted"
+        return self.stats_arena.data_ptr() + 8 * off
 
     def end_forward(self):
         """nn.BatchNorm's num_batches_tracked counters of every layer touched by this forward, one launch."""
@@ -443,8 +459,10 @@ class Engine:
                     out[i].append(Act(t.view(a.B, a.T, a.H, a.W, a.C), a.B, a.T, a.H, a.W, a.C))
         return out
 
-    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None, wgrad_split=None):
+    def conv(self, name, srcs, w, geom, out, bias=None, cin_real=None, ep=None, wgrad_split=None, stats=None):
         """out <- raw conv of the (virtual T-concat of) srcs; returns a backward closure taking dY.
+        stats: device pointer of the layer's statistics slice (stats_slice): the TMA-fed kernels add the per-channel sum and sum
+        of squares of the raw output to it from their fp32 accumulators (BatchNorm batch statistics without a read pass).
         ep = (scale, shift, act): fused per-channel epilogue (inference-mode BatchNorm folding).
         wgrad_split = [(parameter name, out channels)]: `w` is a concatenation of several parameters along Cout; the
         weight gradient is unpacked straight into each member's gradient tensor.
@@ -502,6 +520,9 @@ class Engine:
             d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
             d.out_dtype, d.accumulate = self.dt, (0 if ti == 0 else 1)
             d.ep_scale, d.ep_shift, d.ep_act = None, (_ptr(bias) if ti == 0 else None), L.ACT_NONE
+            if stats is not None:
+                assert kern == L.KERNEL_TMA and not self.split and bias is None and ep is None
+                d.stats = stats
             if ep is not None:
                 assert bias is None
                 d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
@@ -626,8 +647,11 @@ class Engine:
             self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
             return
         raw = Act(self.buf(name_conv + ".raw", (out.B, out.T, out.H, out.W, Cn), self.tdtype), out.B, out.T, out.H, out.W, Cn)
-        conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real)
-        self._bn_tail(name_bn, bn, raw, out, conv_bwd, None)
+        st = None
+        if self.epi_stats and (isinstance(srcs[0], WinAct) or self.tma_ok(srcs, geom)) and (self.epi_stats_1x1 or geom.kt * geom.kh * geom.kw > 1):
+            st = (self.stats_slice(Cn), Cn)
+        conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real, stats=st[0] if st else None)
+        self._bn_tail(name_bn, bn, raw, out, conv_bwd, None, stats=st)
 
     def _bn_finalize(self, name_bn, bn, rows, Cn, raw, apply=None):
         """Batch statistics of `raw` (training) or the running statistics -> (mean/invstd, scale/shift) buffers.
@@ -690,19 +714,25 @@ class Engine:
             for i in range(0, len(members), 4):
                 self._bn_batch(members[i:i + 4])
 
-    def _bn_batch(self, members):
-        """members: [(name_bn, bn, raw, out, conv_bwd, dy_slot)] - small train-mode layers: one stats+finalise launch, one
-        apply launch; backward one reduce launch + one apply launch, then each member's convolution backward."""
+    def _bn_fwd_multi(self, members):
+        """Training forward of n <= 4 BatchNorm(+ReLU) layers: (statistics ->) finalise -> materialise.  Members whose statistics
+        came out of the convolution epilogue need ONE launch (vinet_bn_apply_stats_multi); the others a statistics + finalise
+        launch and an apply launch.  Returns [(mean/invstd buffer, scale/shift buffer)] per member."""
         n = len(members)
         sds, fins, aps, keep = (L.BnStats * n)(), (L.BnFinalize * n)(), (L.BnApply * n)(), []
-        for i, (name_bn, bn, raw, out, conv_bwd, dy_slot) in enumerate(members):
+        epi = all(mbr[6] is not None for mbr in members)
+        for i, (name_bn, bn, raw, out, conv_bwd, dy_slot, stats) in enumerate(members):
             Cn, rows = out.C, out.rows
             st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)
             ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)
-            sums = self.buf(name_bn + ".sums", (2 * Cn + 4,), torch.float64, zero=True)
             sd, fin, ap = sds[i], fins[i], aps[i]
-            sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
-            fin.sums, fin.rows, fin.C, fin.gamma, fin.beta = sums.data_ptr(), rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
+            if epi:
+                fin.sums, fin.sq_stride = stats
+            else:
+                sums = self.buf(name_bn + ".sums", (2 * Cn + 4,), torch.float64, zero=True)
+                sd.y, sd.ld, sd.dtype, sd.rows, sd.C, sd.sums = raw.ptr(), raw.ld, self.dt, rows, Cn, sums.data_ptr()
+                fin.sums, fin.sq_stride = sums.data_ptr(), 0
+            fin.rows, fin.C, fin.gamma, fin.beta = rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
             fin.eps, fin.momentum, fin.training = bn.eps, bn.momentum, 1
             fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
@@ -711,14 +741,24 @@ class Engine:
             out.xform, out.scale, out.shift = L.XF_IDENT, None, None
             self.bn_counters.append(bn.num_batches_tracked)
             keep.append((st, ss))
-        self.lib.call("vinet_bn_stats_finalize_multi", sds, fins, n, self.stream())
-        self.lib.call("vinet_bn_apply_multi", aps, n, self.stream())
+        if epi:
+            self.lib.call("vinet_bn_apply_stats_multi", fins, aps, n, self.stream())
+        else:
+            self.lib.call("vinet_bn_stats_finalize_multi", sds, fins, n, self.stream())
+            self.lib.call("vinet_bn_apply_multi", aps, n, self.stream())
+        return keep
+
+    def _bn_batch(self, members):
+        """members: [(name_bn, bn, raw, out, conv_bwd, dy_slot, stats)] - small train-mode layers: one (statistics +) finalise +
+        apply pass; backward one reduce launch + one apply launch, then each member's convolution backward."""
+        n = len(members)
+        keep = self._bn_fwd_multi(members)
         if not self.record:
             return
 
         def backward():
             bs, outs = (L.BnBwd * n)(), []
-            for i, (name_bn, bn, raw, out, conv_bwd, dy_slot) in enumerate(members):
+            for i, (name_bn, bn, raw, out, conv_bwd, dy_slot, _) in enumerate(members):
                 Cn, rows = out.C, out.rows
                 st, ss = keep[i]
                 bsums = self.buf(name_bn + ".bsums", (2 * Cn + 4,), torch.float64, zero=True)
@@ -737,25 +777,29 @@ class Engine:
                 self.param_grads[name_bn + ".weight"] = dgamma
                 self.param_grads[name_bn + ".bias"] = dbeta
                 outs.append((conv_bwd, dy_ptr, lddy))
-            assert len({o.gdt for _, _, _, o, _, _ in members}) == 1
+            assert len({mbr[3].gdt for mbr in members}) == 1
             self.lib.call("vinet_bn_bwd_multi", bs, n, self.stream())
             for conv_bwd, dy_ptr, lddy in reversed(outs):
                 if conv_bwd is not None:
                     conv_bwd(dy_ptr, lddy)
         self.tape.append(backward)
 
-    def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot):
+    def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot, stats=None):
         """BatchNorm + ReLU of the raw conv output `raw` into `out`, and its backward.  The backward either
-        hands dY to `conv_bwd` (own conv) or writes it into `dy_slot` = (ptr, ld) of a fused group's dY buffer."""
+        hands dY to `conv_bwd` (own conv) or writes it into `dy_slot` = (ptr, ld) of a fused group's dY buffer.
+        stats = (device pointer, sum-of-squares stride): batch statistics already accumulated by the convolution epilogue."""
         Cn, rows = out.C, out.rows
         if self._bn_pending is not None and self.training and rows * Cn * raw.buf.element_size() < (24 << 20):
-            self._bn_pending.append((name_bn, bn, raw, out, conv_bwd, dy_slot))      # small layer: wait for its launch mates
+            self._bn_pending.append((name_bn, bn, raw, out, conv_bwd, dy_slot, stats))      # small layer: wait for its launch mates
             return
-        out.xform, out.scale, out.shift = L.XF_IDENT, None, None
-        ap = L.BnApply()
-        ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
-        ap.out, ap.ldo, ap.out_dtype = out.ptr(), out.ld, self.dt
-        st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw, apply=ap)
+        if stats is not None:          # large layer, statistics from the conv epilogue: ONE finalise + apply launch
+            ((st, ss),) = self._bn_fwd_multi([(name_bn, bn, raw, out, conv_bwd, dy_slot, stats)])
+        else:
+            out.xform, out.scale, out.shift = L.XF_IDENT, None, None
+            ap = L.BnApply()
+            ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
+            ap.out, ap.ldo, ap.out_dtype = out.ptr(), out.ld, self.dt
+            st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw, apply=ap)
         if not self.record:
             return
         training = self.training
@@ -809,7 +853,8 @@ class Engine:
             self.wcache[key] = (vers, wcat, [w for _, _, w, _, _ in members])
         wcat = self.wcache[key][1]
         rawcat = Act(self.buf(gname + ".raw", (x.B, x.T, x.H, x.W, tot), self.tdtype), x.B, x.T, x.H, x.W, tot)
-        conv_bwd = self.conv(gname, [x], wcat, _G1, rawcat,
+        gst = self.stats_slice(tot) if (self.epi_stats and self.tma_ok([x], _G1) and self.epi_stats_1x1) else None
+        conv_bwd = self.conv(gname, [x], wcat, _G1, rawcat, stats=gst,
                              wgrad_split=[(nc + ".weight", c) for (nc, _, _, _, _), c in zip(members, couts)])
         dycat = None
         if self.record:
@@ -821,7 +866,7 @@ class Engine:
         off = 0
         for (nc, nb, w, bn, out), c in zip(members, couts):
             slot = None if dycat is None else (dycat.data_ptr() + off * dycat.element_size(), tot)
-            self._bn_tail(nb, bn, rawcat.slice(off, c), out, None, slot)
+            self._bn_tail(nb, bn, rawcat.slice(off, c), out, None, slot, stats=None if gst is None else (gst + 8 * off, tot))
             off += c
 
     # ------------------------------------------------------------------ max pooling

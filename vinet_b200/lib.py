@@ -39,7 +39,7 @@ class Gather(C.Structure):
 class Conv(C.Structure):
     _fields_ = [("g", Gather), ("w", _p), ("N", _i32), ("block_n", _i32), ("n_tiles", _i32), ("k_blocks", _i32),
                 ("out", _p * 2), ("ldo", _i64 * 2), ("out_T", _i32 * 2), ("out_dtype", _i32), ("accumulate", _i32),
-                ("ep_scale", _p), ("ep_shift", _p), ("ep_act", _i32), ("kernel", _i32)]
+                ("ep_scale", _p), ("ep_shift", _p), ("ep_act", _i32), ("kernel", _i32), ("stats", _p)]
 
 
 class Wgrad(C.Structure):
@@ -66,7 +66,7 @@ class BnStats(C.Structure):
 class BnFinalize(C.Structure):
     _fields_ = [("sums", _p), ("rows", _i64), ("C", _i32), ("gamma", _p), ("beta", _p), ("eps", _f32),
                 ("momentum", _f32), ("running_mean", _p), ("running_var", _p), ("training", _i32), ("scale", _p),
-                ("shift", _p), ("mean", _p), ("invstd", _p)]
+                ("shift", _p), ("mean", _p), ("invstd", _p), ("sq_stride", _i64)]
 
 
 class BnApply(C.Structure):
@@ -148,6 +148,7 @@ SIGNATURES = {
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
     "vinet_bn_stats_finalize": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _S]),
     "vinet_bn_apply": (C.c_int, [C.POINTER(BnApply), _S]),
+    "vinet_bn_apply_stats_multi": (C.c_int, [C.POINTER(BnFinalize), C.POINTER(BnApply), _i32, _S]),
     "vinet_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwd), _S]),
     "vinet_bn_fwd_fused": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), C.POINTER(BnApply), _S]),
