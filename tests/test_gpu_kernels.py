@@ -152,7 +152,7 @@ def test_maxpool_backward_gather_matches_scatter_and_autograd(cfg, overwrite):
     torch.nn.functional.max_pool3d(xr, k, s, p).backward(gout.permute(0, 4, 1, 2, 3))
     ref = xr.grad.permute(0, 2, 3, 4, 1) + (0 if overwrite else gin0)
     res = []
-    for fast in (3, 0):          # 3: gather backward, 0: atomic scatter
+    for fast in (3, 5, 9):       # 3: generic gather, 5: atomic scatter, 9: compile-time-specialised gather for every geometry
         lib.call("vinet_debug_set", 3, fast)
         out = torch.empty(B, To, Ho, Wo, Cn, dtype=torch.bfloat16, device="cuda")
         idx = torch.empty(B, To, Ho, Wo, Cn, dtype=torch.uint8, device="cuda")
@@ -171,6 +171,7 @@ def test_maxpool_backward_gather_matches_scatter_and_autograd(cfg, overwrite):
     lib.call("vinet_debug_set", 3, 1)
     assert torch.allclose(res[0], res[1], rtol=1e-6, atol=1e-6)
     assert torch.allclose(res[0], ref.cpu(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(res[0], res[2], rtol=1e-6, atol=1e-6)
 
 
 SWEEP_CONVS = [  # B, T0, T1, H, W, Cin, Cout, k, stride_t, pad  (geometries the 128x192 .. 448x768 / T=8..48 sweep produces)

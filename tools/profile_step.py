@@ -11,6 +11,10 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from vinet_b200 import VideoAudioSaliencyModel, VideoSaliencyModel, kldiv
 
+for kv in os.environ.get("VINET_DEBUG_SET", "").split(","):      # e.g. VINET_DEBUG_SET=3=5 : atomic max-pool backward
+    if "=" in kv:
+        from vinet_b200 import lib as _L
+        _L.get().call("vinet_debug_set", int(kv.split("=")[0]), int(kv.split("=")[1]))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 which = sys.argv[2] if len(sys.argv) > 2 else "vinet"
 mode = sys.argv[3] if len(sys.argv) > 3 else "train"

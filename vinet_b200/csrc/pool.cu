@@ -350,8 +350,123 @@ __global__ void __launch_bounds__(256) maxpool_bwd_gather_kernel(const __grid_co
   }
 }
 
+// The same gather with the window geometry as compile-time constants (the four pools of this model): one block walks one input
+// row (b, t, h), a thread owns (w, 8 channels); the candidate windows are enumerated by tap with the stride-lattice tests
+// folded at compile time, all index arithmetic is 32-bit.  The generic kernel above spends ~450 instructions per item on 64-bit
+// divisions and run-time loop bounds (0.38 ms for the stem pool); this one is bound by its 16-byte loads and stores.
+template <int KT, int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW, typename TGO, typename TGI>
+__global__ void __launch_bounds__(256) maxpool_bwd_gather_fixed_kernel(const __grid_constant__ vinet_pool_t d) {
+  // candidate windows per dimension: to = floor((t + PT) / ST) - j, j < ceil(KT / ST)
+  constexpr int NT = (KT + ST - 1) / ST, NH = (KH + SH - 1) / SH, NW = (KW + SW - 1) / SW, NC = NT * NH * NW;
+  constexpr bool EAGER = NC <= 8;   // few candidates: fetch their gradients unconditionally, all loads in flight at once
+  const int G = d.C / 8;
+  const TGO* __restrict__ gout = reinterpret_cast<const TGO*>(d.gout);
+  TGI* __restrict__ gin = reinterpret_cast<TGI*>(d.gin);
+  const int nrows = d.B * d.Ti * d.Hi;
+  const int items = d.Wi * G;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int h = row % d.Hi;
+    const int bt = row / d.Hi;
+    const int t = bt % d.Ti, b = bt / d.Ti;
+    const int th = (t + PT) / ST, hh = (h + PH) / SH;
+    for (int i = threadIdx.x; i < items; i += 256) {
+      const int w = i / G;
+      const int c = (i - w * G) * 8;
+      const int wh = (w + PW) / SW;
+      // phase 1: every candidate's recorded tap bytes (and, when few, its gradient) - independent loads
+      uint2 pk[NC];
+      int off[NC];          // output position, or -1
+      unsigned tap4[NC];
+      uint4 gq[EAGER ? NC : 1];
+#pragma unroll
+      for (int jt = 0; jt < NT; ++jt) {
+        const int to = th - jt, dt = t + PT - to * ST;
+        const bool vt = to >= 0 && to < d.To && dt < KT;
+#pragma unroll
+        for (int jh = 0; jh < NH; ++jh) {
+          const int ho = hh - jh, dh = h + PH - ho * SH;
+          const bool vh = vt && ho >= 0 && ho < d.Ho && dh < KH;
+#pragma unroll
+          for (int jw = 0; jw < NW; ++jw) {
+            const int wo = wh - jw, dw = w + PW - wo * SW;
+            const bool v = vh && wo >= 0 && wo < d.Wo && dw < KW;
+            const int k = (jt * NH + jh) * NW + jw;
+            const int o = ((b * d.To + to) * d.Ho + ho) * d.Wo + wo;
+            off[k] = v ? o : -1;
+            tap4[k] = (unsigned)((dt * KH + dh) * KW + dw) * 0x01010101u;
+            pk[k] = v ? __ldg(reinterpret_cast<const uint2*>(d.idx + (int64_t)o * d.C + c)) : make_uint2(0xffffffffu, 0xffffffffu);
+            if constexpr (EAGER) {
+              if constexpr (sizeof(TGO) == 2) {
+                gq[k] = v ? __ldg(reinterpret_cast<const uint4*>(gout + (int64_t)o * d.ldgo + c)) : make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+        }
+      }
+      // phase 2: sum the gradients of the windows whose arg-max is this element
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        if (off[k] < 0) continue;
+        const unsigned m0 = __vcmpeq4(pk[k].x, tap4[k]), m1 = __vcmpeq4(pk[k].y, tap4[k]);
+        if ((m0 | m1) == 0u) continue;
+        float g[8];
+        if constexpr (EAGER && sizeof(TGO) == 2) {
+          g[0] = bf16_lo(gq[k].x); g[1] = bf16_hi(gq[k].x); g[2] = bf16_lo(gq[k].y); g[3] = bf16_hi(gq[k].y);
+          g[4] = bf16_lo(gq[k].z); g[5] = bf16_hi(gq[k].z); g[6] = bf16_lo(gq[k].w); g[7] = bf16_hi(gq[k].w);
+        } else {
+          load8(gout + (int64_t)off[k] * d.ldgo + c, g);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if ((m0 >> (8 * e)) & 1u) acc[e] += g[e];
+          if ((m1 >> (8 * e)) & 1u) acc[4 + e] += g[4 + e];
+        }
+      }
+      TGI* dst = gin + ((int64_t)row * d.Wi + w) * d.ldgi + c;
+      if (!d.gin_overwrite) {
+        float o[8];
+        load8(dst, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += o[e];
+      }
+      store8(dst, acc);
+    }
+  }
+}
+
 }  // namespace vinet
 using namespace vinet;
+
+template <int KT, int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW>
+static bool pool_cfg_is(const vinet_pool_t* d) {
+  return d->kt == KT && d->kh == KH && d->kw == KW && d->st == ST && d->sh == SH && d->sw == SW && d->pt == PT && d->ph == PH && d->pw == PW;
+}
+
+// returns true when one of the compile-time-specialised gather kernels took the launch
+static bool pool_bwd_gather_fixed(const vinet_pool_t* d, cudaStream_t stream) {
+  if (!d->idx || (int64_t)d->B * d->To * d->Ho * d->Wo >= (int64_t)0x7fffffff || (int64_t)d->B * d->Ti * d->Hi >= (int64_t)0x7fffffff) return false;
+  const unsigned nb = (unsigned)std::min<int64_t>((int64_t)d->B * d->Ti * d->Hi, 148 * 32);
+#define POOL_TRY(KT, KH, KW, ST, SH, SW, PT, PH, PW)                                                                          \
+  if (pool_cfg_is<KT, KH, KW, ST, SH, SW, PT, PH, PW>(d)) {                                                                   \
+    VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,                                          \
+        (maxpool_bwd_gather_fixed_kernel<KT, KH, KW, ST, SH, SW, PT, PH, PW, TGO, TGI><<<nb, 256, 0, stream>>>(*d))));        \
+    return true;                                                                                                              \
+  }
+  // measured on B200 (tools/pool_bench.py, B=8 workload), gather vs atomic scatter: base1.1 256 vs 374 us, maxp2 225 vs 246 us;
+  // the gather LOSES where an element has 8 or 27 candidate windows (maxp3 233 vs 112 us, Mixed_3c pool 857 vs 325 us), so only
+  // the two (1,3,3)/(1,2,2) stage pools and the non-overlapping (2,2,2) pool take it.  g_pool_fast bit 3 forces it everywhere.
+  POOL_TRY(1, 3, 3, 1, 2, 2, 0, 1, 1)   // base1.1, maxp2      (model.py:696,700)
+  POOL_TRY(2, 2, 2, 2, 2, 2, 0, 0, 0)   // maxt4 + maxp4       (model.py:713-714)
+  if (g_pool_fast & 8) {
+    POOL_TRY(3, 3, 3, 2, 2, 2, 1, 1, 1)   // maxp3               (model.py:705)
+    POOL_TRY(3, 3, 3, 1, 1, 1, 1, 1, 1)   // Mixed_* branch3     (model_utils.py:178)
+  }
+#undef POOL_TRY
+  return false;
+}
 
 static unsigned pool_grid(const vinet_pool_t* d) {
   int64_t total = (int64_t)d->B * d->To * d->Ho * d->Wo * (d->C / 8);
@@ -367,8 +482,9 @@ static int pool_check(const vinet_pool_t* d) {
 }
 
 namespace vinet {
-int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = gather backward
-                       // (deterministic, no atomics; measured slower than the atomic scatter on B200, so off by default)
+int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = force the generic gather
+                       // backward, bit 2 = disable the compile-time-specialised gather backward (atomic scatter instead),
+                       // bit 3 = use the specialised gather for every pool geometry (tests / A-B timing)
 int pool_fast_set(int v) { g_pool_fast = v; return 0; }
 }  // namespace vinet
 
@@ -401,6 +517,11 @@ extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
 
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
   if (pool_check(d)) return -1;
+  // compile-time-specialised gathers for the pools of this model (key 3 bit 2 switches them off for A/B runs)
+  if (!(g_pool_fast & 4) && !(g_pool_fast & 2) && pool_bwd_gather_fixed(d, (cudaStream_t)stream)) {
+    VINET_LAUNCH_OK("maxpool_bwd_gather_fixed");
+    return 0;
+  }
   // windows that can contain one input element: the gather visits all of them, so it only pays for strided pools
   const int cand = (int)(cdiv(d->kt, d->st) * cdiv(d->kh, d->sh) * cdiv(d->kw, d->sw));
   static const int gather_max = getenv("VINET_POOL_GATHER_MAX") ? atoi(getenv("VINET_POOL_GATHER_MAX")) : 0;
