@@ -440,6 +440,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_gather_fixed_kernel(const __g
 }  // namespace vinet
 using namespace vinet;
 
+namespace vinet {
+int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = force the generic gather
+                       // backward, bit 2 = disable the compile-time-specialised gather backward (atomic scatter instead),
+                       // bit 3 = use the specialised gather for every pool geometry (tests / A-B timing)
+int pool_fast_set(int v) { g_pool_fast = v; return 0; }
+}  // namespace vinet
+
 template <int KT, int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW>
 static bool pool_cfg_is(const vinet_pool_t* d) {
   return d->kt == KT && d->kh == KH && d->kw == KW && d->st == ST && d->sh == SH && d->sw == SW && d->pt == PT && d->ph == PH && d->pw == PW;
@@ -481,12 +488,6 @@ static int pool_check(const vinet_pool_t* d) {
   return 0;
 }
 
-namespace vinet {
-int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = force the generic gather
-                       // backward, bit 2 = disable the compile-time-specialised gather backward (atomic scatter instead),
-                       // bit 3 = use the specialised gather for every pool geometry (tests / A-B timing)
-int pool_fast_set(int v) { g_pool_fast = v; return 0; }
-}  // namespace vinet
 
 static bool pool_is_333(const vinet_pool_t* d) {
   return (g_pool_fast & 1) && d->dtype == VINET_BF16 && d->out_dtype == VINET_BF16 && d->xform == VINET_XF_IDENT && d->kt == 3 && d->kh == 3 &&
