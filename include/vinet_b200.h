@@ -437,6 +437,19 @@ typedef struct vinet_avfuse {
 int vinet_avfuse_fwd(const vinet_avfuse_t* d, vinet_stream_t stream);
 int vinet_avfuse_bwd(const vinet_avfuse_t* d, vinet_stream_t stream);
 
+/* ---- sliding-window inference post-processing (generate_result.py:100-104, utils.py:61-78) ---- */
+typedef struct vinet_postproc {
+  const float* x; /* [N, H, W] saliency maps */
+  int32_t N, H, W;
+  int32_t oh, ow;  /* source-video resolution the maps are resized to (cv2.resize, bilinear) */
+  int32_t blur;    /* 1: 11x11 Gaussian blur (sigma 2, reflect-101 border) after the resize */
+  float* ws0;      /* [N, oh, ow] workspace */
+  float* ws1;      /* [N, oh, ow] workspace */
+  float* minmax;   /* [N, 2] workspace: per-map min / max after the blur */
+  uint8_t* out;    /* [N, oh, ow]: round(255 * (v - min) / (max - min + 1e-5) + 0.5) */
+} vinet_postproc_t;
+int vinet_saliency_postprocess(const vinet_postproc_t* d, vinet_stream_t stream);
+
 /* ---- misc ---- */
 int vinet_memset_async(void* ptr, int value, size_t bytes, vinet_stream_t stream);
 /* dst[i] = src[i] (+ dst[i] if accumulate); fp32 */

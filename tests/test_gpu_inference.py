@@ -1,0 +1,81 @@
+"""GPU: SURVEY §8 row f2 — sliding-window inference through the real kernels (folded-BatchNorm eval plan, overlapping window
+views, CUDA-graph replay) against the reference's per-clip loop (generate_result.py:55-73) run with the oracle, and the
+device post-processing (generate_result.py:100-104) against its numpy / cv2 restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import postproc_oracle as PO
+from oracle import torch_oracle as O
+from vinet_b200 import GraphedForward, SlidingWindowSaliency, VideoSaliencyModel
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(T, seed, precision):
+    ref = O.ViNetOracle(T)
+    O.randomize_(ref, seed)
+    ref.eval()
+    m = VideoSaliencyModel(num_clips=T)
+    m.load_state_dict(ref.state_dict())
+    return ref, m.cuda().set_precision(precision).eval()
+
+
+@pytest.mark.parametrize("precision,use_graph", [("fp32", False), ("fp32", True), ("bf16x6", True)])
+def test_sliding_window_matches_reference_loop(precision, use_graph):
+    T, H, W, N = 8, 64, 96, 21
+    ref, m = _pair(T, 13, precision)
+    frames = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(4))
+    want = PO.sliding_window_reference(ref, frames, T)
+    sal = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=4, use_graph=use_graph)
+    got = sal(frames).cpu()
+    assert torch.allclose(got, want, rtol=1e-3, atol=1e-6), ((got - want).abs() / want.abs()).max()
+    got2 = sal(frames.cuda()).cpu()                      # second video through the captured graphs, frames already on the device
+    assert torch.equal(got, got2)
+
+
+def test_sliding_window_bf16_throughput_mode_tracks_fp32():
+    T, H, W, N = 32, 64, 96, 70
+    ref, m = _pair(T, 14, "bf16")
+    frames = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(5))
+    got = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=8)(frames).cpu()
+    _, m32 = _pair(T, 14, "fp32")
+    want = SlidingWindowSaliency(m32, clip_len=T, windows_per_batch=8, use_graph=False)(frames).cpu()
+    assert torch.isfinite(got).all() and (got - want).abs().mean() < 2e-2, (got - want).abs().mean()
+
+
+def test_graphed_forward_replays_eval_forward():
+    T, H, W = 16, 64, 64
+    ref, m = _pair(T, 15, "fp32")
+    d = O.make_inputs(2, T, H, W, 15)
+    x = d["x"].cuda()
+    with torch.no_grad():
+        want = ref(d["x"])
+    fwd = GraphedForward(m, x)
+    assert fwd.launches_per_replay > 50
+    got = fwd(x).cpu()
+    assert torch.allclose(got, want, rtol=1e-3, atol=1e-6)
+    x2 = O.make_inputs(2, T, H, W, 16)["x"]
+    with torch.no_grad():
+        want2 = ref(x2)
+    assert torch.allclose(fwd(x2.cuda()).cpu(), want2, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("size", [(160, 90), (640, 360), (333, 201)])
+def test_postprocess_matches_reference_pipeline(size):
+    g = np.random.default_rng(1)
+    maps = (1 / (1 + np.exp(-3 * g.standard_normal((3, 56, 96))))).astype(np.float32)
+    _, m = _pair(8, 1, "fp32")
+    sal = SlidingWindowSaliency(m, clip_len=8)
+    got = sal.postprocess(torch.from_numpy(maps).cuda(), size).cpu().numpy()
+    assert got.shape == (3, size[1], size[0]) and got.dtype == np.uint8
+    for i in range(3):
+        want = PO.process(maps[i], size)
+        assert np.abs(got[i].astype(int) - want.astype(int)).max() <= 1, i
+        assert (got[i] != want).mean() < 0.02
+    try:
+        import cv2
+    except ImportError:
+        return
+    want = PO.to_uint8(cv2.GaussianBlur(cv2.resize(maps[0], size), (11, 11), 0))
+    assert np.abs(got[0].astype(int) - want.astype(int)).max() <= 1

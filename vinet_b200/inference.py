@@ -1,0 +1,126 @@
+"""Sliding-window video inference (reference generate_result.py:55-73, 96-104).
+
+The reference predicts ONE saliency frame per 32-frame clip forward: frame i (i >= L-1) from the clip of frames [i-L+1 .. i], and
+the first L-1 frames from the same clips reversed in time (``torch.flip(clip, [2])``, generate_result.py:70-71), so consecutive
+clips overlap by L-1 of L frames and every frame is pushed host -> device L times.  Here
+
+  * the pre-processed frames of a video live ONCE in a device buffer ``(N, 3, H, W)``; a batch of B consecutive windows is a
+    strided *view* of it (``x[b, c, t] = frames[i0 + b + t, c]``: batch stride = one frame), which the packing kernel of the
+    model reads through its strides - no clip is ever materialised, no frame is copied twice;
+  * B windows go through one forward of the folded-BatchNorm eval plan, replayed as a CUDA graph (``GraphedForward``);
+  * the time-flipped clips of the first L-1 frames are windows of a reversed copy of the first 2L-2 frames;
+  * resize to the source resolution + 11x11 Gaussian blur + min-max normalisation to 8 bits (generate_result.py:100-104,
+    utils.py:61-78) run on the device (``postprocess``), so only finished 8-bit maps travel back to the host.
+
+    sal = SlidingWindowSaliency(model, clip_len=32, windows_per_batch=8)
+    maps = sal(frames)                    # (N, 3, H, W) normalised fp32 frames -> (N, H, W) fp32 saliency in (0, 1)
+    png = sal.postprocess(maps, (360, 640))   # (N, 360, 640) uint8, what generate_result.py writes to disk
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .graph import GraphedForward
+
+
+def window_view(frames, start, count, clip_len):
+    """(count, 3, clip_len, H, W) view of a (N, 3, H, W) frame buffer: window b holds frames start+b .. start+b+clip_len-1."""
+    n, c, h, w = frames.shape
+    assert frames.is_contiguous() and start >= 0 and start + count + clip_len - 1 <= n
+    s = frames.stride()
+    return torch.as_strided(frames, (count, c, clip_len, h, w), (s[0], s[1], s[0], s[2], s[3]), frames.storage_offset() + start * s[0])
+
+
+class SlidingWindowSaliency:
+    """One saliency map per frame of a video with the reference's windowing (generate_result.py:55-73)."""
+
+    def __init__(self, model, clip_len=32, windows_per_batch=8, use_graph=True):
+        assert not model.training, "call model.eval() first (inference uses the running BatchNorm statistics)"
+        self.model, self.L, self.B, self.use_graph = model, clip_len, windows_per_batch, use_graph
+        self._graphs = {}
+
+    def _forward(self, x):
+        """x: (b, 3, L, H, W) strided window view -> (b, H, W)."""
+        if not self.use_graph:
+            with torch.no_grad():
+                return self.model(x)
+        key = (tuple(x.shape), tuple(x.stride()))
+        g = self._graphs.get(key)
+        if g is None:
+            # the static input keeps the caller's strides: an overlapping (batch stride = 1 frame) window view needs a buffer of
+            # b + L - 1 frames, not b * L
+            b, c, t, h, w = x.shape
+            store = torch.empty((b + t - 1, c, h, w), dtype=x.dtype, device=x.device)
+            static = window_view(store, 0, b, t)
+            assert tuple(static.stride()) == tuple(x.stride())
+            g = self._graphs[key] = (_StaticWindows(self.model, store, static), store)
+        runner, store = g
+        return runner(x)
+
+    def refresh(self):
+        """Model weights changed: drop the captured graphs."""
+        self._graphs = {}
+        self.model.invalidate_weight_cache()
+
+    def __call__(self, frames):
+        """frames: (N, 3, H, W) fp32, pre-processed as by generate_result.py:77-89 (resize, ToTensor, ImageNet normalise), on the
+        host or on the device.  Returns (N, H, W) fp32 saliency maps on the device; N >= 2L-1 like the reference requires."""
+        Lc, n = self.L, frames.shape[0]
+        if n < 2 * Lc - 1:
+            raise ValueError("more frames are needed: %d < %d (generate_result.py:55)" % (n, 2 * Lc - 1))
+        dev = next(self.model.parameters()).device
+        frames = frames.to(dev, non_blocking=True).contiguous()
+        out = torch.empty((n,) + tuple(frames.shape[2:]), dtype=torch.float32, device=dev)
+        # frames L-1 .. N-1: window ending at the frame
+        nwin = n - Lc + 1
+        for w0 in range(0, nwin, self.B):
+            b = min(self.B, nwin - w0)
+            out[w0 + Lc - 1:w0 + Lc - 1 + b] = self._forward(window_view(frames, w0, b, Lc))
+        # frames 0 .. L-2: the clip STARTING at the frame, reversed in time (its last frame is the wanted one)
+        rev = torch.flip(frames[:2 * Lc - 2], [0]).contiguous()          # rev[k] = frames[2L-3-k]
+        for j0 in range(0, Lc - 1, self.B):
+            b = min(self.B, Lc - 1 - j0)
+            # window for frame j starts at k0 = L-2-j in `rev`; windows of a batch must ascend by one frame, so take j descending
+            js = list(range(j0, j0 + b))
+            k_first = Lc - 2 - js[-1]
+            pred = self._forward(window_view(rev, k_first, b, Lc))         # pred[i] belongs to frame j = L-2-(k_first+i)
+            out[torch.tensor([Lc - 2 - (k_first + i) for i in range(b)], device=dev)] = pred
+        return out
+
+    # ------------------------------------------------------------------ device post-processing
+    def postprocess(self, maps, size_wh, blur=True):
+        """generate_result.py:100-104 on the device: bilinear resize of every (H, W) map to the source resolution (cv2.resize
+        semantics), 11x11 Gaussian blur (sigma 2, reflect-101 border), per-map min-max normalisation and rounding to 8 bits
+        (utils.img_save(normalize=True)).  maps: (N, H, W) fp32 -> (N, size_wh[1], size_wh[0]) uint8."""
+        lib = L.get()
+        n, h, w = maps.shape
+        ow, oh = int(size_wh[0]), int(size_wh[1])
+        maps = maps.contiguous().float()
+        out = torch.empty((n, oh, ow), dtype=torch.uint8, device=maps.device)
+        ws = torch.empty((2, n, oh, ow), dtype=torch.float32, device=maps.device)
+        mm = torch.empty((n, 2), dtype=torch.float32, device=maps.device)
+        d = L.PostProc()
+        d.x, d.N, d.H, d.W, d.oh, d.ow, d.blur = maps.data_ptr(), n, h, w, oh, ow, 1 if blur else 0
+        d.ws0, d.ws1, d.minmax, d.out = ws[0].data_ptr(), ws[1].data_ptr(), mm.data_ptr(), out.data_ptr()
+        lib.call("vinet_saliency_postprocess", C.byref(d), torch.cuda.current_stream(maps.device).cuda_stream)
+        return out
+
+
+class _StaticWindows(GraphedForward):
+    """GraphedForward whose static input is an overlapping window view of a small frame store: a call copies the b + L - 1
+    distinct frames of the batch once (device to device) instead of b * L."""
+
+    def __init__(self, model, store, static_view):
+        self.model, self.store = model, store
+        self.inputs = [static_view]
+        self._capture(2)
+
+    def __call__(self, x):
+        b, c, t, h, w = x.shape
+        # the frames behind the window view x: frame f of the batch is x[0, :, f] for f < t and x[f - t + 1, :, t - 1] after
+        self.store[:t].copy_(x[0].permute(1, 0, 2, 3), non_blocking=True)
+        if b > 1:
+            self.store[t:].copy_(x[1:, :, t - 1], non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -131,6 +131,11 @@ class Split(C.Structure):
                 ("xform", _i32), ("nparts", _i32), ("part", _p * 3), ("ldo", _i64)]
 
 
+class PostProc(C.Structure):
+    _fields_ = [("x", _p), ("N", _i32), ("H", _i32), ("W", _i32), ("oh", _i32), ("ow", _i32), ("blur", _i32), ("ws0", _p),
+                ("ws1", _p), ("minmax", _p), ("out", _p)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinet_b200.h
 _S = C.c_void_p  # stream
 SIGNATURES = {
@@ -144,6 +149,7 @@ SIGNATURES = {
     "vinet_unpack_wgrad_win8": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _S]),
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_split_bf16": (C.c_int, [C.POINTER(Split), _S]),
+    "vinet_saliency_postprocess": (C.c_int, [C.POINTER(PostProc), _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
     "vinet_bn_stats_finalize": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _S]),
@@ -184,7 +190,7 @@ SIGNATURES = {
 
 # declaration order of the structs in the header (vinet_abi_sizes)
 ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
-               Conv1d, Bn1d, AvFuse, Split]
+               Conv1d, Bn1d, AvFuse, Split, PostProc]
 
 
 class VinetError(RuntimeError):
