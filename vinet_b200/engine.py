@@ -157,6 +157,7 @@ class Engine:
         self.weights_dirty = False   # set by GraphedTrainStep: parameters changed without a Tensor._version bump
         self._repack_all = False
         self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)}, {name: parameter})
+        self.realloc_count = 0  # pooled buffers re-allocated because a forward came with another shape
         self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
         self.consumed_gen = -1  # generation whose tape has been run: a second backward through it must fail loudly
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
@@ -176,6 +177,8 @@ class Engine:
         (BN statistics, packed weight gradients), so accumulate-into buffers need no per-step memset."""
         t = self.pool.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device:
+            if t is not None:
+                self.realloc_count += 1      # a captured CUDA graph that used the old buffer is stale now (graph.py checks)
             if zero:
                 t = torch.zeros(shape, dtype=dtype, device=self.device)
                 self.pool[name] = t

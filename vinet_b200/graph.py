@@ -53,6 +53,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._eager_step(zero=False) if capture_optimizer else self._fwd_bwd()
         self.launches_per_replay = _lib.get().launch_count() - n0     # kernels of this library inside one replay
+        self._epoch = self._buffers_epoch()
         with torch.no_grad():
             for t, s in zip(list(model.parameters()) + list(model.buffers()), saved):
                 t.copy_(s)
@@ -76,6 +77,9 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss
 
+    def _buffers_epoch(self):
+        return tuple(e.realloc_count for e in self.model.__dict__.get("_engines", {}).values())
+
     def _mark_weights_dirty(self):
         # replays update the parameters without bumping Tensor._version: tell the engines that their packed weight copies
         # must be refreshed by the next eager forward (the captured step re-packs by itself)
@@ -87,6 +91,9 @@ class GraphedTrainStep:
         self.gt.copy_(gt, non_blocking=True)
         for dst, src in zip(self.extra, extra):
             dst.copy_(src, non_blocking=True)
+        if self._epoch != self._buffers_epoch():
+            raise RuntimeError("vinet_b200: the model ran with another input shape since this step was captured and its activation "
+                               "buffers were re-allocated; capture a new GraphedTrainStep")
         self.graph.replay()
         if not self.capture_optimizer:       # gradients live in static tensors (param.grad) that every replay overwrites
             if self.after_backward is not None:
@@ -127,14 +134,21 @@ class GraphedForward:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.out = self.model(*self.inputs)
         self.launches_per_replay = _lib.get().launch_count() - n0
+        self._epoch = tuple(e.realloc_count for e in self.model.__dict__.get("_engines", {}).values())
 
     def refresh(self):
         """Parameters changed (load_state_dict, training steps in between): re-pack and re-capture."""
         self.model.invalidate_weight_cache()
         self._capture(1)
 
+    def stale(self):
+        """True when a forward with another input shape re-allocated the engine's activation buffers after the capture."""
+        return self._epoch != tuple(e.realloc_count for e in self.model.__dict__.get("_engines", {}).values())
+
     def __call__(self, x, *extra):
         for dst, src in zip(self.inputs, (x,) + extra):
             dst.copy_(src, non_blocking=True)
+        if self.stale():
+            self._capture(1)
         self.graph.replay()
         return self.out

@@ -47,7 +47,10 @@ class SlidingWindowSaliency:
                 return self.model(x)
         key = (tuple(x.shape), tuple(x.stride()))
         g = self._graphs.get(key)
+        if g is not None and g[0].stale():        # another shape ran through the model since: its buffers were re-allocated
+            g = None
         if g is None:
+            self._graphs.clear()                   # one live graph: the engine keeps one set of activation buffers per model
             # the static input keeps the caller's strides: an overlapping (batch stride = 1 frame) window view needs a buffer of
             # b + L - 1 frames, not b * L
             b, c, t, h, w = x.shape
@@ -72,20 +75,21 @@ class SlidingWindowSaliency:
         dev = next(self.model.parameters()).device
         frames = frames.to(dev, non_blocking=True).contiguous()
         out = torch.empty((n,) + tuple(frames.shape[2:]), dtype=torch.float32, device=dev)
+        # Every batch has the SAME number of windows (one captured graph, one set of activation buffers): the last batch of a
+        # pass is shifted back to be full and recomputes a few windows of the previous one.
         # frames L-1 .. N-1: window ending at the frame
         nwin = n - Lc + 1
-        for w0 in range(0, nwin, self.B):
-            b = min(self.B, nwin - w0)
+        b = min(self.B, Lc - 1, nwin)
+        for w0 in range(0, nwin, b):
+            w0 = min(w0, nwin - b)
             out[w0 + Lc - 1:w0 + Lc - 1 + b] = self._forward(window_view(frames, w0, b, Lc))
-        # frames 0 .. L-2: the clip STARTING at the frame, reversed in time (its last frame is the wanted one)
-        rev = torch.flip(frames[:2 * Lc - 2], [0]).contiguous()          # rev[k] = frames[2L-3-k]
-        for j0 in range(0, Lc - 1, self.B):
-            b = min(self.B, Lc - 1 - j0)
-            # window for frame j starts at k0 = L-2-j in `rev`; windows of a batch must ascend by one frame, so take j descending
-            js = list(range(j0, j0 + b))
-            k_first = Lc - 2 - js[-1]
-            pred = self._forward(window_view(rev, k_first, b, Lc))         # pred[i] belongs to frame j = L-2-(k_first+i)
-            out[torch.tensor([Lc - 2 - (k_first + i) for i in range(b)], device=dev)] = pred
+        # frames 0 .. L-2: the clip STARTING at the frame, reversed in time (its last frame is the wanted one):
+        # rev[k] = frames[2L-3-k]; the reversed clip of frame j is the window of `rev` starting at k = L-2-j
+        rev = torch.flip(frames[:2 * Lc - 2], [0]).contiguous()
+        for k0 in range(0, Lc - 1, b):
+            k0 = min(k0, Lc - 1 - b)
+            pred = self._forward(window_view(rev, k0, b, Lc))                # pred[i] belongs to frame j = L-2-(k0+i)
+            out[Lc - 2 - k0 - b + 1:Lc - 2 - k0 + 1] = torch.flip(pred, [0])
         return out
 
     # ------------------------------------------------------------------ device post-processing
