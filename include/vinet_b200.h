@@ -450,6 +450,25 @@ typedef struct vinet_postproc {
 } vinet_postproc_t;
 int vinet_saliency_postprocess(const vinet_postproc_t* d, vinet_stream_t stream);
 
+/* ---- input pipeline (dataloader.py:242-249, generate_result.py:77-89; dataloader.py:113-118) ---- */
+typedef struct vinet_preproc {
+  const uint8_t* frames; /* [N, h, w, 3] decoded RGB frames */
+  int32_t N, h, w;
+  int32_t H, W;          /* output size (224, 384 in the reference) */
+  const int32_t* xb;     /* [W][2] first source column / tap count per output column  (Pillow Resample.c precompute_coeffs) */
+  const int32_t* xk;     /* [W][xks] 22-bit fixed-point coefficients                   (normalize_coeffs_8bpc) */
+  int32_t xks;
+  const int32_t* yb;     /* [H][2], [H][yks]: the same for the vertical pass */
+  const int32_t* yk;
+  int32_t yks;
+  uint8_t* tmp;          /* [N, h, W, 3] workspace: the 8-bit image after the horizontal pass */
+  float mean[3], std[3]; /* transforms.Normalize */
+  float* out;            /* [N, 3, H, W] fp32: ((resized / 255) - mean) / std, bit-identical to the PIL + torchvision pipeline */
+} vinet_preproc_t;
+int vinet_preprocess_frames(const vinet_preproc_t* d, vinet_stream_t stream);
+/* out[b, :] = zeros(total) with excerpt[b, :n] * np.hanning(n) centred (dataloader.py:113-118) */
+int vinet_audio_window(const float* excerpt, int32_t B, int32_t n, float* out, int32_t total, vinet_stream_t stream);
+
 /* ---- misc ---- */
 int vinet_memset_async(void* ptr, int value, size_t bytes, vinet_stream_t stream);
 /* dst[i] = src[i] (+ dst[i] if accumulate); fp32 */

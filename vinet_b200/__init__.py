@@ -8,6 +8,7 @@ from .loss import cc, get_loss, kldiv, loss_func, nss, similarity  # noqa: F401
 from .graph import GraphedForward, GraphedTrainStep  # noqa: F401
 from .inference import SlidingWindowSaliency  # noqa: F401
 from .model import VideoSaliencyModel  # noqa: F401
+from .preprocess import FramePreprocessor, audio_window  # noqa: F401
 
 try:  # AViNet lives in its own module so a ViNet-only user never touches the audio kernels
     from .avmodel import VideoAudioSaliencyModel  # noqa: F401
@@ -15,4 +16,4 @@ except ImportError:  # pragma: no cover
     pass
 
 __all__ = ["VideoSaliencyModel", "VideoAudioSaliencyModel", "kldiv", "cc", "similarity", "nss", "loss_func",
-           "get_loss", "GraphedTrainStep", "GraphedForward", "SlidingWindowSaliency"]
+           "get_loss", "GraphedTrainStep", "GraphedForward", "SlidingWindowSaliency", "FramePreprocessor", "audio_window"]

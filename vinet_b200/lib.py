@@ -136,6 +136,11 @@ class PostProc(C.Structure):
                 ("ws1", _p), ("minmax", _p), ("out", _p)]
 
 
+class PreProc(C.Structure):
+    _fields_ = [("frames", _p), ("N", _i32), ("h", _i32), ("w", _i32), ("H", _i32), ("W", _i32), ("xb", _p), ("xk", _p),
+                ("xks", _i32), ("yb", _p), ("yk", _p), ("yks", _i32), ("tmp", _p), ("mean", _f32 * 3), ("std", _f32 * 3), ("out", _p)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinet_b200.h
 _S = C.c_void_p  # stream
 SIGNATURES = {
@@ -150,6 +155,8 @@ SIGNATURES = {
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_split_bf16": (C.c_int, [C.POINTER(Split), _S]),
     "vinet_saliency_postprocess": (C.c_int, [C.POINTER(PostProc), _S]),
+    "vinet_preprocess_frames": (C.c_int, [C.POINTER(PreProc), _S]),
+    "vinet_audio_window": (C.c_int, [_p, _i32, _i32, _p, _i32, _S]),
     "vinet_bn_stats": (C.c_int, [C.POINTER(BnStats), _S]),
     "vinet_bn_finalize": (C.c_int, [C.POINTER(BnFinalize), _S]),
     "vinet_bn_stats_finalize": (C.c_int, [C.POINTER(BnStats), C.POINTER(BnFinalize), _S]),
@@ -190,7 +197,7 @@ SIGNATURES = {
 
 # declaration order of the structs in the header (vinet_abi_sizes)
 ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
-               Conv1d, Bn1d, AvFuse, Split, PostProc]
+               Conv1d, Bn1d, AvFuse, Split, PostProc, PreProc]
 
 
 class VinetError(RuntimeError):
