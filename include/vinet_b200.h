@@ -160,6 +160,18 @@ int vinet_unpack_wgrad_win8(float* dwp, int32_t lddw, float* grad, int32_t Cout,
 int vinet_unpack_wgrad(float* dwp, int32_t lddw, int32_t cs, float* grad, int32_t Cout, int32_t Cin,
                        int32_t ntaps, vinet_stream_t stream);
 
+/* n <= VINET_UNPACK_MAX unpacks in ONE launch (descriptors by value: no device table, CUDA-graph safe): a backward pass of this
+ * model ends with ~80 of these 4-us kernels. */
+#define VINET_UNPACK_MAX 48
+typedef struct vinet_unpack {
+  const float* dwp;
+  float* grad;
+  int32_t lddw, cs, Cout, Cin, ntaps;
+  int32_t win8_kh, win8_kw; /* both 0: vinet_unpack_wgrad layout; else the WIN8 layout of vinet_unpack_wgrad_win8 */
+  int32_t begin;            /* first flat output element of this entry in the launch's concatenated element space */
+} vinet_unpack_t;
+int vinet_unpack_wgrad_multi(const vinet_unpack_t* d, int32_t n, vinet_stream_t stream);
+
 /* (B,C,T,H,W) strided fp32 clip (train.py:205 hands a permuted view) -> NDHWC with C padded to cpad. */
 typedef struct vinet_pack_input {
   const float* x;

@@ -39,6 +39,7 @@ def run_tape(e, out, gen):
     out.grad.copy_(go)
     for fn in reversed(e.tape):
         fn()
+    e.unpack_flush()          # weight-gradient unpacks are queued and launched in batches (Engine.backward does this)
     if e.device.type == "cuda":
         torch.cuda.synchronize()
     return go

@@ -38,6 +38,7 @@ def child(dbg):
         for gb in e.grad_bufs:
             gb.zero_()
         bwd(dy.data_ptr(), Cout)
+        e.unpack_flush()
         torch.cuda.synchronize()
         res["dW"] = e.param_grads["c.weight"].float().cpu()
         res["dx"] = x.grad.float().cpu()

@@ -46,6 +46,7 @@ def run(precision, use_tma, *case):
     for gb in e.grad_bufs:
         gb.zero_()
     bwd(dy.data_ptr(), out.C)
+    e.unpack_flush()
     torch.cuda.synchronize()
     res["dW"] = e.param_grads["c.weight"].float().cpu()
     for i, s in enumerate(srcs):

@@ -16,5 +16,6 @@ dy = torch.randn(out.buf.shape, device="cuda").to(e.tdtype)
 for it in range(iters):
     bwd = e.conv("c", srcs, w, geom, out, cin_real=3 if case is None else None)
     bwd(dy.data_ptr(), out.C)
+    e.unpack_flush()
 torch.cuda.synchronize()
 print("done", name)

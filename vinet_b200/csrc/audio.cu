@@ -1,114 +1,181 @@
 // AViNet audio branch: SoundNet 1-D convolutions (model.py:750-786, nn.Conv2d with (k,1) kernels on a
 // (B,1,L,1) waveform), BatchNorm2d+ReLU+MaxPool, and the audio-visual bilinear fusion (model.py:229-237).
 // 0.19 GFLOP per clip: warp-per-output kernels with shuffle reductions, fp32 throughout.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vinet {
 
-// ------------------------------------------------------------------ conv1d
-// warp per output (b,co,l); lanes stride over the (ci,k) reduction (contiguous in both x and w)
-__global__ void conv1d_fwd_kernel(const __grid_constant__ vinet_conv1d_t d) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t total = (int64_t)d.B * d.Cout * d.Lout;
-  if (warp >= total) return;
-  const int l = (int)(warp % d.Lout);
-  const int co = (int)((warp / d.Lout) % d.Cout);
-  const int b = (int)(warp / ((int64_t)d.Lout * d.Cout));
-  const int R = d.Cin * d.k;
-  const float* __restrict__ w = d.w + (int64_t)co * R;
-  const float* __restrict__ x = d.x + (int64_t)b * d.Cin * d.Lin;
-  const int i0 = l * d.stride - d.pad;
-  float acc = 0.f;
-  for (int r = lane; r < R; r += 32) {
-    const int ci = r / d.k, kk = r - ci * d.k;
-    const int i = i0 + kk;
-    if ((unsigned)i < (unsigned)d.Lin) acc = fmaf(w[r], x[(int64_t)ci * d.Lin + i], acc);
+// ------------------------------------------------------------------ conv1d as tiled fp32 GEMMs
+// The SoundNet convolutions are small GEMMs (0.19 GFLOP per clip in total) with awkward shapes: 141k x 64 x 16 for the first layer,
+// 12 x 2048 x 1024 for the last.  One 64 x 64 x 16 tiled FFMA kernel serves forward, data gradient and weight gradient through
+// three operand loaders; the reduction dimension is split across CTAs (fp32 atomics into a zeroed output) whenever the tile
+// grid alone would leave most of the 148 SMs idle.  (Round 1 ran one warp per output element: 7.5 ms per step for AViNet.)
+enum { A1D_FWD = 0, A1D_DGRAD = 1, A1D_WGRAD = 2 };
+constexpr int A1D_BM = 64, A1D_BN = 64, A1D_BK = 16;
+
+template <int MODE>
+struct A1dOps {
+  const vinet_conv1d_t& d;
+  __device__ __forceinline__ A1dOps(const vinet_conv1d_t& d_) : d(d_) {}
+  __device__ __forceinline__ int M() const { return MODE == A1D_FWD ? d.B * d.Lout : (MODE == A1D_DGRAD ? d.B * d.Lin : d.Cout); }
+  __device__ __forceinline__ int N() const { return MODE == A1D_FWD ? d.Cout : (MODE == A1D_DGRAD ? d.Cin : d.Cin * d.k); }
+  __device__ __forceinline__ int K() const { return MODE == A1D_FWD ? d.Cin * d.k : (MODE == A1D_DGRAD ? d.Cout * d.k : d.B * d.Lout); }
+  __device__ __forceinline__ float a(int m, int kk) const {
+    if (MODE == A1D_FWD) {            // x[b, ci, l*stride - pad + t]
+      const int b = m / d.Lout, l = m - b * d.Lout;
+      const int ci = kk / d.k, t = kk - ci * d.k;
+      const int i = l * d.stride - d.pad + t;
+      return (unsigned)i < (unsigned)d.Lin ? __ldg(d.x + ((int64_t)b * d.Cin + ci) * d.Lin + i) : 0.f;
+    } else if (MODE == A1D_DGRAD) {   // dy[b, co, (i + pad - t) / stride]
+      const int b = m / d.Lin, i = m - b * d.Lin;
+      const int co = kk / d.k, t = kk - co * d.k;
+      const int num = i + d.pad - t;
+      if (num < 0 || num % d.stride) return 0.f;
+      const int l = num / d.stride;
+      return l < d.Lout ? __ldg(d.dy + ((int64_t)b * d.Cout + co) * d.Lout + l) : 0.f;
+    } else {                          // dy[b, co = m, l]
+      const int b = kk / d.Lout, l = kk - b * d.Lout;
+      return __ldg(d.dy + ((int64_t)b * d.Cout + m) * d.Lout + l);
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) d.y[warp] = acc + (d.bias ? d.bias[co] : 0.f);
+  __device__ __forceinline__ float b(int kk, int n) const {
+    if (MODE == A1D_FWD) return __ldg(d.w + (int64_t)n * (d.Cin * d.k) + kk);      // w[co = n][ci*k + t]
+    if (MODE == A1D_DGRAD) {                                                        // w[co][ci = n][t]
+      const int co = kk / d.k, t = kk - co * d.k;
+      return __ldg(d.w + ((int64_t)co * d.Cin + n) * d.k + t);
+    }
+    const int bb = kk / d.Lout, l = kk - bb * d.Lout;                               // x[b, ci, l*stride - pad + t], n = ci*k + t
+    const int ci = n / d.k, t = n - ci * d.k;
+    const int i = l * d.stride - d.pad + t;
+    return (unsigned)i < (unsigned)d.Lin ? __ldg(d.x + ((int64_t)bb * d.Cin + ci) * d.Lin + i) : 0.f;
+  }
+  __device__ __forceinline__ float* out(int m, int n) const {
+    if (MODE == A1D_FWD) { const int b = m / d.Lout, l = m - b * d.Lout; return d.y + ((int64_t)b * d.Cout + n) * d.Lout + l; }
+    if (MODE == A1D_DGRAD) { const int b = m / d.Lin, i = m - b * d.Lin; return d.dx + ((int64_t)b * d.Cin + n) * d.Lin + i; }
+    return d.dw + (int64_t)m * (d.Cin * d.k) + n;
+  }
+};
+
+// grid = (tiles over N, tiles over M, K splits); 256 threads, each a 4 x 4 micro-tile.  MODE FWD/DGRAD map M to long contiguous
+// runs in memory, so the m index of the A tile is the fast thread index there; WGRAD reads dy / x along K.
+template <int MODE>
+__global__ void __launch_bounds__(256) audio_gemm_kernel(const __grid_constant__ vinet_conv1d_t d, int ksplit_len, int atomic) {
+  __shared__ float As[A1D_BK][A1D_BM + 4], Bs[A1D_BK][A1D_BN + 4];
+  const A1dOps<MODE> op(d);
+  const int M = op.M(), N = op.N(), K = op.K();
+  const int m0 = blockIdx.y * A1D_BM, n0 = blockIdx.x * A1D_BN;
+  const int k_begin = blockIdx.z * ksplit_len, k_end = min(K, k_begin + ksplit_len);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += A1D_BK) {
+    // 64 x 16 elements of each operand, 4 per thread
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      int mm, kk;
+      if (MODE == A1D_WGRAD) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < k_end) ? op.a(m, k) : 0.f;
+      int nn, kb;
+      if (MODE == A1D_FWD) { kb = idx & 15; nn = idx >> 4; } else { nn = idx & 63; kb = idx >> 6; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      Bs[kb][nn] = (n < N && k2 < k_end) ? op.b(k2, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < A1D_BK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (MODE == A1D_FWD && d.bias && blockIdx.z == 0) v += __ldg(d.bias + n);
+      if (atomic) atomicAdd(op.out(m, n), v); else *op.out(m, n) = v;
+    }
+  }
 }
 
-// warp per input element (b,ci,i); lanes stride over (co,k)
-__global__ void conv1d_dgrad_kernel(const __grid_constant__ vinet_conv1d_t d) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t total = (int64_t)d.B * d.Cin * d.Lin;
-  if (warp >= total) return;
-  const int i = (int)(warp % d.Lin);
-  const int ci = (int)((warp / d.Lin) % d.Cin);
-  const int b = (int)(warp / ((int64_t)d.Lin * d.Cin));
-  const int R = d.Cout * d.k;
+// dbias[co] = sum over (b, l) of dy: one block per output channel
+__global__ void __launch_bounds__(256) conv1d_dbias_kernel(const __grid_constant__ vinet_conv1d_t d) {
+  __shared__ float sh[8];
+  const int co = blockIdx.x;
   float acc = 0.f;
-  for (int r = lane; r < R; r += 32) {
-    const int co = r / d.k, kk = r - co * d.k;
-    const int num = i + d.pad - kk;
-    if (num < 0 || num % d.stride) continue;
-    const int l = num / d.stride;
-    if (l >= d.Lout) continue;
-    acc = fmaf(d.w[((int64_t)co * d.Cin + ci) * d.k + kk], d.dy[((int64_t)b * d.Cout + co) * d.Lout + l], acc);
+  for (int64_t r = threadIdx.x; r < (int64_t)d.B * d.Lout; r += 256) {
+    const int b = (int)(r / d.Lout), l = (int)(r - (int64_t)b * d.Lout);
+    acc += d.dy[((int64_t)b * d.Cout + co) * d.Lout + l];
   }
   acc = warp_sum(acc);
-  if (lane == 0) d.dx[warp] = acc;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += sh[i];
+    d.dbias[co] = s;
+  }
 }
 
-// warp per weight (co,ci,k) (+ one warp per bias); lanes stride over (b,l)
-__global__ void conv1d_wgrad_kernel(const __grid_constant__ vinet_conv1d_t d) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = (int64_t)d.Cout * d.Cin * d.k;
-  if (warp >= nw + d.Cout) return;
-  const int64_t BL = (int64_t)d.B * d.Lout;
-  float acc = 0.f;
-  if (warp < nw) {
-    const int kk = (int)(warp % d.k);
-    const int ci = (int)((warp / d.k) % d.Cin);
-    const int co = (int)(warp / ((int64_t)d.k * d.Cin));
-    for (int64_t r = lane; r < BL; r += 32) {
-      const int b = (int)(r / d.Lout), l = (int)(r - (int64_t)b * d.Lout);
-      const int i = l * d.stride - d.pad + kk;
-      if ((unsigned)i < (unsigned)d.Lin)
-        acc = fmaf(d.dy[((int64_t)b * d.Cout + co) * d.Lout + l], d.x[((int64_t)b * d.Cin + ci) * d.Lin + i], acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) d.dw[warp] = acc;
-  } else {
-    const int co = (int)(warp - nw);
-    for (int64_t r = lane; r < BL; r += 32) {
-      const int b = (int)(r / d.Lout), l = (int)(r - (int64_t)b * d.Lout);
-      acc += d.dy[((int64_t)b * d.Cout + co) * d.Lout + l];
-    }
-    acc = warp_sum(acc);
-    if (lane == 0 && d.dbias) d.dbias[co] = acc;
-  }
+template <int MODE>
+static int audio_gemm_launch(const vinet_conv1d_t* d, int M, int N, int K, float* out, size_t out_elems, cudaStream_t stream, const char* what) {
+  const int tm = (int)cdiv(M, A1D_BM), tn = (int)cdiv(N, A1D_BN);
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * 148, (int64_t)tm * tn), cdiv(K, 4 * A1D_BK)));
+  int len = (int)round_up(cdiv(K, splits), A1D_BK);
+  splits = (int)cdiv(K, len);
+  if (splits > 1) cudaMemsetAsync(out, 0, out_elems * sizeof(float), stream);
+  audio_gemm_kernel<MODE><<<dim3((unsigned)tn, (unsigned)tm, (unsigned)splits), 256, 0, stream>>>(*d, len, splits > 1 ? 1 : 0);
+  VINET_LAUNCH_OK(what);
+  return 0;
 }
 
 // ------------------------------------------------------------------ BatchNorm2d + ReLU + MaxPool((p,1))
-__device__ __forceinline__ double block_sum256(double v, double* sh) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   v = warp_sum(v);
   __syncthreads();
   if (lane == 0) sh[warp] = v;
   __syncthreads();
   double s = 0.0;
-  for (int i = 0; i < 8; ++i) s += sh[i];
+  for (int i = 0; i < nw; ++i) s += sh[i];
   return s;
 }
 
-// block per channel
-__global__ void __launch_bounds__(256) bn1d_fwd_kernel(const __grid_constant__ vinet_bn1d_t d) {
-  __shared__ double sh[8];
+constexpr int BN1D_T = 1024;
+
+// block per channel (1024 threads: the first layers have 16 / 32 channels and 10^5 elements each)
+__global__ void __launch_bounds__(BN1D_T) bn1d_fwd_kernel(const __grid_constant__ vinet_bn1d_t d) {
+  __shared__ double sh[32];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int64_t N = (int64_t)d.B * d.L;
   float mean, invstd;
   if (d.training) {
     double s = 0.0, ss = 0.0;
-    for (int64_t r = tid; r < N; r += 256) {
+    for (int64_t r = tid; r < N; r += BN1D_T) {
       const int b = (int)(r / d.L), l = (int)(r - (int64_t)b * d.L);
       const double v = d.y[((int64_t)b * d.C + c) * d.L + l];
       s += v; ss += v * v;
     }
-    s = block_sum256(s, sh); ss = block_sum256(ss, sh);
+    s = block_sum(s, sh); ss = block_sum(ss, sh);
     const double m = s / (double)N;
     double var = ss / (double)N - m * m;
     if (var < 0.0) var = 0.0;
@@ -126,7 +193,7 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const __grid_constant__ v
   if (tid == 0) { d.mean[c] = mean; d.invstd[c] = invstd; }
   const float sc = d.gamma[c] * invstd, shf = d.beta[c] - mean * sc;
   const int Lo = d.L / d.pool;
-  for (int64_t r = tid; r < (int64_t)d.B * Lo; r += 256) {
+  for (int64_t r = tid; r < (int64_t)d.B * Lo; r += BN1D_T) {
     const int b = (int)(r / Lo), lo = (int)(r - (int64_t)b * Lo);
     const float* y = d.y + ((int64_t)b * d.C + c) * d.L + (int64_t)lo * d.pool;
     float best = -INFINITY;
@@ -135,43 +202,57 @@ __global__ void __launch_bounds__(256) bn1d_fwd_kernel(const __grid_constant__ v
   }
 }
 
-__global__ void __launch_bounds__(256) bn1d_bwd_kernel(const __grid_constant__ vinet_bn1d_t d) {
-  __shared__ double sh[8];
+// Backward walks pooling WINDOWS: one scan finds the (first) maximum, which alone receives the window's gradient.
+__global__ void __launch_bounds__(BN1D_T) bn1d_bwd_kernel(const __grid_constant__ vinet_bn1d_t d) {
+  __shared__ double sh[32];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int64_t N = (int64_t)d.B * d.L;
   const float mean = d.mean[c], invstd = d.invstd[c];
   const float sc = d.gamma[c] * invstd, shf = d.beta[c] - mean * sc;
   const int Lo = d.L / d.pool;
-  // gradient w.r.t. the activated, pre-pool value of element (b,l): routed to the first window maximum
-  auto g_act = [&](int b, int l) -> float {
-    const int lo = l / d.pool;
-    if (lo >= Lo) return 0.f;
+  const int64_t nwin = (int64_t)d.B * Lo;
+  // argmax of window r and its masked gradient
+  auto window = [&](int64_t r, int& arg, float& g) {
+    const int b = (int)(r / Lo), lo = (int)(r - (int64_t)b * Lo);
     const float* y = d.y + ((int64_t)b * d.C + c) * d.L + (int64_t)lo * d.pool;
     float best = -INFINITY;
-    int arg = 0;
+    arg = 0;
     for (int p = 0; p < d.pool; ++p) {
       const float v = fmaxf(fmaf(y[p], sc, shf), 0.f);
       if (v > best) { best = v; arg = p; }
     }
-    if (lo * d.pool + arg != l) return 0.f;
-    if (!(fmaf(y[arg], sc, shf) > 0.f)) return 0.f;
-    return d.gout[((int64_t)b * d.C + c) * Lo + lo];
+    g = (fmaf(y[arg], sc, shf) > 0.f) ? d.gout[((int64_t)b * d.C + c) * Lo + lo] : 0.f;
   };
   double s1 = 0.0, s2 = 0.0;
-  for (int64_t r = tid; r < N; r += 256) {
-    const int b = (int)(r / d.L), l = (int)(r - (int64_t)b * d.L);
-    const float g = g_act(b, l);
-    const float yn = (d.y[((int64_t)b * d.C + c) * d.L + l] - mean) * invstd;
+  for (int64_t r = tid; r < nwin; r += BN1D_T) {
+    int arg;
+    float g;
+    window(r, arg, g);
+    const int b = (int)(r / Lo), lo = (int)(r - (int64_t)b * Lo);
+    const float yn = (d.y[((int64_t)b * d.C + c) * d.L + (int64_t)lo * d.pool + arg] - mean) * invstd;
     s1 += g; s2 += (double)g * yn;
   }
-  s1 = block_sum256(s1, sh); s2 = block_sum256(s2, sh);
+  s1 = block_sum(s1, sh); s2 = block_sum(s2, sh);
   if (tid == 0) { d.dbeta[c] = (float)s1; d.dgamma[c] = (float)s2; }
   const float k1 = d.training ? (float)(s1 / (double)N) : 0.f, k2 = d.training ? (float)(s2 / (double)N) : 0.f;
-  for (int64_t r = tid; r < N; r += 256) {
-    const int b = (int)(r / d.L), l = (int)(r - (int64_t)b * d.L);
-    const float g = g_act(b, l);
-    const float yn = (d.y[((int64_t)b * d.C + c) * d.L + l] - mean) * invstd;
-    d.dy[((int64_t)b * d.C + c) * d.L + l] = sc * (g - k1 - yn * k2);
+  for (int64_t r = tid; r < nwin; r += BN1D_T) {
+    int arg;
+    float g;
+    window(r, arg, g);
+    const int b = (int)(r / Lo), lo = (int)(r - (int64_t)b * Lo);
+    const int64_t base = ((int64_t)b * d.C + c) * d.L + (int64_t)lo * d.pool;
+    for (int p = 0; p < d.pool; ++p) {
+      const float yn = (d.y[base + p] - mean) * invstd;
+      d.dy[base + p] = sc * ((p == arg ? g : 0.f) - k1 - yn * k2);
+    }
+  }
+  // elements past the last full window (L % pool) receive no gradient through the pool
+  const int tail = d.L - Lo * d.pool;
+  for (int64_t r = tid; r < (int64_t)d.B * tail; r += BN1D_T) {
+    const int b = (int)(r / tail), l = Lo * d.pool + (int)(r - (int64_t)b * tail);
+    const int64_t at = ((int64_t)b * d.C + c) * d.L + l;
+    const float yn = (d.y[at] - mean) * invstd;
+    d.dy[at] = sc * (0.f - k1 - yn * k2);
   }
 }
 
@@ -297,30 +378,36 @@ static unsigned warps_grid(int64_t warps) { return (unsigned)cdiv(warps * 32, 25
 using namespace vinet;
 
 extern "C" int vinet_conv1d_fwd(const vinet_conv1d_t* d, vinet_stream_t stream) {
-  conv1d_fwd_kernel<<<warps_grid((int64_t)d->B * d->Cout * d->Lout), 256, 0, (cudaStream_t)stream>>>(*d);
-  VINET_LAUNCH_OK("conv1d_fwd");
-  return 0;
+  VINET_CHECK(d->B >= 1 && d->Cin >= 1 && d->Cout >= 1 && d->k >= 1 && d->stride >= 1 && d->Lout >= 1, "conv1d_fwd: bad shape");
+  VINET_CHECK((int64_t)d->B * std::max(d->Lin, d->Lout) * std::max(d->Cin, d->Cout) < (int64_t)0x7fffffff, "conv1d: too large");
+  return audio_gemm_launch<A1D_FWD>(d, d->B * d->Lout, d->Cout, d->Cin * d->k, d->y, (size_t)d->B * d->Cout * d->Lout, (cudaStream_t)stream,
+                                    "conv1d_fwd");
 }
 
 extern "C" int vinet_conv1d_bwd(const vinet_conv1d_t* d, vinet_stream_t stream) {
+  VINET_CHECK(d->B >= 1 && d->Cin >= 1 && d->Cout >= 1 && d->k >= 1 && d->stride >= 1 && d->Lout >= 1, "conv1d_bwd: bad shape");
   if (d->dx) {
-    conv1d_dgrad_kernel<<<warps_grid((int64_t)d->B * d->Cin * d->Lin), 256, 0, (cudaStream_t)stream>>>(*d);
-    VINET_LAUNCH_OK("conv1d_dgrad");
+    if (audio_gemm_launch<A1D_DGRAD>(d, d->B * d->Lin, d->Cin, d->Cout * d->k, d->dx, (size_t)d->B * d->Cin * d->Lin, (cudaStream_t)stream,
+                                     "conv1d_dgrad")) return -1;
   }
-  conv1d_wgrad_kernel<<<warps_grid((int64_t)d->Cout * d->Cin * d->k + d->Cout), 256, 0, (cudaStream_t)stream>>>(*d);
-  VINET_LAUNCH_OK("conv1d_wgrad");
+  if (audio_gemm_launch<A1D_WGRAD>(d, d->Cout, d->Cin * d->k, d->B * d->Lout, d->dw, (size_t)d->Cout * d->Cin * d->k, (cudaStream_t)stream,
+                                   "conv1d_wgrad")) return -1;
+  if (d->dbias) {
+    conv1d_dbias_kernel<<<(unsigned)d->Cout, 256, 0, (cudaStream_t)stream>>>(*d);
+    VINET_LAUNCH_OK("conv1d_dbias");
+  }
   return 0;
 }
 
 extern "C" int vinet_bn1d_fwd(const vinet_bn1d_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->pool >= 1, "bn1d: pool");
-  bn1d_fwd_kernel<<<d->C, 256, 0, (cudaStream_t)stream>>>(*d);
+  bn1d_fwd_kernel<<<d->C, BN1D_T, 0, (cudaStream_t)stream>>>(*d);
   VINET_LAUNCH_OK("bn1d_fwd");
   return 0;
 }
 
 extern "C" int vinet_bn1d_bwd(const vinet_bn1d_t* d, vinet_stream_t stream) {
-  bn1d_bwd_kernel<<<d->C, 256, 0, (cudaStream_t)stream>>>(*d);
+  bn1d_bwd_kernel<<<d->C, BN1D_T, 0, (cudaStream_t)stream>>>(*d);
   VINET_LAUNCH_OK("bn1d_bwd");
   return 0;
 }

@@ -193,6 +193,35 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const __grid_constant__
   }
 }
 
+struct UnpackMulti {
+  vinet_unpack_t e[VINET_UNPACK_MAX];
+  int32_t n, total;
+};
+
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const __grid_constant__ UnpackMulti p) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = p.n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.e[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const vinet_unpack_t& d = p.e[lo];
+    const int li = i - d.begin;
+    if (d.win8_kh == 0) {
+      const int tap = li % d.ntaps;
+      const int r = li / d.ntaps;
+      const int ci = r % d.Cin, co = r / d.Cin;
+      d.grad[li] = d.dwp[((int64_t)tap * d.cs + ci) * d.lddw + co];
+    } else {
+      const int dw = li % d.win8_kw;
+      int r = li / d.win8_kw;
+      const int dh = r % d.win8_kh; r /= d.win8_kh;
+      const int ci = r % d.Cin, co = r / d.Cin;
+      d.grad[li] = d.dwp[((int64_t)dh * 64 + dw * 8 + ci) * d.lddw + co];
+    }
+  }
+}
+
 static inline unsigned grid_for(int64_t n, int block) {
   int64_t g = cdiv(n, block);
   if (g > 148 * 16) g = 148 * 16;
@@ -272,6 +301,23 @@ extern "C" int vinet_unpack_wgrad_win8(float* dwp, int32_t lddw, float* grad, in
   const int64_t total = (int64_t)Cout * Cin * kh * kw;
   unpack_wgrad_win8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dwp, lddw, grad, Cout, Cin, kh, kw);
   VINET_LAUNCH_OK("unpack_wgrad_win8");
+  return 0;
+}
+
+extern "C" int vinet_unpack_wgrad_multi(const vinet_unpack_t* d, int32_t n, vinet_stream_t stream) {
+  VINET_CHECK(d && n >= 1 && n <= VINET_UNPACK_MAX, "unpack_wgrad_multi: %d entries", n);
+  UnpackMulti p;
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    p.e[i] = d[i];
+    p.e[i].begin = (int32_t)total;
+    total += (int64_t)d[i].Cout * d[i].Cin * (d[i].win8_kh ? d[i].win8_kh * d[i].win8_kw : d[i].ntaps);
+    VINET_CHECK(total < (int64_t)0x7fffffff, "unpack_wgrad_multi: too many elements");
+  }
+  p.n = n;
+  p.total = (int32_t)total;
+  unpack_wgrad_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  VINET_LAUNCH_OK("unpack_wgrad_multi");
   return 0;
 }
 

@@ -294,6 +294,19 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __grid_constant_
   }
 }
 
+// acc (4 x bf16x2) += g (8 packed bf16) where the recorded tap bytes equal tap4: branch-free (a warp would otherwise run the
+// per-channel test-and-add body for nearly every candidate window, because SOME lane always matches).  The few terms per element
+// are summed in bf16, like the red.add.bf16x2 of the scatter kernel.
+__device__ __forceinline__ void masked_add_bf16x8(__nv_bfloat162 (&acc)[4], const uint4& g, const uint2& pk, unsigned tap4) {
+  const unsigned m0 = __vcmpeq4(pk.x, tap4), m1 = __vcmpeq4(pk.y, tap4);
+  const unsigned w0 = g.x & __byte_perm(m0, 0, 0x1100), w1 = g.y & __byte_perm(m0, 0, 0x3322);
+  const unsigned w2 = g.z & __byte_perm(m1, 0, 0x1100), w3 = g.w & __byte_perm(m1, 0, 0x3322);
+  acc[0] = __hadd2(acc[0], *reinterpret_cast<const __nv_bfloat162*>(&w0));
+  acc[1] = __hadd2(acc[1], *reinterpret_cast<const __nv_bfloat162*>(&w1));
+  acc[2] = __hadd2(acc[2], *reinterpret_cast<const __nv_bfloat162*>(&w2));
+  acc[3] = __hadd2(acc[3], *reinterpret_cast<const __nv_bfloat162*>(&w3));
+}
+
 // Backward as a GATHER over the recorded arg-max taps: one thread = one INPUT position x 8 channels.  It visits the (at most
 // ceil(k/s)^3) windows that contain the position, compares their recorded tap bytes with the tap this position would be in
 // that window, and sums the matching output gradients.  No atomics (deterministic), no zero-initialised gradient buffer.
@@ -407,8 +420,18 @@ __global__ void __launch_bounds__(256) maxpool_bwd_gather_fixed_kernel(const __g
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      if constexpr (EAGER && sizeof(TGO) == 2) {      // branch-free packed accumulation (invalid candidates carry 0xff taps)
+        __nv_bfloat162 acc2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc2[q] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) masked_add_bf16x8(acc2, gq[k], pk[k], tap4[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[2 * q] = __low2float(acc2[q]); acc[2 * q + 1] = __high2float(acc2[q]); }
+      }
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
+        if constexpr (EAGER && sizeof(TGO) == 2) break;
         if (off[k] < 0) continue;
         const unsigned m0 = __vcmpeq4(pk[k].x, tap4[k]), m1 = __vcmpeq4(pk[k].y, tap4[k]);
         if ((m0 | m1) == 0u) continue;
@@ -439,6 +462,134 @@ __global__ void __launch_bounds__(256) maxpool_bwd_gather_fixed_kernel(const __g
 
 }  // namespace vinet
 using namespace vinet;
+
+namespace vinet {
+
+// ---- backward of the 3x3x3 / stride 1 / pad 1 pools (the nine Mixed_* branch pools) without atomics ---------------------------------
+// Every input element belongs to 27 windows.  A block owns an 8 x 8 spatial tile x 32 channels and walks the frames: it stages
+// the recorded arg-max bytes and the gradients of the 10 x 10 windows around its tile for three consecutive output frames in
+// shared memory (ring of 3), and each thread then gathers for ONE input element (8 channels) from its 27 windows with LDS only:
+// no global atomics (the scatter kernel is bound by ~8 L2 red.add per window, 325 us for Mixed_3c at batch 8), no zero-filled
+// gradient buffer, deterministic summation order.
+constexpr int PT_TS = 8, PT_HS = PT_TS + 2, PT_NP = PT_HS * PT_HS, PT_CG = 4;
+
+
+
+template <typename TGO, typename TGI>
+__global__ void __launch_bounds__(256) maxpool333_bwd_tile_kernel(const __grid_constant__ vinet_pool_t d, int tiles_w, int tiles_h, int nchunk) {
+  constexpr int GW = sizeof(TGO) / 2;                      // uint4 words per 8-channel gradient vector
+  __shared__ uint2 s_idx[3][PT_NP][PT_CG];
+  __shared__ uint4 s_g[3][PT_NP][PT_CG * GW];
+  int bid = blockIdx.x;
+  const int chunk = bid % nchunk; bid /= nchunk;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h;
+  const int b = bid / tiles_h;
+  const int h0 = th * PT_TS, w0 = tw * PT_TS, c0 = chunk * (8 * PT_CG);
+  const int tid = threadIdx.x, grp = tid & (PT_CG - 1), pos = tid >> 2;
+  const int ih = pos >> 3, iw = pos & 7;
+  const int h = h0 + ih, w = w0 + iw;
+  const bool mine = h < d.Hi && w < d.Wi && c0 + grp * 8 < d.C;
+  const TGO* __restrict__ gout = reinterpret_cast<const TGO*>(d.gout);
+  TGI* __restrict__ gin = reinterpret_cast<TGI*>(d.gin);
+
+  auto load_frame = [&](int t) {
+    const int slot = (t + 3) % 3;
+    for (int e = tid; e < PT_NP * PT_CG; e += 256) {
+      const int p = e >> 2, g = e & (PT_CG - 1);
+      const int oh = h0 - 1 + p / PT_HS, ow = w0 - 1 + p % PT_HS;
+      const bool v = t >= 0 && t < d.To && oh >= 0 && oh < d.Ho && ow >= 0 && ow < d.Wo && c0 + g * 8 < d.C;
+      uint2 ix = make_uint2(0xffffffffu, 0xffffffffu);
+      uint4 gv[GW];
+#pragma unroll
+      for (int q = 0; q < GW; ++q) gv[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (v) {
+        const int64_t o = (((int64_t)b * d.To + t) * d.Ho + oh) * d.Wo + ow;
+        ix = __ldg(reinterpret_cast<const uint2*>(d.idx + o * d.C + c0 + g * 8));
+        const uint4* gp = reinterpret_cast<const uint4*>(gout + o * d.ldgo + c0 + g * 8);
+#pragma unroll
+        for (int q = 0; q < GW; ++q) gv[q] = __ldg(gp + q);
+      }
+      s_idx[slot][p][g] = ix;
+#pragma unroll
+      for (int q = 0; q < GW; ++q) s_g[slot][p][g * GW + q] = gv[q];
+    }
+  };
+
+  load_frame(-1);
+  load_frame(0);
+  for (int t = 0; t < d.Ti; ++t) {
+    load_frame(t + 1);
+    __syncthreads();
+    if (mine) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      __nv_bfloat162 acc2[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc2[q] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const int slot = (t + 1 - dt + 3) % 3;        // window frame to = t + 1 - dt reads input frame t through tap dt
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const int pl = (ih + 2 - dh) * PT_HS + (iw + 2 - dw);
+            const unsigned tap4 = (unsigned)((dt * 3 + dh) * 3 + dw) * 0x01010101u;
+            const uint2 pk = s_idx[slot][pl][grp];
+            if constexpr (GW == 1) {      // bf16 gradients: branch-free packed accumulation
+              masked_add_bf16x8(acc2, s_g[slot][pl][grp], pk, tap4);
+              continue;
+            }
+            const unsigned m0 = __vcmpeq4(pk.x, tap4), m1 = __vcmpeq4(pk.y, tap4);
+            if ((m0 | m1) == 0u) continue;
+            float g[8];
+            if constexpr (GW == 1) {
+              const uint4 u = s_g[slot][pl][grp];
+              g[0] = bf16_lo(u.x); g[1] = bf16_hi(u.x); g[2] = bf16_lo(u.y); g[3] = bf16_hi(u.y);
+              g[4] = bf16_lo(u.z); g[5] = bf16_hi(u.z); g[6] = bf16_lo(u.w); g[7] = bf16_hi(u.w);
+            } else {
+              const uint4 u0 = s_g[slot][pl][grp * 2], u1 = s_g[slot][pl][grp * 2 + 1];
+              g[0] = __uint_as_float(u0.x); g[1] = __uint_as_float(u0.y); g[2] = __uint_as_float(u0.z); g[3] = __uint_as_float(u0.w);
+              g[4] = __uint_as_float(u1.x); g[5] = __uint_as_float(u1.y); g[6] = __uint_as_float(u1.z); g[7] = __uint_as_float(u1.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if ((m0 >> (8 * e)) & 1u) acc[e] += g[e];
+              if ((m1 >> (8 * e)) & 1u) acc[4 + e] += g[4 + e];
+            }
+          }
+        }
+      }
+      if constexpr (GW == 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[2 * q] = __low2float(acc2[q]); acc[2 * q + 1] = __high2float(acc2[q]); }
+      }
+      TGI* dst = gin + ((((int64_t)b * d.Ti + t) * d.Hi + h) * d.Wi + w) * d.ldgi + c0 + grp * 8;
+      if (!d.gin_overwrite) {
+        float o[8];
+        load8(dst, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += o[e];
+      }
+      store8(dst, acc);
+    }
+    __syncthreads();
+  }
+}
+
+static bool pool_bwd_tile333(const vinet_pool_t* d, cudaStream_t stream) {
+  if (!d->idx || d->kt != 3 || d->kh != 3 || d->kw != 3 || d->st != 1 || d->sh != 1 || d->sw != 1 || d->pt != 1 || d->ph != 1 || d->pw != 1)
+    return false;
+  const int tiles_w = (int)cdiv(d->Wi, PT_TS), tiles_h = (int)cdiv(d->Hi, PT_TS), nchunk = (int)cdiv(d->C, 8 * PT_CG);
+  const int64_t blocks = (int64_t)d->B * tiles_h * tiles_w * nchunk;
+  if (blocks >= (int64_t)0x7fffffff) return false;
+  VINET_DISPATCH_DTYPE(d->gout_dtype, TGO, VINET_DISPATCH_DTYPE(d->gin_dtype, TGI,
+      (maxpool333_bwd_tile_kernel<TGO, TGI><<<(unsigned)blocks, 256, 0, stream>>>(*d, tiles_w, tiles_h, nchunk))));
+  return true;
+}
+}  // namespace vinet
 
 namespace vinet {
 int g_pool_fast = 1;   // vinet_debug_set key 3: bit 0 = frame-walking 3x3x3 forward (production), bit 1 = force the generic gather
@@ -519,6 +670,10 @@ extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
 extern "C" int vinet_maxpool_bwd(const vinet_pool_t* d, vinet_stream_t stream) {
   if (pool_check(d)) return -1;
   // compile-time-specialised gathers for the pools of this model (key 3 bit 2 switches them off for A/B runs)
+  if (!(g_pool_fast & 4) && !(g_pool_fast & 2) && pool_bwd_tile333(d, (cudaStream_t)stream)) {
+    VINET_LAUNCH_OK("maxpool333_bwd_tile");
+    return 0;
+  }
   if (!(g_pool_fast & 4) && !(g_pool_fast & 2) && pool_bwd_gather_fixed(d, (cudaStream_t)stream)) {
     VINET_LAUNCH_OK("maxpool_bwd_gather_fixed");
     return 0;

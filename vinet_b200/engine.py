@@ -158,6 +158,7 @@ class Engine:
         self._repack_all = False
         self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)}, {name: parameter})
         self.realloc_count = 0  # pooled buffers re-allocated because a forward came with another shape
+        self.dwp_arena, self.dwp_layout, self.dwp_dirty, self.unpack_queue = None, {}, False, []
         self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
         self.consumed_gen = -1  # generation whose tape has been run: a second backward through it must fail loudly
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
@@ -406,6 +407,58 @@ class Engine:
             self.wcache[ck] = (_wstamp(hit[3]), hit[1], None, hit[3])
         self._repack_all = False
 
+    # ---- packed weight gradients: one zeroed arena per backward pass, unpacked by a handful of batched launches ----
+    def dwp_buf(self, name, rows, lddw):
+        """Zeroed fp32 [rows, lddw] accumulator of one convolution's packed weight gradient.  All of a step's accumulators live in
+        ONE arena that the backward pass clears with a single memset (they used to cost ~66 memset launches per step); the arena
+        layout is discovered on the first backward pass and fixed afterwards."""
+        n = rows * lddw
+        lay = self.dwp_layout.get(name)
+        if self.dwp_arena is not None and lay is not None and lay[1] == n:
+            return self.dwp_arena[lay[0]:lay[0] + n].view(rows, lddw)
+        self.dwp_layout[name] = (None, n)          # not (or no longer) in the arena: private buffer now, arena rebuilt next pass
+        self.dwp_dirty = True
+        t = self.buf(name + ".dwp", (rows, lddw), torch.float32)
+        self.memset(t)
+        return t
+
+    def dwp_begin(self):
+        if self.dwp_dirty and self.dwp_layout:
+            off = 0
+            for k, (_, n) in self.dwp_layout.items():
+                self.dwp_layout[k] = (off, n)
+                off += (n + 63) // 64 * 64
+            self.dwp_arena = torch.empty(off, dtype=torch.float32, device=self.device)
+            for k in self.dwp_layout:
+                self.pool.pop(k + ".dwp", None)          # the private first-pass buffers are no longer needed
+            self.realloc_count += 1
+            self.dwp_dirty = False
+        if self.dwp_arena is not None:
+            self.memset(self.dwp_arena)
+
+    def unpack(self, dwp_ptr, lddw, cs, grad, cout, cin, ntaps, win8=None):
+        """Queue `grad <- packed gradient` (flushed in batches of UNPACK_MAX launches-worth by unpack_flush)."""
+        if "vinet_unpack_wgrad_multi" not in self.lib.fn:
+            if win8:
+                self.lib.call("vinet_unpack_wgrad_win8", dwp_ptr, lddw, grad.data_ptr(), cout, cin, win8[0], win8[1], self.stream())
+            else:
+                self.lib.call("vinet_unpack_wgrad", dwp_ptr, lddw, cs, grad.data_ptr(), cout, cin, ntaps, self.stream())
+            return
+        self.unpack_queue.append((dwp_ptr, lddw, cs, grad, cout, cin, ntaps, win8 or (0, 0)))
+        if len(self.unpack_queue) == L.UNPACK_MAX:
+            self.unpack_flush()
+
+    def unpack_flush(self):
+        q, self.unpack_queue = self.unpack_queue, []
+        if not q:
+            return
+        tab = (L.Unpack * len(q))()
+        for i, (dwp_ptr, lddw, cs, grad, cout, cin, ntaps, win8) in enumerate(q):
+            e = tab[i]
+            e.dwp, e.grad, e.lddw, e.cs, e.Cout, e.Cin, e.ntaps = dwp_ptr, grad.data_ptr(), lddw, cs, cout, cin, ntaps
+            e.win8_kh, e.win8_kw = win8
+        self.lib.call("vinet_unpack_wgrad_multi", tab, len(q), self.stream())
+
     # ------------------------------------------------------------------ convolution
     def tma_ok(self, srcs, geom):
         """The TMA-fed kernels need bf16 sources without pending transforms and spatial stride 1."""
@@ -550,8 +603,7 @@ class Engine:
             csk = round_up(cs, 64) if tma else cs          # TAP64 rows of the packed gradient
             ktot = len(taps) * csk
             lddw = round_up(Cout, 64)
-            dwp = self.buf(name + ".dwp", (round_up(ktot, 128), lddw), torch.float32)
-            self.memset(dwp)
+            dwp = self.dwp_buf(name, round_up(ktot, 128), lddw)
             for pa, pd in terms:
                 wg = L.Wgrad()
                 wg.kernel = kern
@@ -569,18 +621,15 @@ class Engine:
                 off = 0
                 for pname, c in wgrad_split:      # member columns [off, off+c) of the packed gradient
                     gwm = self.grad_tensor(pname, w[off:off + c])
-                    self.lib.call("vinet_unpack_wgrad", dwp.data_ptr() + 4 * off, lddw, csk, gwm.data_ptr(), c, w.shape[1],
-                                  len(taps), self.stream())
+                    self.unpack(dwp.data_ptr() + 4 * off, lddw, csk, gwm, c, w.shape[1], len(taps))
                     self.param_grads[pname] = gwm
                     off += c
             else:
                 gw = self.grad_tensor(name + ".weight", w)
                 if win:
-                    self.lib.call("vinet_unpack_wgrad_win8", dwp.data_ptr(), lddw, gw.data_ptr(), Cout, w.shape[1], geom.kh,
-                                  geom.kw, self.stream())
+                    self.unpack(dwp.data_ptr(), lddw, 0, gw, Cout, w.shape[1], 0, win8=(geom.kh, geom.kw))
                 else:
-                    self.lib.call("vinet_unpack_wgrad", dwp.data_ptr(), lddw, csk, gw.data_ptr(), Cout, w.shape[1], len(taps),
-                                  self.stream())
+                    self.unpack(dwp.data_ptr(), lddw, csk, gw, Cout, w.shape[1], len(taps))
                 self.param_grads[name + ".weight"] = gw
             if bias is not None:
                 gb = self.grad_tensor(name + ".bias", bias)
@@ -962,9 +1011,12 @@ class Engine:
     def backward(self, gout):
         """gout: fp32 (B,H,W) gradient w.r.t. the saliency map. Fills self.param_grads."""
         self.gwritten = set()
+        self.unpack_queue = []
+        self.dwp_begin()
         self.head_backward(gout)
         for fn in reversed(self.tape):
             fn()
+        self.unpack_flush()
         self.tape = []
         self.consumed_gen = getattr(self, "generation", -1)
         grads, self.param_grads = self.param_grads, {}     # hand over the only references: autograd can adopt the tensors

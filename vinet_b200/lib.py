@@ -141,6 +141,14 @@ class PreProc(C.Structure):
                 ("xks", _i32), ("yb", _p), ("yk", _p), ("yks", _i32), ("tmp", _p), ("mean", _f32 * 3), ("std", _f32 * 3), ("out", _p)]
 
 
+UNPACK_MAX = 48
+
+
+class Unpack(C.Structure):
+    _fields_ = [("dwp", _p), ("grad", _p), ("lddw", _i32), ("cs", _i32), ("Cout", _i32), ("Cin", _i32), ("ntaps", _i32),
+                ("win8_kh", _i32), ("win8_kw", _i32), ("begin", _i32)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinet_b200.h
 _S = C.c_void_p  # stream
 SIGNATURES = {
@@ -152,6 +160,7 @@ SIGNATURES = {
     "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
     "vinet_unpack_wgrad": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _S]),
     "vinet_unpack_wgrad_win8": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _S]),
+    "vinet_unpack_wgrad_multi": (C.c_int, [C.POINTER(Unpack), _i32, _S]),
     "vinet_pack_input": (C.c_int, [C.POINTER(PackInput), _S]),
     "vinet_split_bf16": (C.c_int, [C.POINTER(Split), _S]),
     "vinet_saliency_postprocess": (C.c_int, [C.POINTER(PostProc), _S]),
@@ -197,7 +206,7 @@ SIGNATURES = {
 
 # declaration order of the structs in the header (vinet_abi_sizes)
 ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
-               Conv1d, Bn1d, AvFuse, Split, PostProc, PreProc]
+               Conv1d, Bn1d, AvFuse, Split, PostProc, PreProc, Unpack]
 
 
 class VinetError(RuntimeError):
