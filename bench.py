@@ -256,6 +256,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the accuracy probe of the benchmarked precision mode")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--graph-nccl", type=int, default=1, help="N>1: 1 = the NCCL all-reduce and the optimizer are captured in the "
+                    "step's CUDA graph, 0 = they run eagerly after every replay")
     ap.add_argument("--kernel-table", default="", help="write the per-conv-launch timing table to this JSON file")
     args = ap.parse_args()
     assert args.height % 32 == 0 and args.width % 32 == 0, "the reference supports H, W multiples of 32 only (SURVEY fact 8)"
@@ -277,6 +279,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))      # communicator set-up and first collective before anything is captured
     torch.manual_seed(0)
     train = args.mode == "train"
     T, H, W, B = args.clip_len, args.height, args.width, args.batch
@@ -297,9 +300,10 @@ def main():
         model.enable_grad_arena()
     use_graph = not args.no_graph and not (train and args.no_adam) and not (world > 1 and args.ddp)
     opt = None
+    nccl_in_graph = world > 1 and bool(args.graph_nccl) and use_graph and not args.ddp
     if train and not args.no_adam:
         opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, fused=True,
-                               capturable=use_graph and world == 1)
+                               capturable=use_graph and (world == 1 or nccl_in_graph))
     g = torch.Generator().manual_seed(1234 + rank)
     # caller layout: (B,T,3,H,W) memory viewed as (B,3,T,H,W)  (train.py:204-205)
     hx = torch.randn(B, T, 3, H, W, generator=g).pin_memory()
@@ -364,7 +368,8 @@ def main():
         try:
             if train:
                 graphed = GraphedTrainStep(model, kldiv, opt, clip_view(dx), dgt, example_extra=dextra,
-                                           after_backward=model.sync_gradients if world > 1 else None, capture_optimizer=world == 1)
+                                           after_backward=model.sync_gradients if world > 1 else None,
+                                           capture_optimizer=world == 1 or nccl_in_graph)
 
                 def step(x_btchw, gt, *extra):          # noqa: F811
                     return graphed(clip_view(x_btchw), gt, *extra)
@@ -453,7 +458,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s, batch %d x %dx%dx%d clips per GPU, %s" % (workload_name(args), B, T, H, W, args.precision),
                        "global_batch": B * world, "parallelism": "dp%d" % world, "gflop_per_clip": gf_clip,
-                       "cuda_graph": graphed is not None,
+                       "cuda_graph": graphed is not None, "nccl_in_graph": bool(nccl_in_graph and graphed is not None),
                        "grad_sync": "none" if (world == 1 or not train) else ("DistributedDataParallel" if args.ddp else "flat arena, one NCCL all-reduce"),
                        "l2": "inputs (%d MB per batch) and activations (GBs) exceed the 126 MB L2; no explicit flush" % (h2d >> 20),
                        "e2e_pipeline": "H2D of step i+1 (pinned host, copy stream) overlaps the kernels of step i; result read back every step"},

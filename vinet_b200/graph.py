@@ -50,7 +50,9 @@ class GraphedTrainStep:
         from . import lib as _lib
         self._mark_weights_dirty()        # the re-pack of the cached tensor-core weights must be part of the captured step
         n0 = _lib.get().launch_count()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (the NCCL watchdog of torch.distributed polls CUDA events) may keep calling the CUDA API
+        # while this thread captures; the default "global" mode turns those calls into capture errors
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._eager_step(zero=False) if capture_optimizer else self._fwd_bwd()
         self.launches_per_replay = _lib.get().launch_count() - n0     # kernels of this library inside one replay
         self._epoch = self._buffers_epoch()
