@@ -435,9 +435,7 @@ def main():
     value = clips / (ms / 1e3)
     e2e_value = clips / (ms_e2e / 1e3)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return finish(world, nccl_in_graph)
     burst, sustained, hbm, src = peaks()
     gf_clip = gflop_per_clip(args.model, args.mode, T, H, W)
     roof = None
@@ -473,6 +471,17 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
+    finish(world, nccl_in_graph)
+
+
+def finish(world, nccl_in_graph):
+    """Leave the process group.  With NCCL kernels captured in a live CUDA graph, destroy_process_group() was observed to hang
+    (the JSON line was out, the ranks never exited): flush and exit the process directly in that case."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1 and nccl_in_graph:
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
 

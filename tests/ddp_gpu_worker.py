@@ -34,8 +34,15 @@ m.broadcast_parameters(0)
 m.enable_grad_arena()
 pred = m(x[rank:rank + 1])
 kldiv(pred, gt[rank:rank + 1]).backward()
+# exact identity first: after the ONE all-reduce of the flat arena every rank holds the mean of the ranks' local gradients
+local = torch.cat([p.grad.float().flatten() for p in m.parameters()])
+both = [torch.empty_like(local) for _ in range(2)]
+dist.all_gather(both, local)
 m.sync_gradients()
 torch.cuda.synchronize()
+synced = torch.cat([p.grad.float().flatten() for p in m.parameters()])
+mean = 0.5 * (both[0] + both[1])
+assert torch.allclose(synced, mean, rtol=1e-5, atol=1e-6 * float(mean.abs().max())), float((synced - mean).abs().max())
 if rank == 0:
     shard = []
     for i in range(2):
@@ -51,8 +58,8 @@ if rank == 0:
     print("averaged gradient vs mean of shards, rel-L2: median %.3e worst %.3e" % (median, worst), flush=True)
     if precision == "fp32":
         assert worst < 2e-3, worst
-    else:       # bf16 storage + bf16 atomics in the max-pool backward: two runs of the SAME shard differ in summation order, and
-        assert median < 3e-2 and worst < 1.0, (median, worst)      # the tiny-batch BatchNorm stack amplifies that in a few layers
+    else:       # bf16 storage + bf16 atomics in the max-pool backward: two runs of the SAME shard differ in summation order and the
+        assert median < 2e-1, (median, worst)       # tiny-batch BatchNorm stack amplifies it; the exact check is the identity above
 ok = torch.ones(1, device=dev)
 dist.all_reduce(ok)
 if rank == 0:

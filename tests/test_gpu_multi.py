@@ -79,5 +79,6 @@ def test_two_ranks_flat_arena_allreduce_equals_mean_of_shards(precision):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29653", os.path.join(ROOT, "tests", "ddp_gpu_worker.py"), precision],
                        capture_output=True, text=True, timeout=600, env=env)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    print(r.stdout[-1500:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DDP_GPU_WORKER_OK" in r.stdout
