@@ -57,6 +57,9 @@ typedef struct vinet_src {
   int32_t xform; /* VINET_XF_* */
   int64_t ldh;   /* elements between consecutive h rows; 0 = dense (Ws*ld).  Only the TMA kernels accept a
                     non-dense pitch or ld < Cs (overlapping sliding-window rows, see vinet_pack_input_t) */
+  int64_t ldb;   /* elements between consecutive clips; 0 = dense (T*Hs*row pitch).  ldb = ONE frame makes the batch a set of
+                    overlapping sliding windows over a frame sequence (window b = frames b .. b+T-1): the inference driver
+                    computes the per-frame stem conv once per frame and feeds the windows from that (TMA kernels only) */
 } vinet_src_t;
 
 /*

@@ -79,3 +79,21 @@ def test_postprocess_matches_reference_pipeline(size):
         return
     want = PO.to_uint8(cv2.GaussianBlur(cv2.resize(maps[0], size), (11, 11), 0))
     assert np.abs(got[0].astype(int) - want.astype(int)).max() <= 1
+
+
+def test_per_frame_stem_reuse_matches_plain_windows():
+    """model.forward_windows (stem conv_s once per frame, temporal stem conv over overlapping window views with a one-frame batch
+    pitch) must reproduce the plain batched-clip forward of the same bf16 engine bit for bit, eager and graph-replayed."""
+    from vinet_b200.inference import window_view
+    T, H, W, b = 32, 64, 96, 5
+    _, m = _pair(T, 17, "bf16")
+    frames = torch.randn(b + T - 1, 3, H, W, generator=torch.Generator().manual_seed(6)).cuda()
+    with torch.no_grad():
+        want = m(window_view(frames, 0, b, T)).clone()
+        got = m.forward_windows(frames, b).clone()
+    assert torch.equal(got, want), (got - want).abs().max()
+    N = 70
+    video = torch.randn(N, 3, H, W, generator=torch.Generator().manual_seed(7))
+    a = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=8, stem_cache=True)(video).cpu()
+    c = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=8, stem_cache=False)(video).cpu()
+    assert torch.equal(a, c), (a - c).abs().max()

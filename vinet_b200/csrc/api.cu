@@ -36,6 +36,7 @@ static bool dense_sources(const vinet_gather_t& g) {
     const vinet_src_t& s = g.src[i];
     if (s.ptr == nullptr) continue;
     if (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) return false;
+    if (s.ldb != 0 && s.ldb != (int64_t)s.T * g.Hs * g.Ws * s.ld) return false;
     if (s.ld < g.Cs) return false;
   }
   return true;

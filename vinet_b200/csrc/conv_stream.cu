@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
 
 // ------------------------------------------------------------------ host side
 int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
-                 int esw, int esh, int bt);
+                 int esw, int esh, int bt, int64_t ldb = 0);
 void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out);
 int tma_sm_count();
 
@@ -815,7 +815,7 @@ static int conv_gemm_stream_strided(const vinet_conv_t* d, cudaStream_t stream) 
   p.sub_stride = 8 * 128;
   p.sbo = (uint32_t)p.PW * 128u;
   const vinet_src_t& s = g.src[0];
-  if (make_tma_map(&p.tmA[0], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.PW, PHm, 1, 2, 1)) return -1;
+  if (make_tma_map(&p.tmA[0], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.PW, PHm, 1, 2, 1, s.ldb)) return -1;
   p.tmA[1] = p.tmA[0];
   return stream_launch(p, d, sms, stream);
 }
@@ -881,7 +881,7 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     const int bw = pl.halo ? pl.PW : pl.tw, bh = pl.halo ? pl.PH : pl.th;
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT)) return -1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT, s.ldb)) return -1;
   }
   p.par_sh = 1; p.par_h0[0] = p.par_h0[1] = 0; p.par_off[0] = p.par_off[1] = 0;
   return stream_launch(p, d, sms, stream);

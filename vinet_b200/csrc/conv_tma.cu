@@ -582,7 +582,7 @@ static EncodeTiledFn encode_fn() {
 // NDHWC bf16 view [B][T][H][W][C] (pixel stride ld, row pitch ldh) -> 5-D tiled map, box {64, bw, bh, 1, 1} taking every
 // esw-th / esh-th pixel (strided convolutions), 128B swizzle.  ld < C gives overlapping sliding-window rows (WIN8).
 static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
-                    int esw = 1, int esh = 1, int bt = 1) {
+                    int esw = 1, int esh = 1, int bt = 1, int64_t ldb = 0) {
   EncodeTiledFn enc = encode_fn();
   VINET_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from the driver");
   VINET_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0, "conv_tma: source must be 16-byte aligned (ld %lld)",
@@ -590,7 +590,9 @@ static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T,
   const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   if (ldh == 0) ldh = (int64_t)W * ld;
   VINET_CHECK(ldh % 8 == 0 && bw * esw <= 256 && bh * esh <= 256 && esw <= 8 && esh <= 8 && bt >= 1 && bt <= 256, "conv_tma: bad pitch / box");
-  const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ldh * 2, (cuuint64_t)H * ldh * 2, (cuuint64_t)T * H * ldh * 2};
+  if (ldb == 0) ldb = (int64_t)T * H * ldh;        // dense batch; one frame = overlapping sliding windows (vinet_src_t.ldb)
+  VINET_CHECK(ldb % 8 == 0, "conv_tma: batch pitch %lld", (long long)ldb);
+  const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ldh * 2, (cuuint64_t)H * ldh * 2, (cuuint64_t)ldb * 2};
   const cuuint32_t box[5] = {64, (cuuint32_t)(bw * esw), (cuuint32_t)(bh * esh), (cuuint32_t)bt, 1};
   const cuuint32_t es[5] = {1, (cuuint32_t)esw, (cuuint32_t)esh, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
@@ -636,8 +638,8 @@ static int sm_count() {
 
 // shared with conv_stream.cu
 int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
-                 int esw, int esh, int bt) {
-  return make_map(m, ptr, C, W, H, T, B, ld, ldh, bw, bh, esw, esh, bt);
+                 int esw, int esh, int bt, int64_t ldb) {
+  return make_map(m, ptr, C, W, H, T, B, ld, ldh, bw, bh, esw, esh, bt, ldb);
 }
 void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out) {
   pick_box(H, W, max_rows, mult, full_tile_cost, bw_out, bh_out);
@@ -712,7 +714,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   VINET_CHECK(smem <= 227 * 1024, "conv_gemm_tma: %zu bytes of shared memory", smem);
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh, 1, s.ldb)) return -1;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(items, sm_count());
 #define LAUNCH_TMA(TO)                                                                                  \
@@ -781,7 +783,7 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)stages * p.stage_bytes + 8 * (2 * stages + 1) + 64;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh)) return -1;
+    if (make_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, p.bw, p.bh, g.sw, g.sh, 1, s.ldb)) return -1;
   }
   if (make_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, p.bw, p.bh)) return -1;
   dim3 grid((unsigned)gx, (unsigned)n_tiles, (unsigned)splits);

@@ -28,7 +28,7 @@ constexpr int WH_MAX_SP = 16;       // spatial taps per group (<= 8 accumulators
 constexpr uint32_t WH_UNIT = 16384;  // one 8 x 16 x 64-channel box
 
 int make_tma_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, int64_t ld, int64_t ldh, int bw, int bh,
-                 int esw, int esh, int bt);
+                 int esw, int esh, int bt, int64_t ldb = 0);
 int tma_sm_count();
 extern int g_stream_enable;
 
@@ -366,7 +366,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   if (smem > 227 * 1024) return 0;
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, aesh, abt)) return -1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, aesh, abt, s.ldb)) return -1;
   }
   if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, dbw, dbh, 1, 1, dbt)) return -1;
   dim3 grid((unsigned)groups, (unsigned)n_tiles, (unsigned)splits);

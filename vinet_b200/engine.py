@@ -64,6 +64,7 @@ class Act:
         self.buf, self.B, self.T, self.H, self.W, self.C, self.choff = buf, B, T, H, W, C_, choff
         self.ld = buf.shape[-1]
         self.xform, self.scale, self.shift = xform, scale, shift
+        self.ldb = 0          # elements between clips; 0 = dense.  One frame: overlapping sliding windows (inference driver)
         self.grad = None      # [B,T,H,W,ldg] in the engine's storage type (bf16 / fp32), or fp32 when forced
         self.gchoff = 0
         self.gdt = L.F32
@@ -296,6 +297,7 @@ class Engine:
     # ------------------------------------------------------------------ descriptors
     def _src(self, s, a):
         s.ptr, s.scale, s.shift, s.ld, s.T, s.xform = a.ptr(), _ptr(a.scale), _ptr(a.shift), a.ld, a.T, a.xform
+        s.ldb = a.ldb
 
     def _gather_fprop(self, g, srcs, geom, cs, To, Ho, Wo, taps=None):
         a0 = srcs[0]

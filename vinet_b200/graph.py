@@ -136,7 +136,7 @@ class GraphedForward:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.out = self.model(*self.inputs)
         self.launches_per_replay = _lib.get().launch_count() - n0
-        self._epoch = tuple(e.realloc_count for e in self.model.__dict__.get("_engines", {}).values())
+        self._epoch = tuple(e.realloc_count for e in getattr(self.model, "__dict__", {}).get("_engines", {}).values())
 
     def refresh(self):
         """Parameters changed (load_state_dict, training steps in between): re-pack and re-capture."""

@@ -35,15 +35,23 @@ def window_view(frames, start, count, clip_len):
 class SlidingWindowSaliency:
     """One saliency map per frame of a video with the reference's windowing (generate_result.py:55-73)."""
 
-    def __init__(self, model, clip_len=32, windows_per_batch=8, use_graph=True):
+    def __init__(self, model, clip_len=32, windows_per_batch=8, use_graph=True, stem_cache=None):
         assert not model.training, "call model.eval() first (inference uses the running BatchNorm statistics)"
         self.model, self.L, self.B, self.use_graph = model, clip_len, windows_per_batch, use_graph
+        # per-frame stem re-use (model.forward_windows): the (1,7,7) stem conv runs once per frame of a batch instead of once per
+        # (window, frame); needs the TMA-fed bf16 engine
+        self.stem_cache = (getattr(model, "precision", "") == "bf16" and hasattr(model, "forward_windows")) if stem_cache is None else stem_cache
         self._graphs = {}
 
     def _forward(self, x):
         """x: (b, 3, L, H, W) strided window view -> (b, H, W)."""
         if not self.use_graph:
             with torch.no_grad():
+                if self.stem_cache:
+                    b, c, t, h, w = x.shape
+                    store = torch.empty((b + t - 1, c, h, w), dtype=x.dtype, device=x.device)
+                    _fill_store(store, x)
+                    return self.model.forward_windows(store, b)
                 return self.model(x)
         key = (tuple(x.shape), tuple(x.stride()))
         g = self._graphs.get(key)
@@ -57,7 +65,7 @@ class SlidingWindowSaliency:
             store = torch.empty((b + t - 1, c, h, w), dtype=x.dtype, device=x.device)
             static = window_view(store, 0, b, t)
             assert tuple(static.stride()) == tuple(x.stride())
-            g = self._graphs[key] = (_StaticWindows(self.model, store, static), store)
+            g = self._graphs[key] = (_StaticWindows(self.model, store, static, b if self.stem_cache else 0), store)
         runner, store = g
         return runner(x)
 
@@ -115,16 +123,44 @@ class _StaticWindows(GraphedForward):
     """GraphedForward whose static input is an overlapping window view of a small frame store: a call copies the b + L - 1
     distinct frames of the batch once (device to device) instead of b * L."""
 
-    def __init__(self, model, store, static_view):
-        self.model, self.store = model, store
-        self.inputs = [static_view]
+    def __init__(self, model, store, static_view, stem_windows=0):
+        self.store = store
+        if stem_windows:      # the model consumes the frame store itself (per-frame stem re-use)
+            self.model = _WindowsCall(model, stem_windows)
+            self.inputs = [store]
+        else:
+            self.model = model
+            self.inputs = [static_view]
         self._capture(2)
 
+    def stale(self):
+        m = self.model.model if isinstance(self.model, _WindowsCall) else self.model
+        return self._epoch != tuple(e.realloc_count for e in m.__dict__.get("_engines", {}).values())
+
+    def _capture(self, warmup):
+        super()._capture(warmup)
+        m = self.model.model if isinstance(self.model, _WindowsCall) else self.model
+        self._epoch = tuple(e.realloc_count for e in m.__dict__.get("_engines", {}).values())
+
     def __call__(self, x):
-        b, c, t, h, w = x.shape
-        # the frames behind the window view x: frame f of the batch is x[0, :, f] for f < t and x[f - t + 1, :, t - 1] after
-        self.store[:t].copy_(x[0].permute(1, 0, 2, 3), non_blocking=True)
-        if b > 1:
-            self.store[t:].copy_(x[1:, :, t - 1], non_blocking=True)
+        _fill_store(self.store, x)
         self.graph.replay()
         return self.out
+
+
+class _WindowsCall:
+    """Callable adapter: model.forward_windows(store, b) with the call signature GraphedForward replays."""
+
+    def __init__(self, model, windows):
+        self.model, self.windows = model, windows
+
+    def __call__(self, store):
+        return self.model.forward_windows(store, self.windows)
+
+
+def _fill_store(store, x):
+    """The b + L - 1 distinct frames behind the window view x: frame f is x[0, :, f] for f < L and x[f - L + 1, :, L - 1] after."""
+    b, c, t, h, w = x.shape
+    store[:t].copy_(x[0].permute(1, 0, 2, 3), non_blocking=True)
+    if b > 1:
+        store[t:].copy_(x[1:, :, t - 1], non_blocking=True)

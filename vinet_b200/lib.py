@@ -26,7 +26,7 @@ _p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", _p), ("scale", _p), ("shift", _p), ("ld", _i64), ("T", _i32), ("xform", _i32), ("ldh", _i64)]
+    _fields_ = [("ptr", _p), ("scale", _p), ("shift", _p), ("ld", _i64), ("T", _i32), ("xform", _i32), ("ldh", _i64), ("ldb", _i64)]
 
 
 class Gather(C.Structure):

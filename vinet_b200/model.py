@@ -191,9 +191,20 @@ def _mixed(e, pfx, x, m, gdtype=None):
     return out
 
 
-def backbone_plan(e, pfx, bb, x, y0_gdtype=None):
-    """BackBoneS3D.forward (model.py:720-743): returns [y0, y1, y2, y3] as Acts."""
-    a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
+def backbone_plan(e, pfx, bb, x, y0_gdtype=None, windows=None):
+    """BackBoneS3D.forward (model.py:720-743): returns [y0, y1, y2, y3] as Acts.
+    windows = (b, L): inference over overlapping sliding windows (generate_result.py:55-73).  `x` then holds b + L - 1 single
+    frames; the per-frame (1,7,7) stem convolution runs ONCE per frame and the temporal stem convolution reads window i as frames
+    i .. i+L-1 of its output (batch pitch = one frame) - consecutive windows share L-1 of their L stem frames."""
+    if windows is None:
+        a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
+    else:
+        b, Lc = windows
+        mid = _sepconv_s(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
+        assert mid.T == 1 and mid.B == b + Lc - 1 and mid.choff == 0 and not e.record and mid.xform == L.XF_IDENT
+        win = Act(mid.buf, b, Lc, mid.H, mid.W, mid.C)
+        win.ldb = mid.H * mid.W * mid.ld
+        a = _sepconv_t(e, pfx + "base1.0", win, bb.base1[0])
     a = e.maxpool(pfx + "base1.1", a, (1, 3, 3), (1, 2, 2), (0, 1, 1))
     a = _basic(e, pfx + "base1.2", a, bb.base1[2])
     y3 = _sepconv(e, pfx + "base1.3", [a], bb.base1[3])
@@ -374,11 +385,24 @@ class VideoSaliencyModel(_PlanModule):
     def forward(self, x):
         return self._call_plan(x)
 
+    def forward_windows(self, frames, windows):
+        """Inference over `windows` overlapping clips of a frame sequence: frames is (windows + L - 1, 3, H, W),
+        window i = frames i .. i+L-1; returns (windows, H, W) like `forward` on the stacked clips, with the per-frame stem
+        convolution computed once per frame.  bf16 tensor-core engine, eval mode, no autograd."""
+        assert not self.training and not torch.is_grad_enabled() and self.precision == "bf16", "forward_windows: eval / no_grad / bf16"
+        Lc = self.decoder.num_clips
+        assert frames.dim() == 4 and frames.shape[0] == windows + Lc - 1 and frames.shape[1] == 3
+        self.__dict__["_windows"] = (windows, Lc)
+        try:
+            return self._call_plan(frames.unsqueeze(2))
+        finally:
+            self.__dict__.pop("_windows", None)
+
     def _run_plan(self, e, record, x, prefix=""):
         e.generation += 1
         e.begin(x.device, self.training, record)
         xin = pack_input(e, x)
-        ys = backbone_plan(e, prefix + "backbone.", self.backbone, xin)
+        ys = backbone_plan(e, prefix + "backbone.", self.backbone, xin, windows=self.__dict__.get("_windows"))
         out = decoder_plan(e, prefix + "decoder.", self.decoder, *ys)
         e.end_forward()
         return out
