@@ -108,6 +108,7 @@ PERF = [  # name, case (B=8 layers of the north-star workload)
     ("base1.3.conv_t", (8, 16, 0, 56, 96, 192, 192, (3, 1, 1), 1, (1, 0, 0))),
     ("base1.0.conv_t", (8, 32, 0, 112, 192, 64, 64, (7, 1, 1), 2, (3, 0, 0))),
     ("3c.b1.conv_s", (8, 16, 0, 28, 48, 128, 192, (1, 3, 3), 1, (0, 1, 1))),
+    ("3c.b1.conv_t", (8, 16, 0, 28, 48, 192, 192, (3, 1, 1), 1, (1, 0, 0))),
     ("3c.b0 1x1", (8, 16, 0, 28, 48, 256, 128, (1, 1, 1), 1, (0, 0, 0))),
     ("convtsp1", (8, 4, 0, 7, 12, 1024, 832, (1, 3, 3), 1, (0, 1, 1))),
     ("convtsp2", (8, 4, 8, 14, 24, 832, 480, (3, 3, 3), 3, (0, 1, 1))),

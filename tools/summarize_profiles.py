@@ -15,20 +15,32 @@ os.makedirs(P, exist_ok=True)
 
 def launches():
     lines = [l for l in open(os.path.join(G, "launches_step.csv")) if not l.startswith("==")]
-    rows = list(csv.DictReader(lines))
+    allrows = list(csv.DictReader(lines))
+    rows = [x for x in allrows if x["Metric Name"] == "gpu__time_duration.sum"]
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for x in rows:
         name = re.sub(r"[<(].*", "", x["Kernel Name"]).replace("void ", "")
         tot[name] += float(x["Metric Value"].replace(",", "")) / 1e6
         cnt[name] += 1
     s = sum(tot.values())
+    # DRAM bytes of the same window (when the launch list was taken with dram__bytes_read.sum / dram__bytes_write.sum)
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = collections.defaultdict(float)
+    for x in allrows:
+        if x["Metric Name"].startswith("dram__bytes"):
+            dram[re.sub(r"[<(].*", "", x["Kernel Name"]).replace("void ", "")] += float(x["Metric Value"].replace(",", "")) * unit.get(x["Metric Unit"], 1)
     out = ["# %s: ncu launch list of the training step (B=8 x 32x224x384, bf16, eager launches), gpu__time_duration.sum" % R,
-           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 650 --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph",
-           "# a window of %d consecutive launches (about 1.15 steps: ~565 launches per step), %.2f ms; per-launch times are" % (len(rows), s),
+           "# command: tools/make_profiles.sh (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+           "-s ... -c ... --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --no-graph)",
+           "# a window of %d consecutive launches (~%s launches per step), %.2f ms; per-launch times are" % (len(rows), os.environ.get("VINET_LAUNCHES_PER_STEP", "430"), s),
            "# cold-cache and serialised: compare SHARES with profiles/%s_profile_step.txt (CUPTI, one step, warm)" % R,
            "%-40s %7s %10s %7s" % ("kernel", "count", "ms", "share")]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
-        out.append("%-40s %7d %10.3f %6.1f%%" % (k[:40], cnt[k], v, 100 * v / s))
+        out.append("%-40s %7d %10.3f %6.1f%%%s" % (k[:40], cnt[k], v, 100 * v / s, ("  %9.1f MB DRAM" % (dram[k] / 1e6)) if dram else ""))
+    if dram:
+        steps = len(rows) / float(os.environ.get("VINET_LAUNCHES_PER_STEP", "430"))
+        out.append("# DRAM traffic of the window: %.2f GB over ~%.2f steps of 8 clips = %.0f MB per clip (read + write, fwd + bwd + optimizer); "
+                   "algorithmic minimum of the convolutions alone: 823 MB/clip forward (SURVEY 8d)" % (sum(dram.values()) / 1e9, steps, sum(dram.values()) / 1e6 / steps / 8))
     open(os.path.join(P, "%s_launches_step_summary.txt" % R), "w").write("\n".join(out) + "\n")
     # compact per-launch list (id, kernel, grid, block, us)
     with open(os.path.join(P, "%s_launches_step.csv" % R), "w") as f:
@@ -82,6 +94,10 @@ if __name__ == "__main__":
     B = 8
     fl = 2.0 * B * 4 * 28 * 48 * (5 * 9 * 480) * 192          # decoder.convtsp3.0, SURVEY Appendix A x B
     fl13 = 2.0 * B * 16 * 56 * 96 * (9 * 64) * 192            # backbone.base1.3.conv_s
+    fl13t = 2.0 * B * 16 * 56 * 96 * (3 * 192) * 192          # backbone.base1.3.conv_t
+    fl3cs = 2.0 * B * 16 * 28 * 48 * (9 * 128) * 192          # Mixed_3c branch1 conv_s
+    fl3ct = 2.0 * B * 16 * 28 * 48 * (3 * 192) * 192          # Mixed_3c branch1 conv_t
+    fl2 = 2.0 * B * 4 * 14 * 24 * (27 * 832) * 480            # decoder.convtsp2.0
     caps = {}
     for rep, key, title, flops in [
             ("prof_tsp3_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp3.0",
@@ -89,7 +105,15 @@ if __name__ == "__main__":
             ("prof_tsp3_wgrad.ncu-rep", "conv_wgrad_halo_kernel/wgrad:decoder.convtsp3.0",
              "decoder.convtsp3.0 wgrad (conv_wgrad_halo_kernel), B=8", fl),
             ("prof_b13s_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.3.conv_s",
-             "SepConv3d stack: backbone.base1.3.conv_s fprop (conv_stream_kernel), B=8", fl13)]:
+             "SepConv3d stack: backbone.base1.3.conv_s fprop (conv_stream_kernel), B=8", fl13),
+            ("prof_b13t_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.3.conv_t",
+             "SepConv3d stack: backbone.base1.3.conv_t fprop (conv_stream_kernel, temporal-halo tiles), B=8", fl13t),
+            ("prof_3cs_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base2.1.branch1.1.conv_s",
+             "SepConv3d stack: Mixed_3c branch1 conv_s fprop (conv_stream_kernel), B=8", fl3cs),
+            ("prof_3ct_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base2.1.branch1.1.conv_t",
+             "SepConv3d stack: Mixed_3c branch1 conv_t fprop (conv_stream_kernel), B=8", fl3ct),
+            ("prof_tsp2_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp2.0",
+             "best launch of the dominant kernel: decoder.convtsp2.0 fprop (conv_stream_kernel), B=8", fl2)]:
         r = ncu_summary(rep, title, flops)
         if r:
             caps[key] = r

@@ -146,7 +146,12 @@ class VideoAudioSaliencyModel(_PlanModule):
     def _run_plan(self, e, record, x, audio):
         e.generation += 1
         e.begin(x.device, self.training, record)
+        # the audio branch is independent of the backbone until the fusion: its ~20 small launches run on the side stream
+        audio_side = e.fork()
+        e.on_side(True)
         a, ga = soundnet_plan(e, "audionet.", self.audionet, audio)
+        if audio_side:
+            e._side_active = False          # keep the fork open: the backbone below forks / joins the same side stream itself
         xin = pack_input(e, x)
         y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin,
                                        y0_gdtype=torch.float32)

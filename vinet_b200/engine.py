@@ -158,6 +158,8 @@ class Engine:
         self.weights_dirty = False   # set by GraphedTrainStep: parameters changed without a Tensor._version bump
         self._repack_all = False
         self.arena = None       # optional flat fp32 gradient arena: (flat tensor, {param name: (offset, numel)}, {name: parameter})
+        self.par_branches = True
+        self._side, self._side_active, self._forked = None, False, False
         self.realloc_count = 0  # pooled buffers re-allocated because a forward came with another shape
         self.dwp_arena, self.dwp_layout, self.dwp_dirty, self.unpack_queue = None, {}, False, []
         self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
@@ -169,7 +171,43 @@ class Engine:
     def stream(self):
         if self.device.type != "cuda":
             return None
+        if self._side_active:
+            return self._side.cuda_stream
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- branch concurrency: independent convolutions of a Mixed block (branch1 / branch2 chains, the pool branch) are small
+    # launches that leave most SMs idle; issuing one of each pair on a side stream lets them overlap.  Only KERNEL LAUNCHES move
+    # to the side stream (torch's current stream is untouched, so every allocation stays on the main stream); fork / join are
+    # events, which a CUDA-graph capture turns into plain dependency edges.
+    def par_enabled(self):
+        return (self.device is not None and self.device.type == "cuda" and self.profile is None and self.par_branches
+                and not os.environ.get("VINET_NO_PAR_BRANCH"))
+
+    def fork(self):
+        """Make the side stream wait for everything issued so far on the main stream."""
+        if not self.par_enabled():
+            return False
+        if self._side is None or self._side.device != self.device:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        self._forked = True
+        return True
+
+    def on_side(self, flag):
+        """Route the following kernel launches to the side stream (True) or back to the main stream (False)."""
+        self._side_active = bool(flag) and self._forked
+
+    def join(self):
+        """The main stream waits for the side stream; launches go to the main stream again."""
+        self._side_active = False
+        if not self._forked:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._forked = False
 
     def call(self, name, desc):
         self.lib.call(name, C.byref(desc), self.stream())
@@ -833,9 +871,13 @@ class Engine:
                 outs.append((conv_bwd, dy_ptr, lddy))
             assert len({mbr[3].gdt for mbr in members}) == 1
             self.lib.call("vinet_bn_bwd_multi", bs, n, self.stream())
-            for conv_bwd, dy_ptr, lddy in reversed(outs):
-                if conv_bwd is not None:
-                    conv_bwd(dy_ptr, lddy)
+            todo = [o for o in reversed(outs) if o[0] is not None]
+            if len(todo) > 1:
+                self.fork()
+            for i, (conv_bwd, dy_ptr, lddy) in enumerate(todo):      # independent convolutions: alternate the two streams
+                self.on_side(i % 2 == 1)
+                conv_bwd(dy_ptr, lddy)
+            self.join()
         self.tape.append(backward)
 
     def _bn_tail(self, name_bn, bn, raw, out, conv_bwd, dy_slot, stats=None):

@@ -172,21 +172,33 @@ def _mixed(e, pfx, x, m, gdtype=None):
     # The BatchNorm layers that are ready together run as ONE multi-layer launch per pass (Engine.bn_begin / bn_flush):
     # {branch0, branch1.0, branch2.0, branch3.1}, then both conv_s, then both conv_t - 3 launch groups instead of 7 layers.
     e.bn_begin()
+    # Independent launches of the block alternate between the main and a side stream (Engine.fork / on_side / join): the pool
+    # branch beside the fused 1x1 GEMM, branch1 beside branch2 - small layers that each leave most of the 148 SMs idle.
+    e.fork()
+    e.on_side(True)
     # pool branch first: its backward (a scatter-add) then runs after the convs' data gradients have written x.grad
     p = e.maxpool(pfx + ".branch3.pool", x, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     _basic(e, pfx + ".branch3.1", p, m.branch3[1], out.slice(b0 + b1 + b2, b3))
+    e.on_side(False)
     t1 = e.new_act(pfx + ".branch1.0.o", x.B, x.T, x.H, x.W, b1r)
     t2 = e.new_act(pfx + ".branch2.0.o", x.B, x.T, x.H, x.W, b2r)
     e.conv_bn_group(pfx + ".fused1x1", x, [
         (pfx + ".branch0.0.conv", pfx + ".branch0.0.bn", m.branch0[0].conv.weight, m.branch0[0].bn, out.slice(0, b0)),
         (pfx + ".branch1.0.conv", pfx + ".branch1.0.bn", m.branch1[0].conv.weight, m.branch1[0].bn, t1),
         (pfx + ".branch2.0.conv", pfx + ".branch2.0.bn", m.branch2[0].conv.weight, m.branch2[0].bn, t2)])
+    e.join()
     e.bn_flush()
+    e.fork()
     m1 = _sepconv_s(e, pfx + ".branch1.1", [t1], m.branch1[1])
+    e.on_side(True)
     m2 = _sepconv_s(e, pfx + ".branch2.1", [t2], m.branch2[1])
+    e.join()
     e.bn_flush()
+    e.fork()
     _sepconv_t(e, pfx + ".branch1.1", m1, m.branch1[1], out.slice(b0, b1))
+    e.on_side(True)
     _sepconv_t(e, pfx + ".branch2.1", m2, m.branch2[1], out.slice(b0 + b1, b2))
+    e.join()
     e.bn_end()
     return out
 
