@@ -172,10 +172,11 @@ def test_maxpool_backward_gather_matches_scatter_and_autograd(cfg, overwrite, gd
         torch.cuda.synchronize()
         res.append(gin.float().cpu())
     lib.call("vinet_debug_set", 3, 1)
-    tol = 1e-6 if gdt == "f32" else 4e-2       # bf16 gradients: a few terms summed / stored in bf16 (|values| up to ~8)
-    assert torch.allclose(res[0], res[1], rtol=tol, atol=tol)
-    assert torch.allclose(res[0], ref.cpu(), rtol=tol, atol=tol)
-    assert torch.allclose(res[0], res[2], rtol=tol, atol=tol)
+    # bf16 gradients: up to 27 terms summed and stored in bf16 (|values| reach ~16, where one bf16 ulp is 0.0625)
+    rtol, atol = (1e-6, 1e-6) if gdt == "f32" else (2e-2, 1.3e-1)
+    assert torch.allclose(res[0], res[1], rtol=rtol, atol=atol)
+    assert torch.allclose(res[0], ref.cpu(), rtol=rtol, atol=atol)
+    assert torch.allclose(res[0], res[2], rtol=rtol, atol=atol)
 
 
 SWEEP_CONVS = [  # B, T0, T1, H, W, Cin, Cout, k, stride_t, pad  (geometries the 128x192 .. 448x768 / T=8..48 sweep produces)
