@@ -1,9 +1,11 @@
 #!/bin/bash
-# compute-sanitizer evidence: memcheck / racecheck / synccheck over the hand-rolled mbarrier / TMEM kernels on small
-# shapes (one conv scenario with concat + upsample, one Mixed block, the stem, a tiny whole-model train step).
+# compute-sanitizer evidence: memcheck / racecheck / synccheck over every kernel test (hand-rolled mbarrier / TMEM /
+# TMA conv kernels in all modes incl. the epilogue-statistics path, BatchNorm, pools, upsample, losses, audio GEMMs), the input /
+# output pipeline kernels and one whole-model train step on the tensor-core parity mode.  Logs -> gpurun_out/sanitizer_*.log
 mkdir -p gpurun_out
-SEL='conv_concat_relu_upsample and bf16 and 0 or mixed_block and bf16 and 3b or stem_sepconv and bf16'
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "$SEL" > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "$tool rc=$?"; tail -4 gpurun_out/sanitizer_$tool.log
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_preprocess.py \
+      "tests/test_gpu_inference.py::test_postprocess_matches_reference_pipeline" "tests/test_gpu_parity_tc.py::test_two_term_split_is_close_but_reported_separately" \
+      -m gpu -q -x > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_$tool.log
 done

@@ -1,7 +1,7 @@
 """Architecture tables of the ViNet / AViNet hot path (product-owned copy).
 
 Only *numbers* (channel counts, kernel sizes) read off the reference; consumed by the plan builder
-(``vinet_b200/plan.py``) and the parameter-holder modules (``vinet_b200/model.py``).
+and the parameter-holder modules (both in ``vinet_b200/model.py`` / ``avmodel.py``).
 
 Reference sites:
   * Inception ("Mixed") blocks ........ model_utils.py:162-420
