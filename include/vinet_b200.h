@@ -27,7 +27,13 @@ typedef void* vinet_stream_t; /* cudaStream_t */
 
 enum { VINET_BF16 = 0, VINET_F32 = 1 };
 /* transform applied to a source element when it is read ("pending" BN/ReLU of the producer layer) */
-enum { VINET_XF_IDENT = 0, VINET_XF_RELU = 1, VINET_XF_AFFINE = 2, VINET_XF_AFFINE_RELU = 3 };
+enum { VINET_XF_IDENT = 0, VINET_XF_RELU = 1, VINET_XF_AFFINE = 2, VINET_XF_AFFINE_RELU = 3,
+       /* bit 2: the source is STORED AT HALF RESOLUTION, [B,T,Hs/2,Ws/2,ld], and read through nn.Upsample(scale_factor=(1,2,2),
+        * mode='trilinear') (model.py:254; applied after the ReLU of bit 0, not combinable with AFFINE): the up-sampled tensor of
+        * the decoder (model.py:286-311) is never materialised.  Hs, Ws of the gather stay the (even) hi-res extents.  Accepted by the
+        * FFMA engine and, for FPROP gathers, by the TMA-fed tensor-core kernels whose producer warps interpolate straight into
+        * the swizzled shared-memory tile (vinet_conv_up2_fused tells); everything else reports an error. */
+       VINET_XF_UP2 = 4, VINET_XF_RELU_UP2 = 5 };
 enum { VINET_GATHER_FPROP = 0, VINET_GATHER_DGRAD = 1 };
 /* VINET_ENGINE_TC: bf16 tcgen05.mma with fp32 TMEM accumulators; VINET_ENGINE_SIMT: fp32 FFMA (parity mode) */
 enum { VINET_ENGINE_TC = 0, VINET_ENGINE_SIMT = 1 };
@@ -132,6 +138,10 @@ typedef struct vinet_wgrad {
   int32_t kernel; /* VINET_KERNEL_* (TC engine) */
 } vinet_wgrad_t;
 int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream);
+/* 1 when BOTH vinet_conv_gemm and vinet_conv_wgrad serve the FPROP gather g (N output channels, VINET_KERNEL_* kernel) with a
+ * VINET_XF_UP2 source 0 through their fused interpolating input stage, 0 when the caller has to materialise the up-sampled
+ * tensor (vinet_upsample_fwd) first.  Host only. */
+int vinet_conv_up2_fused(const vinet_gather_t* g, int32_t N, int32_t engine, int32_t kernel);
 
 /* Weight (re)packing: PyTorch (Cout,Cin,kt,kh,kw) fp32 -> GEMM B operand. */
 typedef struct vinet_pack {
@@ -208,6 +218,8 @@ typedef struct vinet_split {
   int32_t nparts; /* 2 or 3 */
   void* part[3];  /* bf16 [rows, ldo] each */
   int64_t ldo;
+  int32_t up_h, up_w; /* xform & VINET_XF_UP2: x holds rows / (4*up_h*up_w) low-res frames [up_h, up_w, ld]; `rows` counts the
+                         hi-res rows the planes hold (the interpolation happens while splitting) */
 } vinet_split_t;
 int vinet_split_bf16(const vinet_split_t* d, vinet_stream_t stream);
 
@@ -352,7 +364,16 @@ typedef struct vinet_upsample {
 int vinet_upsample_fwd(const vinet_upsample_t* d, vinet_stream_t stream);
 int vinet_upsample_bwd(const vinet_upsample_t* d, vinet_stream_t stream);
 
-/* ---- decoder head: relu? -> Conv3d(C,1,1x1x1,bias) -> Sigmoid (model.py:280-283) ---- */
+/* dz = g where z > 0 else 0: backward of a ReLU whose input (or output: same mask) was kept (decoder convs, model.py:256-281) */
+int vinet_relu_bwd(const void* g, int64_t ldg, int32_t g_dtype, const void* z, int64_t ldz, int32_t z_dtype, int64_t rows, int32_t C,
+                   void* dz, int64_t lddz, int32_t dz_dtype, vinet_stream_t stream);
+
+/* ---- decoder head: relu? -> Conv3d(C,1,1x1x1,bias) -> Sigmoid (model.py:280-283) ----
+ * up2 != 0: the 2x bilinear up-sampling in front of the head (model.py:278, 340, 402, 464) is fused into its input stage: x holds
+ * rows / (4*up_h*up_w) low-res frames [up_h, up_w, ldx], `rows` counts hi-res pixels, relu_pre applies a ReLU to x BEFORE the
+ * interpolation (conv -> ReLU -> up -> head, T = 8 / 16) and relu AFTER it (conv -> ReLU -> up -> (kt,1,1) conv -> ReLU -> head, T = 32 / 48, where
+ * the pointwise-in-space conv has been commuted in front of the up-sampling); dx is the hi-res gradient w.r.t. the interpolated
+ * value (vinet_upsample_bwd turns it into the gradient w.r.t. x). */
 typedef struct vinet_head {
   const void* x;
   int64_t ldx;
@@ -369,6 +390,7 @@ typedef struct vinet_head {
   int32_t dx_dtype;
   float* dw; /* [C], atomics; caller zeroes */
   float* db; /* [1] */
+  int32_t up2, up_h, up_w, relu_pre;
 } vinet_head_t;
 int vinet_head_fwd(const vinet_head_t* d, vinet_stream_t stream);
 int vinet_head_bwd(const vinet_head_t* d, vinet_stream_t stream);
@@ -505,6 +527,8 @@ int vinet_abi_sizes(int64_t* out, int32_t n);
 int vinet_debug_set(int32_t key, int32_t value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vinet_launch_count(void);
+/* how many of them were tensor-core launches whose producer warps interpolated a VINET_XF_UP2 source (the fused up-sampling) */
+int64_t vinet_up2_launch_count(void);
 
 #ifdef __cplusplus
 }

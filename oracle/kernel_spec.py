@@ -52,6 +52,29 @@ def _xform(v, xf, scale, shift, c0, c):
     return v.astype(np.float32)
 
 
+def _up_axis(Y, n):
+    """Taps of hi-res coordinates Y on a low-res axis of length n: nn.Upsample(scale_factor=2, align_corners=False) =
+    (i0, i1, weight of i1), in the kernel's float32 arithmetic (model.py:254)."""
+    src = np.maximum((Y.astype(np.float32) + np.float32(0.5)) * np.float32(0.5) - np.float32(0.5), np.float32(0))
+    i0 = src.astype(np.int64)
+    return i0, np.minimum(i0 + 1, n - 1), (src - i0.astype(np.float32)).astype(np.float32)
+
+
+def _up2_rows(low, n, Y, X, relu):
+    """low: [N, h, w, C] fp32; returns relu? -> 2x bilinear values at frames n, hi-res pixels (Y, X): [len, C] fp32, blended in the
+    order of the CUDA implementation (up2.cuh: x first, then y)."""
+    h, w = low.shape[1], low.shape[2]
+    y0, y1, ly = _up_axis(Y, h)
+    x0, x1, lx = _up_axis(X, w)
+    f = (lambda v: np.maximum(v, 0)) if relu else (lambda v: v)
+    a, b, e0, e1 = f(low[n, y0, x0]), f(low[n, y0, x1]), f(low[n, y1, x0]), f(low[n, y1, x1])
+    lx, ly = lx[:, None], ly[:, None]
+    one = np.float32(1)
+    top = (one - lx) * a + lx * b
+    bot = (one - lx) * e0 + lx * e1
+    return ((one - ly) * top + ly * bot).astype(np.float32)
+
+
 def _taps(g):
     return [(g.tap[i][0], g.tap[i][1], g.tap[i][2]) for i in range(g.ntaps)]
 
@@ -88,6 +111,13 @@ def gather_matrix(g):
             if not sel.any():
                 continue
             tl = ts[sel] - (T0 if si else 0)
+            if s.xform & L.XF_UP2:      # low-res source [B,T,Hs/2,Ws/2,ld] read through relu? + the 2x bilinear up-sampling
+                assert si == 0 and g.mode == L.GATHER_FPROP and not (s.xform & 2) and g.Hs % 2 == 0 and g.Ws % 2 == 0
+                lh, lw = g.Hs // 2, g.Ws // 2
+                low = _rows_view(s.ptr, g.B * s.T * lh * lw, s.ld, g.Cs, g.dtype).reshape(g.B * s.T, lh, lw, g.Cs)
+                v = _up2_rows(low, b[sel] * s.T + tl, hs[sel], ws[sel], bool(s.xform & 1))
+                A[np.nonzero(sel)[0], ti * g.Cs:(ti + 1) * g.Cs] = _bf16_round(v) if g.dtype == L.BF16 else v
+                continue
             pos = ((b[sel] * s.T + tl) * g.Hs + hs[sel]) * g.Ws + ws[sel]
             src = _rows_view(s.ptr, g.B * s.T * g.Hs * g.Ws, s.ld, g.Cs, g.dtype)
             A[np.nonzero(sel)[0], ti * g.Cs:(ti + 1) * g.Cs] = _xform(src[pos], s.xform, s.scale, s.shift, 0, g.Cs)
@@ -102,11 +132,16 @@ class Spec:
         # composition of the single-layer specs, so the CPU plan tests walk the same host logic (batching, tape order)
         self.fn = {"vinet_packed_weight_bytes": self._packed_bytes, "vinet_bn_stats_finalize": None, "vinet_bn_fwd_fused": None,
                    "vinet_bn_bwd_fused": None, "vinet_bn_stats_finalize_multi": None, "vinet_bn_apply_multi": None,
-                   "vinet_bn_bwd_multi": None}
+                   "vinet_bn_bwd_multi": None, "vinet_conv_up2_fused": self._up2_fused, "vinet_relu_bwd": None}
         self.launches = 0
 
     def launch_count(self):
         return self.launches
+
+    @staticmethod
+    def _up2_fused(g, n, engine, kernel):
+        g = g._obj if hasattr(g, "_obj") else g
+        return 1 if (g.mode == L.GATHER_FPROP and (g.src[0].xform & ~1) == L.XF_UP2 and g.Hs % 2 == 0 and g.Ws % 2 == 0) else 0
 
     @staticmethod
     def _packed_bytes(engine, n, block_n, n_tiles, k_blocks):
@@ -163,7 +198,13 @@ class Spec:
                 out[ti * d.cs:ti * d.cs + d.Cout, :d.Cin] = w[:, :, dt, dh, dw]
 
     def split_bf16(self, d, stream):
-        v = _xform(_rows_view(d.x, d.rows, d.ld, d.C, d.dtype), d.xform, d.scale, d.shift, 0, d.C)
+        if d.xform & L.XF_UP2:
+            n = d.rows // (4 * d.up_h * d.up_w)
+            low = _rows_view(d.x, n * d.up_h * d.up_w, d.ld, d.C, d.dtype).reshape(n, d.up_h, d.up_w, d.C)
+            r = np.arange(d.rows)
+            v = _up2_rows(low, r // (4 * d.up_h * d.up_w), (r // (2 * d.up_w)) % (2 * d.up_h), r % (2 * d.up_w), bool(d.xform & 1))
+        else:
+            v = _xform(_rows_view(d.x, d.rows, d.ld, d.C, d.dtype), d.xform, d.scale, d.shift, 0, d.C)
         for p in range(d.nparts):
             bits = _bf16_bits(v)
             out = _arr(d.part[p], (d.rows - 1) * d.ldo + d.C, np.uint16)
@@ -368,15 +409,27 @@ class Spec:
         _rows_view(d.dz, d.B * d.T * d.h * d.w, d.lddz, d.C)[:] = dz
 
     # ------------------------------------------------------------------ head
+    def _head_x(self, d):
+        if not d.up2:
+            return _rows_view(d.x, d.rows, d.ldx, d.C)
+        n = d.rows // (4 * d.up_h * d.up_w)
+        low = _rows_view(d.x, n * d.up_h * d.up_w, d.ldx, d.C).reshape(n, d.up_h, d.up_w, d.C)
+        r = np.arange(d.rows)
+        return _up2_rows(low, r // (4 * d.up_h * d.up_w), (r // (2 * d.up_w)) % (2 * d.up_h), r % (2 * d.up_w), bool(d.relu_pre))
+
+    def relu_bwd(self, g, ldg, g_dtype, z, ldz, z_dtype, rows, c, dz, lddz, dz_dtype, stream):
+        assert g_dtype == L.F32 and z_dtype == L.F32 and dz_dtype == L.F32
+        _rows_view(dz, rows, lddz, c)[:] = np.where(_rows_view(z, rows, ldz, c) > 0, _rows_view(g, rows, ldg, c), 0)
+
     def head_fwd(self, d, stream):
-        x = _rows_view(d.x, d.rows, d.ldx, d.C)
+        x = self._head_x(d)
         if d.relu:
             x = np.maximum(x, 0)
         logit = x @ _arr(d.w, d.C) + (_arr(d.b, 1)[0] if d.b else 0)
         _arr(d.out, d.rows)[:] = 1 / (1 + np.exp(-logit))
 
     def head_bwd(self, d, stream):
-        x = _rows_view(d.x, d.rows, d.ldx, d.C)
+        x = self._head_x(d)
         on = (x > 0) | (d.relu == 0)
         a = np.where(on, x, 0)
         o = _arr(d.out, d.rows)

@@ -53,8 +53,52 @@ def conv_up(device, precision, backend=None, B=2, T0=1, T1=2, H=6, W=5, Cin=16, 
     y = fill_act(e, "y", B, T1, H, W, Cin, gen, True)
     w = bf16r(torch.randn(Cout, Cin, kt, 3, 3, generator=gen) * (2.0 / (Cin * kt * 9)) ** 0.5).to(device)
     out = e.conv_relu_up("c", [u, y], w, ConvGeom((kt, 3, 3), (kt, 1, 1), (0, 1, 1)))
+    hi = e.materialize_up2(out)        # the stage's output is virtual (read through the up-sampling): the standalone kernel writes it
     run_tape(e, out, gen)
-    return {"out": ncdhw(out.buf), "dW": e.param_grads["c.weight"].cpu(), "du": ncdhw(u.grad), "dy": ncdhw(y.grad)}
+    return {"out": ncdhw(hi.buf), "dW": e.param_grads["c.weight"].cpu(), "du": ncdhw(u.grad), "dy": ncdhw(y.grad)}
+
+
+def up_fused(device, precision, backend=None, B=2, T0=1, T1=2, h=5, w=6, C0=16, C1=24, C2=16, kt=3, seed=0, fuse=True):
+    """Two decoder stages (model.py:286-298): conv(1,3,3) -> relu -> 2x up -> [T-concat with a skip tensor] -> conv(kt,3,3)/(kt,1,1)
+    -> relu -> 2x up.  The second convolution reads the first stage's output THROUGH the relu + up-sampling in its input stage
+    (fprop and weight gradient); fuse=False materialises the hi-res tensor first (the pre-fusion plan) for an A/B comparison."""
+    gen = torch.Generator().manual_seed(seed)
+    e = make_engine(device, precision, backend)
+    x = fill_act(e, "x", B, T0, h, w, C0, gen, False)
+    y = fill_act(e, "y", B, T1, 2 * h, 2 * w, C1, gen, False)
+    w1 = bf16r(torch.randn(C1, C0, 1, 3, 3, generator=gen) * (2.0 / (C0 * 9)) ** 0.5).to(device)
+    w2 = bf16r(torch.randn(C2, C1, kt, 3, 3, generator=gen) * (2.0 / (C1 * kt * 9)) ** 0.5).to(device)
+    u1 = e.conv_relu_up("c1", [x], w1, ConvGeom((1, 3, 3), (1, 1, 1), (0, 1, 1)))
+    if not fuse:
+        u1 = e.materialize_up2(u1)
+    e.profile = [] if backend is None and device != "cpu" else None
+    n_up2 = L.get().fn["vinet_up2_launch_count"]() if backend is None else 0
+    u2 = e.conv_relu_up("c2", [u1, y], w2, ConvGeom((kt, 3, 3), (kt, 1, 1), (0, 1, 1)))
+    hi = e.materialize_up2(u2)
+    run_tape(e, u2, gen)
+    kernels = sorted({r[5] for r in e.profile}) if e.profile is not None else []
+    e.profile = None
+    return {"out": ncdhw(hi.buf), "dW1": e.param_grads["c1.weight"].cpu(), "dW2": e.param_grads["c2.weight"].cpu(),
+            "dx": ncdhw(x.grad), "dy": ncdhw(y.grad), "_kernels": kernels, "_materialized": list(e.up2_mat_log),
+            "_up2_launches": (L.get().fn["vinet_up2_launch_count"]() - n_up2) if backend is None else 0}
+
+
+def up_fused_torch(B=2, T0=1, T1=2, h=5, w=6, C0=16, C1=24, C2=16, kt=3, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+
+    def rnd(*s):
+        return bf16r(torch.randn(*s, generator=gen))
+    xb = rnd(B, T0, h, w, C0)
+    yb = rnd(B, T1, 2 * h, 2 * w, C1)
+    w1 = bf16r(torch.randn(C1, C0, 1, 3, 3, generator=gen) * (2.0 / (C0 * 9)) ** 0.5).requires_grad_(True)
+    w2 = bf16r(torch.randn(C2, C1, kt, 3, 3, generator=gen) * (2.0 / (C1 * kt * 9)) ** 0.5).requires_grad_(True)
+    x = xb.permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    y = yb.permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    u1 = F.interpolate(F.relu(F.conv3d(x, w1, None, 1, (0, 1, 1))), scale_factor=(1, 2, 2), mode="trilinear")
+    u2 = F.interpolate(F.relu(F.conv3d(torch.cat([u1, y], 2), w2, None, (kt, 1, 1), (0, 1, 1))), scale_factor=(1, 2, 2), mode="trilinear")
+    go = bf16r(torch.randn(B, u2.shape[2], u2.shape[3], u2.shape[4], C2, generator=gen)).permute(0, 4, 1, 2, 3)
+    u2.backward(go)
+    return {"out": u2.detach(), "dW1": w1.grad, "dW2": w2.grad, "dx": x.grad, "dy": y.grad}
 
 
 def conv_up_torch(B=2, T0=1, T1=2, H=6, W=5, Cin=16, Cout=24, kt=3, seed=0):
@@ -132,7 +176,7 @@ def compare(a, b, rtol, what="", skip=()):
     two correct implementations moves a few elements by a lot, never the bulk). Returns the failures."""
     bad = []
     for k in b:
-        if any(s in k for s in skip):
+        if k.startswith("_") or any(s in k for s in skip):
             continue
         ref = b[k].float()
         got = a[k].float().reshape(ref.shape)

@@ -40,6 +40,54 @@ def test_conv_concat_relu_upsample(precision, case):
         assert not S.compare({"out": got["out"]}, {"out": spec["out"]}, 1e-2)
 
 
+# a6 (north_star: "trilinear upsample fused into the following conv's input stage"): geometries of the decoder stages
+# convtsp2 / convtsp3 / convtsp4.0 / convtsp4.3 (channel counts incl. a ragged last 64-block, T-concat with a skip tensor, maps
+# that are not multiples of the 8 x 16 tiles) + a map too small for the halo kernels (falls back to materialising)
+UP_CASES = [dict(B=2, T0=1, T1=2, kt=3, h=7, w=12, C0=64, C1=96, C2=48),
+            dict(B=1, T0=2, T1=3, kt=5, h=14, w=24, C0=32, C1=480, C2=192),
+            dict(B=2, T0=1, T1=1, kt=2, h=11, w=19, C0=16, C1=64, C2=32),
+            dict(B=1, T0=2, T1=4, kt=3, h=28, w=20, C0=24, C1=192, C2=64)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x6"])
+@pytest.mark.parametrize("case", range(len(UP_CASES)))
+def test_upsample_fused_into_conv_input_stage(precision, case):
+    """The consumer convolution reads relu + 2x bilinear of the LOW-RES tensor in its input stage.  bf16: the interpolating
+    producer warps of conv_stream_kernel / conv_wgrad_halo_kernel must reproduce the plan that materialises the hi-res tensor
+    BIT FOR BIT (same arithmetic, same bf16 rounding point, same MMA order) - borders, ragged tiles and all; fp32 / bf16x6 are
+    held against the numpy spec / PyTorch autograd."""
+    kw = UP_CASES[case]
+    got = S.up_fused("cuda", precision, **kw)
+    assert got["_materialized"] == ["c2"], got["_materialized"]      # only the scenario's explicit output materialisation
+    if precision == "bf16":
+        assert got["_up2_launches"] == 2, (got["_up2_launches"], got["_kernels"])     # fprop + weight gradient of c2
+        assert set(got["_kernels"]) <= {"conv_stream_kernel", "conv_wgrad_halo_kernel", "conv_gemm_tma_kernel", "conv_wgrad_tma_kernel"}
+        ref = S.up_fused("cuda", precision, fuse=False, **kw)
+        assert ref["_materialized"] == ["c1", "c2"] and ref["_up2_launches"] == 0
+        for k in ("out", "dx", "dy"):
+            assert torch.equal(got[k], ref[k]), (k, (got[k].float() - ref[k].float()).abs().max())
+        # weight gradients accumulate with fp32 atomics over position chunks (order varies run to run)
+        dw = S.compare({k: got[k] for k in ("dW1", "dW2")}, {k: ref[k] for k in ("dW1", "dW2")}, 1e-5)
+        assert not dw, dw
+        simt = S.up_fused("cuda", "bf16_simt", **kw)
+        assert not S.compare(got, simt, 1e-2), S.compare(got, simt, 1e-2)
+    else:
+        ref = S.up_fused_torch(**kw)
+        tol = 1e-3 if precision == "fp32" else 2e-4
+        assert not S.compare(got, ref, tol), S.compare(got, ref, tol)
+        if precision == "fp32" and case == 0:
+            spec = S.up_fused("cpu", "fp32", Spec(), **kw)
+            assert not S.compare(got, spec, 1e-4), S.compare(got, spec, 1e-4)
+
+
+def test_upsample_fusion_falls_back_on_small_maps():
+    """7 x 12 hi-res maps are below the halo kernels' tile: the engine asks vinet_conv_up2_fused and materialises instead."""
+    got = S.up_fused("cuda", "bf16", B=1, T0=1, T1=2, kt=3, h=3, w=6, C0=16, C1=32, C2=16)
+    assert got["_materialized"] == ["c1", "c2"] and got["_up2_launches"] == 0
+    ref = S.up_fused("cuda", "bf16_simt", B=1, T0=1, T1=2, kt=3, h=3, w=6, C0=16, C1=32, C2=16)
+    assert not S.compare(got, ref, 1e-2), S.compare(got, ref, 1e-2)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["3b", "4c", "5c"])
 def test_mixed_block(precision, name):

@@ -20,6 +20,19 @@ def test_conv_concat_relu_upsample_vs_torch():
         assert not S.compare(a, b, 1e-4), S.compare(a, b, 1e-4)
 
 
+def test_upsample_fused_into_next_conv_vs_torch():
+    """a6: the second decoder conv reads the first stage's output through relu + the 2x bilinear up-sampling in its input stage
+    (VINET_XF_UP2); border-exact against PyTorch autograd, and identical to the plan that materialises the hi-res tensor."""
+    for kw in ({}, {"B": 1, "T0": 2, "T1": 3, "kt": 5, "h": 3, "w": 4, "C0": 8, "C1": 16, "C2": 8}, {"h": 1, "w": 2, "T1": 2}):
+        a = S.up_fused("cpu", "fp32", Spec(), **kw)
+        assert a["_materialized"] == ["c2"], a["_materialized"]          # only the scenario's explicit output materialisation
+        b = S.up_fused_torch(**kw)
+        assert not S.compare(a, b, 1e-4), S.compare(a, b, 1e-4)
+        c = S.up_fused("cpu", "fp32", Spec(), fuse=False, **kw)
+        assert c["_materialized"] == ["c1", "c2"]
+        assert not S.compare(a, c, 1e-6), S.compare(a, c, 1e-6)
+
+
 def test_model_state_dict_layout_matches_oracle():
     for t, h in [(8, 3), (16, 3), (32, 3), (48, 3), (32, 0), (32, 1), (32, 2)]:
         a, b = VideoSaliencyModel(num_clips=t, num_hier=h).state_dict(), O.ViNetOracle(t, h).state_dict()

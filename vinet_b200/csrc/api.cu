@@ -8,6 +8,7 @@ namespace vinet {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_up2_launches{0};
 static thread_local const char* g_last_kernel = "";
 void note_kernel(const char* name) { g_last_kernel = name; }
 
@@ -29,6 +30,8 @@ int tma_pair_set(int v);
 int stream_enable_set(int v);
 int pool_fast_set(int v);
 int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles);
+int conv_stream_up2_ok(const vinet_conv_t* d);
+int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream, bool dry_run);
 
 // the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
 static bool dense_sources(const vinet_gather_t& g) {
@@ -57,7 +60,14 @@ extern "C" int vinet_conv_gemm(const vinet_conv_t* d, int32_t engine, vinet_stre
   if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA) return conv_gemm_tma(d, (cudaStream_t)stream);
   VINET_CHECK(d->stats == nullptr, "conv_gemm: epilogue BatchNorm statistics are a feature of the TMA-fed tensor-core kernels");
   VINET_CHECK(dense_sources(d->g), "conv_gemm: only the TMA kernel reads pitched / sliding-window sources");
-  if (engine == VINET_ENGINE_TC) return conv_gemm_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC) {
+    VINET_CHECK(!((d->g.src[0].xform | (d->g.src[1].ptr ? d->g.src[1].xform : 0)) & VINET_XF_UP2),
+                "conv_gemm: the register-gather tensor-core kernel has no up-sampling input stage");
+    return conv_gemm_tc(d, (cudaStream_t)stream);
+  }
+  VINET_CHECK(!(d->g.src[1].ptr && (d->g.src[1].xform & VINET_XF_UP2)) && (!(d->g.src[0].xform & VINET_XF_UP2) ||
+              (d->g.mode == VINET_GATHER_FPROP && !(d->g.src[0].xform & 2) && d->g.Hs % 2 == 0 && d->g.Ws % 2 == 0)),
+              "conv_gemm: VINET_XF_UP2 is for source 0 of an FPROP gather with even extents and no affine transform");
   if (engine == VINET_ENGINE_SIMT) return conv_gemm_simt(d, (cudaStream_t)stream);
   set_error("conv_gemm: unknown engine %d", engine);
   return -1;
@@ -79,13 +89,46 @@ extern "C" int vinet_conv_tiling(const vinet_conv_t* d, int32_t engine, int32_t*
   return 0;
 }
 
+extern "C" int vinet_conv_up2_fused(const vinet_gather_t* g, int32_t N, int32_t engine, int32_t kernel) {
+  if (!g || g->mode != VINET_GATHER_FPROP || g->src[0].ptr == nullptr) return 0;
+  if ((g->src[0].xform & ~VINET_XF_RELU) != VINET_XF_UP2 || (g->Hs & 1) || (g->Ws & 1)) return 0;
+  if (g->src[1].ptr != nullptr && g->src[1].xform != VINET_XF_IDENT && engine == VINET_ENGINE_TC) return 0;
+  if (engine == VINET_ENGINE_SIMT) return dense_sources(*g) ? 1 : 0;     // the FFMA gather interpolates on read (gather.cuh)
+  if (engine != VINET_ENGINE_TC || kernel != VINET_KERNEL_TMA || g->dtype != VINET_BF16) return 0;
+  // tensor-core engine: both the streaming fprop kernel and the halo weight-gradient kernel need their interpolating producer
+  vinet_conv_t c;
+  memset(&c, 0, sizeof(c));
+  c.g = *g;
+  c.N = N;
+  c.kernel = kernel;
+  c.out_dtype = VINET_BF16;
+  if (!conv_stream_up2_ok(&c)) return 0;
+  vinet_wgrad_t w;
+  memset(&w, 0, sizeof(w));
+  w.g = *g;
+  w.N = N;
+  w.dy_dtype = VINET_BF16;
+  w.lddy = (N + 7) / 8 * 8;
+  w.lddw = (N + 63) / 64 * 64;
+  w.splits = 1;
+  w.kernel = kernel;
+  return conv_wgrad_halo(&w, nullptr, true) == 1 ? 1 : 0;
+}
+
 extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream) {
   VINET_CHECK(d && d->g.ntaps >= 1 && d->g.ntaps <= VINET_MAX_TAPS, "conv_wgrad: bad tap count");
   VINET_CHECK(d->splits >= 1, "conv_wgrad: splits");
   VINET_CHECK(d->lddw >= d->N, "conv_wgrad: lddw");
   if (engine == VINET_ENGINE_TC && d->kernel == VINET_KERNEL_TMA) return conv_wgrad_tma(d, (cudaStream_t)stream);
   VINET_CHECK(dense_sources(d->g), "conv_wgrad: only the TMA kernel reads pitched / sliding-window sources");
-  if (engine == VINET_ENGINE_TC) return conv_wgrad_tc(d, (cudaStream_t)stream);
+  if (engine == VINET_ENGINE_TC) {
+    VINET_CHECK(!((d->g.src[0].xform | (d->g.src[1].ptr ? d->g.src[1].xform : 0)) & VINET_XF_UP2),
+                "conv_wgrad: the register-gather tensor-core kernel has no up-sampling input stage");
+    return conv_wgrad_tc(d, (cudaStream_t)stream);
+  }
+  VINET_CHECK(!(d->g.src[1].ptr && (d->g.src[1].xform & VINET_XF_UP2)) && (!(d->g.src[0].xform & VINET_XF_UP2) ||
+              (d->g.mode == VINET_GATHER_FPROP && !(d->g.src[0].xform & 2) && d->g.Hs % 2 == 0 && d->g.Ws % 2 == 0)),
+              "conv_wgrad: VINET_XF_UP2 is for source 0 of an FPROP gather with even extents and no affine transform");
   if (engine == VINET_ENGINE_SIMT) return conv_wgrad_simt(d, (cudaStream_t)stream);
   set_error("conv_wgrad: unknown engine %d", engine);
   return -1;
@@ -110,6 +153,7 @@ extern "C" const char* vinet_last_error(void) { return g_err; }
 extern "C" const char* vinet_last_kernel(void) { return g_last_kernel; }
 extern "C" const char* vinet_version(void) { return "vinet_b200 0.3 (sm_100a; streaming halo-tile tcgen05+TMEM conv with multi-warp MMA issue, per-tap TMA conv, fp32 SIMT parity engine)"; }
 extern "C" int64_t vinet_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int64_t vinet_up2_launch_count(void) { return (int64_t)g_up2_launches.load(); }
 
 extern "C" int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;

@@ -13,6 +13,7 @@ namespace vinet {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_up2_launches;   // tensor-core launches whose producer warps interpolated a VINET_XF_UP2 source
 void note_kernel(const char* name);   // which CUDA kernel the last conv / wgrad call of this thread launched (vinet_last_kernel)
 
 #define VINET_CHECK(cond, ...)          \

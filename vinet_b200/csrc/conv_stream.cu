@@ -17,6 +17,12 @@
 //
 // Roles (448 threads): warp 0 activation producer (TMA), warp 1 TMEM allocator + weight producer (bulk copies), warps 2..5 MMA
 // issuers, warps 6..13 epilogue (two per TMEM lane quarter).  grid = (CTAs per N tile, N tiles).
+// UP variant (576 threads; source 0 has VINET_XF_UP2, i.e. the decoder's relu -> 2x bilinear up-sampling, model.py:254, sits in
+// front of this convolution): four epilogue warps (6..9) instead of eight, and warps 10..17 are a second activation producer.  For every halo stage that belongs to source 0 they
+// read the LOW-RES tensor with 128-bit loads, apply ReLU + the bilinear blend and write the bf16 result into the stage in the
+// SWIZZLE_128B layout a TMA box load of the up-sampled tensor would have produced (up2.cuh), fence the generic-proxy writes
+// towards the async proxy and arrive on the stage's full barrier.  The up-sampled tensor never exists in memory; stages of
+// source 1 (the skip tensor of the T-concat) still arrive by TMA from warp 0, in the same ring.
 // Several issuing warps because ONE warp cannot feed the tensor pipe with small-N MMAs: a 128xNx16 MMA lasts max(N/2, 32+N/4)
 // clocks (tools/umma_rate_test.cu) while its issue sequence costs a single warp ~80-100 clocks.  Issuer k owns the sub-tiles
 // k, k+ni, ... of every work item (its own TMEM accumulators), waits on the same full barriers and commits to the same empty
@@ -27,10 +33,17 @@
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
+#include "up2.cuh"
 
 namespace vinet {
 
 constexpr int ST_THREADS = 448;
+// VINET_XF_UP2 sources: the UP variant trades four of the eight epilogue warps for EIGHT interpolating warps (576 threads).  Its
+// decoder convolutions have long K loops (18 .. 45 taps x up to 832 channels), so the epilogue is nowhere near critical, while one
+// interpolating warp per scheduler could not fill a halo stage in the time the tensor core needs to consume one.
+constexpr int ST_UP_EPI_WARPS = 4;
+constexpr int ST_UP_THREADS = 256;
+constexpr int ST_UP_TOTAL = 32 * (2 + 4 + ST_UP_EPI_WARPS) + ST_UP_THREADS;   // 576
 constexpr int ST_MAX_ISSUERS = 4;
 constexpr int ST_MAX_TG = 8;
 constexpr int ST_STATS_FLOATS = 2 * 256;   // per-CTA BatchNorm statistic partials: [sum | sum of squares][column of the N tile]
@@ -135,8 +148,11 @@ __device__ __forceinline__ void st_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t
       : "memory");
 }
 
-template <typename TO, bool EPI>
-__global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid_constant__ StreamParams p) {
+template <typename TO, bool EPI, bool UP>
+__global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_kernel(const __grid_constant__ StreamParams p) {
+  constexpr int EW = UP ? ST_UP_EPI_WARPS : 8;          // epilogue warps (EW / 4 per TMEM lane quarter)
+  constexpr int ET = 32 * EW;                           // epilogue threads
+  constexpr int FIRST_UP_WARP = 2 + ST_MAX_ISSUERS + EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int AS = p.a_stages, BS = p.b_slots;
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < AS; ++s) {
-        mbar_init(full_a + 8 * s, 1);
+        mbar_init(full_a + 8 * s, UP ? 2 : 1);   // UP: the TMA thread and the interpolating group both arrive on every stage
         mbar_init(empty_a + 8 * s, p.ni);
       }
       for (int s = 0; s < BS; ++s) {
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
       }
       for (int a = 0; a < p.nacc; ++a) {
         mbar_init(full_acc + 8 * a, p.ni);
-        mbar_init(empty_acc + 8 * a, 8);
+        mbar_init(empty_acc + 8 * a, EW);
       }
       mbar_init(wbar, 1);
       fence_barrier_init();
@@ -199,7 +215,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
           const int si = (fr >= g.src[0].T && g.src[1].ptr != nullptr) ? 1 : 0;
           const int tl = fr - (si ? g.src[0].T : 0);
           for (int cb = 0; cb < p.ncb; ++cb) {
+            // Two producers share the ring (UP): BOTH wait for every stage to drain and BOTH arrive on its full barrier (count 2),
+            // also for the stages they do not fill.  A producer that merely skipped a stage could run (or fall) more than one ring
+            // revolution away from the consumers, where the parity of an mbarrier wait aliases.
             mbar_wait(empty_a + 8 * s, ph ^ 1u);
+            if (UP && si == 0) {   // filled by the interpolating warps
+              mbar_arrive(full_a + 8 * s);
+              if (++s == AS) { s = 0; ph ^= 1u; }
+              continue;
+            }
             const uint32_t dst = sA0 + (uint32_t)s * p.a_stage_bytes;
             if (p.halo == 2) {   // spatially strided conv: the rows a tile needs form par_sh lattices, one box per lattice
               mbar_arrive_expect_tx(full_a + 8 * s, (uint32_t)p.par_sh * p.a_tx_sub);
@@ -353,10 +377,45 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
       }
     }
     }
+  } else if (UP && warp >= FIRST_UP_WARP) {
+    // ---------------------------------------------------------------- interpolating activation producer (128 threads, halo mode)
+    const int itid = threadIdx.x - 32 * FIRST_UP_WARP;
+    const vinet_src_t& s0 = g.src[0];
+    const int lh = g.Hs >> 1, lw = g.Ws >> 1;
+    const bool relu = (s0.xform & VINET_XF_RELU) != 0;
+    const int64_t frame_elems = (int64_t)lh * lw * s0.ld;
+    const int64_t clip_elems = s0.ldb ? s0.ldb : (int64_t)s0.T * frame_elems;
+    const __nv_bfloat16* src0 = reinterpret_cast<const __nv_bfloat16*>(s0.ptr);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
+      const StItem c = st_decode(p, item);
+      StWalk wk;
+      for (wk.init(p, c); wk.f <= wk.f_end; wk.next(p)) {
+        if (!wk.used(p)) continue;
+        const int fr = wk.f * p.tstep + p.toff;
+        const int si = (fr >= s0.T && g.src[1].ptr != nullptr) ? 1 : 0;
+        for (int cb = 0; cb < p.ncb; ++cb) {
+          mbar_wait(empty_a + 8 * s, ph ^ 1u);   // every stage, see the TMA producer
+          if (si == 0) {
+            const int rem = g.Cs - cb * 64;
+            const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+            up2_fill_box(sA0 + (uint32_t)s * p.a_stage_bytes, src0 + (int64_t)c.b * clip_elems + (int64_t)fr * frame_elems + cb * 64,
+                         fr >= 0 && fr < s0.T, lh, lw, s0.ld, c.tx * 8 * p.nsub + p.ew0, c.ty * p.th + p.eh0, p.PW, p.PH, 2 * nk,
+                         min(8, rem >> 3), relu, itid, ST_UP_THREADS);
+            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          }
+          // the group moves through the ring in lockstep (every stage), its leader arrives for it
+          asm volatile("bar.sync 2, %0;" ::"n"(ST_UP_THREADS) : "memory");
+          if (itid == 0) mbar_arrive(full_a + 8 * s);
+          if (++s == AS) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
   } else {
     // ---------------------------------------------------------------- epilogue: TMEM -> registers -> global
     const int q = warp & 3;
-    const int half = (warp - 2 - ST_MAX_ISSUERS) >> 2;
+    const int half = (warp - 2 - ST_MAX_ISSUERS) >> 2;   // 0 .. EW/4 - 1: column groups are dealt round-robin to the warps of a quarter
     const int row = q * 32 + lane;
     const int rt = row / p.pos, rrem = row - rt * p.pos;   // temporal-halo tiles stack tt frames of pos positions
     const int rh = rrem / p.tw, rw = rrem - rh * p.tw;
@@ -366,8 +425,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
     const bool stats = p.d.stats != nullptr;
     const int etid = threadIdx.x - 32 * (2 + ST_MAX_ISSUERS);   // 0..255 among the epilogue warps
     if (stats) {
-      for (int i = etid; i < ST_STATS_FLOATS; i += 256) s_stats[i] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = etid; i < ST_STATS_FLOATS; i += ET) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     }
     uint32_t slot = 0, ph = 0;
     for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
@@ -402,7 +461,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
             bool accum = false;
             TO* orow = sub_row(sub, accum);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (slot * (uint32_t)p.nsub + (uint32_t)sub) * p.acc_stride;
-            for (int gi = half; gi < BN / 16; gi += 2) {
+            for (int gi = half; gi < BN / 16; gi += EW / 4) {
               uint32_t r[16];
               tmem_ld16(tacc + (uint32_t)(gi * 16), r);
               if (orow == nullptr) continue;
@@ -414,7 +473,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
         } else {
           // BatchNorm statistics of the raw output from the fp32 accumulators: column-group outermost, so that the lane-local
           // partial sums run over every sub-tile of the item before ONE cross-lane reduction per 16 columns
-          for (int gi = half; gi < BN / 16; gi += 2) {
+          for (int gi = half; gi < BN / 16; gi += EW / 4) {
             const int c0 = gi * 16;
             float sv[16], sq[16];
 #pragma unroll
@@ -448,8 +507,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv_stream_kernel(const __grid
       }
     }
     if (stats) {   // per-CTA partials -> fp64 atomics on the layer's statistics
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = etid; i < 2 * BN; i += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      for (int i = etid; i < 2 * BN; i += ET) {
         const int which = i / BN, col = i - which * BN;
         if (col < nlim) atomicAdd(p.d.stats + (size_t)which * p.d.N + nt * BN + col, (double)s_stats[which * 256 + col]);
       }
@@ -688,6 +747,10 @@ Plan plan_stream(const vinet_conv_t& d, const TapMap& tm, int fixed_block_n, int
   return best;
 }
 
+bool stream_up2(const vinet_gather_t& g) {
+  return g.src[0].ptr != nullptr && (g.src[0].xform & ~VINET_XF_RELU) == VINET_XF_UP2;
+}
+
 bool stream_eligible(const vinet_conv_t& d) {
   const vinet_gather_t& g = d.g;
   if (!g_stream_enable) return false;
@@ -695,11 +758,21 @@ bool stream_eligible(const vinet_conv_t& d) {
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[i];
     if (s.ptr == nullptr) continue;
+    if (i == 0 && stream_up2(g)) {   // low-res source read through the fused 2x up-sampling: dense low-res rows only
+      if (g.mode != VINET_GATHER_FPROP || (g.Hs & 1) || (g.Ws & 1) || s.ldh != 0 || s.ld < g.Cs) return false;
+      continue;
+    }
     if (s.xform != VINET_XF_IDENT) return false;
     if (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) return false;   // sliding-window (WIN8) sources stay with conv_tma.cu
     if (s.ld < g.Cs) return false;
   }
   return true;
+}
+
+// the interpolating producer works on 2x2 quads: the halo box must start at odd hi-res coordinates and have even extents
+// (true for the pad-1 3x3 halos of this model's decoder; anything else is materialised by the caller)
+bool up2_plan_ok(const Plan& pl, const TapMap& tm) {
+  return pl.ok && pl.halo == 1 && (tm.ew0 & 1) && (tm.eh0 & 1) && (pl.PW % 2 == 0) && (pl.PH % 2 == 0) && (pl.th % 2 == 0);
 }
 
 }  // namespace
@@ -717,12 +790,19 @@ int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles) {
             d->N, d->g.ntaps, tm.S, tm.L, (int)pl.ok, pl.block_n, pl.n_tiles, pl.nsub, pl.nacc, pl.run, pl.halo, pl.tt,
             pl.halo ? pl.PW : pl.tw, pl.halo ? pl.PH : pl.th, pl.a_stages, pl.b_slots, pl.wres, pl.cost / 1e3);
   if (!pl.ok) return 0;
+  if (stream_up2(d->g) && !up2_plan_ok(pl, tm)) return 0;
   *block_n = pl.block_n;
   *n_tiles = pl.n_tiles;
   return 1;
 }
 
-static int stream_launch(StreamParams& p, const vinet_conv_t* d, int sms, cudaStream_t stream) {
+// 1 when conv_gemm_stream serves this FPROP convolution with a VINET_XF_UP2 source 0 (host only)
+int conv_stream_up2_ok(const vinet_conv_t* d) {
+  int bn = 0, nt = 0;
+  return stream_up2(d->g) && conv_stream_tiling(d, &bn, &nt);
+}
+
+static int stream_launch(StreamParams& p, const vinet_conv_t* d, int sms, cudaStream_t stream, bool up = false) {
   const int nb_slots = p.wres ? d->k_blocks : p.b_slots;
   size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)nb_slots * p.b_bytes +
                 8 * (size_t)(2 * p.a_stages + 2 * p.b_slots + 2 * p.nacc + 1) + 64 + 8 * VINET_MAX_TAPS + 4 * ST_STATS_FLOATS;
@@ -733,15 +813,17 @@ static int stream_launch(StreamParams& p, const vinet_conv_t* d, int sms, cudaSt
   smem = std::max<size_t>(smem, 120 * 1024);   // one CTA per SM: two co-resident CTAs would fight over the 512 TMEM columns
   const int ctas = (int)std::min<int64_t>(p.items_per_nt, std::max(1, sms / d->n_tiles));
   dim3 grid((unsigned)ctas, (unsigned)d->n_tiles);
-#define LAUNCH_STREAM(TO)                                                                             \
-  do {                                                                                                \
-    auto kern = conv_has_epilogue(*d) ? conv_stream_kernel<TO, true> : conv_stream_kernel<TO, false>; \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-    kern<<<grid, ST_THREADS, smem, stream>>>(p);                                                      \
+#define LAUNCH_STREAM(TO)                                                                                              \
+  do {                                                                                                                 \
+    auto kern = up ? (conv_has_epilogue(*d) ? conv_stream_kernel<TO, true, true> : conv_stream_kernel<TO, false, true>)   \
+                   : (conv_has_epilogue(*d) ? conv_stream_kernel<TO, true, false> : conv_stream_kernel<TO, false, false>); \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                \
+    kern<<<grid, up ? ST_UP_TOTAL : ST_THREADS, smem, stream>>>(p);                                                    \
   } while (0)
   VINET_DISPATCH_DTYPE(d->out_dtype, TO, LAUNCH_STREAM(TO));
 #undef LAUNCH_STREAM
   note_kernel("conv_stream_kernel");
+  if (up) g_up2_launches.fetch_add(1, std::memory_order_relaxed);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -830,6 +912,8 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   const int sms = tma_sm_count();
   const Plan pl = plan_stream(*d, tm, d->block_n, d->n_tiles, sms);
   if (!pl.ok) return 0;
+  const bool up = stream_up2(g);
+  if (up && !up2_plan_ok(pl, tm)) return 0;
   StreamParams p;
   p.d = *d;
   p.ncb = (g.Cs + 63) / 64;
@@ -881,10 +965,12 @@ int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
     const int bw = pl.halo ? pl.PW : pl.tw, bh = pl.halo ? pl.PH : pl.th;
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT, s.ldb)) return -1;
+    // an up-sampled source is never fetched by TMA: its map describes the low-res tensor (valid, unused)
+    const int dv = (up && &s == &g.src[0]) ? 2 : 1;
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws / dv, g.Hs / dv, s.T, g.B, s.ld, s.ldh, bw, bh, 1, 1, pl.PT, s.ldb)) return -1;
   }
   p.par_sh = 1; p.par_h0[0] = p.par_h0[1] = 0; p.par_off[0] = p.par_off[1] = 0;
-  return stream_launch(p, d, sms, stream);
+  return stream_launch(p, d, sms, stream, up);
 }
 
 }  // namespace vinet

@@ -646,7 +646,7 @@ void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int
 }
 int tma_sm_count() { return sm_count(); }
 int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream);
-int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream);
+int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream, bool dry_run = false);
 
 // development switch (vinet_debug_set key 1): 0 disables the paired 256-row work items
 int g_tma_pair = 1;
@@ -657,7 +657,9 @@ static int check_tma_gather(const vinet_gather_t& g, const char* what) {
   VINET_CHECK((g.sh == 1 && g.sw == 1) || g.mode == VINET_GATHER_FPROP,
               "%s: the TMA kernel handles spatial strides (%d,%d) only for FPROP gathers", what, g.sh, g.sw);
   VINET_CHECK(g.Cs % 8 == 0, "%s: Cs %d must be a multiple of 8", what, g.Cs);
-  VINET_CHECK(g.src[0].xform == VINET_XF_IDENT && (g.src[1].ptr == nullptr || g.src[1].xform == VINET_XF_IDENT),
+  // source 0 may be a low-res tensor read through the fused relu + 2x up-sampling (FPROP gathers; interpolating producer warps)
+  const bool up2 = (g.src[0].xform & ~VINET_XF_RELU) == VINET_XF_UP2 && g.mode == VINET_GATHER_FPROP;
+  VINET_CHECK((g.src[0].xform == VINET_XF_IDENT || up2) && (g.src[1].ptr == nullptr || g.src[1].xform == VINET_XF_IDENT),
               "%s: the TMA kernel cannot apply pending source transforms", what);
   VINET_CHECK(g.src[0].T + (g.src[1].ptr ? g.src[1].T : 0) == g.Ts, "%s: Ts %d != sum of source frames", what, g.Ts);
   return 0;
@@ -672,6 +674,8 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
     const int r = conv_gemm_stream(d, stream);
     if (r != 0) return r < 0 ? r : 0;
   }
+  VINET_CHECK(g.src[0].xform == VINET_XF_IDENT, "conv_gemm_tma: no fused up-sampling input stage for this geometry "
+              "(vinet_conv_up2_fused tells; materialise with vinet_upsample_fwd)");
   VINET_CHECK(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "conv_gemm_tma: bad block_n %d", d->block_n);
   VINET_CHECK(d->N % 8 == 0, "conv_gemm_tma: N %d must be a multiple of 8", d->N);
   ConvTmaParams p;
@@ -736,6 +740,10 @@ int conv_wgrad_tma(const vinet_wgrad_t* d, cudaStream_t stream) {
   VINET_CHECK(g.mode == VINET_GATHER_FPROP, "conv_wgrad_tma: needs an FPROP gather");
   {  // spatial convolutions: all kh*kw taps of a channel block share one halo tile per chunk (conv_wgrad_halo.cu)
     const int r = conv_wgrad_halo(d, stream);
+    if (r == 0 && g.src[0].xform != VINET_XF_IDENT) {
+      set_error("conv_wgrad_tma: no fused up-sampling input stage for this geometry (vinet_conv_up2_fused tells)");
+      return -1;
+    }
     if (r != 0) return r < 0 ? r : 0;
   }
   VINET_CHECK(d->dy_dtype == VINET_BF16 && d->N % 8 == 0 && d->lddy % 8 == 0, "conv_wgrad_tma: dy must be bf16, N %d lddy %lld",

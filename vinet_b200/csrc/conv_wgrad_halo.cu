@@ -14,15 +14,21 @@
 //     chunks across CTAs, fp32 red.add into the packed TAP64 gradient at the end);
 //   * up to 4 warps issue the MMAs (one accumulator each; a single warp cannot feed the tensor pipe with N <= 96 MMAs).
 // Roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator, warps 2..5 MMA issuers, warps 6..9 epilogue.
+// UP variant (576 threads; source 0 has VINET_XF_UP2: the activation operand is the decoder's relu -> 2x bilinear up-sampling of a
+// low-res tensor, model.py:254): warps 10..17 interpolate the halo box of every chunk that reads source 0 straight into the
+// stage (up2.cuh, same layout and values as a TMA load of the materialised tensor); dY and source-1 boxes still arrive by TMA.
+// The stage's full barrier then counts two arrivals: the TMA thread's expect_tx and the interpolating group's.
 #include <cuda.h>
 
 #include <algorithm>
 
 #include "tc_ptx.cuh"
+#include "up2.cuh"
 
 namespace vinet {
 
 constexpr int WH_THREADS = 320;
+constexpr int WH_UP_THREADS = 256;
 constexpr int WH_MAX_ISSUERS = 4;
 constexpr int WH_MAX_SP = 16;       // spatial taps per group (<= 8 accumulators)
 constexpr uint32_t WH_UNIT = 16384;  // one 8 x 16 x 64-channel box
@@ -39,6 +45,7 @@ struct WgHaloParams {
   int32_t ncb, nsp, naccs, nblk, block_n, splits, stages, ni, tiles_w, tiles_h, nT, temporal;
   int32_t cw, ch, aw0, ah0, at_step, at0, dyt_step;   // chunk (tw, th, tr) -> TMA coordinates of the activation / dY boxes
   int32_t nbox, ah_mul, box_h0[2], box_off[2];        // row-strided convs: one activation box per source-row lattice
+  int32_t abw, abh;                                   // extent of the activation box (positions)
   int32_t uoff16[WH_MAX_SP];                          // window of unit j inside the activation box, in 16-byte units
   uint32_t a_sbo, kstep_a16;                          // stride between 8-position atoms; 16 positions in 16-byte units
   uint32_t acc_cols, tmem_cols, idesc, a_bytes, a_tx, dy_unit, stage_bytes;
@@ -68,7 +75,8 @@ __device__ __forceinline__ void wh_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t
       : "memory");
 }
 
-__global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+template <bool UP>
+__global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
   const vinet_gather_t& g = p.d.g;
   const int64_t nchunks = (int64_t)g.B * p.nT * p.tiles_h * p.tiles_w;
   const int64_t per = cdiv(nchunks, p.splits);
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
-        mbar_init(full0 + 8 * s, 1);
+        mbar_init(full0 + 8 * s, UP ? 2 : 1);
         mbar_init(empty0 + 8 * s, p.ni);
       }
       mbar_init(accum_bar, p.ni);
@@ -126,14 +134,14 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
       const int at0 = p.at0 + (p.temporal ? 0 : g.tap[dt * p.nsp][0]);
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = p.a_tx + (uint32_t)nblk_eff * p.dy_unit;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        mbar_arrive_expect_tx(full0 + 8 * s, tx);
         const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
         const int ts = tr * p.at_step + at0;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
         const int si = (cat && ts >= T0) ? 1 : 0;
-        for (int k = 0; k < p.nbox; ++k)
+        const bool interp = UP && si == 0;     // the activation box of this chunk is built by the interpolating warps
+        mbar_arrive_expect_tx(full0 + 8 * s, (interp ? 0u : p.a_tx) + (uint32_t)nblk_eff * p.dy_unit);
+        for (int k = 0; k < p.nbox && !interp; ++k)
           wh_tma_load_5d(stage + (uint32_t)p.box_off[k], &p.tmA[si], full0 + 8 * s, cb * 64, tw * p.cw + p.aw0,
                          th * p.ch * p.ah_mul + p.ah0 + p.box_h0[k], ts - (si ? T0 : 0), b);
         for (int nb = 0; nb < nblk_eff; ++nb)
@@ -185,7 +193,48 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
         if (++s == stages) { s = 0; ph ^= 1u; st16 = s0_16; }
       }
     }
-  } else if (warp >= 2 + WH_MAX_ISSUERS) {
+  } else if (UP && warp >= WH_THREADS / 32) {
+    // ---------------------------------------------------------------- interpolating producer (128 threads): activation boxes of
+    // source 0 = relu + 2x bilinear of the low-res tensor, written in the TMA box layout
+    const int itid = threadIdx.x - WH_THREADS;
+    const vinet_src_t& src = g.src[0];
+    const int lh = g.Hs >> 1, lw = g.Ws >> 1;
+    const bool relu = (src.xform & VINET_XF_RELU) != 0;
+    const int64_t frame_elems = (int64_t)lh * lw * src.ld;
+    const int64_t clip_elems = src.ldb ? src.ldb : (int64_t)src.T * frame_elems;
+    const __nv_bfloat16* src0 = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
+    int64_t m = c_begin;
+    int tw = (int)(m % p.tiles_w); m /= p.tiles_w;
+    int th = (int)(m % p.tiles_h); m /= p.tiles_h;
+    int tr = (int)(m % p.nT);
+    int b = (int)(m / p.nT);
+    const bool cat = g.src[1].ptr != nullptr;
+    const int T0 = src.T;
+    const int at0 = p.at0 + (p.temporal ? 0 : g.tap[dt * p.nsp][0]);
+    const int rem = g.Cs - cb * 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      const int ts = tr * p.at_step + at0;
+      if (!(cat && ts >= T0)) {
+        up2_fill_box(s0 + (uint32_t)s * p.stage_bytes, src0 + (int64_t)b * clip_elems + (int64_t)ts * frame_elems + cb * 64,
+                     ts >= 0 && ts < T0, lh, lw, src.ld, tw * p.cw + p.aw0, th * p.ch + p.ah0, p.abw, p.abh, 8, min(8, rem >> 3), relu,
+                     itid, WH_UP_THREADS);
+        fence_proxy_async();
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(WH_UP_THREADS) : "memory");
+      if (itid == 0) mbar_arrive(full0 + 8 * s);
+      if (++s == stages) { s = 0; ph ^= 1u; }
+      if (++tw == p.tiles_w) {
+        tw = 0;
+        if (++th == p.tiles_h) {
+          th = 0;
+          if (++tr == p.nT) { tr = 0; ++b; }
+        }
+      }
+    }
+  } else if (warp >= 2 + WH_MAX_ISSUERS && warp < WH_THREADS / 32) {
     // ---------------------------------------------------------------- epilogue: TMEM -> smem transpose -> coalesced red.add
     mbar_wait(accum_bar, 0);  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
     tc_fence_after();
@@ -228,7 +277,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_wgrad_halo_kernel(const __
 void pick_tma_box(int H, int W, int max_rows, int mult, bool full_tile_cost, int* bw_out, int* bh_out);
 
 // returns 1 when the launch was handled here, 0 when the caller should use its own kernel, <0 on error
-int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
+int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream, bool dry_run) {
   const vinet_gather_t& g = d->g;
   if (!g_stream_enable) return 0;
   if (g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16 || d->dy_dtype != VINET_BF16) return 0;
@@ -237,9 +286,15 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   const bool rowstride = g.sh == 2 && g.src[1].ptr == nullptr && g.src[0].ld < g.Cs && g.Cs == 64 && g.st == 1 && g.pt == 0 &&
                          g.row_tstep == 1 && g.row_toff == 0 && g.src[0].xform == VINET_XF_IDENT;
   if (g.sh != 1 && !rowstride) return 0;
+  // source 0 read through the fused relu + 2x up-sampling (interpolating warps; spatial mode with quad-aligned halo boxes only)
+  const bool up = !rowstride && (g.src[0].xform & ~VINET_XF_RELU) == VINET_XF_UP2;
   for (int i = 0; i < 2 && !rowstride; ++i) {
     const vinet_src_t& s = g.src[i];
     if (s.ptr == nullptr) continue;
+    if (i == 0 && up) {
+      if ((g.Hs & 1) || (g.Ws & 1) || s.ldh != 0 || s.ld < g.Cs) return 0;
+      continue;
+    }
     if (s.xform != VINET_XF_IDENT || (s.ldh != 0 && s.ldh != (int64_t)g.Ws * s.ld) || s.ld < g.Cs) return 0;
   }
   // taps must be the natural (dt, dh, dw) enumeration of a kt x kh x kw kernel
@@ -258,6 +313,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   const bool temporal = !rowstride && nspat == 1 && kt > 1 && g.src[1].ptr == nullptr && g.row_tstep == 1 && g.row_toff == 0;
   if (rowstride && (kt != 1 || kw != 1 || kh < 2)) return 0;
   if (!temporal && (nspat < 2 || g.Hr < 10)) return 0;
+  if (up && (temporal || !(g.pw & 1) || !(g.ph & 1) || !(kw & 1) || !(kh & 1))) return 0;
   WgHaloParams p;
   p.d = *d;
   p.temporal = temporal ? 1 : 0;
@@ -338,6 +394,7 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
     p.a_sbo = g.st > 1 ? (uint32_t)(g.st * pos * 128) : 1024u;
     p.kstep_a16 = (2u * p.a_sbo) >> 4;
   }
+  p.abw = abw; p.abh = abh;
   p.a_tx = (uint32_t)(abw * abh * abt * 128) * (uint32_t)p.nbox;
   p.a_bytes = (uint32_t)round_up(p.a_tx, 1024);
   p.stage_bytes = p.a_bytes + (uint32_t)p.nblk * p.dy_unit;
@@ -364,15 +421,23 @@ int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream) {
   if (ring < (size_t)128 * (p.block_n + 1) * sizeof(float)) return 0;   // the epilogue transposes through the ring
   const size_t smem = std::max<size_t>(1024 + ring + 8 * (2 * stages + 1) + 64, 120 * 1024);
   if (smem > 227 * 1024) return 0;
+  if (dry_run) return 1;      // host-only eligibility query (vinet_conv_up2_fused): no tensor maps, no launch
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
-    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws, g.Hs, s.T, g.B, s.ld, s.ldh, abw, abh, 1, aesh, abt, s.ldb)) return -1;
+    const int dv = (up && &s == &g.src[0]) ? 2 : 1;   // an up-sampled source is never fetched by TMA: valid map of the low-res tensor, unused
+    if (make_tma_map(&p.tmA[i], s.ptr, g.Cs, g.Ws / dv, g.Hs / dv, s.T, g.B, s.ld, s.ldh, abw, abh, 1, aesh, abt, s.ldb)) return -1;
   }
   if (make_tma_map(&p.tmDy, d->dy, d->N, g.Wr, g.Hr, g.Tr, g.B, d->lddy, 0, dbw, dbh, 1, 1, dbt)) return -1;
   dim3 grid((unsigned)groups, (unsigned)n_tiles, (unsigned)splits);
-  cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  conv_wgrad_halo_kernel<<<grid, WH_THREADS, smem, stream>>>(p);
+  if (up) {
+    cudaFuncSetAttribute(conv_wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conv_wgrad_halo_kernel<true><<<grid, WH_THREADS + WH_UP_THREADS, smem, stream>>>(p);
+  } else {
+    cudaFuncSetAttribute(conv_wgrad_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conv_wgrad_halo_kernel<false><<<grid, WH_THREADS, smem, stream>>>(p);
+  }
   note_kernel("conv_wgrad_halo_kernel");
+  if (up) g_up2_launches.fetch_add(1, std::memory_order_relaxed);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -2,6 +2,7 @@
 // Semantics are defined in include/vinet_b200.h (vinet_gather_t).
 #pragma once
 #include "common.cuh"
+#include "up2.cuh"
 
 namespace vinet {
 
@@ -27,12 +28,12 @@ __device__ __forceinline__ RowCoord decode_row(const vinet_gather_t& g, int64_t 
   return rc;
 }
 
-// Locate the source element (b, tap-shifted position, channel 0). Returns false for zero fill.
-__device__ __forceinline__ bool gather_locate(const vinet_gather_t& g, const RowCoord& rc, int tap, int& si,
-                                              int64_t& off) {
+// Locate the source position of (row, tap): source index si, its local frame ts and the position (hs, ws) inside the
+// frame. Returns false for zero fill.
+__device__ __forceinline__ bool gather_coords(const vinet_gather_t& g, const RowCoord& rc, int tap, int& si, int& ts, int& hs,
+                                              int& ws) {
   if (rc.b < 0 || tap >= g.ntaps) return false;
   const int dt = g.tap[tap][0], dh = g.tap[tap][1], dw = g.tap[tap][2];
-  int ts, hs, ws;
   if (g.mode == VINET_GATHER_FPROP) {
     ts = rc.t * g.st - g.pt + dt;
     hs = rc.h * g.sh - g.ph + dh;
@@ -47,6 +48,14 @@ __device__ __forceinline__ bool gather_locate(const vinet_gather_t& g, const Row
     return false;
   si = (ts >= g.src[0].T) ? 1 : 0;
   if (si) ts -= g.src[0].T;
+  return true;
+}
+
+// Locate the source element (b, tap-shifted position, channel 0). Returns false for zero fill.
+__device__ __forceinline__ bool gather_locate(const vinet_gather_t& g, const RowCoord& rc, int tap, int& si,
+                                              int64_t& off) {
+  int ts, hs, ws;
+  if (!gather_coords(g, rc, tap, si, ts, hs, ws)) return false;
   off = ((((int64_t)rc.b * g.src[si].T + ts) * g.Hs + hs) * g.Ws + ws) * g.src[si].ld;
   return true;
 }
@@ -56,14 +65,26 @@ template <typename T, int V>
 __device__ __forceinline__ void gather_vec(const vinet_gather_t& g, const RowCoord& rc, int k, float (&v)[V]) {
   const int tap = k / g.Cs;
   const int c = k - tap * g.Cs;
-  int si;
-  int64_t off;
-  if (!gather_locate(g, rc, tap, si, off)) {
+  int si, ts, hs, ws;
+  if (!gather_coords(g, rc, tap, si, ts, hs, ws)) {
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = 0.f;
     return;
   }
   const vinet_src_t& s = g.src[si];
+  if (s.xform & VINET_XF_UP2) {
+    // the source is stored at half resolution and read through the 2x bilinear up-sampling (after its ReLU)
+    const int h = g.Hs >> 1, w = g.Ws >> 1;
+    const T* frame = reinterpret_cast<const T*>(s.ptr) + ((int64_t)rc.b * s.T + ts) * h * w * s.ld + c;
+    if constexpr (V == 8) up2_load8(frame, h, w, s.ld, hs, ws, (s.xform & 1) != 0, v);
+    else up2_load4(frame, h, w, s.ld, hs, ws, (s.xform & 1) != 0, v);
+    if constexpr (sizeof(T) == 2) {   // bf16 storage: round where the materialised up-sampled tensor would have been rounded
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    }
+    return;
+  }
+  const int64_t off = ((((int64_t)rc.b * s.T + ts) * g.Hs + hs) * g.Ws + ws) * s.ld;
   const T* p = reinterpret_cast<const T*>(s.ptr) + off + c;
   if constexpr (V == 8) load8(p, v); else load4(p, v);
   apply_xform<V>(v, s.xform, s.scale, s.shift, c);

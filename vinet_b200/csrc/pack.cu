@@ -2,6 +2,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "up2.cuh"
 
 namespace vinet {
 
@@ -179,8 +180,17 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const __grid_constant__
     const int64_t r = i / G;
     const int c = (int)(i - r * G) * 8;
     float v[8];
-    load8(x + r * d.ld + c, v);
-    apply_xform<8>(v, d.xform, d.scale, d.shift, c);
+    if (d.xform & VINET_XF_UP2) {   // r enumerates hi-res pixels (n, Y, X) of low-res frames [up_h, up_w, ld]
+      const int W2 = 2 * d.up_w, H2 = 2 * d.up_h;
+      const int X = (int)(r % W2);
+      const int64_t q = r / W2;
+      const int Y = (int)(q % H2);
+      const int64_t n = q / H2;
+      up2_load8(x + n * d.up_h * d.up_w * d.ld + c, d.up_h, d.up_w, d.ld, Y, X, (d.xform & 1) != 0, v);
+    } else {
+      load8(x + r * d.ld + c, v);
+      apply_xform<8>(v, d.xform, d.scale, d.shift, c);
+    }
     for (int p = 0; p < d.nparts; ++p) {
       float h[8];
 #pragma unroll
@@ -254,6 +264,9 @@ extern "C" int vinet_split_bf16(const vinet_split_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->nparts >= 1 && d->nparts <= 3 && d->ldo >= d->C && d->ldo % 8 == 0, "split_bf16: nparts %d ldo %lld", d->nparts,
               (long long)d->ldo);
   for (int p = 0; p < d->nparts; ++p) VINET_CHECK(d->part[p] != nullptr, "split_bf16: part %d is null", p);
+  if (d->xform & VINET_XF_UP2)
+    VINET_CHECK(!(d->xform & 2) && d->up_h >= 1 && d->up_w >= 1 && d->rows % (4ll * d->up_h * d->up_w) == 0,
+                "split_bf16: up-sampled source needs up_h/up_w with rows a multiple of 4*up_h*up_w, and no affine transform");
   const int64_t total = d->rows * (d->C / 8);
   VINET_DISPATCH_DTYPE(d->dtype, T, (split_bf16_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d)));
   VINET_LAUNCH_OK("split_bf16");

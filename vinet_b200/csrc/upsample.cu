@@ -1,16 +1,10 @@
 // relu? + nn.Upsample(scale_factor=(1,2,2), mode='trilinear', align_corners=False) (model.py:254):
 // per-frame 2x bilinear with taps {.25,.75} and index clamp at the borders.
-#include "common.cuh"
+// The forward arithmetic lives in up2.cuh, shared with the consumers that read a low-res tensor THROUGH the up-sampling
+// (VINET_XF_UP2); this standalone kernel is the fallback for consumers without a fused input stage.
+#include "up2.cuh"
 
 namespace vinet {
-
-// source taps of output coordinate Y on an axis of length n: indices i0,i1 and the weight of i1
-__device__ __forceinline__ void up_taps(int Y, int n, int& i0, int& i1, float& l1) {
-  float src = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f);
-  i0 = (int)src;
-  i1 = min(i0 + 1, n - 1);
-  l1 = src - (float)i0;
-}
 
 template <typename T, typename TO>
 __global__ void upsample_fwd_kernel(const __grid_constant__ vinet_upsample_t d) {
@@ -23,23 +17,8 @@ __global__ void upsample_fwd_kernel(const __grid_constant__ vinet_upsample_t d) 
     const int c = (int)(r % G) * 8; r /= G;
     const int X = (int)(r % W2); r /= W2;
     const int Y = (int)(r % H2); r /= H2;  // r = b*T + t
-    int y0, y1, x0, x1;
-    float ly, lx;
-    up_taps(Y, d.h, y0, y1, ly);
-    up_taps(X, d.w, x0, x1, lx);
-    const int64_t base = r * d.h;
-    float a[8], b[8], e0[8], e1[8], o[8];
-    load8(z + ((base + y0) * d.w + x0) * d.ldz + c, a);
-    load8(z + ((base + y0) * d.w + x1) * d.ldz + c, b);
-    load8(z + ((base + y1) * d.w + x0) * d.ldz + c, e0);
-    load8(z + ((base + y1) * d.w + x1) * d.ldz + c, e1);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (d.relu) { a[e] = fmaxf(a[e], 0.f); b[e] = fmaxf(b[e], 0.f); e0[e] = fmaxf(e0[e], 0.f); e1[e] = fmaxf(e1[e], 0.f); }
-      const float top = (1.f - lx) * a[e] + lx * b[e];
-      const float bot = (1.f - lx) * e0[e] + lx * e1[e];
-      o[e] = (1.f - ly) * top + ly * bot;
-    }
+    float o[8];
+    up2_load8(z + r * d.h * d.w * d.ldz + c, d.h, d.w, d.ldz, Y, X, d.relu != 0, o);
     store8(u + ((r * H2 + Y) * W2 + X) * d.ldu + c, o);
   }
 }
@@ -93,6 +72,25 @@ __global__ void upsample_bwd_kernel(const __grid_constant__ vinet_upsample_t d) 
   }
 }
 
+// dz = g where z > 0 else 0
+template <typename TG, typename TZ, typename TD>
+__global__ void relu_bwd_kernel(const TG* __restrict__ g, int64_t ldg, const TZ* __restrict__ z, int64_t ldz, int64_t rows, int C,
+                                TD* __restrict__ dz, int64_t lddz) {
+  const int G = C / 8;
+  const int64_t total = rows * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / G;
+    const int c = (int)(i - r * G) * 8;
+    float gv[8], zv[8];
+    load8(g + r * ldg + c, gv);
+    load8(z + r * ldz + c, zv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(zv[e] > 0.f)) gv[e] = 0.f;
+    store8(dz + r * lddz + c, gv);
+  }
+}
+
 }  // namespace vinet
 using namespace vinet;
 
@@ -117,5 +115,16 @@ extern "C" int vinet_upsample_bwd(const vinet_upsample_t* d, vinet_stream_t stre
   VINET_DISPATCH_DTYPE(d->dtype, T, VINET_DISPATCH_DTYPE(d->dz_dtype, TD, VINET_DISPATCH_DTYPE(d->gu_dtype, TG,
       (upsample_bwd_kernel<T, TD, TG><<<up_grid(total), 256, 0, (cudaStream_t)stream>>>(*d)))));
   VINET_LAUNCH_OK("upsample_bwd");
+  return 0;
+}
+
+extern "C" int vinet_relu_bwd(const void* g, int64_t ldg, int32_t g_dtype, const void* z, int64_t ldz, int32_t z_dtype, int64_t rows,
+                              int32_t C, void* dz, int64_t lddz, int32_t dz_dtype, vinet_stream_t stream) {
+  VINET_CHECK(C % 8 == 0 && rows >= 1 && ldg % 8 == 0 && ldz % 8 == 0 && lddz % 8 == 0, "relu_bwd: C %d rows %lld", C, (long long)rows);
+  const int64_t total = rows * (C / 8);
+  VINET_DISPATCH_DTYPE(g_dtype, TG, VINET_DISPATCH_DTYPE(z_dtype, TZ, VINET_DISPATCH_DTYPE(dz_dtype, TD,
+      (relu_bwd_kernel<TG, TZ, TD><<<up_grid(total), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const TG*>(g), ldg, reinterpret_cast<const TZ*>(z), ldz, rows, C, reinterpret_cast<TD*>(dz), lddz)))));
+  VINET_LAUNCH_OK("relu_bwd");
   return 0;
 }

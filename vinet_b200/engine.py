@@ -65,6 +65,8 @@ class Act:
         self.ld = buf.shape[-1]
         self.xform, self.scale, self.shift = xform, scale, shift
         self.ldb = 0          # elements between clips; 0 = dense.  One frame: overlapping sliding windows (inference driver)
+        self.up2 = False      # VIRTUAL 2x up-sampled activation: buf holds [B,T,H/2,W/2,ld], xform has XF_UP2, H and W are the
+        self.mat = None       # hi-res extents consumers see; mat = its materialised copy, made only for consumers that cannot fuse
         self.grad = None      # [B,T,H,W,ldg] in the engine's storage type (bf16 / fp32), or fp32 when forced
         self.gchoff = 0
         self.gdt = L.F32
@@ -89,6 +91,7 @@ class Act:
                 None if self.scale is None else self.scale[c0:c0 + c],
                 None if self.shift is None else self.shift[c0:c0 + c])
         a.grad, a.gchoff, a.needs_grad, a.gdt = self.grad, self.gchoff + c0, self.needs_grad, self.gdt
+        a.up2 = self.up2
         return a
 
 
@@ -164,6 +167,7 @@ class Engine:
         self.dwp_arena, self.dwp_layout, self.dwp_dirty, self.unpack_queue = None, {}, False, []
         self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
         self.consumed_gen = -1  # generation whose tape has been run: a second backward through it must fail loudly
+        self.up2_mat_log = []   # names of the virtual up-sampled activations that had to be materialised (tests assert on it)
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
 
@@ -503,15 +507,53 @@ class Engine:
     def tma_ok(self, srcs, geom):
         """The TMA-fed kernels need bf16 sources without pending transforms and spatial stride 1."""
         return (self.eng == L.ENGINE_TC and self.use_tma and geom.sh == 1 and geom.sw == 1
-                and all(s.xform == L.XF_IDENT for s in srcs))
+                and all(s.xform == L.XF_IDENT or (i == 0 and s.up2) for i, s in enumerate(srcs)))
+
+    # ---- 2x bilinear up-sampling fused into the consumer's input stage (model.py:254 in front of model.py:260-275) ----
+    def materialize_up2(self, a):
+        """Hi-res copy of a virtual up-sampled activation, for a consumer without a fused input stage (small maps, the
+        register-gather tensor-core kernels).  Shares the gradient buffer of `a`."""
+        if a.mat is None:
+            low_h, low_w = a.H // 2, a.W // 2
+            m = Act(self.buf(a.name + ".up", (a.B, a.T, a.H, a.W, a.C), self.tdtype), a.B, a.T, a.H, a.W, a.C)
+            m.grad, m.gchoff, m.needs_grad, m.gdt = a.grad, a.gchoff, a.needs_grad, a.gdt
+            d = L.Upsample()
+            d.z, d.ldz, d.dtype, d.relu, d.B, d.T, d.h, d.w, d.C = a.ptr(), a.ld, self.dt, a.xform & 1, a.B, a.T, low_h, low_w, a.C
+            d.u, d.ldu, d.u_dtype = m.ptr(), m.ld, self.dt
+            self.call("vinet_upsample_fwd", d)
+            a.mat = m
+            self.up2_mat_log.append(a.name)
+        return a.mat
+
+    def resolve_up2(self, srcs, geom, cout):
+        """Sources a convolution can read as they are: a virtual up-sampled source stays virtual when the kernels that will
+        serve this convolution (forward AND weight gradient) interpolate in their input stage, else it is materialised."""
+        if not any(s.up2 for s in srcs):
+            return srcs
+        keep = srcs[0].up2 and not any(s.up2 for s in srcs[1:]) and "vinet_conv_up2_fused" in self.lib.fn
+        if keep and not self.split:          # (split-precision mode: the operand split interpolates while it splits)
+            if self.eng == L.ENGINE_TC and not (self.use_tma and geom.sh == 1 and geom.sw == 1
+                                                and all(s.xform == L.XF_IDENT for s in srcs[1:])):
+                keep = False
+            else:
+                g = L.Gather()
+                To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), srcs[0].H, srcs[0].W)
+                self._gather_fprop(g, srcs, geom, srcs[0].C, To, Ho, Wo)
+                keep = bool(self.lib.fn["vinet_conv_up2_fused"](C.byref(g), cout, self.eng, L.KERNEL_TMA))
+        if keep:
+            return srcs
+        return [self.materialize_up2(s) if s.up2 else s for s in srcs]
 
     # ---- split-precision operands (parity mode "bf16x3" / "bf16x6") ----
-    def split_view(self, name, ptr, ld, dtype, rows, C_, xform=L.XF_IDENT, scale=None, shift=None):
-        """bf16 expansion planes [rows, C] of an fp32 view (after its pending transform): x ~= part0 + part1 (+ part2)."""
+    def split_view(self, name, ptr, ld, dtype, rows, C_, xform=L.XF_IDENT, scale=None, shift=None, up=None):
+        """bf16 expansion planes [rows, C] of an fp32 view (after its pending transform): x ~= part0 + part1 (+ part2).
+        up = (h, w): the view is a low-res tensor read through the 2x up-sampling (xform has XF_UP2); rows are hi-res rows."""
         parts = [self.buf("%s.%d" % (name, i), (rows, C_), torch.bfloat16) for i in range(self.split)]
         d = L.Split()
         d.x, d.ld, d.dtype, d.rows, d.C = ptr, ld, dtype, rows, C_
         d.scale, d.shift, d.xform, d.nparts, d.ldo = _ptr(scale), _ptr(shift), xform, self.split, C_
+        if up is not None:
+            d.up_h, d.up_w = up
         for i, t in enumerate(parts):
             d.part[i] = t.data_ptr()
         self.call("vinet_split_bf16", d)
@@ -550,7 +592,8 @@ class Engine:
                 for i, t in enumerate(planes):
                     out[i].append(WinAct(t.view(a.B, a.T, a.H, a.Wp, 8), a.B, a.T, a.H, a.W, a.wl, a.Wp))
             else:
-                planes = self.split_view("%s.sp%d" % (name, si), a.ptr(), a.ld, self.dt, a.rows, a.C, a.xform, a.scale, a.shift)
+                planes = self.split_view("%s.sp%d" % (name, si), a.ptr(), a.ld, self.dt, a.rows, a.C, a.xform, a.scale, a.shift,
+                                         up=(a.H // 2, a.W // 2) if a.up2 else None)
                 for i, t in enumerate(planes):
                     out[i].append(Act(t.view(a.B, a.T, a.H, a.W, a.C), a.B, a.T, a.H, a.W, a.C))
         return out
@@ -564,6 +607,7 @@ class Engine:
         weight gradient is unpacked straight into each member's gradient tensor.
         Split-precision parity mode: every GEMM below is issued once per (operand part, weight part) term into the same fp32
         output (first term stores, the others accumulate); the kernels are the ones the bf16 mode runs."""
+        srcs = self.resolve_up2(srcs, geom, w.shape[0])
         if self.split:
             assert ep is None, "the split-precision mode accumulates raw terms: no non-linear epilogue"
             psrcs = self.split_sources(name, srcs)
@@ -994,18 +1038,24 @@ class Engine:
 
     # ------------------------------------------------------------------ decoder: conv -> ReLU -> 2x bilinear
     def conv_relu_up(self, name, srcs, w, geom):
+        """Conv3d -> ReLU -> nn.Upsample((1,2,2), 'trilinear') (model.py:256-275).  Returns a VIRTUAL activation: the raw conv output
+        z at low resolution, tagged XF_RELU | XF_UP2 with hi-res logical extents.  The next convolution reads it THROUGH the ReLU +
+        interpolation in its own input stage (interpolating producer warps of the tcgen05 kernels, the FFMA gather, the operand
+        split of the parity mode); only consumers without such a stage make `materialize_up2` write the hi-res tensor.  The
+        gradient buffer is hi-res (the consumer's data gradient lands there); vinet_upsample_bwd folds it back onto z."""
         a0 = srcs[0]
         To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
         Cout = w.shape[0]
         z = Act(self.buf(name + ".z", (a0.B, To, Ho, Wo, Cout), self.tdtype), a0.B, To, Ho, Wo, Cout, 0, L.XF_RELU)
         conv_bwd = self.conv(name, srcs, w, geom, z)
-        u = self.new_act(name + ".up", a0.B, To, 2 * Ho, 2 * Wo, Cout)
-        d = L.Upsample()
-        d.z, d.ldz, d.dtype, d.relu, d.B, d.T, d.h, d.w, d.C = z.ptr(), z.ld, self.dt, 1, a0.B, To, Ho, Wo, Cout
-        d.u, d.ldu, d.u_dtype = u.ptr(), u.ld, self.dt
-        self.call("vinet_upsample_fwd", d)
+        u = Act(z.buf, a0.B, To, 2 * Ho, 2 * Wo, Cout, 0, L.XF_RELU | L.XF_UP2)
+        u.up2, u.name = True, name
         if self.record:
+            self.want_grad(u, name + ".up")
+
             def backward():
+                d = L.Upsample()
+                d.z, d.ldz, d.dtype, d.relu, d.B, d.T, d.h, d.w, d.C = z.ptr(), z.ld, self.dt, 1, a0.B, To, Ho, Wo, Cout
                 dz = self.buf("dy.%d" % (z.rows * Cout), (z.rows, Cout), self.tdtype)
                 d.gu, d.ldgu, d.dz, d.lddz, d.dz_dtype = u.gptr(), u.ldg, dz.data_ptr(), Cout, self.dt
                 d.gu_dtype = u.gdt
@@ -1023,14 +1073,43 @@ class Engine:
         h = Act(self.buf(name + ".h", (a0.B, To, Ho, Wo, Cout), self.tdtype), a0.B, To, Ho, Wo, Cout, 0, L.XF_RELU)
         return h, self.conv(name, srcs, w, geom, h, bias=bias)
 
-    def head(self, name, a, w, b, conv_bwd=None):
-        """relu? -> Conv3d(C,1,1) + bias -> Sigmoid -> (B,H,W) fp32 (model.py:282-283 + the final view)."""
+    def conv_relu_act(self, name, srcs, w, geom):
+        """Conv3d (no bias) -> ReLU as a layer of its own (the decoder tail once the (kt,1,1) convolution has been commuted in front of
+        the last up-sampling, see model.decoder_plan): the ReLU runs in the convolution's epilogue, so the next convolution reads a
+        plain activation (TMA-fetchable); the parity mode sums raw terms and leaves the ReLU pending instead.  Backward masks the
+        incoming gradient with (value > 0) - the same mask for the raw and the rectified tensor - and runs the conv backward."""
+        a0 = srcs[0]
+        To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
+        Cout = w.shape[0]
+        fuse = not self.split
+        a = self.new_act(name + ".a", a0.B, To, Ho, Wo, Cout, xform=L.XF_IDENT if fuse else L.XF_RELU)
+        conv_bwd = self.conv(name, srcs, w, geom, a, ep=(None, None, L.ACT_RELU) if fuse else None)
+        if self.record:
+            def backward():
+                dz = self.buf("dy.%d" % (a.rows * Cout), (a.rows, Cout), self.tdtype)
+                self.lib.call("vinet_relu_bwd", a.gptr(), a.ldg, a.gdt, a.ptr(), a.ld, self.dt, a.rows, Cout, dz.data_ptr(), Cout,
+                              self.dt, self.stream())
+                conv_bwd(dz.data_ptr(), Cout)
+            self.tape.append(backward)
+        return a
+
+    def head(self, name, a, w, b, conv_bwd=None, up2=None):
+        """relu? -> Conv3d(C,1,1) + bias -> Sigmoid -> (B,H,W) fp32 (model.py:282-283 + the final view).
+        up2 = "pre" | "post": `a` is a LOW-RES raw conv output and the decoder's last 2x up-sampling happens in the head's input
+        stage (the hi-res 32-channel tensor - the largest activation of the decoder - is never written).  "pre": relu -> up ->
+        head (T = 8 / 16 decoders, model.py:340, 402); "post": up -> relu -> head (T = 32 / 48 with the (kt,1,1) conv commuted)."""
         assert a.T == 1, "the decoder collapses time to one frame before the head"
-        out = torch.empty((a.B, a.H, a.W), dtype=torch.float32, device=self.device)
+        H, W = (2 * a.H, 2 * a.W) if up2 else (a.H, a.W)
+        rows = a.B * H * W
+        out = torch.empty((a.B, H, W), dtype=torch.float32, device=self.device)
         d = L.Head()
         relu = 1 if a.xform == L.XF_RELU else 0
-        assert a.xform in (L.XF_RELU, L.XF_IDENT)
-        d.x, d.ldx, d.dtype, d.relu, d.rows, d.C = a.ptr(), a.ld, self.dt, relu, a.rows, a.C
+        assert a.xform in (L.XF_RELU, L.XF_IDENT) and up2 in (None, "pre", "post")
+        d.x, d.ldx, d.dtype, d.rows, d.C = a.ptr(), a.ld, self.dt, rows, a.C
+        d.relu = relu if up2 != "pre" else 0
+        if up2:
+            assert conv_bwd is not None or not self.record
+            d.up2, d.up_h, d.up_w, d.relu_pre = 1, a.H, a.W, (relu if up2 == "pre" else 0)
         d.w, d.b, d.out = w.data_ptr(), b.data_ptr(), out.data_ptr()
         self.call("vinet_head_fwd", d)
         if self.record:
@@ -1038,7 +1117,7 @@ class Engine:
                 gw, gb = self.grad_tensor(name + ".weight", w, zero=True), self.grad_tensor(name + ".bias", b, zero=True)
                 d.gout, d.dw, d.db = gout.data_ptr(), gw.data_ptr(), gb.data_ptr()
                 if conv_bwd is not None:        # input is a raw conv output: dx is that conv's dY
-                    dx = self.buf("dy.%d" % (a.rows * a.C), (a.rows, a.C), self.tdtype)
+                    dx = self.buf("dy.%d" % (rows * a.C), (rows, a.C), self.tdtype)
                     d.dx, d.lddx, d.dx_dtype = dx.data_ptr(), a.C, self.dt
                 else:                           # input is a materialised activation: dx is its fp32 gradient
                     assert self.first_write(a), "the head must be the only consumer of its input"
@@ -1046,7 +1125,14 @@ class Engine:
                 self.call("vinet_head_bwd", d)
                 self.param_grads[name + ".weight"] = gw
                 self.param_grads[name + ".bias"] = gb
-                if conv_bwd is not None:
+                if conv_bwd is not None and up2:   # dx is the gradient at hi-res: fold it through the transposed interpolation
+                    u = L.Upsample()
+                    u.z, u.ldz, u.dtype, u.relu, u.B, u.T, u.h, u.w, u.C = a.ptr(), a.ld, self.dt, d.relu_pre, a.B, 1, a.H, a.W, a.C
+                    dz = self.buf("dy.%d" % (a.rows * a.C), (a.rows, a.C), self.tdtype)
+                    u.gu, u.ldgu, u.gu_dtype, u.dz, u.lddz, u.dz_dtype = dx.data_ptr(), a.C, self.dt, dz.data_ptr(), a.C, self.dt
+                    self.call("vinet_upsample_bwd", u)
+                    conv_bwd(dz.data_ptr(), a.C)
+                elif conv_bwd is not None:
                     conv_bwd(dx.data_ptr(), a.C)
             self.head_backward = backward
         return out

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libvinet_b200.so")
 
 BF16, F32 = 0, 1
 XF_IDENT, XF_RELU, XF_AFFINE, XF_AFFINE_RELU = 0, 1, 2, 3
+XF_UP2 = 4          # source stored at half resolution, read through the 2x bilinear up-sampling (after the ReLU bit)
 GATHER_FPROP, GATHER_DGRAD = 0, 1
 ENGINE_TC, ENGINE_SIMT = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -99,7 +100,7 @@ class Upsample(C.Structure):
 class Head(C.Structure):
     _fields_ = [("x", _p), ("ldx", _i64), ("dtype", _i32), ("relu", _i32), ("rows", _i64), ("C", _i32), ("w", _p),
                 ("b", _p), ("out", _p), ("gout", _p), ("dx", _p), ("lddx", _i64), ("dx_dtype", _i32), ("dw", _p),
-                ("db", _p)]
+                ("db", _p), ("up2", _i32), ("up_h", _i32), ("up_w", _i32), ("relu_pre", _i32)]
 
 
 class Loss(C.Structure):
@@ -128,7 +129,7 @@ class AvFuse(C.Structure):
 
 class Split(C.Structure):
     _fields_ = [("x", _p), ("ld", _i64), ("dtype", _i32), ("rows", _i64), ("C", _i32), ("scale", _p), ("shift", _p),
-                ("xform", _i32), ("nparts", _i32), ("part", _p * 3), ("ldo", _i64)]
+                ("xform", _i32), ("nparts", _i32), ("part", _p * 3), ("ldo", _i64), ("up_h", _i32), ("up_w", _i32)]
 
 
 class PostProc(C.Structure):
@@ -155,6 +156,8 @@ SIGNATURES = {
     "vinet_conv_gemm": (C.c_int, [C.POINTER(Conv), _i32, _S]),
     "vinet_conv_tiling": (C.c_int, [C.POINTER(Conv), _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), _i32, _S]),
+    "vinet_conv_up2_fused": (C.c_int, [C.POINTER(Gather), _i32, _i32, _i32]),
+    "vinet_relu_bwd": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i64, _i32, _p, _i64, _i32, _S]),
     "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
     "vinet_pack_weights_multi": (C.c_int, [_p, _p, _i32, _i64, _S]),
     "vinet_packed_weight_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
@@ -200,6 +203,7 @@ SIGNATURES = {
     "vinet_version": (C.c_char_p, []),
     "vinet_device_info": (C.c_int, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_launch_count": (_i64, []),
+    "vinet_up2_launch_count": (_i64, []),
     "vinet_abi_sizes": (C.c_int, [C.POINTER(_i64), _i32]),
     "vinet_debug_set": (C.c_int, [_i32, _i32]),
 }

@@ -248,17 +248,26 @@ def decoder_plan(e, pfx, dec, y0, y1, y2, y3):
         z = e.conv_relu_up(pfx + nm, srcs, m.weight, ConvGeom((kt, 3, 3), (kt, 1, 1), (0, 1, 1)))
     tail = arch.decoder_tail(dec.num_clips)
     convs = [(i + 3, it) for i, it in enumerate(tail) if not isinstance(it, str)]
-    # first tail conv: conv -> relu -> up
+    # Tail: conv A (kt,3,3) -> relu -> up [-> conv B (kt,1,1) (+bias) -> relu] -> 1x1x1 head -> sigmoid.  The last 2x up-sampling
+    # writes the largest tensor of the decoder and feeds only pointwise-in-space work, so it never runs as such:
+    #   * conv B is linear and pointwise in space, the interpolation weights sum to one: B(up(x)) + b == up(B(x) + b).  B therefore
+    #     runs on the LOW-RES grid (a quarter of the rows) and the head interpolates its output (then relu, dot, sigmoid);
+    #   * without conv B (T = 8 / 16) the head interpolates relu(A's output) directly.
     idx, (_, cin, cout, k, s, p, bias) = convs[0]
-    z = e.conv_relu_up(pfx + "convtsp4.%d" % idx, [z], dec.convtsp4[idx].weight, ConvGeom(k, s, (0, p, p)))
-    conv_bwd = None
-    if len(convs) == 3:      # (kt,1,1) time-collapsing conv -> relu, then the 1x1x1 head
+    geomA = ConvGeom(k, s, (0, p, p))
+    wA = dec.convtsp4[idx].weight
+    if len(convs) == 3:
+        a = e.conv_relu_act(pfx + "convtsp4.%d" % idx, [z], wA, geomA)
         idx, (_, cin, cout, k, s, p, bias) = convs[1]
         m = dec.convtsp4[idx]
-        z, conv_bwd = e.conv_relu(pfx + "convtsp4.%d" % idx, [z], m.weight, ConvGeom(k, s, (0, p, p)), bias=m.bias)
+        z, conv_bwd = e.conv_relu(pfx + "convtsp4.%d" % idx, [a], m.weight, ConvGeom(k, s, (0, p, p)), bias=m.bias)
+        order = "post"
+    else:
+        z, conv_bwd = e.conv_relu(pfx + "convtsp4.%d" % idx, [z], wA, geomA)
+        order = "pre"
     idx, _ = convs[-1]
     m = dec.convtsp4[idx]
-    return e.head(pfx + "convtsp4.%d" % idx, z, m.weight, m.bias, conv_bwd)
+    return e.head(pfx + "convtsp4.%d" % idx, z, m.weight, m.bias, conv_bwd, up2=order)
 
 
 class _PlanFunction(torch.autograd.Function):
