@@ -291,8 +291,12 @@ __global__ void bn_bwd_fused_kernel(const __grid_constant__ vinet_bn_bwd_t d, in
   }
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r_end = min(d.rows, r_begin + rows_per_block);
+  // second pass over g and y: walk the block's rows BACKWARDS - the reduction pass above read them front to back, so the tail of
+  // the chunk is what the 126 MB L2 still holds (every block is resident: cooperative launch)
+  const int64_t n_it = r_end > r_begin + threadIdx.y ? (r_end - r_begin - threadIdx.y + Ry - 1) / Ry : 0;
 #pragma unroll 4
-  for (int64_t r = r_begin + threadIdx.y; r < r_end; r += Ry) {
+  for (int64_t it = n_it - 1; it >= 0; --it) {
+    const int64_t r = r_begin + threadIdx.y + it * Ry;
     float v[8], g[8], o[8];
     load8(y + r * d.ldy + c, v);
     load8(gp + r * d.ldg + c, g);
@@ -482,10 +486,14 @@ __global__ void __launch_bounds__(BN_MT) bn_apply_multi_kernel(const __grid_cons
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sc[e] = __ldg(d.scale + c + e); sh[e] = __ldg(d.shift + c + e); }
   const bool relu = d.relu != 0;
-  const int64_t r_begin = (int64_t)blockIdx.x * p.rpb[seg];
+  // the convolution wrote the raw output front to back: read it back to front (blocks in reverse order, rows downwards), so that
+  // the part the L2 still holds is consumed before this kernel's own traffic evicts it
+  const int64_t r_begin = (int64_t)(p.nb[seg] - 1 - (int)blockIdx.x) * p.rpb[seg];
   const int64_t r_end = min(d.rows, r_begin + p.rpb[seg]);
+  const int64_t n_it = r_end > r_begin + m.ry ? (r_end - r_begin - m.ry + m.Ry - 1) / m.Ry : 0;
 #pragma unroll 4
-  for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) {
+  for (int64_t it = n_it - 1; it >= 0; --it) {
+    const int64_t r = r_begin + m.ry + it * m.Ry;
     float v[8];
     load8(y + r * d.ldy + c, v);
 #pragma unroll
@@ -556,10 +564,14 @@ __global__ void __launch_bounds__(BN_MT) bn_apply_stats_multi_kernel(const __gri
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sc[e] = s_sc[c + e]; sh[e] = s_sh[c + e]; }
   const bool relu = d.relu != 0;
-  const int64_t r_begin = (int64_t)blockIdx.x * p.rpb[seg];
+  // the convolution wrote the raw output front to back: read it back to front (blocks in reverse order, rows downwards), so that
+  // the part the L2 still holds is consumed before this kernel's own traffic evicts it
+  const int64_t r_begin = (int64_t)(p.nb[seg] - 1 - (int)blockIdx.x) * p.rpb[seg];
   const int64_t r_end = min(d.rows, r_begin + p.rpb[seg]);
+  const int64_t n_it = r_end > r_begin + m.ry ? (r_end - r_begin - m.ry + m.Ry - 1) / m.Ry : 0;
 #pragma unroll 4
-  for (int64_t r = r_begin + m.ry; r < r_end; r += m.Ry) {
+  for (int64_t it = n_it - 1; it >= 0; --it) {
+    const int64_t r = r_begin + m.ry + it * m.Ry;
     float v[8];
     load8(y + r * d.ldy + c, v);
 #pragma unroll
