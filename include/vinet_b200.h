@@ -46,8 +46,12 @@ enum { VINET_KERNEL_GATHER = 0, VINET_KERNEL_TMA = 1 };
 /* K index of packed weights / packed weight gradients. DENSE: k = tap*cs + c.  TAP64: every tap is padded to a
  * multiple of 64 channels, k = (tap*ceil(cs/64) + c/64)*64 + c%64 (one 64-wide K block per TMA box).
  * WIN8 (stem, Cin <= 8, kw <= 8): the gather's taps enumerate dh only and one 64-wide K block holds the whole
- * (dw, c) window of a padded NDHWC8 row: k = dh*64 + dw*8 + c.  The matching source view has Cs = 64, ld = 8*sw. */
-enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1, VINET_KLAYOUT_WIN8 = 2 };
+ * (dw, c) window of a padded NDHWC8 row: k = dh*64 + dw*8 + c.  The matching source view has Cs = 64, ld = 8*sw.
+ * WIN4 (stem forward, Cin <= 4, kw <= 8): the same idea on the 4-channel copy of the clip (vinet_pack_input_t.out4):
+ * k = dh*64 + dw*4 + c, only the lower 32 entries of a block are used; the source view has Cs = 32, ld = 4*sw.  With sw = 2
+ * consecutive windows start 16 bytes apart, which lets the streaming kernel read them in place from a compact patch through
+ * un-swizzled UMMA descriptors (csrc/conv_stream.cu, conv_gemm_stream_win4; vinet_conv_win4_fused tells). */
+enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1, VINET_KLAYOUT_WIN8 = 2, VINET_KLAYOUT_WIN4 = 3 };
 
 #define VINET_MAX_TAPS 64
 #define VINET_TC_BLOCK_M 128
@@ -142,6 +146,9 @@ int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stre
  * VINET_XF_UP2 source 0 through their fused interpolating input stage, 0 when the caller has to materialise the up-sampled
  * tensor (vinet_upsample_fwd) first.  Host only. */
 int vinet_conv_up2_fused(const vinet_gather_t* g, int32_t N, int32_t engine, int32_t kernel);
+/* 1 when vinet_conv_gemm serves the FPROP gather g over the 4-channel clip (Cs = 32, ld = 8, VINET_KLAYOUT_WIN4 weights) with the
+ * compact-patch streaming kernel; 0: use the 8-channel window view (VINET_KLAYOUT_WIN8).  Host only. */
+int vinet_conv_win4_fused(const vinet_gather_t* g, int32_t N);
 
 /* Weight (re)packing: PyTorch (Cout,Cin,kt,kh,kw) fp32 -> GEMM B operand. */
 typedef struct vinet_pack {
@@ -195,6 +202,8 @@ typedef struct vinet_pack_input {
   int32_t out_dtype;
   int32_t wl, Wp; /* rows are written Wp >= wl + W pixels wide: wl zero pixels, the W pixels, zeros (0,0 = dense).
                      With explicit zero columns the stem conv can address a row as overlapping windows (WIN8). */
+  void* out4;     /* optional (bf16 output, C <= 4): a second copy [B,T,H,Wp,4] with FOUR channels per pixel (same wl / Wp, Wp even):
+                     the forward stem convolution reads it in place (VINET_KLAYOUT_WIN4); NULL = not written */
 } vinet_pack_input_t;
 int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream);
 

@@ -31,6 +31,7 @@ int stream_enable_set(int v);
 int pool_fast_set(int v);
 int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles);
 int conv_stream_up2_ok(const vinet_conv_t* d);
+int conv_stream_win4_ok(const vinet_conv_t* d);
 int conv_wgrad_halo(const vinet_wgrad_t* d, cudaStream_t stream, bool dry_run);
 
 // the SIMT and register-gather kernels address sources densely: h pitch == Ws*ld and non-overlapping pixels
@@ -113,6 +114,17 @@ extern "C" int vinet_conv_up2_fused(const vinet_gather_t* g, int32_t N, int32_t 
   w.splits = 1;
   w.kernel = kernel;
   return conv_wgrad_halo(&w, nullptr, true) == 1 ? 1 : 0;
+}
+
+extern "C" int vinet_conv_win4_fused(const vinet_gather_t* g, int32_t N) {
+  if (!g) return 0;
+  vinet_conv_t c;
+  memset(&c, 0, sizeof(c));
+  c.g = *g;
+  c.N = N;
+  c.kernel = VINET_KERNEL_TMA;
+  c.out_dtype = VINET_BF16;
+  return conv_stream_win4_ok(&c);
 }
 
 extern "C" int vinet_conv_wgrad(const vinet_wgrad_t* d, int32_t engine, vinet_stream_t stream) {

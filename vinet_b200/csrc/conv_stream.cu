@@ -225,7 +225,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
               continue;
             }
             const uint32_t dst = sA0 + (uint32_t)s * p.a_stage_bytes;
-            if (p.halo == 2) {   // spatially strided conv: the rows a tile needs form par_sh lattices, one box per lattice
+            if (p.halo == 3) {   // compact patch of the 4-channel clip: {2 pixels, PW pairs, PH rows}, rows 2*h0 - ph ..
+              mbar_arrive_expect_tx(full_a + 8 * s, p.a_tx_sub);
+              st_tma_load_5d(dst, &p.tmA[0], full_a + 8 * s, 0, c.tx * 8 * p.nsub, c.ty * p.th * 2 + p.par_h0[0], tl, c.b);
+            } else if (p.halo == 2) {   // spatially strided conv: the rows a tile needs form par_sh lattices, one box per lattice
               mbar_arrive_expect_tx(full_a + 8 * s, (uint32_t)p.par_sh * p.a_tx_sub);
               for (int par = 0; par < p.par_sh; ++par)
                 st_tma_load_5d(dst + (uint32_t)p.par_off[par], &p.tmA[0], full_a + 8 * s, cb * 64, c.tx * 8 * p.nsub + p.ew0,
@@ -282,7 +285,8 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
     // warp is the critical resource (a 128xNx16 MMA only lasts max(N/2, 32+N/4) clocks), so this loop is kept as short as
     // possible: 32-bit descriptor words, per-tap constants straight from the parameter bank, no divisions.
     const uint32_t hi_common = (1u << 14) | (2u << 29);  // descriptor version 1, SWIZZLE_128B
-    const uint32_t a_hi = (p.sbo >> 4) | hi_common, b_hi = (1024u >> 4) | hi_common;
+    // halo == 3: the activation operand is read straight out of a compact, UN-swizzled patch (see conv_gemm_stream_win4)
+    const uint32_t a_hi = (p.sbo >> 4) | (p.halo == 3 ? (1u << 14) : hi_common), b_hi = (1024u >> 4) | hi_common;
     const uint32_t sA_lo = ((sA0 & 0x3FFFFu) >> 4) | (1u << 16), sB_lo = ((sB0 & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t a_stage16 = p.a_stage_bytes >> 4, b16 = p.b_bytes >> 4, sub16 = p.sub_stride >> 4;
     const uint32_t nacc = (uint32_t)p.nacc, acc_set = (uint32_t)p.nsub * p.acc_stride;
@@ -466,8 +470,7 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
               tmem_ld16(tacc + (uint32_t)(gi * 16), r);
               if (orow == nullptr) continue;
               const int c0 = gi * 16;
-              if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum);
-              if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, nt * BN + c0 + 8, accum);
+              epilogue_store16<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum, nlim - c0);
             }
           }
         } else {
@@ -491,8 +494,7 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
                 sv[e] += x;
                 sq[e] = fmaf(x, x, sq[e]);
               }
-              if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum);
-              if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, nt * BN + c0 + 8, accum);
+              epilogue_store16<TO, EPI>(p.d, orow + c0, r, nt * BN + c0, accum, nlim - c0);
             }
             warp_colsum16(sv, lane);
             warp_colsum16(sq, lane);
@@ -902,10 +904,96 @@ static int conv_gemm_stream_strided(const vinet_conv_t* d, cudaStream_t stream) 
   return stream_launch(p, d, sms, stream);
 }
 
+// Stem conv_s on the 4-CHANNEL clip (VINET_KLAYOUT_WIN4: (1,kh,kw<=7)/(1,2,2), Cin <= 4): no im2col, no window expansion at all.
+// A pixel is 8 bytes, so the kw-wide windows of consecutive output pixels (stride 2) start 16 bytes apart - exactly the row
+// pitch of an UN-swizzled K-major core matrix (8 rows x 16 bytes, rows 16 bytes apart).  The tensor core therefore reads the
+// A operand of kernel row dh straight out of a COMPACT patch of the clip {PH = 30 + kh source rows, 8*nsub + 3 pixel pairs}:
+//   descriptor start = patch + dh*pitch + sub*128 + kstep*32, LBO (next 8 K elements = next 2 pixels) = 16 bytes: the core
+//   matrices of one MMA overlap in shared memory; SBO (next 8 output pixels = next output row) = 2*pitch.
+// K per kernel row = 8 pixels x 4 channels = 32 (two K=16 MMAs; the 8th pixel and the 4th channel meet zero weights): 14 MMAs
+// per 128 outputs instead of 28, and 21 KB of L2->SM traffic per 512 outputs instead of 155 KB of 4x-overlapping window rows
+// (the halo == 2 mode above), which is what bound this layer.
+int make_tma_map_pairs(CUtensorMap* m, const void* ptr, int Wp, int H, int T, int B, int bw, int bh, int64_t ldb);
+
+static bool win4_geometry(const vinet_conv_t* d, int* nsub_out, int* PH_out) {
+  const vinet_gather_t& g = d->g;
+  if (!g_stream_enable || g.mode != VINET_GATHER_FPROP || g.dtype != VINET_BF16) return false;
+  const vinet_src_t& s = g.src[0];
+  if (g.src[1].ptr != nullptr || s.xform != VINET_XF_IDENT || s.ptr == nullptr) return false;
+  if (g.Cs != 32 || s.ld != 8 || g.sw != 1 || g.sh != 2 || g.st != 1 || g.row_tstep != 1 || g.row_toff != 0 || g.pt != 0) return false;
+  if (s.ldh <= 0 || s.ldh % 8 != 0 || (s.ldh / 4) < 2 * (int64_t)(g.Wr - 1) + 8) return false;   // even padded width, windows inside the row
+  if (d->N % 8 != 0 || d->N > 128 || g.ntaps > 16 || g.Hr < 10) return false;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.tap[t][0] != 0 || g.tap[t][1] != t || g.tap[t][2] != 0) return false;
+  const int PH = 30 + g.ntaps;
+  const int acc = (int)round_up(round_up(d->N, 16), 32);
+  const size_t wbytes = (size_t)g.ntaps * round_up(d->N, 16) * 128;
+  int nsub = 0;
+  for (int ns = 4; ns >= 1; --ns) {
+    const size_t stage = round_up((size_t)PH * (8 * ns + 3) * 16, 1024);
+    if (2 * ns * acc <= 512 && 3 * stage + wbytes + 4096 <= ST_SMEM_BUDGET) { nsub = ns; break; }
+  }
+  if (nsub == 0) return false;
+  *nsub_out = nsub;
+  *PH_out = PH;
+  return true;
+}
+
+int conv_stream_win4_ok(const vinet_conv_t* d) {
+  int nsub, PH;
+  return win4_geometry(d, &nsub, &PH) ? 1 : 0;
+}
+
+static int conv_gemm_stream_win4(const vinet_conv_t* d, cudaStream_t stream) {
+  const vinet_gather_t& g = d->g;
+  int nsub, PH;
+  if (!win4_geometry(d, &nsub, &PH)) return 0;
+  if (d->n_tiles != 1 || d->block_n != (int)round_up(d->N, 16) || d->k_blocks != g.ntaps) return 0;
+  const int sms = tma_sm_count();
+  StreamParams p;
+  p.d = *d;
+  p.ncb = 1;
+  p.acc_stride = (uint32_t)round_up(d->block_n, 32);
+  p.b_bytes = (uint32_t)d->block_n * 128u;
+  const size_t wbytes = (size_t)d->k_blocks * p.b_bytes;
+  const int PWp = 8 * nsub + 3;                       // pixel pairs per patch row
+  const uint32_t pitch = (uint32_t)PWp * 16u;
+  p.halo = 3; p.nsub = nsub; p.tw = 8; p.th = 16;
+  p.items_w = (int)cdiv(g.Wr, 8 * nsub); p.items_h = (int)cdiv(g.Hr, 16); p.tiles_w = 0; p.tpf = 0;
+  p.PW = PWp; p.PH = PH; p.ew0 = 0; p.eh0 = 0;
+  p.par_sh = 1; p.par_h0[0] = -g.ph; p.par_h0[1] = 0; p.par_off[0] = p.par_off[1] = 0;
+  p.a_tx_sub = (uint32_t)PH * pitch;
+  p.a_stage_bytes = (uint32_t)round_up(p.a_tx_sub, 1024);   // the SWIZZLE_128B weight blocks behind the ring need 1024-byte alignment
+  p.tt = 1; p.pos = 128; p.tstep = 1; p.toff = 0; p.walk_Tr = g.Tr; p.walk_Ts = g.Ts;
+  p.run = 1; p.nruns = g.Tr; p.S = 1; p.ntg = 1; p.e_min = 0; p.e_max = 0;
+  for (int k = 0; k < ST_MAX_TG; ++k) { p.tg_er[k] = 0; p.tg_eq[k] = 0; }
+  for (int k = 0; k <= ST_MAX_TG; ++k) p.tg_first[k] = k == 0 ? 0 : g.ntaps;
+  for (int j = 0; j < VINET_MAX_TAPS; ++j) {
+    p.sp_aoff[j] = j < g.ntaps ? j * (int)pitch : 0;      // kernel row dh = patch row dh (+ 2 per output row: SBO)
+    p.sp_kb[j] = j < g.ntaps ? j : 0;
+    p.sp_aoff16[j] = p.sp_aoff[j] >> 4;
+    p.sp_boff16[j] = (int32_t)(((int64_t)p.sp_kb[j] * d->block_n * 128) >> 4);
+  }
+  p.nacc = 2; p.b_slots = 1; p.wres = 1; p.ni = std::min(ST_MAX_ISSUERS, nsub);
+  p.a_stages = (int)std::min<size_t>(6, (ST_SMEM_BUDGET - 4096 - wbytes) / p.a_stage_bytes);
+  const int64_t items = (int64_t)g.B * g.Tr * p.items_w * p.items_h;
+  if (items >= (1ll << 31)) return 0;
+  p.items_per_nt = (int)items;
+  p.tmem_cols = tmem_cols_for(p.nacc * nsub * (int)p.acc_stride);
+  p.idesc = make_idesc(TC_BM, d->block_n, 0, 0);
+  p.sub_stride = 8 * 16;                              // 8 output pixels = 16 source pixels of 8 bytes
+  p.sbo = 2u * pitch;                                 // next output row = two source rows down
+  const vinet_src_t& s = g.src[0];
+  if (make_tma_map_pairs(&p.tmA[0], s.ptr, (int)(s.ldh / 4), g.Hs, s.T, g.B, PWp, PH, s.ldb)) return -1;
+  p.tmA[1] = p.tmA[0];
+  return stream_launch(p, d, sms, stream);
+}
+
 // returns 1 when the launch was handled here, 0 when the caller should use its own kernel, <0 on error
 int conv_gemm_stream(const vinet_conv_t* d, cudaStream_t stream) {
   const vinet_gather_t& g = d->g;
-  if (g.sh != 1 && g.src[0].ptr != nullptr && g.src[0].ld < g.Cs) return conv_gemm_stream_strided(d, stream);
+  if (g.sh != 1 && g.src[0].ptr != nullptr && g.src[0].ld < g.Cs)
+    return g.Cs == 32 ? conv_gemm_stream_win4(d, stream) : conv_gemm_stream_strided(d, stream);
   if (!stream_eligible(*d)) return 0;
   TapMap tm;
   if (!build_tap_map(g, &tm)) return 0;

@@ -311,8 +311,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
             }
             if (orow == nullptr) continue;
             const int c0 = gi * 16;
-            if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
-            if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
+            epilogue_store16<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum, nlim - c0);
           }
         }
       } else {
@@ -345,8 +344,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
               sv[e] += x;
               sq[e] = fmaf(x, x, sq[e]);
             }
-            if (c0 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum);
-            if (c0 + 8 < nlim) epilogue_store8<TO, EPI>(p.d, orow + c0 + 8, r + 8, ic.nt * BN + c0 + 8, accum);
+            epilogue_store16<TO, EPI>(p.d, orow + c0, r, ic.nt * BN + c0, accum, nlim - c0);
           }
           warp_colsum16(sv, lane);
           warp_colsum16(sq, lane);
@@ -600,6 +598,28 @@ static int make_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VINET_CHECK(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d,%d] ld %lld box %dx%d", (int)r,
               B, T, H, W, C, (long long)ld, bw, bh);
+  return 0;
+}
+
+// The 4-channel clip [B][T][H][Wp][4] (bf16, Wp even) as pixel PAIRS: 5-D map {8 elements, Wp/2, H, T, B}, box {8, bw pairs, bh
+// rows, 1, 1}, no swizzle: a compact row-major patch the un-swizzled UMMA descriptors of conv_gemm_stream_win4 read in place.
+int make_tma_map_pairs(CUtensorMap* m, const void* ptr, int Wp, int H, int T, int B, int bw, int bh, int64_t ldb) {
+  EncodeTiledFn enc = encode_fn();
+  VINET_CHECK(enc != nullptr, "conv_tma: cuTensorMapEncodeTiled is not available from the driver");
+  VINET_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && Wp % 2 == 0 && bw >= 1 && bw <= 256 && bh >= 1 && bh <= 256,
+              "conv_tma: bad 4-channel clip view (Wp %d box %dx%d)", Wp, bw, bh);
+  const int64_t ldh = (int64_t)Wp * 4;
+  if (ldb == 0) ldb = (int64_t)T * H * ldh;
+  VINET_CHECK(ldb % 8 == 0, "conv_tma: batch pitch %lld", (long long)ldb);
+  const cuuint64_t dims[5] = {8, (cuuint64_t)(Wp / 2), (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)ldh * 2, (cuuint64_t)H * ldh * 2, (cuuint64_t)ldb * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VINET_CHECK(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled failed (%d) for the 4-channel clip [%d,%d,%d,%d] box %dx%d", (int)r,
+              B, T, H, Wp, bw, bh);
   return 0;
 }
 

@@ -110,6 +110,15 @@ __device__ __forceinline__ TO* out_row_ptr(const vinet_conv_t& d, const RowCoord
   return reinterpret_cast<TO*>(d.out[i]) + pos * d.ldo[i];
 }
 
+// per-element epilogue (scale, shift, activation) - same arithmetic as epilogue_store8's vector form
+__device__ __forceinline__ float epilogue_value_fast(const vinet_conv_t& d, float acc, int n) {
+  if (d.ep_scale) acc *= __ldg(d.ep_scale + n);
+  if (d.ep_shift) acc += __ldg(d.ep_shift + n);
+  if (d.ep_act == VINET_ACT_RELU) acc = fmaxf(acc, 0.f);
+  else if (d.ep_act == VINET_ACT_SIGMOID) acc = 1.f / (1.f + __expf(-acc));
+  return acc;
+}
+
 // Epilogue of 8 consecutive output channels [n, n+8) of one row: optional per-channel scale/shift/activation
 // (EPI; vector loads, branches hoisted out of the element loop), optional read-modify-write, one 16/32-byte store.
 template <typename TO, bool EPI>
@@ -144,6 +153,44 @@ __device__ __forceinline__ void epilogue_store8(const vinet_conv_t& d, TO* p, co
   }
   store8(p, v);
 }
+// 16 consecutive output channels [n, n+16) of one row, nvalid = channels that exist (columns up to the N tile's edge).
+// bf16 rows whose 16-column group is 32-byte aligned go out as ONE 256-bit store (sm_100 STG.256): an epilogue lane owns a row, so
+// every lane of a store instruction hits a different 128-byte line - two 16-byte stores per group made every 32-byte sector
+// arrive at the L2 as two partial writes, and the L1/L2 write path (not HBM) bound the 64-channel layers (ncu, stem conv_s:
+// 44 M sector writes for 22 M sectors).  The read-modify-write path loads the same way.
+template <typename TO, bool EPI>
+__device__ __forceinline__ void epilogue_store16(const vinet_conv_t& d, TO* p, const uint32_t* r, int n, bool accum, int nvalid) {
+  if constexpr (sizeof(TO) == 2) {
+    if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+      if constexpr (EPI) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = epilogue_value_fast(d, v[e], n + e);
+      }
+      if (accum) {
+        uint32_t o[8];
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+                     : "l"(p)
+                     : "memory");
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[2 * e] += bf16_lo(o[e]); v[2 * e + 1] += bf16_hi(o[e]); }
+      }
+      uint32_t u[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+                   "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                   : "memory");
+      return;
+    }
+  }
+  if (nvalid > 0) epilogue_store8<TO, EPI>(d, p, r, n, accum);
+  if (nvalid > 8) epilogue_store8<TO, EPI>(d, p + 8, r + 8, n + 8, accum);
+}
+
 __host__ __device__ static inline bool conv_has_epilogue(const vinet_conv_t& d) {
   return d.ep_scale != nullptr || d.ep_shift != nullptr || d.ep_act != VINET_ACT_NONE;
 }

@@ -27,6 +27,12 @@ __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) 
       for (int e = 0; e < 8; ++e) v[e] = (in && c0 + e < d.C) ? __ldg(src + (c0 + e) * d.sc) : 0.f;
       store8(dst + c0, v);
     }
+    if (d.out4 != nullptr) {   // (bf16 only, C <= 4: checked by the host)
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (in && e < d.C) ? __ldg(src + e * d.sc) : 0.f;
+      reinterpret_cast<uint2*>(d.out4)[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
   }
 }
 
@@ -57,6 +63,18 @@ __global__ void __launch_bounds__(256) pack_input_vec4_kernel(const __grid_const
       for (int k = 0; k < d.wl; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
     if (gq == G - 1)
       for (int k = d.wl + d.W; k < Wp; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (d.out4 != nullptr) {   // the 4-channel copy: one uint2 per pixel
+      uint2* row4 = reinterpret_cast<uint2*>(d.out4) + (((int64_t)b * d.T + t) * d.H + h) * Wp;
+      uint2* dst4 = row4 + d.wl + gq * 4;
+      dst4[0] = make_uint2(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f));
+      dst4[1] = make_uint2(pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f));
+      dst4[2] = make_uint2(pack_bf16x2(c0.z, c1.z), pack_bf16x2(c2.z, 0.f));
+      dst4[3] = make_uint2(pack_bf16x2(c0.w, c1.w), pack_bf16x2(c2.w, 0.f));
+      if (gq == 0)
+        for (int k = 0; k < d.wl; ++k) row4[k] = make_uint2(0u, 0u);
+      if (gq == G - 1)
+        for (int k = d.wl + d.W; k < Wp; ++k) row4[k] = make_uint2(0u, 0u);
+    }
   }
 }
 
@@ -67,6 +85,12 @@ __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k
   if (d.layout == VINET_KLAYOUT_WIN8) {  // k = dh_tap*64 + dw*8 + ci; FPROP only
     const int tap = k >> 6, dw = (k >> 3) & 7, ci = k & 7;
     if (tap >= d.ntaps || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
+    const int dt = d.tap[tap][0], dh = d.tap[tap][1];
+    return __ldg(d.w + ((((int64_t)n * ldc + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
+  }
+  if (d.layout == VINET_KLAYOUT_WIN4) {  // k = dh_tap*64 + dw*4 + ci in the lower half of each 64-wide block; FPROP only
+    const int tap = k >> 6, dw = (k >> 2) & 15, ci = k & 3;
+    if (tap >= d.ntaps || dw >= 8 || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
     const int dt = d.tap[tap][0], dh = d.tap[tap][1];
     return __ldg(d.w + ((((int64_t)n * ldc + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
   }
@@ -246,6 +270,9 @@ using namespace vinet;
 extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->cpad % 8 == 0 && d->cpad >= d->C, "pack_input: cpad %d", d->cpad);
   VINET_CHECK(d->Wp == 0 || d->Wp >= d->wl + d->W, "pack_input: Wp %d < wl %d + W %d", d->Wp, d->wl, d->W);
+  VINET_CHECK(d->out4 == nullptr || (d->out_dtype == VINET_BF16 && d->C <= 4 && (d->Wp > 0 ? d->Wp : d->W) % 2 == 0 &&
+                                     (reinterpret_cast<uintptr_t>(d->out4) & 15) == 0),
+              "pack_input: the 4-channel copy needs bf16 output, C <= 4 and an even row width");
   const int64_t total = (int64_t)d->B * d->T * d->H * (d->Wp > 0 ? d->Wp : d->W);
   const bool vec4 = d->out_dtype == VINET_BF16 && d->C == 3 && d->cpad == 8 && d->sw == 1 && d->W % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && d->sb % 4 == 0 && d->sc % 4 == 0 && d->st % 4 == 0 && d->sh % 4 == 0;
@@ -280,7 +307,9 @@ extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t b
 
 extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
-  VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN8, "pack_weights: layout %d", d->layout);
+  VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN4, "pack_weights: layout %d", d->layout);
+  VINET_CHECK(d->layout != VINET_KLAYOUT_WIN4 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 4 && d->kw <= 8 && d->cs == 32),
+              "pack_weights: WIN4 needs an FPROP pack with Cin <= 4, kw <= 8, cs == 32");
   VINET_CHECK(d->part >= 0 && d->part <= 2 && (d->part == 0 || d->engine == VINET_ENGINE_TC), "pack_weights: part %d", d->part);
   VINET_CHECK(d->ld_cin == 0 || d->ld_cin >= d->Cin, "pack_weights: ld_cin %d < Cin %d", d->ld_cin, d->Cin);
   VINET_CHECK(d->layout != VINET_KLAYOUT_WIN8 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 8 && d->kw <= 8 && d->cs == 64),

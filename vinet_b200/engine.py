@@ -102,6 +102,7 @@ class WinAct(Act):
     def __init__(self, buf, B, T, H, W, wl, Wp):
         super().__init__(buf, B, T, H, W, 8)
         self.wl, self.Wp = wl, Wp
+        self.buf4 = None      # optional [B,T,H,Wp,4] copy with four channels per pixel (forward stem conv, VINET_KLAYOUT_WIN4)
 
 
 def _ptr(t):
@@ -356,6 +357,20 @@ class Engine:
             self._src(g.src[1], srcs[1])
         else:
             g.src[1].ptr, g.src[1].T = None, 0
+
+    def _fill_win_gather(self, g, aw, geom, To, Ho, Wo, taps, cpp):
+        """FPROP gather over the padded clip as overlapping pixel windows: one K block per kernel row dh holds the (dw, c) window
+        of 8 (cpp = 8 channels per pixel, the NDHWC8 clip) or 8 of 16 (cpp = 4, its 4-channel copy) pixels."""
+        g.mode, g.dtype = L.GATHER_FPROP, self.opdt
+        g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = aw.B, To, Ho, Wo, 1, 0
+        g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 8 * cpp, len(taps)
+        _fill_taps(g.tap, taps)
+        g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
+        s0 = g.src[0]
+        buf = aw.buf if cpp == 8 else aw.buf4
+        s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = buf.data_ptr(), None, None, cpp * geom.sw, aw.T, L.XF_IDENT
+        s0.ldh = aw.Wp * cpp
+        g.src[1].ptr, g.src[1].T = None, 0
 
     @staticmethod
     def tiling(n):
@@ -652,10 +667,22 @@ class Engine:
 
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
+        # forward of the stem on the 4-channel copy of the clip: windows of 8 pixels x 4 channels (Cs = 32) that start
+        # 4*sw elements apart, read in place by the streaming kernel (csrc/conv_stream.cu, conv_gemm_stream_win4)
+        win4 = False
+        if win and getattr(a0, "buf4", None) is not None and w.shape[1] <= 4 and geom.sw == 2 and a0.Wp % 2 == 0:
+            g4 = L.Gather()
+            self._fill_win_gather(g4, a0, geom, To, Ho, Wo, taps, 4)
+            win4 = bool(self.lib.fn["vinet_conv_win4_fused"](C.byref(g4), Cout))
         for ti, (pa, pw, tp, c0, cc) in enumerate(self.term_launches(taps, cs, chunk_channels=not win)):
             d = L.Conv()
             d.kernel = kern
-            fill_gather(d.g, psrcs[pa], tp, c0, cc)
+            if win4:
+                self._fill_win_gather(d.g, a0, geom, To, Ho, Wo, tp, 4)
+                cc, lay = 32, L.KLAYOUT_WIN4
+            else:
+                fill_gather(d.g, psrcs[pa], tp, c0, cc)
+                lay = layout
             d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
             d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
             d.out_dtype, d.accumulate = self.dt, (0 if ti == 0 else 1)
@@ -666,11 +693,11 @@ class Engine:
             if ep is not None:
                 assert bias is None
                 d.ep_scale, d.ep_shift, d.ep_act = _ptr(ep[0]), _ptr(ep[1]), ep[2]
-            wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, tp, cc, Cout, layout,
+            wp, block_n, n_tiles, k_blocks = self.packed_weight(w, name, L.GATHER_FPROP, tp, cc, Cout, lay,
                                                                 tiling=self.conv_tiling(d, Cout), part=pw,
-                                                                cslice=None if cc == cs else (c0, cc))
+                                                                cslice=None if (cc == cs or win4) else (c0, cc))
             d.w, d.N, d.block_n, d.n_tiles, d.k_blocks = wp.data_ptr(), Cout, block_n, n_tiles, k_blocks
-            self.timed(name, "fprop", flops * len(tp) * cc / (len(taps) * cs),
+            self.timed(name, "fprop", flops * len(tp) * (cs if win4 else cc) / (len(taps) * cs),
                        lambda: self.lib.call("vinet_conv_gemm", C.byref(d), self.eng, self.stream()))
         if not self.record:
             return None

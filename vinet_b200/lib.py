@@ -19,7 +19,7 @@ ENGINE_TC, ENGINE_SIMT = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 LOSS_KLDIV, LOSS_CC, LOSS_SIM, LOSS_NSS = 0, 1, 2, 3
 KERNEL_GATHER, KERNEL_TMA = 0, 1
-KLAYOUT_DENSE, KLAYOUT_TAP64, KLAYOUT_WIN8 = 0, 1, 2
+KLAYOUT_DENSE, KLAYOUT_TAP64, KLAYOUT_WIN8, KLAYOUT_WIN4 = 0, 1, 2, 3
 MAX_TAPS = 64
 TC_BLOCK_M, TC_BLOCK_K = 128, 64
 
@@ -57,7 +57,7 @@ class Pack(C.Structure):
 class PackInput(C.Structure):
     _fields_ = [("x", _p), ("sb", _i64), ("sc", _i64), ("st", _i64), ("sh", _i64), ("sw", _i64), ("B", _i32),
                 ("C", _i32), ("T", _i32), ("H", _i32), ("W", _i32), ("cpad", _i32), ("out", _p), ("out_dtype", _i32),
-                ("wl", _i32), ("Wp", _i32)]
+                ("wl", _i32), ("Wp", _i32), ("out4", _p)]
 
 
 class BnStats(C.Structure):
@@ -157,6 +157,7 @@ SIGNATURES = {
     "vinet_conv_tiling": (C.c_int, [C.POINTER(Conv), _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "vinet_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), _i32, _S]),
     "vinet_conv_up2_fused": (C.c_int, [C.POINTER(Gather), _i32, _i32, _i32]),
+    "vinet_conv_win4_fused": (C.c_int, [C.POINTER(Gather), _i32]),
     "vinet_relu_bwd": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i64, _i32, _p, _i64, _i32, _S]),
     "vinet_pack_weights": (C.c_int, [C.POINTER(Pack), _S]),
     "vinet_pack_weights_multi": (C.c_int, [_p, _p, _i32, _i64, _S]),

@@ -442,5 +442,15 @@ def pack_input(e, x):
     d.sb, d.sc, d.st, d.sh, d.sw = x.stride()
     d.B, d.C, d.T, d.H, d.W, d.cpad, d.out, d.out_dtype = B, 3, T, H, W, 8, buf.data_ptr(), e.dt
     d.wl, d.Wp = (wl, Wp) if win else (0, 0)
+    # bf16 tensor-core mode: a second, 4-channel copy of the clip - the forward stem convolution reads it in place through
+    # un-swizzled UMMA descriptors (VINET_KLAYOUT_WIN4, csrc/conv_stream.cu); the weight gradient keeps the 8-channel windows
+    buf4 = None
+    if win and not e.split and e.dt == L.BF16 and "vinet_conv_win4_fused" in e.lib.fn and not os.environ.get("VINET_NO_WIN4"):
+        buf4 = e.buf("input.packed4", (B, T, H, Wp, 4), torch.bfloat16)
+        d.out4 = buf4.data_ptr()
     e.call("vinet_pack_input", d)
-    return WinAct(buf, B, T, H, W, wl, Wp) if win else Act(buf, B, T, H, W, 8)
+    if not win:
+        return Act(buf, B, T, H, W, 8)
+    a = WinAct(buf, B, T, H, W, wl, Wp)
+    a.buf4 = buf4
+    return a
