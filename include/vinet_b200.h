@@ -48,7 +48,8 @@ enum { VINET_KERNEL_GATHER = 0, VINET_KERNEL_TMA = 1 };
  * WIN8 (stem, Cin <= 8, kw <= 8): the gather's taps enumerate dh only and one 64-wide K block holds the whole
  * (dw, c) window of a padded NDHWC8 row: k = dh*64 + dw*8 + c.  The matching source view has Cs = 64, ld = 8*sw.
  * WIN4 (stem forward, Cin <= 4, kw <= 8): the same idea on the 4-channel copy of the clip (vinet_pack_input_t.out4):
- * k = dh*64 + dw*4 + c, only the lower 32 entries of a block are used; the source view has Cs = 32, ld = 4*sw.  With sw = 2
+ * k = dh*64 + dw*4 + c (dw < 16; a forward gather with Cs = 32 reads the 8 pixels of the lower half, the weight gradient and
+ * the fallback kernels take 16-pixel windows, Cs = 64); the source view has ld = 4*sw.  With sw = 2
  * consecutive windows start 16 bytes apart, which lets the streaming kernel read them in place from a compact patch through
  * un-swizzled UMMA descriptors (csrc/conv_stream.cu, conv_gemm_stream_win4; vinet_conv_win4_fused tells). */
 enum { VINET_KLAYOUT_DENSE = 0, VINET_KLAYOUT_TAP64 = 1, VINET_KLAYOUT_WIN8 = 2, VINET_KLAYOUT_WIN4 = 3 };
@@ -187,7 +188,8 @@ typedef struct vinet_unpack {
   const float* dwp;
   float* grad;
   int32_t lddw, cs, Cout, Cin, ntaps;
-  int32_t win8_kh, win8_kw; /* both 0: vinet_unpack_wgrad layout; else the WIN8 layout of vinet_unpack_wgrad_win8 */
+  int32_t win8_kh, win8_kw; /* both 0: vinet_unpack_wgrad layout; else the window layout of vinet_unpack_wgrad_win8, with `cs` =
+                               channels per pixel of the window (0 or 8: WIN8; 4: WIN4, dwp row = dh*64 + dw*4 + ci) */
   int32_t begin;            /* first flat output element of this entry in the launch's concatenated element space */
 } vinet_unpack_t;
 int vinet_unpack_wgrad_multi(const vinet_unpack_t* d, int32_t n, vinet_stream_t stream);
@@ -202,8 +204,9 @@ typedef struct vinet_pack_input {
   int32_t out_dtype;
   int32_t wl, Wp; /* rows are written Wp >= wl + W pixels wide: wl zero pixels, the W pixels, zeros (0,0 = dense).
                      With explicit zero columns the stem conv can address a row as overlapping windows (WIN8). */
-  void* out4;     /* optional (bf16 output, C <= 4): a second copy [B,T,H,Wp,4] with FOUR channels per pixel (same wl / Wp, Wp even):
-                     the forward stem convolution reads it in place (VINET_KLAYOUT_WIN4); NULL = not written */
+  void* out4;     /* optional (bf16 output, C <= 4): the clip as [B,T,H,Wp,4], FOUR channels per pixel (same wl / Wp, Wp even): the
+                     forward stem convolution reads it in place, its weight gradient as 16-pixel windows (VINET_KLAYOUT_WIN4);
+                     NULL = not written.  `out` may be NULL when out4 is given (the bf16 tensor-core mode needs only this copy) */
 } vinet_pack_input_t;
 int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream);
 

@@ -21,7 +21,7 @@ __global__ void pack_input_kernel(const __grid_constant__ vinet_pack_input_t d) 
     const bool in = (unsigned)w < (unsigned)d.W;
     const float* src = d.x + b * d.sb + t * d.st + h * d.sh + (in ? w : 0) * d.sw;
     TO* dst = reinterpret_cast<TO*>(d.out) + i * d.cpad;
-    for (int c0 = 0; c0 < d.cpad; c0 += 8) {
+    for (int c0 = 0; c0 < d.cpad && d.out != nullptr; c0 += 8) {
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = (in && c0 + e < d.C) ? __ldg(src + (c0 + e) * d.sc) : 0.f;
@@ -53,16 +53,18 @@ __global__ void __launch_bounds__(256) pack_input_vec4_kernel(const __grid_const
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(src));
     const float4 c1 = __ldg(reinterpret_cast<const float4*>(src + d.sc));
     const float4 c2 = __ldg(reinterpret_cast<const float4*>(src + 2 * d.sc));
-    uint4* row = reinterpret_cast<uint4*>(d.out) + (((int64_t)b * d.T + t) * d.H + h) * Wp;   // one uint4 = one 8-channel pixel
-    uint4* dst = row + d.wl + gq * 4;
-    dst[0] = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), 0u, 0u);
-    dst[1] = make_uint4(pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f), 0u, 0u);
-    dst[2] = make_uint4(pack_bf16x2(c0.z, c1.z), pack_bf16x2(c2.z, 0.f), 0u, 0u);
-    dst[3] = make_uint4(pack_bf16x2(c0.w, c1.w), pack_bf16x2(c2.w, 0.f), 0u, 0u);
-    if (gq == 0)
-      for (int k = 0; k < d.wl; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (gq == G - 1)
-      for (int k = d.wl + d.W; k < Wp; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (d.out != nullptr) {
+      uint4* row = reinterpret_cast<uint4*>(d.out) + (((int64_t)b * d.T + t) * d.H + h) * Wp;   // one uint4 = one 8-channel pixel
+      uint4* dst = row + d.wl + gq * 4;
+      dst[0] = make_uint4(pack_bf16x2(c0.x, c1.x), pack_bf16x2(c2.x, 0.f), 0u, 0u);
+      dst[1] = make_uint4(pack_bf16x2(c0.y, c1.y), pack_bf16x2(c2.y, 0.f), 0u, 0u);
+      dst[2] = make_uint4(pack_bf16x2(c0.z, c1.z), pack_bf16x2(c2.z, 0.f), 0u, 0u);
+      dst[3] = make_uint4(pack_bf16x2(c0.w, c1.w), pack_bf16x2(c2.w, 0.f), 0u, 0u);
+      if (gq == 0)
+        for (int k = 0; k < d.wl; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (gq == G - 1)
+        for (int k = d.wl + d.W; k < Wp; ++k) row[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (d.out4 != nullptr) {   // the 4-channel copy: one uint2 per pixel
       uint2* row4 = reinterpret_cast<uint2*>(d.out4) + (((int64_t)b * d.T + t) * d.H + h) * Wp;
       uint2* dst4 = row4 + d.wl + gq * 4;
@@ -90,7 +92,7 @@ __device__ __forceinline__ float weight_elem(const vinet_pack_t& d, int n, int k
   }
   if (d.layout == VINET_KLAYOUT_WIN4) {  // k = dh_tap*64 + dw*4 + ci in the lower half of each 64-wide block; FPROP only
     const int tap = k >> 6, dw = (k >> 2) & 15, ci = k & 3;
-    if (tap >= d.ntaps || dw >= 8 || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
+    if (tap >= d.ntaps || dw >= d.kw || ci >= d.Cin || n >= d.Cout) return 0.f;
     const int dt = d.tap[tap][0], dh = d.tap[tap][1];
     return __ldg(d.w + ((((int64_t)n * ldc + ci) * d.kt + dt) * d.kh + dh) * d.kw + dw);
   }
@@ -110,15 +112,32 @@ __device__ __forceinline__ float weight_part(float v, int part) {
   return v;
 }
 
+// Which (row nl, K block kb, N tile nt) the r-th 128-byte row of a pack is.  Tap-aligned layouts enumerate the TAP innermost:
+// the threads of a warp / block that handle the taps of one (row, 64-channel block) read the same few sectors of the PyTorch
+// weight (elements of one (co, ci) pair are its kt*kh*kw consecutive floats), so they are fetched once instead of once per tap
+// by some other SM (measured: the every-step re-pack of all weights 0.35 ms -> see DESIGN.md).
+__device__ __forceinline__ void pack_chunk_coords(const vinet_pack_t& d, int64_t r, int& nl, int& kb, int& nt) {
+  if (d.layout != VINET_KLAYOUT_DENSE && d.ntaps > 1 && d.k_blocks % d.ntaps == 0) {
+    const int ncb = d.k_blocks / d.ntaps;
+    const int tap = (int)(r % d.ntaps); r /= d.ntaps;
+    nl = (int)(r % d.block_n); r /= d.block_n;
+    const int cb = (int)(r % ncb);
+    nt = (int)(r / ncb);
+    kb = tap * ncb + cb;
+  } else {
+    nl = (int)(r % d.block_n); r /= d.block_n;
+    kb = (int)(r % d.k_blocks);
+    nt = (int)(r / d.k_blocks);
+  }
+}
+
 // TC: one thread per 16-byte chunk (8 consecutive k) of [n_tiles][k_blocks][block_n][64], 128B-swizzled.
 __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
   const int64_t chunks = (int64_t)d.n_tiles * d.k_blocks * d.block_n * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
-    int64_t r = i >> 3;
-    const int nl = (int)(r % d.block_n); r /= d.block_n;
-    const int kb = (int)(r % d.k_blocks);
-    const int nt = (int)(r / d.k_blocks);
+    int nl, kb, nt;
+    pack_chunk_coords(d, i >> 3, nl, kb, nt);
     const int n = nt * d.block_n + nl;
     float v[8];
 #pragma unroll
@@ -143,10 +162,8 @@ __global__ void pack_weights_tc_multi_kernel(const vinet_pack_t* __restrict__ ta
     const vinet_pack_t& d = tab[lo];
     const int64_t li = i - __ldg(begin + lo);
     const int j = (int)(li & 7);
-    int64_t r = li >> 3;
-    const int nl = (int)(r % d.block_n); r /= d.block_n;
-    const int kb = (int)(r % d.k_blocks);
-    const int nt = (int)(r / d.k_blocks);
+    int nl, kb, nt;
+    pack_chunk_coords(d, li >> 3, nl, kb, nt);
     const int nn = nt * d.block_n + nl;
     float v[8];
 #pragma unroll
@@ -251,7 +268,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const __grid_co
       int r = li / d.win8_kw;
       const int dh = r % d.win8_kh; r /= d.win8_kh;
       const int ci = r % d.Cin, co = r / d.Cin;
-      d.grad[li] = d.dwp[((int64_t)dh * 64 + dw * 8 + ci) * d.lddw + co];
+      const int cpp = d.cs > 0 ? d.cs : 8;     // channels per pixel of the window layout: WIN8 (default) or WIN4
+      d.grad[li] = d.dwp[((int64_t)dh * 64 + dw * cpp + ci) * d.lddw + co];
     }
   }
 }
@@ -270,6 +288,7 @@ using namespace vinet;
 extern "C" int vinet_pack_input(const vinet_pack_input_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->cpad % 8 == 0 && d->cpad >= d->C, "pack_input: cpad %d", d->cpad);
   VINET_CHECK(d->Wp == 0 || d->Wp >= d->wl + d->W, "pack_input: Wp %d < wl %d + W %d", d->Wp, d->wl, d->W);
+  VINET_CHECK(d->out != nullptr || d->out4 != nullptr, "pack_input: no output");
   VINET_CHECK(d->out4 == nullptr || (d->out_dtype == VINET_BF16 && d->C <= 4 && (d->Wp > 0 ? d->Wp : d->W) % 2 == 0 &&
                                      (reinterpret_cast<uintptr_t>(d->out4) & 15) == 0),
               "pack_input: the 4-channel copy needs bf16 output, C <= 4 and an even row width");
@@ -308,8 +327,8 @@ extern "C" size_t vinet_packed_weight_bytes(int32_t engine, int32_t N, int32_t b
 extern "C" int vinet_pack_weights(const vinet_pack_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->ntaps <= VINET_MAX_TAPS && d->cs % 8 == 0, "pack_weights: ntaps %d cs %d", d->ntaps, d->cs);
   VINET_CHECK(d->layout >= VINET_KLAYOUT_DENSE && d->layout <= VINET_KLAYOUT_WIN4, "pack_weights: layout %d", d->layout);
-  VINET_CHECK(d->layout != VINET_KLAYOUT_WIN4 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 4 && d->kw <= 8 && d->cs == 32),
-              "pack_weights: WIN4 needs an FPROP pack with Cin <= 4, kw <= 8, cs == 32");
+  VINET_CHECK(d->layout != VINET_KLAYOUT_WIN4 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 4 && d->kw <= 8 && (d->cs == 32 || d->cs == 64)),
+              "pack_weights: WIN4 needs an FPROP pack with Cin <= 4, kw <= 8, cs 32 (8-pixel windows) or 64 (16-pixel windows)");
   VINET_CHECK(d->part >= 0 && d->part <= 2 && (d->part == 0 || d->engine == VINET_ENGINE_TC), "pack_weights: part %d", d->part);
   VINET_CHECK(d->ld_cin == 0 || d->ld_cin >= d->Cin, "pack_weights: ld_cin %d < Cin %d", d->ld_cin, d->Cin);
   VINET_CHECK(d->layout != VINET_KLAYOUT_WIN8 || (d->mode == VINET_GATHER_FPROP && d->Cin <= 8 && d->kw <= 8 && d->cs == 64),

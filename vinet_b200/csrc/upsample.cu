@@ -23,15 +23,14 @@ __global__ void upsample_fwd_kernel(const __grid_constant__ vinet_upsample_t d) 
   }
 }
 
-// weight with which low-res index i contributes to output coordinate Y
-__device__ __forceinline__ float up_weight(int Y, int n, int i) {
-  int i0, i1;
-  float l1;
-  up_taps(Y, n, i0, i1, l1);
-  float w = 0.f;
-  if (i0 == i) w += 1.f - l1;
-  if (i1 == i) w += l1;
-  return w;
+// Transposed interpolation: low-res index i receives from the hi-res coordinates 2i-1, 2i, 2i+1, 2i+2 with weights .25, .75, .75,
+// .25 (up_taps: Y = 2k+1 -> (k: .75, k+1: .25), Y = 2k+2 -> (k: .25, k+1: .75)); at the borders the clamped tap folds its weight
+// onto the edge pixel (2i -> 1 for i = 0, 2i+1 -> 1 for i = n-1) and the coordinates outside the image do not exist.
+__device__ __forceinline__ void up_bwd_taps(int i, int n, float (&w)[4]) {
+  w[0] = i > 0 ? 0.25f : 0.f;
+  w[1] = i > 0 ? 0.75f : 1.f;
+  w[2] = i < n - 1 ? 0.75f : 1.f;
+  w[3] = i < n - 1 ? 0.25f : 0.f;
 }
 
 template <typename T, typename TD, typename TG>
@@ -46,19 +45,25 @@ __global__ void upsample_bwd_kernel(const __grid_constant__ vinet_upsample_t d) 
     const int c = (int)(r % G) * 8; r /= G;
     const int x = (int)(r % d.w); r /= d.w;
     const int y = (int)(r % d.h); r /= d.h;  // r = b*T + t
+    float wy[4], wx[4];
+    up_bwd_taps(y, d.h, wy);
+    up_bwd_taps(x, d.w, wx);
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int Y = max(0, 2 * y - 2); Y <= min(H2 - 1, 2 * y + 3); ++Y) {
-      const float wy = up_weight(Y, d.h, y);
-      if (wy == 0.f) continue;
-      for (int X = max(0, 2 * x - 2); X <= min(W2 - 1, 2 * x + 3); ++X) {
-        const float wx = up_weight(X, d.w, x);
-        if (wx == 0.f) continue;
-        float g[8];
-        load8(gu + ((r * H2 + Y) * W2 + X) * d.ldgu + c, g);
+    const TG* frame = gu + r * H2 * W2 * d.ldgu + c;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wy * wx, g[e], acc[e]);
+    for (int a = 0; a < 4; ++a) {
+      if (wy[a] == 0.f) continue;
+      const TG* row = frame + (int64_t)(2 * y - 1 + a) * W2 * d.ldgu;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (wx[b] == 0.f) continue;
+        float g[8];
+        load8(row + (int64_t)(2 * x - 1 + b) * d.ldgu, g);
+        const float wgt = wy[a] * wx[b];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, g[e], acc[e]);
       }
     }
     if (d.relu) {

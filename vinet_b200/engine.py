@@ -99,10 +99,10 @@ class WinAct(Act):
     """The packed input clip stored with explicit zero columns ([B,T,H,Wp,8], image at columns wl..wl+W) so that
     the TMA-fed stem conv can address every row as overlapping sliding windows (VINET_KLAYOUT_WIN8)."""
 
-    def __init__(self, buf, B, T, H, W, wl, Wp):
+    def __init__(self, buf, B, T, H, W, wl, Wp, cpp=8):
         super().__init__(buf, B, T, H, W, 8)
         self.wl, self.Wp = wl, Wp
-        self.buf4 = None      # optional [B,T,H,Wp,4] copy with four channels per pixel (forward stem conv, VINET_KLAYOUT_WIN4)
+        self.cpp = cpp        # channels per stored pixel: 8 (VINET_KLAYOUT_WIN8) or 4 (bf16 tensor-core mode, VINET_KLAYOUT_WIN4)
 
 
 def _ptr(t):
@@ -358,18 +358,18 @@ class Engine:
         else:
             g.src[1].ptr, g.src[1].T = None, 0
 
-    def _fill_win_gather(self, g, aw, geom, To, Ho, Wo, taps, cpp):
+    def _fill_win_gather(self, g, aw, geom, To, Ho, Wo, taps, npx):
         """FPROP gather over the padded clip as overlapping pixel windows: one K block per kernel row dh holds the (dw, c) window
-        of 8 (cpp = 8 channels per pixel, the NDHWC8 clip) or 8 of 16 (cpp = 4, its 4-channel copy) pixels."""
+        of npx pixels x aw.cpp channels (64 elements: 8 pixels of the 8-channel clip or 16 of the 4-channel one; 32 elements:
+        the 8-pixel windows the streaming kernel reads in place from the 4-channel clip)."""
         g.mode, g.dtype = L.GATHER_FPROP, self.opdt
         g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = aw.B, To, Ho, Wo, 1, 0
-        g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 8 * cpp, len(taps)
+        g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, npx * aw.cpp, len(taps)
         _fill_taps(g.tap, taps)
         g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
         s0 = g.src[0]
-        buf = aw.buf if cpp == 8 else aw.buf4
-        s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = buf.data_ptr(), None, None, cpp * geom.sw, aw.T, L.XF_IDENT
-        s0.ldh = aw.Wp * cpp
+        s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = aw.buf.data_ptr(), None, None, aw.cpp * geom.sw, aw.T, L.XF_IDENT
+        s0.ldh = aw.Wp * aw.cpp
         g.src[1].ptr, g.src[1].T = None, 0
 
     @staticmethod
@@ -605,6 +605,7 @@ class Engine:
                 rows, C_ = a.B * a.T * a.H * a.Wp, 8
                 planes = self.split_view("%s.sp%d" % (name, si), a.buf.data_ptr(), 8, self.dt, rows, C_)
                 for i, t in enumerate(planes):
+                    assert a.cpp == 8
                     out[i].append(WinAct(t.view(a.B, a.T, a.H, a.Wp, 8), a.B, a.T, a.H, a.W, a.wl, a.Wp))
             else:
                 planes = self.split_view("%s.sp%d" % (name, si), a.ptr(), a.ld, self.dt, a.rows, a.C, a.xform, a.scale, a.shift,
@@ -635,7 +636,7 @@ class Engine:
         win = isinstance(a0, WinAct)
         tma = win or self.tma_ok(psrcs[0], geom)
         kern = L.KERNEL_TMA if tma else L.KERNEL_GATHER
-        layout = L.KLAYOUT_WIN8 if win else (L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE)
+        layout = ((L.KLAYOUT_WIN8 if a0.cpp == 8 else L.KLAYOUT_WIN4) if win else (L.KLAYOUT_TAP64 if tma else L.KLAYOUT_DENSE))
         To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
         assert (To, Ho, Wo, Cout) == (out.T, out.H, out.W, out.C), (name, (To, Ho, Wo, Cout), (out.T, out.H, out.W, out.C))
         assert w.shape[1] == (cin_real or cs), name
@@ -645,7 +646,7 @@ class Engine:
             # stem: one 64-wide K block per kernel row dh holds the (dw, c) window of 8 pixels x 8 channels;
             # output column wo reads padded pixels wo*sw .. wo*sw+7, i.e. consecutive windows overlap
             assert len(srcs) == 1 and geom.kt == 1 and geom.st == 1 and geom.kw <= 8 and geom.pw == a0.wl and w.shape[1] <= 8
-            assert (Wo - 1) * geom.sw + 8 <= a0.Wp
+            assert (Wo - 1) * geom.sw + 64 // a0.cpp <= a0.Wp
             taps, cs = [(0, dh, 0) for dh in range(geom.kh)], 64
 
         def fill_gather(g, ss, tp=None, c0=0, c=None):
@@ -654,35 +655,26 @@ class Engine:
                 if c is not None and c != cs:
                     ss = [a.slice(c0, c) for a in ss]
                 return self._gather_fprop(g, ss, geom, cs if c is None else c, To, Ho, Wo, tp)
-            aw = ss[0]
-            g.mode, g.dtype = L.GATHER_FPROP, self.opdt
-            g.B, g.Tr, g.Hr, g.Wr, g.row_tstep, g.row_toff = aw.B, To, Ho, Wo, 1, 0
-            g.Ts, g.Hs, g.Ws, g.Cs, g.ntaps = aw.T, aw.H, Wo, 64, len(tp)
-            _fill_taps(g.tap, tp)
-            g.st, g.sh, g.sw, g.pt, g.ph, g.pw = 1, geom.sh, 1, 0, geom.ph, 0
-            s0 = g.src[0]
-            s0.ptr, s0.scale, s0.shift, s0.ld, s0.T, s0.xform = aw.buf.data_ptr(), None, None, 8 * geom.sw, aw.T, L.XF_IDENT
-            s0.ldh = aw.Wp * 8
-            g.src[1].ptr, g.src[1].T = None, 0
+            self._fill_win_gather(g, ss[0], geom, To, Ho, Wo, tp, 64 // ss[0].cpp)
 
         cin_r = w.shape[1]
         flops = 2.0 * a0.B * To * Ho * Wo * nreal * cin_r * Cout
         # forward of the stem on the 4-channel copy of the clip: windows of 8 pixels x 4 channels (Cs = 32) that start
         # 4*sw elements apart, read in place by the streaming kernel (csrc/conv_stream.cu, conv_gemm_stream_win4)
         win4 = False
-        if win and getattr(a0, "buf4", None) is not None and w.shape[1] <= 4 and geom.sw == 2 and a0.Wp % 2 == 0:
+        if win and a0.cpp == 4 and w.shape[1] <= 4 and geom.sw == 2 and a0.Wp % 2 == 0 and "vinet_conv_win4_fused" in self.lib.fn:
             g4 = L.Gather()
-            self._fill_win_gather(g4, a0, geom, To, Ho, Wo, taps, 4)
+            self._fill_win_gather(g4, a0, geom, To, Ho, Wo, taps, 8)
             win4 = bool(self.lib.fn["vinet_conv_win4_fused"](C.byref(g4), Cout))
         for ti, (pa, pw, tp, c0, cc) in enumerate(self.term_launches(taps, cs, chunk_channels=not win)):
             d = L.Conv()
             d.kernel = kern
             if win4:
-                self._fill_win_gather(d.g, a0, geom, To, Ho, Wo, tp, 4)
-                cc, lay = 32, L.KLAYOUT_WIN4
+                self._fill_win_gather(d.g, a0, geom, To, Ho, Wo, tp, 8)
+                cc = 32
             else:
                 fill_gather(d.g, psrcs[pa], tp, c0, cc)
-                lay = layout
+            lay = layout
             d.out[0], d.ldo[0], d.out_T[0] = out.ptr(), out.ld, To
             d.out[1], d.ldo[1], d.out_T[1] = None, 0, 0
             d.out_dtype, d.accumulate = self.dt, (0 if ti == 0 else 1)
@@ -738,7 +730,7 @@ class Engine:
             else:
                 gw = self.grad_tensor(name + ".weight", w)
                 if win:
-                    self.unpack(dwp.data_ptr(), lddw, 0, gw, Cout, w.shape[1], 0, win8=(geom.kh, geom.kw))
+                    self.unpack(dwp.data_ptr(), lddw, 0 if a0.cpp == 8 else a0.cpp, gw, Cout, w.shape[1], 0, win8=(geom.kh, geom.kw))
                 else:
                     self.unpack(dwp.data_ptr(), lddw, csk, gw, Cout, w.shape[1], len(taps))
                 self.param_grads[name + ".weight"] = gw

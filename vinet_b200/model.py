@@ -434,23 +434,24 @@ def pack_input(e, x):
     assert x.dim() == 5 and x.shape[1] == 3 and x.dtype == torch.float32, "expected a (B,3,T,H,W) fp32 clip"
     B, _, T, H, W = x.shape
     assert H % 32 == 0 and W % 32 == 0, "H and W must be multiples of 32 (the reference fails otherwise)"
-    win = e.eng == L.ENGINE_TC and e.use_tma      # TMA engine: rows padded with zero columns (3 left, 5 right)
-    wl, Wp = (3, W + 8) if win else (0, W)
-    buf = e.buf("input.packed", (B, T, H, Wp, 8), e.tdtype)
+    win = e.eng == L.ENGINE_TC and e.use_tma      # TMA engine: rows padded with zero columns (3 left, >= 5 right)
+    # bf16 tensor-core mode: FOUR channels per pixel - the forward stem convolution reads the clip in place through un-swizzled
+    # UMMA descriptors and its weight gradient as 16-pixel windows (VINET_KLAYOUT_WIN4, csrc/conv_stream.cu); the parity modes
+    # keep the 8-channel fp32 clip they split into bf16 planes
+    win4 = (win and not e.split and e.dt == L.BF16 and "vinet_conv_win4_fused" in e.lib.fn and not os.environ.get("VINET_NO_WIN4"))
     d = L.PackInput()
     d.x = x.data_ptr()
     d.sb, d.sc, d.st, d.sh, d.sw = x.stride()
-    d.B, d.C, d.T, d.H, d.W, d.cpad, d.out, d.out_dtype = B, 3, T, H, W, 8, buf.data_ptr(), e.dt
+    d.B, d.C, d.T, d.H, d.W, d.cpad, d.out_dtype = B, 3, T, H, W, 8, e.dt
+    if win4:
+        wl, Wp = 3, W + 16                        # 16-pixel windows of the last output column stay inside the row
+        buf = e.buf("input.packed4", (B, T, H, Wp, 4), torch.bfloat16)
+        d.out, d.out4, d.wl, d.Wp = None, buf.data_ptr(), wl, Wp
+        e.call("vinet_pack_input", d)
+        return WinAct(buf, B, T, H, W, wl, Wp, cpp=4)
+    wl, Wp = (3, W + 8) if win else (0, W)
+    buf = e.buf("input.packed", (B, T, H, Wp, 8), e.tdtype)
+    d.out = buf.data_ptr()
     d.wl, d.Wp = (wl, Wp) if win else (0, 0)
-    # bf16 tensor-core mode: a second, 4-channel copy of the clip - the forward stem convolution reads it in place through
-    # un-swizzled UMMA descriptors (VINET_KLAYOUT_WIN4, csrc/conv_stream.cu); the weight gradient keeps the 8-channel windows
-    buf4 = None
-    if win and not e.split and e.dt == L.BF16 and "vinet_conv_win4_fused" in e.lib.fn and not os.environ.get("VINET_NO_WIN4"):
-        buf4 = e.buf("input.packed4", (B, T, H, Wp, 4), torch.bfloat16)
-        d.out4 = buf4.data_ptr()
     e.call("vinet_pack_input", d)
-    if not win:
-        return Act(buf, B, T, H, W, 8)
-    a = WinAct(buf, B, T, H, W, wl, Wp)
-    a.buf4 = buf4
-    return a
+    return WinAct(buf, B, T, H, W, wl, Wp) if win else Act(buf, B, T, H, W, 8)
