@@ -131,6 +131,32 @@ __device__ __forceinline__ void pack_chunk_coords(const vinet_pack_t& d, int64_t
   }
 }
 
+// The 8 bf16 of chunk j of row n of K block kb.  TAP64 (every pack but the stem's): the 8 elements share their tap and are 8
+// consecutive channels, so ONE address computation and a constant stride replace eight general weight_elem() index chains
+// (the every-step re-pack of all weights was instruction-bound: ~500 instructions per 16 output bytes).
+__device__ __forceinline__ uint4 pack_chunk(const vinet_pack_t& d, int n, int kb, int j) {
+  float v[8];
+  if (d.layout == VINET_KLAYOUT_TAP64) {
+    const int ncb = (d.cs + 63) >> 6;
+    const int tap = kb / ncb, c0 = (kb - tap * ncb) * 64 + j * 8;
+    const int ldc = d.ld_cin > 0 ? d.ld_cin : d.Cin;
+    const int KT = d.kt * d.kh * d.kw;
+    const int toff = (d.tap[tap][0] * d.kh + d.tap[tap][1]) * d.kw + d.tap[tap][2];
+    const bool fprop = d.mode == VINET_GATHER_FPROP;
+    const int nmax = fprop ? d.Cout : d.Cin, cmax = min(d.cs, fprop ? d.Cin : d.Cout);
+    // FPROP: (co, ci) = (n, c); DGRAD: (co, ci) = (c, n)
+    const float* p = d.w + (fprop ? ((int64_t)n * ldc + c0) : ((int64_t)c0 * ldc + n)) * KT + toff;
+    const int64_t step = fprop ? KT : (int64_t)ldc * KT;
+    const bool row_ok = tap < d.ntaps && n < nmax;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (row_ok && c0 + e < cmax) ? weight_part(__ldg(p + e * step), d.part) : 0.f;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = weight_part(weight_elem(d, n, kb * 64 + j * 8 + e), d.part);
+  }
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
 // TC: one thread per 16-byte chunk (8 consecutive k) of [n_tiles][k_blocks][block_n][64], 128B-swizzled.
 __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
   const int64_t chunks = (int64_t)d.n_tiles * d.k_blocks * d.block_n * 8;
@@ -139,12 +165,8 @@ __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
     int nl, kb, nt;
     pack_chunk_coords(d, i >> 3, nl, kb, nt);
     const int n = nt * d.block_n + nl;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = weight_part(weight_elem(d, n, kb * 64 + j * 8 + e), d.part);
     uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
-    uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
+    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = pack_chunk(d, n, kb, j);
   }
 }
 
@@ -153,11 +175,26 @@ __global__ void pack_weights_tc_kernel(const __grid_constant__ vinet_pack_t d) {
 // begin[e] is the first 16-byte chunk of entry e in the concatenated chunk space.
 __global__ void pack_weights_tc_multi_kernel(const vinet_pack_t* __restrict__ tab, const int64_t* __restrict__ begin, int n,
                                              int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  // (warp-uniform loop bound: the shuffles below need the whole warp; lanes past the end idle inside)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - lane < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // entry of this chunk: the warp's first lane searches, the others only when they lie past that entry's end
+    const int64_t i0 = i - lane;
     int lo = 0, hi = n - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(begin + mid) <= i) lo = mid; else hi = mid - 1;
+    if (lane == 0) {
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(begin + mid) <= i0) lo = mid; else hi = mid - 1;
+      }
+    }
+    lo = __shfl_sync(0xffffffffu, lo, 0);
+    if (i >= total) continue;
+    if (lo + 1 < n && __ldg(begin + lo + 1) <= i) {
+      hi = n - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(begin + mid) <= i) lo = mid; else hi = mid - 1;
+      }
     }
     const vinet_pack_t& d = tab[lo];
     const int64_t li = i - __ldg(begin + lo);
@@ -165,12 +202,8 @@ __global__ void pack_weights_tc_multi_kernel(const vinet_pack_t* __restrict__ ta
     int nl, kb, nt;
     pack_chunk_coords(d, li >> 3, nl, kb, nt);
     const int nn = nt * d.block_n + nl;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = weight_part(weight_elem(d, nn, kb * 64 + j * 8 + e), d.part);
     uint8_t* tile = reinterpret_cast<uint8_t*>(d.out) + ((int64_t)nt * d.k_blocks + kb) * d.block_n * 128;
-    uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = u;
+    *reinterpret_cast<uint4*>(tile + nl * 128 + ((j ^ (nl & 7)) << 4)) = pack_chunk(d, nn, kb, j);
   }
 }
 
