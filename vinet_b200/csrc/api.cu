@@ -29,6 +29,7 @@ int tc_debug_set(unsigned int v);
 int tma_pair_set(int v);
 int stream_enable_set(int v);
 int pool_fast_set(int v);
+int stream_issue_clk_set(int v);
 int conv_stream_tiling(const vinet_conv_t* d, int* block_n, int* n_tiles);
 int conv_stream_up2_ok(const vinet_conv_t* d);
 int conv_stream_win4_ok(const vinet_conv_t* d);
@@ -196,6 +197,7 @@ extern "C" int vinet_debug_set(int32_t key, int32_t value) {
   if (key == 1) return tma_pair_set(value);
   if (key == 2) return stream_enable_set(value);
   if (key == 3) return pool_fast_set(value);
+  if (key == 4) return stream_issue_clk_set(value);
   VINET_CHECK(key == 0, "debug_set: unknown key %d", key);
   VINET_CHECK(tc_debug_set((unsigned int)value) == 0, "debug_set: cudaMemcpyToSymbol failed");
   return 0;

@@ -37,6 +37,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef VINET_WAIT_SLEEP
+    __nanosleep(VINET_WAIT_SLEEP);
+#endif
     if (++spins > (1u << 26)) {
       printf("vinet_b200: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
              blockIdx.y, threadIdx.x, bar, parity);

@@ -238,6 +238,9 @@ class Library:
         mine = [C.sizeof(t) for t in ABI_STRUCTS]
         if n != len(ABI_STRUCTS) or list(sizes) != mine:
             raise VinetError("ABI mismatch between lib.py and %s: %s vs %s" % (path, list(sizes), mine))
+        for kv in os.environ.get("VINET_DEBUG_SET", "").split(","):      # development knobs, e.g. VINET_DEBUG_SET=4=200
+            if "=" in kv:
+                self.call("vinet_debug_set", int(kv.split("=")[0]), int(kv.split("=")[1]))
 
     def call(self, name, *args):
         rc = self.fn[name](*args)
