@@ -98,12 +98,20 @@ if __name__ == "__main__":
     fl3cs = 2.0 * B * 16 * 28 * 48 * (9 * 128) * 192          # Mixed_3c branch1 conv_s
     fl3ct = 2.0 * B * 16 * 28 * 48 * (3 * 192) * 192          # Mixed_3c branch1 conv_t
     fl2 = 2.0 * B * 4 * 14 * 24 * (27 * 832) * 480            # decoder.convtsp2.0
+    fl43 = 2.0 * B * 2 * 112 * 192 * (18 * 64) * 32           # decoder.convtsp4.3
+    flstem = 2.0 * B * 32 * 112 * 192 * 147 * 64              # backbone.base1.0.conv_s (real taps: 7x7x3)
     caps = {}
     for rep, key, title, flops in [
             ("prof_tsp3_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp3.0",
-             "dominant kernel, largest launch: decoder.convtsp3.0 fprop (conv_stream_kernel: halo tiles, 3 sub-tiles, 3 issuing warps), B=8", fl),
+             "dominant kernel, largest launch: decoder.convtsp3.0 fprop (conv_stream_kernel<UP>: halo tiles, source 0 read through relu + "
+             "2x bilinear by the interpolating producer warps), B=8", fl),
             ("prof_tsp3_wgrad.ncu-rep", "conv_wgrad_halo_kernel/wgrad:decoder.convtsp3.0",
-             "decoder.convtsp3.0 wgrad (conv_wgrad_halo_kernel), B=8", fl),
+             "decoder.convtsp3.0 wgrad (conv_wgrad_halo_kernel<UP>: activation boxes of source 0 interpolated in the kernel), B=8", fl),
+            ("prof_tsp43_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp4.3",
+             "decoder.convtsp4.3 fprop (conv_stream_kernel<UP>: EVERY activation stage is interpolated, no TMA activation traffic), B=8", fl43),
+            ("prof_stem_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.0.conv_s",
+             "stem conv_s fprop (conv_stream_kernel, VINET_KLAYOUT_WIN4: compact 4-channel patch read in place through un-swizzled "
+             "overlapping UMMA descriptors), B=8", flstem),
             ("prof_b13s_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.3.conv_s",
              "SepConv3d stack: backbone.base1.3.conv_s fprop (conv_stream_kernel), B=8", fl13),
             ("prof_b13t_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base1.3.conv_t",
@@ -113,13 +121,14 @@ if __name__ == "__main__":
             ("prof_3ct_fprop.ncu-rep", "conv_stream_kernel/fprop:backbone.base2.1.branch1.1.conv_t",
              "SepConv3d stack: Mixed_3c branch1 conv_t fprop (conv_stream_kernel), B=8", fl3ct),
             ("prof_tsp2_fprop.ncu-rep", "conv_stream_kernel/fprop:decoder.convtsp2.0",
-             "best launch of the dominant kernel: decoder.convtsp2.0 fprop (conv_stream_kernel), B=8", fl2)]:
+             "best launch of the dominant kernel: decoder.convtsp2.0 fprop (conv_stream_kernel<UP>), B=8", fl2)]:
         r = ncu_summary(rep, title, flops)
         if r:
             caps[key] = r
     json.dump({"round": R, "dominant_kernel": "conv_stream_kernel/fprop:decoder.convtsp3.0", "captures": caps},
               open(os.path.join(P, "%s_top_kernel.json" % R), "w"), indent=1)
-    for f in ("profile_step.log", "diag_tma.log"):
+    for f in ("profile_step.log", "diag_tma.log", "up2_bench.txt"):
         if os.path.isfile(os.path.join(G, f)):
-            open(os.path.join(P, "%s_%s" % (R, f.replace(".log", ".txt"))), "w").write(open(os.path.join(G, f)).read())
+            txt = "\n".join(l for l in open(os.path.join(G, f)).read().splitlines() if "UserWarning" not in l and "_warn_once" not in l)
+            open(os.path.join(P, "%s_%s" % (R, f.replace(".log", ".txt"))), "w").write(txt + "\n")
     print("launch list total %.2f ms; captures" % s, caps)

@@ -86,6 +86,44 @@ __device__ __forceinline__ StItem st_decode(const StreamParams& p, int item) {
   return c;
 }
 
+// The work items of one CTA (item = blockIdx.x, += gridDim.x) decoded INCREMENTALLY: the stride is split into its (tx, ty, run,
+// clip) digits once, every further item costs a few adds and compares instead of four divisions (the item prologue is on the MMA
+// issuers' critical path: the layers with few taps spend as long there as in their MMAs).
+struct StItemIter {
+  int tx, ty, r, b, dtx, dty, dr, db;
+  __device__ __forceinline__ void init(const StreamParams& p, int first, int stride) {
+    int m = first;
+    tx = m % p.items_w; m /= p.items_w;
+    ty = m % p.items_h; m /= p.items_h;
+    r = m % p.nruns;
+    b = m / p.nruns;
+    m = stride;
+    dtx = m % p.items_w; m /= p.items_w;
+    dty = m % p.items_h; m /= p.items_h;
+    dr = m % p.nruns;
+    db = m / p.nruns;
+  }
+  __device__ __forceinline__ StItem get(const StreamParams& p) const {
+    StItem c;
+    c.tx = tx; c.ty = ty; c.b = b;
+    c.i0 = r * p.run;
+    c.i1 = min(p.walk_Tr, c.i0 + p.run);
+    return c;
+  }
+  __device__ __forceinline__ void next(const StreamParams& p) {
+    tx += dtx;
+    int carry = tx >= p.items_w;
+    tx -= carry ? p.items_w : 0;
+    ty += dty + carry;
+    carry = ty >= p.items_h;
+    ty -= carry ? p.items_h : 0;
+    r += dr + carry;
+    carry = r >= p.nruns;
+    r -= carry ? p.nruns : 0;
+    b += db + carry;
+  }
+};
+
 // Walk of the real source frames [max(first,0), min(last,Ts-1)] of one work item, carrying f = q*S + r without divisions.
 struct StWalk {
   int f, f_end, q, r, i0, n;  // n = i1 - i0
@@ -148,6 +186,62 @@ __device__ __forceinline__ void st_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t
       : "memory");
 }
 
+// The MMAs of taps [j0, j1) of one (stage, accumulator) for ONE sub-tile, issued by the calling thread alone (the elected lane of
+// an issuing warp).  Resident weights: the tap's block sits at b_cb + its table offset.  Streamed weights: the taps arrive through
+// the ring (sb, phb, b_lo_slot are the ring position at entry; every lane of the warp advances its copy by j1 - j0 afterwards).
+__device__ __forceinline__ void st_issue_taps(const int2* s_tap, int j0, int j1, int nk, uint32_t td, uint32_t a_base, uint32_t a_hi,
+                                              uint32_t b_cb, uint32_t b_hi, uint32_t idesc, uint32_t keep, bool wres, uint32_t full_b,
+                                              uint32_t empty_b, int sb, uint32_t phb, uint32_t b_lo_slot, uint32_t sB_lo, uint32_t b16,
+                                              int BS) {
+  if (nk == 4) {
+#pragma unroll 3
+    for (int j = j0; j < j1; ++j) {
+      const int2 tj = s_tap[j];
+      uint32_t b_lo;
+      if (wres) {
+        b_lo = b_cb + (uint32_t)tj.y;
+      } else {
+        mbar_wait(full_b + 8 * sb, phb);
+        tc_fence_after();
+        b_lo = b_lo_slot;
+      }
+      const uint32_t a_lo = a_base + (uint32_t)tj.x;
+      st_umma(td, a_lo, a_hi, b_lo, b_hi, idesc, keep);
+      st_umma(td, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+      st_umma(td, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+      st_umma(td, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+      keep = 1u;
+      if (!wres) {
+        umma_commit(empty_b + 8 * sb);
+        b_lo_slot += b16;
+        if (++sb == BS) { sb = 0; phb ^= 1u; b_lo_slot = sB_lo; }
+      }
+    }
+  } else {
+    for (int j = j0; j < j1; ++j) {
+      const int2 tj = s_tap[j];
+      uint32_t b_lo;
+      if (wres) {
+        b_lo = b_cb + (uint32_t)tj.y;
+      } else {
+        mbar_wait(full_b + 8 * sb, phb);
+        tc_fence_after();
+        b_lo = b_lo_slot;
+      }
+      const uint32_t a_lo = a_base + (uint32_t)tj.x;
+      st_umma(td, a_lo, a_hi, b_lo, b_hi, idesc, keep);
+      if (nk > 1) st_umma(td, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+      if (nk > 2) st_umma(td, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+      keep = 1u;
+      if (!wres) {
+        umma_commit(empty_b + 8 * sb);
+        b_lo_slot += b16;
+        if (++sb == BS) { sb = 0; phb ^= 1u; b_lo_slot = sB_lo; }
+      }
+    }
+  }
+}
+
 // -DVINET_ST_PROF (development builds only): every role accumulates the clocks it spends in its mbarrier waits (the issuers also
 // the clocks inside their tcgen05.mma groups) and CTA (0,0) prints them at the end.
 #ifdef VINET_ST_PROF
@@ -190,6 +284,11 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
   const uint32_t full_acc = empty_b + 8 * BS, empty_acc = full_acc + 8 * p.nacc, wbar = empty_acc + 8 * p.nacc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 2 * p.nacc + 1);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // ST_STATS_FLOATS floats, used when p.d.stats != nullptr
+  // per-tap descriptor offsets (activation window, weight block) in shared memory: the issue loop reads them once per tap, and an
+  // indexed load from the parameter bank (c[0][R + ...]) costs it several times an LDS
+  int2* s_tap = reinterpret_cast<int2*>(s_stats + ST_STATS_FLOATS);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + VINET_MAX_TAPS)
+    s_tap[threadIdx.x - 64] = make_int2(p.sp_aoff16[threadIdx.x - 64], p.sp_boff16[threadIdx.x - 64]);
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const vinet_gather_t& g = p.d.g;
@@ -229,8 +328,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
-        const StItem c = st_decode(p, item);
+      StItemIter it;
+      it.init(p, blockIdx.x, gridDim.x);
+      for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+        const StItem c = it.get(p);
         const int ns = st_nsub_eff(p, c);
         StWalk wk;
         for (wk.init(p, c); wk.f <= wk.f_end; wk.next(p)) {
@@ -283,8 +384,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
       } else {
         int s = 0;
         uint32_t ph = 0;
-        for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
-          const StItem c = st_decode(p, item);
+        StItemIter it;
+        it.init(p, blockIdx.x, gridDim.x);
+        for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+          const StItem c = it.get(p);
           StWalk wk;
           for (wk.init(p, c); wk.f <= wk.f_end; wk.next(p)) {
             for (int cb = 0; cb < p.ncb; ++cb) {
@@ -325,8 +428,62 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
     uint32_t a_lo_stage = sA_lo, b_lo_slot = sB_lo;
     uint32_t slot_done = 0, slot_start = 0, ph_start = 0, fresh = 0;
     if (wres) mbar_wait(wbar, 0);
-    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
-      const StItem c = st_decode(p, item);
+    StItemIter it;
+    it.init(p, blockIdx.x, gridDim.x);
+    // One tap group at offset 0 (every (1,k,k) convolution and every temporal-halo tile: most launches of the model) with resident
+    // weights and one sub-tile per issuer: output i reads exactly stage i, so the frame walk, the tap-group search and the slot
+    // arithmetic of the general loop below collapse - and those ~150 scalar instructions per item were as long as the MMAs of a
+    // 7-tap item.  Same barrier sequence as the general loop (the producers and the epilogue do not change).
+    if (p.ntg == 1 && p.S == 1 && p.e_min == 0 && p.e_max == 0 && p.walk_Ts >= p.walk_Tr && p.nsub <= p.ni) {
+      const int j0 = p.tg_first[0], j1 = p.tg_first[1];
+      const uint32_t a_sub = sub16_0, td_sub = td_0;
+      uint32_t slot = 0, ph_acc = 0;
+      for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+        const StItem c = it.get(p);
+        const bool mine = sub0 < st_nsub_eff(p, c);
+        for (int i = c.i0; i < c.i1; ++i) {
+          ST_PROF_WAIT(prof_w1, mbar_wait(empty_acc + 8 * slot, ph_acc ^ 1u));
+          tc_fence_after();
+          const uint32_t td = tmem_base + slot * acc_set + td_sub;
+          uint32_t keep = 0u;
+          for (int cb = 0; cb < p.ncb; ++cb) {
+            ST_PROF_WAIT(prof_w0, mbar_wait(full_a + 8 * sa, pha));
+            tc_fence_after();
+            const int rem = g.Cs - cb * 64;
+            const int nk = rem >= 64 ? 4 : (rem + 15) >> 4;
+            const uint32_t b_cb = sB_lo + (uint32_t)cb * b16;
+            if (st_elect_one()) {
+              if (mine) {
+                st_issue_taps(s_tap, j0, j1, nk, td, a_lo_stage + a_sub, a_hi, b_cb, b_hi, idesc, keep, wres, full_b, empty_b, sb, phb,
+                              b_lo_slot, sB_lo, b16, BS);
+              } else if (!wres) {   // a sub-tile past the right edge: nothing to add, the weight ring still counts this issuer
+                int s2 = sb;
+                uint32_t ph2 = phb;
+                for (int j = j0; j < j1; ++j) {
+                  mbar_wait(full_b + 8 * s2, ph2);
+                  umma_commit(empty_b + 8 * s2);
+                  if (++s2 == BS) { s2 = 0; ph2 ^= 1u; }
+                }
+              }
+              umma_commit(empty_a + 8 * sa);
+              if (cb == p.ncb - 1) umma_commit(full_acc + 8 * slot);
+            }
+            if (!wres) {      // every lane advances its copy of the weight ring position
+              sb += j1 - j0;
+              while (sb >= BS) { sb -= BS; phb ^= 1u; }
+              b_lo_slot = sB_lo + (uint32_t)sb * b16;
+            }
+            __syncwarp();
+            keep = 1u;
+            a_lo_stage += a_stage16;
+            if (++sa == AS) { sa = 0; pha ^= 1u; a_lo_stage = sA_lo; }
+          }
+          if (++slot == nacc) { slot = 0; ph_acc ^= 1u; }
+        }
+      }
+    } else
+    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+      const StItem c = it.get(p);
       const int ns = st_nsub_eff(p, c);
       int i_done = c.i0, i_start = c.i0;  // next output frame to commit / to start (slot_start == slot_done here)
       StWalk wk;
@@ -354,22 +511,47 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
               uint32_t keep = ((fresh >> slot) & 1u) ^ 1u;
               fresh &= ~(1u << slot);
               const int j_end = p.tg_first[tg + 1];
+              if (sub0 + ni >= ns) {
+                // lean path (one sub-tile per issuer): ONE elected lane issues the MMAs of all taps of the group back to back -
+                // per tap one LDS, two adds and four tcgen05.mma (+ the weight ring's wait / commit when the weights stream)
+                const int j_first = p.tg_first[tg];
+                if (st_elect_one()) {
+                  if (sub0 < ns)
+                    st_issue_taps(s_tap, j_first, j_end, nk, tacc + td_0, a_lo_stage + sub16_0, a_hi, b_cb, b_hi, idesc, keep, wres, full_b,
+                                  empty_b, sb, phb, b_lo_slot, sB_lo, b16, BS);
+                  else if (!wres) {  // a sub-tile past the right edge: nothing to add, but the weight ring counts this issuer (it
+                    int s2 = sb;     // waits like the others: an arrival ahead of the ring would land in the wrong phase)
+                    uint32_t ph2 = phb;
+                    for (int j = j_first; j < j_end; ++j) {
+                      mbar_wait(full_b + 8 * s2, ph2);
+                      umma_commit(empty_b + 8 * s2);
+                      if (++s2 == BS) { s2 = 0; ph2 ^= 1u; }
+                    }
+                  }
+                }
+                __syncwarp();
+                if (!wres) {      // every lane advances its copy of the ring position
+                  const int n = j_end - j_first;
+                  sb += n;
+                  while (sb >= BS) { sb -= BS; phb ^= 1u; }
+                  b_lo_slot = sB_lo + (uint32_t)sb * b16;
+                }
+                continue;
+              }
               for (int j = p.tg_first[tg]; j < j_end; ++j) {
+                const int2 tj = s_tap[j];
                 uint32_t b_lo;
                 if (wres) {
-                  b_lo = b_cb + (uint32_t)p.sp_boff16[j];
+                  b_lo = b_cb + (uint32_t)tj.y;
                 } else {
                   mbar_wait(full_b + 8 * sb, phb);
                   tc_fence_after();
                   b_lo = b_lo_slot;
                 }
-                uint32_t a_lo = a_lo_stage + (uint32_t)p.sp_aoff16[j] + sub16_0;
+                uint32_t a_lo = a_lo_stage + (uint32_t)tj.x + sub16_0;
                 uint32_t td = tacc + td_0;
                 for (int sub = sub0; sub < ns; sub += ni, a_lo += sub16_step, td += td_step) {
                   if (st_elect_one()) {
-#ifdef VINET_ST_PROF
-                    const long long tm0 = clock64();
-#endif
                     st_umma(td, a_lo, a_hi, b_lo, b_hi, idesc, keep);
                     if (nk == 4) {
                       st_umma(td, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
@@ -379,9 +561,6 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
                       if (nk > 1) st_umma(td, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                       if (nk > 2) st_umma(td, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                     }
-#ifdef VINET_ST_PROF
-                    prof_w2 += clock64() - tm0;
-#endif
                   }
                 }
                 keep = 1u;
@@ -422,8 +601,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
     const __nv_bfloat16* src0 = reinterpret_cast<const __nv_bfloat16*>(s0.ptr);
     int s = 0;
     uint32_t ph = 0;
-    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
-      const StItem c = st_decode(p, item);
+    StItemIter it;
+    it.init(p, blockIdx.x, gridDim.x);
+    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+      const StItem c = it.get(p);
       StWalk wk;
       for (wk.init(p, c); wk.f <= wk.f_end; wk.next(p)) {
         if (!wk.used(p)) continue;
@@ -463,8 +644,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     }
     uint32_t slot = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x) {
-      const StItem c = st_decode(p, item);
+    StItemIter it;
+    it.init(p, blockIdx.x, gridDim.x);
+    for (int item = blockIdx.x; item < p.items_per_nt; item += gridDim.x, it.next(p)) {
+      const StItem c = it.get(p);
       const int ns = st_nsub_eff(p, c);
       for (int i = c.i0; i < c.i1; ++i) {
         ST_PROF_WAIT(prof_w0, mbar_wait(full_acc + 8 * slot, ph));
