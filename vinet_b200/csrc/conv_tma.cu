@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           const uint32_t b_lo = sB_lo + (uint32_t)(p.wres ? tap * p.ncb + cb : s) * b16;
           uint32_t a_lo = sA_lo + (uint32_t)s * a_stage16;
           uint32_t td = tacc;
-          for (int hf = 0; hf < ic.nh; ++hf, a_lo += (TC_A_BYTES >> 4), td += p.acc_stride) {
-            if (tma_elect_one()) {
+          if (tma_elect_one()) {   // ONE elected lane issues both halves of the stage and releases it (see conv_stream.cu: the
+            for (int hf = 0; hf < ic.nh; ++hf, a_lo += (TC_A_BYTES >> 4), td += p.acc_stride) {   // issue path is the critical one)
               tma_umma(td, a_lo, hi, b_lo, hi, idesc, acc);
               if (nk == 4) {
                 tma_umma(td, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
@@ -240,9 +240,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
                 if (nk > 2) tma_umma(td, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
               }
             }
+            umma_commit(empty0 + 8 * s);
           }
+          __syncwarp();
           acc = 1;
-          if (tma_elect_one()) umma_commit(empty0 + 8 * s);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -490,19 +491,18 @@ __global__ void __launch_bounds__(TMA_WGRAD_THREADS, 1) conv_wgrad_tma_kernel(co
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
       const uint32_t b_lo0 = (st16 + (uint32_t)upc * unit16) | lbo;
-      for (int mbi = 0; mbi < nmb; ++mbi) {
-        const uint32_t a_lo0 = (st16 + (uint32_t)(2 * mbi) * unit16) | lbo;
-        const uint32_t tacc = tmem_base + (uint32_t)mbi * p.acc_cols;
-        if (tma_elect_one()) {
+      if (tma_elect_one()) {   // one elected lane issues every accumulator's MMAs of the stage and releases it
+        for (int mbi = 0; mbi < nmb; ++mbi) {
+          const uint32_t a_lo0 = (st16 + (uint32_t)(2 * mbi) * unit16) | lbo;
+          const uint32_t tacc = tmem_base + (uint32_t)mbi * p.acc_cols;
           // 16 reduction rows (positions) per MMA = two 8-row swizzle atoms = 2048 B
           for (int kk = 0; kk < ksteps; ++kk)
             tma_umma(tacc, a_lo0 + (uint32_t)kk * 128u, hi, b_lo0 + (uint32_t)kk * 128u, hi, idesc, (uint32_t)((kb | kk) != 0));
         }
-      }
-      if (tma_elect_one()) {
         umma_commit(empty0 + 8 * s);
         if (kb == KB - 1) umma_commit(accum_bar);
       }
+      __syncwarp();
       st16 += stage16;
       if (++s == stages) { s = 0; ph ^= 1u; st16 = s0_16; }
     }

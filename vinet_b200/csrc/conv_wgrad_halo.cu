@@ -174,21 +174,20 @@ __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         const uint32_t b_lo0 = (st16 + (p.a_bytes >> 4)) | b_lbo;
-        for (int a = k; a < p.naccs; a += p.ni) {
-          const int j0 = 2 * a, j1 = min(2 * a + 1, p.nsp - 1);
-          const int o0 = p.uoff16[j0], o1 = p.uoff16[j1];
-          const uint32_t a_lo0 = (st16 + (uint32_t)o0) | ((uint32_t)(o1 - o0) << 16);   // LBO = distance between the two taps
-          const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
-          if (wh_elect_one()) {
+        if (wh_elect_one()) {   // one elected lane issues this issuer's accumulators of the chunk and releases the stage
+          for (int a = k; a < p.naccs; a += p.ni) {
+            const int j0 = 2 * a, j1 = min(2 * a + 1, p.nsp - 1);
+            const int o0 = p.uoff16[j0], o1 = p.uoff16[j1];
+            const uint32_t a_lo0 = (st16 + (uint32_t)o0) | ((uint32_t)(o1 - o0) << 16);   // LBO = distance between the two taps
+            const uint32_t tacc = tmem_base + (uint32_t)a * p.acc_cols;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               wh_umma(tacc, a_lo0 + (uint32_t)kk * kstep_a, a_hi, b_lo0 + (uint32_t)kk * 128u, b_hi, p.idesc, (uint32_t)((kb | kk) != 0));
           }
-        }
-        if (wh_elect_one()) {
           umma_commit(empty0 + 8 * s);
           if (kb == KB - 1) umma_commit(accum_bar);
         }
+        __syncwarp();
         st16 += stage16;
         if (++s == stages) { s = 0; ph ^= 1u; st16 = s0_16; }
       }
