@@ -75,8 +75,24 @@ __device__ __forceinline__ void wh_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t
       : "memory");
 }
 
+#ifdef VINET_ST_PROF
+#define WH_PROF_WAIT(acc, ...)            \
+  do {                                    \
+    const long long t0__ = clock64();     \
+    __VA_ARGS__;                          \
+    (acc) += clock64() - t0__;            \
+  } while (0)
+#else
+#define WH_PROF_WAIT(acc, ...) \
+  do {                         \
+    __VA_ARGS__;               \
+  } while (0)
+#endif
+
 template <bool UP>
 __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  [[maybe_unused]] long long prof_w = 0, prof_e = 0;
+  [[maybe_unused]] const long long prof_t0 = clock64();
   const vinet_gather_t& g = p.d.g;
   const int64_t nchunks = (int64_t)g.B * p.nT * p.tiles_h * p.tiles_w;
   const int64_t per = cdiv(nchunks, p.splits);
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        WH_PROF_WAIT(prof_w, mbar_wait(empty0 + 8 * s, ph ^ 1u));
         const uint32_t stage = s0 + (uint32_t)s * p.stage_bytes;
         const int ts = tr * p.at_step + at0;   // out-of-range frames are addressed on purpose: TMA zero-fills the temporal padding
         const int si = (cat && ts >= T0) ? 1 : 0;
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 
       int s = 0;
       uint32_t ph = 0, st16 = s0_16;
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(full0 + 8 * s, ph);
+        WH_PROF_WAIT(prof_w, mbar_wait(full0 + 8 * s, ph));
         tc_fence_after();
         const uint32_t b_lo0 = (st16 + (p.a_bytes >> 4)) | b_lbo;
         if (wh_elect_one()) {   // one elected lane issues this issuer's accumulators of the chunk and releases the stage
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 
     }
   } else if (warp >= 2 + WH_MAX_ISSUERS && warp < WH_THREADS / 32) {
     // ---------------------------------------------------------------- epilogue: TMEM -> smem transpose -> coalesced red.add
-    mbar_wait(accum_bar, 0);  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
+    WH_PROF_WAIT(prof_w, mbar_wait(accum_bar, 0));  // every MMA (hence every TMA write) of this CTA has completed: the stage ring is free
     tc_fence_after();
     fence_proxy_async();
     const int q = warp & 3;
@@ -265,6 +281,12 @@ __global__ void __launch_bounds__(UP ? WH_THREADS + WH_UP_THREADS : WH_THREADS, 
       __syncwarp();
     }
   }
+#ifdef VINET_ST_PROF
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 2 || warp == 6))
+    printf("wh_prof warp %d (%s): total %lld clk, waiting %lld | chunks/cta %d naccs %d ni %d block_n %d stages %d splits %d groups %d\n", warp,
+           warp == 0 ? "tma: free stage" : warp == 2 ? "mma: stage data" : "epilogue: all MMAs done; rest = transpose + red.add",
+           clock64() - prof_t0, prof_w, KB, p.naccs, p.ni, p.block_n, p.stages, p.splits, (int)gridDim.x);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -110,15 +110,6 @@ __device__ __forceinline__ TO* out_row_ptr(const vinet_conv_t& d, const RowCoord
   return reinterpret_cast<TO*>(d.out[i]) + pos * d.ldo[i];
 }
 
-// per-element epilogue (scale, shift, activation) - same arithmetic as epilogue_store8's vector form
-__device__ __forceinline__ float epilogue_value_fast(const vinet_conv_t& d, float acc, int n) {
-  if (d.ep_scale) acc *= __ldg(d.ep_scale + n);
-  if (d.ep_shift) acc += __ldg(d.ep_shift + n);
-  if (d.ep_act == VINET_ACT_RELU) acc = fmaxf(acc, 0.f);
-  else if (d.ep_act == VINET_ACT_SIGMOID) acc = 1.f / (1.f + __expf(-acc));
-  return acc;
-}
-
 // Epilogue of 8 consecutive output channels [n, n+8) of one row: optional per-channel scale/shift/activation
 // (EPI; vector loads, branches hoisted out of the element loop), optional read-modify-write, one 16/32-byte store.
 template <typename TO, bool EPI>
@@ -165,9 +156,28 @@ __device__ __forceinline__ void epilogue_store16(const vinet_conv_t& d, TO* p, c
       float v[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-      if constexpr (EPI) {
+      if constexpr (EPI) {     // per-channel scale / shift as 128-bit loads (n is a multiple of 16), activation on registers
+        if (d.ep_scale) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = epilogue_value_fast(d, v[e], n + e);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(d.ep_scale + n) + q4);
+            v[4 * q4] *= a.x; v[4 * q4 + 1] *= a.y; v[4 * q4 + 2] *= a.z; v[4 * q4 + 3] *= a.w;
+          }
+        }
+        if (d.ep_shift) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(d.ep_shift + n) + q4);
+            v[4 * q4] += a.x; v[4 * q4 + 1] += a.y; v[4 * q4 + 2] += a.z; v[4 * q4 + 3] += a.w;
+          }
+        }
+        if (d.ep_act == VINET_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (d.ep_act == VINET_ACT_SIGMOID) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
+        }
       }
       if (accum) {
         uint32_t o[8];
