@@ -46,7 +46,10 @@ constexpr int ST_UP_THREADS = 256;
 constexpr int ST_UP_TOTAL = 32 * (2 + 4 + ST_UP_EPI_WARPS) + ST_UP_THREADS;   // 576
 constexpr int ST_MAX_ISSUERS = 4;
 constexpr int ST_MAX_TG = 8;
-constexpr int ST_STATS_FLOATS = 2 * 256;   // per-CTA BatchNorm statistic partials: [sum | sum of squares][column of the N tile]
+// per-CTA BatchNorm statistic partials: [sum | sum of squares][column of the N tile], kept in fp64: the epilogue warps of a CTA add
+// their lane-reduced sums in whatever order they finish, and an fp32 accumulator made the batch statistics (hence the whole
+// train-mode forward, through ~60 normalisations of tiny batches) differ in the last bit from run to run
+constexpr int ST_STATS_FLOATS = 2 * 2 * 256;   // in units of 4 bytes
 
 struct StreamParams {
   CUtensorMap tmA[2];
@@ -283,10 +286,10 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
   const uint32_t full_a = smem_u32(bars), empty_a = full_a + 8 * AS, full_b = empty_a + 8 * AS, empty_b = full_b + 8 * BS;
   const uint32_t full_acc = empty_b + 8 * BS, empty_acc = full_acc + 8 * p.nacc, wbar = empty_acc + 8 * p.nacc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 2 * p.nacc + 1);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // ST_STATS_FLOATS floats, used when p.d.stats != nullptr
+  double* s_stats = reinterpret_cast<double*>(tmem_slot + 4);   // [2][256] doubles, used when p.d.stats != nullptr
   // per-tap descriptor offsets (activation window, weight block) in shared memory: the issue loop reads them once per tap, and an
   // indexed load from the parameter bank (c[0][R + ...]) costs it several times an LDS
-  int2* s_tap = reinterpret_cast<int2*>(s_stats + ST_STATS_FLOATS);
+  int2* s_tap = reinterpret_cast<int2*>(s_stats + 2 * 256);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + VINET_MAX_TAPS)
     s_tap[threadIdx.x - 64] = make_int2(p.sp_aoff16[threadIdx.x - 64], p.sp_boff16[threadIdx.x - 64]);
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
     const bool stats = p.d.stats != nullptr;
     const int etid = threadIdx.x - 32 * FIRST_EPI_WARP;   // 0..255 among the epilogue warps
     if (stats) {
-      for (int i = etid; i < ST_STATS_FLOATS; i += ET) s_stats[i] = 0.f;
+      for (int i = etid; i < 2 * 256; i += ET) s_stats[i] = 0.0;
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     }
     uint32_t slot = 0, ph = 0;
@@ -712,7 +715,7 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
             warp_colsum16(sv, lane);
             warp_colsum16(sq, lane);
             const int col = c0 + colsum16_col(lane);
-            if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (lane & 1) ? sq[0] : sv[0]);
+            if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (double)((lane & 1) ? sq[0] : sv[0]));
           }
         }
         tc_fence_before();
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(UP ? ST_UP_TOTAL : ST_THREADS, 1) conv_stream_
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       for (int i = etid; i < 2 * BN; i += ET) {
         const int which = i / BN, col = i - which * BN;
-        if (col < nlim) atomicAdd(p.d.stats + (size_t)which * p.d.N + nt * BN + col, (double)s_stats[which * 256 + col]);
+        if (col < nlim) atomicAdd(p.d.stats + (size_t)which * p.d.N + nt * BN + col, s_stats[which * 256 + col]);
       }
     }
   }

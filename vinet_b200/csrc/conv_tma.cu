@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
   const int nb_slots = p.wres ? p.d.k_blocks : stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_slots * p.b_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // [2][256] per-CTA BatchNorm statistic partials (p.d.stats != nullptr)
+  double* s_stats = reinterpret_cast<double*>(tmem_slot + 4);   // [2][256] per-CTA BatchNorm statistic partials (p.d.stats != nullptr),
+                                                                // fp64: order-independent to the last fp32 bit (see conv_stream.cu)
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * stages, tfull0 = empty0 + 8 * stages, tempty0 = tfull0 + 16;
   const uint32_t wbar = tempty0 + 16;
   const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
     const bool stats = p.d.stats != nullptr;
     const int etid = threadIdx.x - 64;   // 0..255 among the epilogue warps
     if (stats) {
-      for (int i = etid; i < 512; i += 256) s_stats[i] = 0.f;
+      for (int i = etid; i < 512; i += 256) s_stats[i] = 0.0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     int stats_nt = -1;                   // N tile the partials in shared memory belong to
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
       for (int i = etid; i < 2 * BN; i += 256) {
         const int which = i / BN, col = i - which * BN;
         if (col < nl) {
-          atomicAdd(p.d.stats + (size_t)which * p.d.N + stats_nt * BN + col, (double)s_stats[which * 256 + col]);
-          s_stats[which * 256 + col] = 0.f;
+          atomicAdd(p.d.stats + (size_t)which * p.d.N + stats_nt * BN + col, s_stats[which * 256 + col]);
+          s_stats[which * 256 + col] = 0.0;
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_gemm_tma_kernel(const __g
           warp_colsum16(sv, lane);
           warp_colsum16(sq, lane);
           const int col = c0 + colsum16_col(lane);
-          if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (lane & 1) ? sq[0] : sv[0]);
+          if (col < nlim) atomicAdd(&s_stats[(lane & 1) * 256 + col], (double)((lane & 1) ? sq[0] : sv[0]));
         }
       }
       if (any) {
@@ -734,7 +735,7 @@ int conv_gemm_tma(const vinet_conv_t* d, cudaStream_t stream) {
   if (stages > 12) stages = 12;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64 + 2048;
+  const size_t smem = 1024 + stages * stage_bytes + (p.wres ? wbytes : 0) + 8 * (2 * stages + 5) + 64 + 4096;
   VINET_CHECK(smem <= 227 * 1024, "conv_gemm_tma: %zu bytes of shared memory", smem);
   for (int i = 0; i < 2; ++i) {
     const vinet_src_t& s = g.src[(i == 1 && g.src[1].ptr == nullptr) ? 0 : i];
