@@ -188,12 +188,16 @@ __device__ __forceinline__ void frame_max(const vinet_pool_t& d, const __nv_bflo
   }
 }
 
+// A thread owns a (h, w, 8-channel) column and a run of `tc` output frames (blockIdx.y): the deep stages have few positions and
+// few frames, and one thread per column walking ALL frames left most of the machine idle (0.7 TB/s); a run re-computes the
+// 3x3 maxima of its two boundary frames.
 template <bool IDX>
-__global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const __grid_constant__ vinet_pool_t d) {
+__global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const __grid_constant__ vinet_pool_t d, int tc) {
   const __nv_bfloat16* __restrict__ x = reinterpret_cast<const __nv_bfloat16*>(d.x);
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(d.out);
   const int G = d.C / 8;
   const int64_t total = (int64_t)d.B * d.Hi * d.Wi * G;
+  const int t_begin = blockIdx.y * tc, t_end = min(d.Ti, t_begin + tc);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     unsigned r = (unsigned)i;
     const int c = (int)(r % (unsigned)G) * 8; r /= (unsigned)G;
@@ -201,9 +205,10 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const __grid_consta
     const int h = (int)(r % (unsigned)d.Hi);
     const int b = (int)(r / (unsigned)d.Hi);
     FrameMax prev, cur, next;
-    frame_max(d, x, b, 0, h, w, c, cur);
-    if (d.Ti > 1) frame_max(d, x, b, 1, h, w, c, next);
-    for (int t = 0; t < d.Ti; ++t) {
+    if (t_begin > 0) frame_max(d, x, b, t_begin - 1, h, w, c, prev);
+    frame_max(d, x, b, t_begin, h, w, c, cur);
+    if (t_begin + 1 < d.Ti) frame_max(d, x, b, t_begin + 1, h, w, c, next);
+    for (int t = t_begin; t < t_end; ++t) {
       __nv_bfloat162 bv[4];
       unsigned bi[4];
       if (t > 0) {
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(256) maxpool333_fwd_kernel(const __grid_consta
       }
       prev = cur;
       cur = next;
-      if (t + 2 < d.Ti) frame_max(d, x, b, t + 2, h, w, c, next);
+      if (t + 1 < t_end && t + 2 < d.Ti) frame_max(d, x, b, t + 2, h, w, c, next);
     }
   }
 }
@@ -651,8 +656,12 @@ extern "C" int vinet_maxpool_fwd(const vinet_pool_t* d, vinet_stream_t stream) {
   if (pool_is_333(d)) {  // frame-walking kernel: every 3x3 spatial maximum is computed once and used by three outputs
     const int64_t total = (int64_t)d->B * d->Hi * d->Wi * (d->C / 8);
     const unsigned nb = (unsigned)std::min<int64_t>(cdiv(total, 256), 148 * 64);
-    if (d->idx) maxpool333_fwd_kernel<true><<<nb, 256, 0, (cudaStream_t)stream>>>(*d);
-    else maxpool333_fwd_kernel<false><<<nb, 256, 0, (cudaStream_t)stream>>>(*d);
+    // frames per thread: as long as possible (fewer re-computed boundary frames) while the launch still fills the machine twice
+    int tc = d->Ti;
+    while (tc > 2 && (int64_t)cdiv(d->Ti, tc) * total < (int64_t)2 * 148 * 2048) tc = (tc + 1) / 2;
+    const dim3 grid(nb, (unsigned)cdiv(d->Ti, tc));
+    if (d->idx) maxpool333_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*d, tc);
+    else maxpool333_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*d, tc);
     VINET_LAUNCH_OK("maxpool333_fwd");
     return 0;
   }
