@@ -34,6 +34,13 @@ for name, (B, T, H, W, Cn), k, s, p, ow in CASES:
     (d.kt, d.kh, d.kw), (d.st, d.sh, d.sw), (d.pt, d.ph, d.pw) = k, s, p
     d.To, d.Ho, d.Wo, d.out, d.ldo, d.out_dtype, d.idx = To, Ho, Wo, out.data_ptr(), Cn, L.BF16, idx.data_ptr()
     lib.call("vinet_maxpool_fwd", C.byref(d), st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        lib.call("vinet_maxpool_fwd", C.byref(d), st)
+    e1.record()
+    torch.cuda.synchronize()
+    fwd_us = e0.elapsed_time(e1) / 5 * 1e3
     d.gout, d.ldgo, d.gin, d.ldgi, d.gout_dtype, d.gin_dtype, d.gin_overwrite = gout.data_ptr(), Cn, gin.data_ptr(), Cn, L.BF16, L.BF16, ow
     res = []
     for mode in modes:
@@ -49,4 +56,6 @@ for name, (B, T, H, W, Cn), k, s, p, ow in CASES:
         res.append("mode %d: %7.1f us" % (mode, e0.elapsed_time(e1) / 5 * 1e3))
     lib.call("vinet_debug_set", 3, 1)
     mb = (gin.numel() * 2 * (1 if ow else 2) + gout.numel() * 2 + idx.numel()) / 1e6
-    print("%-8s in %s: %s   (min traffic %.0f MB = %.0f us at 6.5 TB/s)" % (name, (B, T, H, W, Cn), "  ".join(res), mb, mb / 6.5), flush=True)
+    fmb = (x.numel() * 2 + out.numel() * 2 + idx.numel()) / 1e6
+    print("%-8s in %s: fwd %7.1f us (min %.0f us) | bwd %s   (min traffic %.0f MB = %.0f us at 6.5 TB/s)"
+          % (name, (B, T, H, W, Cn), fwd_us, fmb / 6.5, "  ".join(res), mb, mb / 6.5), flush=True)
