@@ -298,6 +298,8 @@ def main():
         # with a single NCCL all-reduce per step (model.sync_gradients) - no per-tensor bucket copies
         model.broadcast_parameters(0)
         model.enable_grad_arena()
+        if not os.environ.get("VINET_NO_OVERLAP_SYNC"):
+            model.overlap_gradient_sync()     # the decoder's slice of the arena is reduced while the backbone's backward runs
     use_graph = not args.no_graph and not (train and args.no_adam) and not (world > 1 and args.ddp)
     opt = None
     nccl_in_graph = world > 1 and bool(args.graph_nccl) and use_graph and not args.ddp

@@ -43,6 +43,18 @@ torch.cuda.synchronize()
 synced = torch.cat([p.grad.float().flatten() for p in m.parameters()])
 mean = 0.5 * (both[0] + both[1])
 assert torch.allclose(synced, mean, rtol=1e-5, atol=1e-6 * float(mean.abs().max())), float((synced - mean).abs().max())
+# the same step again with the decoder's slice reduced EARLY on a side stream (model.overlap_gradient_sync): same averages
+m.overlap_gradient_sync()
+for p in m.parameters():
+    p.grad = None
+kldiv(m(x[rank:rank + 1]), gt[rank:rank + 1]).backward()
+assert m.__dict__.get("_early_sync") is not None, "the early all-reduce of the decoder slice did not start"
+m.sync_gradients()
+torch.cuda.synchronize()
+again = torch.cat([p.grad.float().flatten() for p in m.parameters()])
+tol = 1e-4 if precision == "fp32" else 5e-2          # (bf16: atomics in the pool / weight-gradient kernels reorder sums)
+assert float((again - synced).norm() / synced.norm()) < tol, float((again - synced).norm() / synced.norm())
+m.overlap_gradient_sync(False)
 if rank == 0:
     shard = []
     for i in range(2):

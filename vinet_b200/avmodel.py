@@ -156,6 +156,7 @@ class VideoAudioSaliencyModel(_PlanModule):
         y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin,
                                        y0_gdtype=torch.float32)
         fused = avfuse_plan(e, "bilinear", y0, a, ga, self.bilinear)
+        e.mark_backward_point("decoder")
         out = decoder_plan(e, "visual_model.decoder.", self.visual_model.decoder, fused, y1, y2, y3)
         e.end_forward()
         return out

@@ -169,6 +169,8 @@ class Engine:
         self.replica = False    # nn.DataParallel replica: its weights are fresh broadcast copies every forward (no multi-repack)
         self.consumed_gen = -1  # generation whose tape has been run: a second backward through it must fail loudly
         self.up2_mat_log = []   # names of the virtual up-sampled activations that had to be materialised (tests assert on it)
+        self.backward_point_cb = None   # callable(name): invoked from the backward pass at the points marked in the forward plan
+        self.arena_bypassed = False     # a gradient of this pass was handed out as a scratch tensor instead of its arena slice
         self.profile = None     # bench.py: list of (layer, kind, flops, start_event, end_event) per conv launch
         self.l2_flush = None
 
@@ -247,6 +249,7 @@ class Engine:
                 p = self.arena[2].get(name) if len(self.arena) > 2 else None
                 if p is None or p.grad is None or p.grad.data_ptr() != t.data_ptr():
                     return t.zero_() if zero else t
+                self.arena_bypassed = True
         return torch.zeros_like(like) if zero else torch.empty_like(like)
 
     def timed(self, label, kind, flops, fn):
@@ -1156,11 +1159,24 @@ class Engine:
             self.head_backward = backward
         return out
 
+    def mark_backward_point(self, name):
+        """Tape marker: when the backward pass reaches it, every gradient of the layers planned AFTER this call has been written
+        (the queued weight-gradient unpacks are flushed first); the model's call-back may start communicating them."""
+        if not self.record:
+            return
+
+        def reached():
+            if self.backward_point_cb is not None:
+                self.unpack_flush()
+                self.backward_point_cb(name)
+        self.tape.append(reached)
+
     # ------------------------------------------------------------------ backward driver
     def backward(self, gout):
         """gout: fp32 (B,H,W) gradient w.r.t. the saliency map. Fills self.param_grads."""
         self.gwritten = set()
         self.unpack_queue = []
+        self.arena_bypassed = False
         self.dwp_begin()
         self.head_backward(gout)
         for fn in reversed(self.tape):

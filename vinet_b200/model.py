@@ -334,17 +334,61 @@ class _PlanModule(nn.Module):
 
     def sync_gradients(self, group=None):
         """Average the gradients of the last backward over the process group: one NCCL all-reduce of the flat arena
-        (124.4 MB for ViNet).  BatchNorm statistics stay per replica (the reference's nn.DataParallel semantics)."""
+        (124.4 MB for ViNet).  BatchNorm statistics stay per replica (the reference's nn.DataParallel semantics).
+        With ``overlap_gradient_sync()`` the decoder's slice (3/4 of the bytes, complete after the first fifth of the backward pass)
+        has already been reduced on a side stream while the backbone's backward ran; only the rest is reduced here."""
         import torch.distributed as dist
         arenas = self.__dict__.get("_arenas")
         assert arenas, "sync_gradients() needs enable_grad_arena() and a backward pass"
         world = dist.get_world_size(group)
+        early = self.__dict__.pop("_early_sync", None)
         for flat, *_ in arenas.values():
-            if dist.get_backend(group) == "nccl":
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
-            else:
-                dist.all_reduce(flat, group=group)
-                flat.div_(world)
+            parts = [flat]
+            if early is not None and early[0] is flat:
+                lo, hi = early[1], early[2]
+                parts = [t for t in (flat[:lo], flat[hi:]) if t.numel()]
+            for t in parts:
+                if dist.get_backend(group) == "nccl":
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+                else:
+                    dist.all_reduce(t, group=group)
+                    t.div_(world)
+        if early is not None:
+            torch.cuda.current_stream(early[0].device).wait_event(early[3])
+
+    def overlap_gradient_sync(self, on=True, group=None):
+        """Start the all-reduce of the decoder's gradients as soon as the decoder's backward has finished, on a side stream, so
+        that it overlaps the backbone's backward (train.py's loop has no such hook: this is an opt-in of the flat-arena path,
+        used by bench.py at N > 1; inside a captured step the fork / join become graph edges).  Needs ``enable_grad_arena()``,
+        ``zero_grad(set_to_none=True)`` discipline and ``sync_gradients()`` after every backward."""
+        self.__dict__["_overlap_sync"] = (group,) if on else None
+        return self
+
+    def _decoder_backward_done(self, e):
+        """Engine call-back (tape marker in front of the decoder plan): every decoder gradient sits in its arena slice."""
+        cfg = self.__dict__.get("_overlap_sync")
+        if cfg is None or e.arena is None or e.device.type != "cuda" or e.arena_bypassed:
+            return
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(cfg[0]) != "nccl":
+            return
+        flat, layout = e.arena[0], e.arena[1]
+        spans = [(off, off + (n + 3) // 4 * 4) for name, (off, n) in layout.items() if ".decoder." in "." + name]
+        if not spans:
+            return
+        lo, hi = min(a for a, _ in spans), min(max(b for _, b in spans), flat.numel())
+        if any(not (lo <= off < hi) == (".decoder." in "." + name) for name, (off, n) in layout.items()):
+            return                                                   # the decoder's parameters are not one contiguous run
+        main = torch.cuda.current_stream(e.device)
+        side = self.__dict__.get("_sync_stream")
+        if side is None or side.device != e.device:
+            side = self.__dict__["_sync_stream"] = torch.cuda.Stream(device=e.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.AVG, group=cfg[0])
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self.__dict__["_early_sync"] = (flat, lo, hi, ev)
 
     def broadcast_parameters(self, src=0, group=None):
         """Rank `src`'s parameters and buffers to every rank (what DistributedDataParallel does at construction)."""
@@ -381,6 +425,7 @@ class _PlanModule(nn.Module):
         e = self._engine_for(x.device)
         e.replica = replica
         e.arena = self._arena_for(x.device, named) if (record and self.__dict__.get("_use_arena") and not replica) else None
+        e.backward_point_cb = (lambda name, e=e: self._decoder_backward_done(e)) if (e.arena is not None and self.__dict__.get("_overlap_sync")) else None
         return _PlanFunction.apply(self, record, names, x, *extra, *[p for _, p in named])
 
     def _plan_uses(self, name):
@@ -424,6 +469,7 @@ class VideoSaliencyModel(_PlanModule):
         e.begin(x.device, self.training, record)
         xin = pack_input(e, x)
         ys = backbone_plan(e, prefix + "backbone.", self.backbone, xin, windows=self.__dict__.get("_windows"))
+        e.mark_backward_point("decoder")     # reached in the backward pass once every decoder gradient has been written
         out = decoder_plan(e, prefix + "decoder.", self.decoder, *ys)
         e.end_forward()
         return out
