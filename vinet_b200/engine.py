@@ -792,24 +792,54 @@ class Engine:
         return backward
 
     # ------------------------------------------------------------------ conv + BatchNorm (+ReLU pending)
-    def conv_bn(self, name_conv, name_bn, srcs, w, bn, geom, out, cin_real=None):
+    def conv_bn(self, name_conv, name_bn, srcs, w, bn, geom, out, cin_real=None, defer_to=None):
         """BasicConv3d / one half of SepConv3d (model_utils.py:128-160).
         Training: raw conv -> batch statistics -> finalize (scale/shift, running stats) -> materialise
         relu(scale*y+shift) into `out` (possibly a channel slice of a Mixed concat buffer).  Consumers then read
         plain activations, which is what lets the TMA-fed kernels fetch them.  Pure inference (no tape, running
-        statistics): scale/shift/ReLU are folded into the conv epilogue and nothing else is launched."""
+        statistics): scale/shift/ReLU are folded into the conv epilogue and nothing else is launched.
+        out=None, defer_to=name: the caller's only consumer applies pending transforms itself (a max-pool): in the bf16 training
+        mode the layer is NOT materialised - the returned activation is the raw output tagged scale/shift/ReLU (statistics from
+        the conv epilogue, one tiny finalise launch), which saves a full read + write pass (the stem's second half: 1.4 GB)."""
+        if out is None:
+            a0 = srcs[0]
+            To, Ho, Wo = geom.out_dims(sum(s.T for s in srcs), a0.H, a0.W)
+            Cn = w.shape[0]
+            deferred = (self.training and not self.split and self.epi_stats and self.tma_ok(srcs, geom) and "vinet_bn_finalize" in self.lib.fn
+                        and not os.environ.get("VINET_NO_DEFER_BN"))
+            if deferred:
+                raw = Act(self.buf(name_conv + ".raw", (a0.B, To, Ho, Wo, Cn), self.tdtype), a0.B, To, Ho, Wo, Cn)
+                stats = (self.stats_slice(Cn), Cn)
+                conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real, stats=stats[0])
+                st = self.buf(name_bn + ".stat", (2, Cn), torch.float32)      # mean, invstd
+                ss = self.buf(name_bn + ".ss", (2, Cn), torch.float32)        # scale, shift
+                fin = L.BnFinalize()
+                fin.rows, fin.C, fin.gamma, fin.beta = raw.rows, Cn, bn.weight.data_ptr(), bn.bias.data_ptr()
+                fin.eps, fin.momentum, fin.training = bn.eps, bn.momentum, 1
+                fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                fin.scale, fin.shift, fin.mean, fin.invstd = ss[0].data_ptr(), ss[1].data_ptr(), st[0].data_ptr(), st[1].data_ptr()
+                fin.sums = stats[0]
+                self.call("vinet_bn_finalize", fin)
+                self.bn_counters.append(bn.num_batches_tracked)
+                out = Act(raw.buf, a0.B, To, Ho, Wo, Cn, 0, L.XF_AFFINE_RELU, ss[0], ss[1])
+                if self.record:
+                    self.want_grad(out, defer_to)
+                    self._bn_tape(name_bn, bn, raw, out, conv_bwd, None, st, ss)
+                return out
+            out = self.new_act(defer_to, a0.B, To, Ho, Wo, Cn)
         Cn = out.C
         if not self.training and not self.record and not self.split:
             ss = self._bn_finalize(name_bn, bn, out.rows, Cn, None)[1]
             out.xform, out.scale, out.shift = L.XF_IDENT, None, None
             self.conv(name_conv, srcs, w, geom, out, cin_real=cin_real, ep=(ss[0], ss[1], L.ACT_RELU))
-            return
+            return out
         raw = Act(self.buf(name_conv + ".raw", (out.B, out.T, out.H, out.W, Cn), self.tdtype), out.B, out.T, out.H, out.W, Cn)
         st = None
         if self.epi_stats and (isinstance(srcs[0], WinAct) or self.tma_ok(srcs, geom)) and (self.epi_stats_1x1 or geom.kt * geom.kh * geom.kw > 1):
             st = (self.stats_slice(Cn), Cn)
         conv_bwd = self.conv(name_conv, srcs, w, geom, raw, cin_real=cin_real, stats=st[0] if st else None)
         self._bn_tail(name_bn, bn, raw, out, conv_bwd, None, stats=st)
+        return out
 
     def _bn_finalize(self, name_bn, bn, rows, Cn, raw, apply=None):
         """Batch statistics of `raw` (training) or the running statistics -> (mean/invstd, scale/shift) buffers.
@@ -962,8 +992,12 @@ class Engine:
             ap.y, ap.ldy, ap.dtype, ap.rows, ap.C, ap.relu = raw.ptr(), raw.ld, self.dt, rows, Cn, 1
             ap.out, ap.ldo, ap.out_dtype = out.ptr(), out.ld, self.dt
             st, ss = self._bn_finalize(name_bn, bn, rows, Cn, raw, apply=ap)
-        if not self.record:
-            return
+        if self.record:
+            self._bn_tape(name_bn, bn, raw, out, conv_bwd, dy_slot, st, ss)
+
+    def _bn_tape(self, name_bn, bn, raw, out, conv_bwd, dy_slot, st, ss):
+        """Backward of one (large) BatchNorm + ReLU layer: reduce + apply (one cooperative launch above 24 MB), then the conv's."""
+        Cn, rows = out.C, out.rows
         training = self.training
 
         def backward():

@@ -139,19 +139,19 @@ def _sepconv_s(e, pfx, srcs, m, cin_real=None):
     return mid
 
 
-def _sepconv_t(e, pfx, mid, m, out=None):
-    """Second half of SepConv3d (model_utils.py:148-150): (k,1,1) conv + BN + ReLU."""
+def _sepconv_t(e, pfx, mid, m, out=None, defer_bn=False):
+    """Second half of SepConv3d (model_utils.py:148-150): (k,1,1) conv + BN + ReLU.
+    defer_bn: the only consumer is a max-pool, which applies scale / shift / ReLU on read - the engine may skip the apply pass."""
     k, s, p = m.k, m.stride, m.padding
     gt = ConvGeom((k, 1, 1), (s, 1, 1), (p, 0, 0))
     To2, _, _ = gt.out_dims(mid.T, mid.H, mid.W)
-    if out is None:
+    if out is None and not defer_bn:
         out = e.new_act(pfx + ".t", mid.B, To2, mid.H, mid.W, m.conv_t.weight.shape[0])
-    e.conv_bn(pfx + ".conv_t", pfx + ".bn_t", [mid], m.conv_t.weight, m.bn_t, gt, out)
-    return out
+    return e.conv_bn(pfx + ".conv_t", pfx + ".bn_t", [mid], m.conv_t.weight, m.bn_t, gt, out, defer_to=pfx + ".t")
 
 
-def _sepconv(e, pfx, srcs, m, out=None, cin_real=None):
-    return _sepconv_t(e, pfx, _sepconv_s(e, pfx, srcs, m, cin_real=cin_real), m, out)
+def _sepconv(e, pfx, srcs, m, out=None, cin_real=None, defer_bn=False):
+    return _sepconv_t(e, pfx, _sepconv_s(e, pfx, srcs, m, cin_real=cin_real), m, out, defer_bn=defer_bn)
 
 
 _G1 = ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 0))
@@ -209,7 +209,7 @@ def backbone_plan(e, pfx, bb, x, y0_gdtype=None, windows=None):
     frames; the per-frame (1,7,7) stem convolution runs ONCE per frame and the temporal stem convolution reads window i as frames
     i .. i+L-1 of its output (batch pitch = one frame) - consecutive windows share L-1 of their L stem frames."""
     if windows is None:
-        a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
+        a = _sepconv(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3, defer_bn=True)   # consumed by the max-pool below only
     else:
         b, Lc = windows
         mid = _sepconv_s(e, pfx + "base1.0", [x], bb.base1[0], cin_real=3)
