@@ -486,6 +486,71 @@ typedef struct vinet_avfuse {
 int vinet_avfuse_fwd(const vinet_avfuse_t* d, vinet_stream_t stream);
 int vinet_avfuse_bwd(const vinet_avfuse_t* d, vinet_stream_t stream);
 
+/* ---- transformer fusion variants (model.py:8-69 PositionalEncoding / Transformer; model.py:211-221,239-247
+ * VideoAudioSaliencyModel(use_transformer=True); model.py:116-189 VideoAudioSaliencyFusionModel).  The path is tiny (32-339 tokens of
+ * 336-512 features): fp32 FFMA kernels; every matrix product, layout shuffle and reduction below is ONE strided batched GEMM. ---- */
+/* C[b1,b2](m,n) = alpha * sum_k A[b1,b2](m,k) * B[b1,b2](n,k) + bias1(m,n) + bias2[b1,b2](m,n)  (then ReLU, then += C if accumulate).
+ * Element (i,j) of batch (b1,b2) of an operand X lives at X[i*sXi + j*sXj + b1*sXb1 + b2*sXb2] (elements, any sign-free stride incl. 0),
+ * so transposes, head slices of a packed QKV matrix, NDHWC rows and broadcast vectors are all views.  K = 0 is a strided copy of
+ * bias2.  Replaces nn.Linear / F.linear of nn.MultiheadAttention + nn.TransformerEncoderLayer, the two bmm of the attention, the
+ * Conv3d/Conv2d 1x1 with bias (model.py:135,148,213-214), permute/flatten/view/cat/mean/repeat (model.py:151-183,240-247). */
+typedef struct vinet_bgemm {
+  const void* A; /* (M,K) */
+  int64_t sAm, sAk, sAb1, sAb2;
+  int32_t a_dtype;
+  int32_t a_relu; /* 1: max(.,0) on read, after the affine below */
+  const float* a_scale; /* optional pending BatchNorm transform of A (NULL: none), per k - or per m when a_xf_on_m */
+  const float* a_shift;
+  const void* B; /* (N,K) */
+  int64_t sBn, sBk, sBb1, sBb2;
+  int32_t b_dtype;
+  int32_t c_dtype;
+  void* C; /* (M,N) */
+  int64_t sCm, sCn, sCb1, sCb2;
+  int32_t M, N, K, nb1, nb2;
+  float alpha;
+  int32_t relu;       /* ReLU epilogue */
+  const float* bias1; /* optional, shared by all batches */
+  int64_t s1m, s1n;
+  const float* bias2; /* optional, per batch */
+  int64_t s2m, s2n, s2b1, s2b2;
+  int32_t accumulate; /* 1: C += result (fp32 C only) */
+  int32_t a_xf_on_m;  /* a_scale / a_shift are indexed by A's row m instead of the reduction index k */
+} vinet_bgemm_t;
+int vinet_bgemm(const vinet_bgemm_t* d, vinet_stream_t stream);
+/* rows of n contiguous fp32: p = softmax(s) in place (F.softmax(attn, dim=-1)); backward in place on dp: ds = p * (dp - sum(dp * p)) */
+int vinet_softmax_fwd(float* s, int64_t rows, int32_t n, vinet_stream_t stream);
+int vinet_softmax_bwd(const float* p, float* dp, int64_t rows, int32_t n, vinet_stream_t stream);
+/* nn.Dropout (train mode): y[i] = keep(i) ? x[i] / (1 - p) : 0, mask[i] = keep(i); keep(i) is a counter-based hash of
+ * (rng[0] = seed, rng[1] = step counter, salt, i), read from DEVICE memory so that a replayed CUDA graph draws fresh masks
+ * (vinet_rng_advance bumps the counter once per forward).  y may alias x.  Not bit-compatible with torch's Philox stream. */
+int vinet_dropout_fwd(const float* x, float* y, uint8_t* mask, int64_t n, float p, const int64_t* rng, uint32_t salt,
+                      vinet_stream_t stream);
+/* out[i] = g[i] * (mask ? mask[i] / (1 - p) : 1) * (relu_ref ? relu_ref[i] > 0 : 1); out may alias g */
+int vinet_dropout_bwd(const float* g, float* out, const uint8_t* mask, const float* relu_ref, int64_t n, float p,
+                      vinet_stream_t stream);
+int vinet_rng_advance(int64_t* rng, vinet_stream_t stream);
+/* out = LayerNorm(x + y) over rows of n <= 512 contiguous fp32 (post-norm residual of nn.TransformerEncoderLayer, eps 1e-5).
+ * Backward: dz = d(x + y), dgamma / dbeta ACCUMULATED (caller zeroes). */
+typedef struct vinet_addln {
+  const float* x; /* residual input [rows, n] */
+  const float* y; /* sub-layer output [rows, n] */
+  float* z;       /* x + y, saved for the backward */
+  float* stat;    /* [rows, 2] mean, rstd */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t n;
+  int64_t rows;
+  float* out;
+  const float* gout; /* backward */
+  float* dz;
+  float* dgamma;
+  float* dbeta;
+} vinet_addln_t;
+int vinet_add_layernorm_fwd(const vinet_addln_t* d, vinet_stream_t stream);
+int vinet_add_layernorm_bwd(const vinet_addln_t* d, vinet_stream_t stream);
+
 /* ---- sliding-window inference post-processing (generate_result.py:100-104, utils.py:61-78) ---- */
 typedef struct vinet_postproc {
   const float* x; /* [N, H, W] saliency maps */
@@ -530,7 +595,7 @@ const char* vinet_last_error(void);
 const char* vinet_last_kernel(void);
 const char* vinet_version(void);
 int vinet_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
-/* sizeof() of every struct above, in declaration order (host-only; lets a binding check its layout) */
+/* sizeof() of every struct above, in declaration order (vinet_bgemm_t and vinet_addln_t last) (host-only; lets a binding check its layout) */
 int vinet_abi_sizes(int64_t* out, int32_t n);
 /* development switches (key 0: tcgen05 descriptor-encoding experiments, csrc/conv_tc.cu, 0 in production;
  * key 1: paired 256-row work items of the TMA conv kernel, 1 in production;

@@ -576,3 +576,123 @@ def _avfuse_bwd(self, d, stream):
 Spec.conv1d_fwd, Spec.conv1d_bwd = _conv1d_fwd, _conv1d_bwd
 Spec.bn1d_fwd, Spec.bn1d_bwd = _bn1d_fwd, _bn1d_bwd
 Spec.avfuse_fwd, Spec.avfuse_bwd = _avfuse_fwd, _avfuse_bwd
+
+
+# ----------------------------------------------------------------------------- transformer fusion variants (csrc/xfmr.cu)
+def _strided(ptr, dtype, n0, s0, n1, s1, off):
+    """(n0, n1) matrix whose element (i, j) is flat[off + i*s0 + j*s1] (a widened COPY; strides may be 0)."""
+    i = off + np.arange(n0, dtype=np.int64)[:, None] * s0 + np.arange(n1, dtype=np.int64)[None, :] * s1
+    hi = int(i.max()) + 1
+    if dtype == L.BF16:
+        flat = (_arr(ptr, hi, np.uint16).astype(np.uint32) << 16).view(np.float32)
+    else:
+        flat = _arr(ptr, hi)
+    return flat[i], i
+
+
+def _bgemm(self, d, stream):
+    for b1 in range(d.nb1):
+        for b2 in range(d.nb2):
+            acc = np.zeros((d.M, d.N), np.float64)
+            if d.K > 0:
+                A, _ = _strided(d.A, d.a_dtype, d.M, d.sAm, d.K, d.sAk, b1 * d.sAb1 + b2 * d.sAb2)
+                if d.a_scale:
+                    if d.a_xf_on_m:
+                        A = A * _arr(d.a_scale, d.M)[:, None] + _arr(d.a_shift, d.M)[:, None]
+                    else:
+                        A = A * _arr(d.a_scale, d.K)[None, :] + _arr(d.a_shift, d.K)[None, :]
+                if d.a_relu:
+                    A = np.maximum(A, 0)
+                Bm, _ = _strided(d.B, d.b_dtype, d.N, d.sBn, d.K, d.sBk, b1 * d.sBb1 + b2 * d.sBb2)
+                acc = A.astype(np.float64) @ Bm.astype(np.float64).T
+            v = np.float64(d.alpha) * acc
+            if d.bias1:
+                v = v + _strided(d.bias1, L.F32, d.M, d.s1m, d.N, d.s1n, 0)[0]
+            if d.bias2:
+                v = v + _strided(d.bias2, L.F32, d.M, d.s2m, d.N, d.s2n, b1 * d.s2b1 + b2 * d.s2b2)[0]
+            if d.relu:
+                v = np.maximum(v, 0)
+            _, ci = _strided(d.C, L.F32, d.M, d.sCm, d.N, d.sCn, b1 * d.sCb1 + b2 * d.sCb2)
+            assert d.c_dtype == L.F32, "the numpy spec keeps fp32 storage"
+            flat = _arr(d.C, int(ci.max()) + 1)
+            flat[ci] = (flat[ci] + v if d.accumulate else v).astype(np.float32)
+
+
+def _softmax_fwd(self, s, rows, n, stream):
+    a = _arr(s, rows * n).reshape(rows, n)
+    e = np.exp(a - a.max(1, keepdims=True))
+    a[:] = e / e.sum(1, keepdims=True)
+
+
+def _softmax_bwd(self, p, dp, rows, n, stream):
+    P, G = _arr(p, rows * n).reshape(rows, n), _arr(dp, rows * n).reshape(rows, n)
+    G[:] = P * (G - (G * P).sum(1, keepdims=True))
+
+
+def _mix32(x):
+    x = x.astype(np.uint64)
+    m = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def dropout_keep(n, p, seed, counter, salt):
+    """The keep mask of csrc/xfmr.cu drop_keep for elements 0..n-1 (n < 2^32)."""
+    m = 0xFFFFFFFF
+    key = ((seed & m) ^ ((counter * 0x85EBCA6B) & m) ^ ((salt * 0xC2B2AE35) & m)) & m
+    rot = ((key << 7) | (key >> 25)) & m
+    i = np.arange(n, dtype=np.uint64)
+    h = _mix32((_mix32(i ^ np.uint64(key)) + np.uint64(rot)) & np.uint64(m))
+    u = (h >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return u >= np.float32(p)
+
+
+def _dropout_fwd(self, x, y, mask, n, p, rng, salt, stream):
+    st = _arr(rng, 4, np.int32).view(np.int64)
+    keep = dropout_keep(n, p, int(st[0]), int(st[1]), int(salt))
+    _arr(mask, n, np.uint8)[:] = keep
+    xv = _arr(x, n).copy()
+    _arr(y, n)[:] = np.where(keep, xv * (np.float32(1) / (np.float32(1) - np.float32(p))), np.float32(0))
+
+
+def _dropout_bwd(self, g, out, mask, relu_ref, n, p, stream):
+    v = _arr(g, n).copy()
+    if mask:
+        v = np.where(_arr(mask, n, np.uint8) != 0, v * (np.float32(1) / (np.float32(1) - np.float32(p))), np.float32(0))
+    if relu_ref:
+        v = np.where(_arr(relu_ref, n) > 0, v, np.float32(0))
+    _arr(out, n)[:] = v
+
+
+def _rng_advance(self, rng, stream):
+    _arr(rng, 4, np.int32).view(np.int64)[1] += 1
+
+
+def _add_layernorm_fwd(self, d, stream):
+    r, n = d.rows, d.n
+    z = _arr(d.x, r * n).reshape(r, n).astype(np.float64) + _arr(d.y, r * n).reshape(r, n)
+    mean = z.mean(1, keepdims=True)
+    rstd = 1.0 / np.sqrt(((z - mean) ** 2).mean(1, keepdims=True) + d.eps)
+    _arr(d.z, r * n).reshape(r, n)[:] = z
+    st = _arr(d.stat, r * 2).reshape(r, 2)
+    st[:, 0:1], st[:, 1:2] = mean, rstd
+    _arr(d.out, r * n).reshape(r, n)[:] = (z - mean) * rstd * _arr(d.gamma, n) + _arr(d.beta, n)
+
+
+def _add_layernorm_bwd(self, d, stream):
+    r, n = d.rows, d.n
+    z = _arr(d.z, r * n).reshape(r, n).astype(np.float64)
+    st = _arr(d.stat, r * 2).reshape(r, 2).astype(np.float64)
+    g = _arr(d.gout, r * n).reshape(r, n).astype(np.float64)
+    xh = (z - st[:, 0:1]) * st[:, 1:2]
+    gy = g * _arr(d.gamma, n)
+    _arr(d.dz, r * n).reshape(r, n)[:] = st[:, 1:2] * (gy - gy.mean(1, keepdims=True) - xh * (gy * xh).mean(1, keepdims=True))
+    _arr(d.dgamma, n)[:] += (g * xh).sum(0).astype(np.float32)
+    _arr(d.dbeta, n)[:] += g.sum(0).astype(np.float32)
+
+
+Spec.bgemm, Spec.softmax_fwd, Spec.softmax_bwd = _bgemm, _softmax_fwd, _softmax_bwd
+Spec.dropout_fwd, Spec.dropout_bwd, Spec.rng_advance = _dropout_fwd, _dropout_bwd, _rng_advance
+Spec.add_layernorm_fwd, Spec.add_layernorm_bwd = _add_layernorm_fwd, _add_layernorm_bwd

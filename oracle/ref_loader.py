@@ -69,17 +69,28 @@ def build_vinet(num_clips=32, num_hier=3):
     return m.VideoSaliencyModel(num_clips=num_clips, num_hier=num_hier)
 
 
-def build_avinet(random_soundnet=False):
-    """random_soundnet: the 57 MB soundnet8_final.pth is not vendored; model.py:224 loads it relative to the cwd, so hand its
-    torch.load a freshly initialised SoundNet state_dict instead (synthetic benchmarks only need the shapes)."""
-    m, _ = load()
+def _with_random_soundnet(m, make, random_soundnet):
+    """random_soundnet: the 57 MB soundnet8_final.pth is not vendored; model.py:147,224 load it relative to the cwd, so hand their
+    torch.load a freshly initialised SoundNet state_dict instead (synthetic benchmarks and goldens only need the shapes)."""
     import torch
     with _cwd(REF_DIR):
         if random_soundnet and not os.path.isfile("soundnet8_final.pth"):
             real_load = torch.load
             torch.load = lambda *a, **k: m.SoundNet().state_dict()
             try:
-                return m.VideoAudioSaliencyModel()
+                return make()
             finally:
                 torch.load = real_load
-        return m.VideoAudioSaliencyModel()
+        return make()
+
+
+def build_avinet(random_soundnet=False, **kwargs):
+    """VideoAudioSaliencyModel(**kwargs) of the unmodified reference (model.py:191), e.g. use_transformer=True."""
+    m, _ = load()
+    return _with_random_soundnet(m, lambda: m.VideoAudioSaliencyModel(**kwargs), random_soundnet)
+
+
+def build_fusion(random_soundnet=False, **kwargs):
+    """VideoAudioSaliencyFusionModel(**kwargs) of the unmodified reference (model.py:116)."""
+    m, _ = load()
+    return _with_random_soundnet(m, lambda: m.VideoAudioSaliencyFusionModel(**kwargs), random_soundnet)

@@ -16,6 +16,8 @@ Reference sites restated here:
   SoundNet ............... model.py:746-825           VideoAudioSaliencyModel model.py:191-249
   kldiv/cc/similarity/nss  loss.py:13-120             loss_func/get_loss utils.py:9-39
 """
+import math
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -166,13 +168,57 @@ class SoundNetOracle(nn.Module):
         return x
 
 
-class AViNetOracle(nn.Module):
-    """SoundNet || backbone -> MaxPool3d((4,1,1),s=(2,1,2)) -> Bilinear(42,3,336) -> decoder
-    (model.py:191-249, use_transformer=False)."""
+class PositionalEncodingOracle(nn.Module):
+    """model.py:8-26: sinusoidal table added to the (S, B, F) tokens; the module's Dropout is never applied (model.py:24-26)."""
 
-    def __init__(self, num_clips=32):
+    def __init__(self, feat_size, dropout=0.1, max_len=4):
         super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, feat_size, 2).float() * (-math.log(10000.0) / feat_size))
+        pe = torch.zeros(max_len, feat_size)
+        pe[:, 0::2], pe[:, 1::2] = torch.sin(pos * div), torch.cos(pos * div)
+        self.register_buffer("pe", pe.unsqueeze(1))
+
+    def forward(self, x):
+        return x + self.pe
+
+
+class TransformerOracle(nn.Module):
+    """model.py:28-69 in the encoder-only form every model of the reference instantiates (num_decoder_layers=-1, spatial_dim=-1)."""
+
+    def __init__(self, feat_size, hidden_size, nhead, num_encoder_layers, max_len):
+        super().__init__()
+        self.pos_encoder = PositionalEncodingOracle(feat_size, max_len=max_len)
+        self.transformer_encoder = nn.TransformerEncoder(nn.TransformerEncoderLayer(feat_size, nhead, hidden_size), num_encoder_layers)
+
+    def forward(self, tokens):
+        return self.transformer_encoder(self.pos_encoder(tokens))
+
+
+def set_dropout(model, p):
+    """Dropout probability of every nn.Dropout and attention module of `model` (works on the reference, the oracle and the
+    drop-in's parameter holders alike).  The parity cases run with p = 0: torch's Philox stream is not reproduced."""
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = p
+        elif isinstance(m, nn.MultiheadAttention):
+            m.dropout = p
+    return model
+
+
+class AViNetOracle(nn.Module):
+    """SoundNet || backbone -> MaxPool3d((4,1,1),s=(2,1,2)) -> Bilinear(42,3,336) [-> conv_in_1x1 -> Transformer over the C'
+    channel tokens -> conv_out_1x1] -> decoder (model.py:191-249)."""
+
+    def __init__(self, num_clips=32, use_transformer=False, transformer_in_channel=32, num_encoder_layers=3, nhead=4):
+        super().__init__()
+        self.use_transformer = use_transformer
         self.visual_model = ViNetOracle(num_clips)
+        if use_transformer:
+            self.conv_in_1x1 = nn.Conv3d(1024, transformer_in_channel, 1)
+            self.conv_out_1x1 = nn.Conv3d(32, 1024, 1)
+            self.transformer = TransformerOracle(4 * 7 * 12, 4 * 7 * 12, nhead, num_encoder_layers, transformer_in_channel)
         self.audionet = SoundNetOracle()
         self.bilinear = nn.Bilinear(42, 3, 4 * 7 * 12)
 
@@ -182,7 +228,35 @@ class AViNetOracle(nn.Module):
         y0 = F.max_pool3d(y0, (4, 1, 1), (2, 1, 2))
         f = self.bilinear(y0.flatten(2), a.flatten(2))
         f = f.view(f.size(0), f.size(1), 4, 7, 12)
+        if self.use_transformer:                      # model.py:239-247
+            t = self.conv_in_1x1(f).flatten(2).permute(1, 0, 2)
+            t = self.transformer(t).permute(1, 0, 2)
+            f = self.conv_out_1x1(t.reshape(t.size(0), t.size(1), 4, 7, 12))
         return self.visual_model.decoder(f, y1, y2, y3)
+
+
+class AVFusionOracle(nn.Module):
+    """VideoAudioSaliencyFusionModel (model.py:116-189): 336 visual tokens (conv_in_1x1 of y0) and 3 audio tokens (audio_conv_1x1 of
+    the SoundNet output) of C' features through one Transformer; decoder input = [visual tokens | mean audio token, broadcast]."""
+
+    def __init__(self, transformer_in_channel=512, num_encoder_layers=3, nhead=4, num_clips=32):
+        super().__init__()
+        self.visual_model = ViNetOracle(num_clips)
+        self.conv_in_1x1 = nn.Conv3d(1024, transformer_in_channel, 1)
+        self.transformer = TransformerOracle(transformer_in_channel, transformer_in_channel, nhead, num_encoder_layers, 4 * 7 * 12 + 3)
+        self.audionet = SoundNetOracle()
+        self.audio_conv_1x1 = nn.Conv2d(1024, transformer_in_channel, 1)
+        self.bilinear = nn.Bilinear(42, 3, 4 * 7 * 12)      # registered but unused, as in the reference (model.py:149)
+
+    def forward(self, x, audio):
+        a = self.audio_conv_1x1(self.audionet(audio)).flatten(2)
+        y0, y1, y2, y3 = self.visual_model.backbone(x)
+        v = self.conv_in_1x1(y0).flatten(2)
+        t = self.transformer(torch.cat((v, a), 2).permute(2, 0, 1)).permute(1, 2, 0)
+        n = 4 * 7 * 12
+        vf = t[..., :n].reshape(t.size(0), t.size(1), 4, 7, 12)
+        af = t[..., n:].mean(2).view(t.size(0), t.size(1), 1, 1, 1).repeat(1, 1, 4, 7, 12)
+        return self.visual_model.decoder(torch.cat((vf, af), 1), y1, y2, y3)
 
 
 # ----------------------------------------------------------------------------- losses (loss.py)
@@ -257,6 +331,11 @@ def randomize_(model, seed=0, head_gain=4.0):
                 m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
                 m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
                 m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+            elif isinstance(m, (nn.LayerNorm, nn.Linear, nn.MultiheadAttention)):
+                for p in m._parameters.values():      # transformer variants: the three encoder layers start as deep copies
+                    if p is not None:
+                        p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() == 1 else (1.0 / p.shape[-1]) ** 0.5)
+                                + (1.0 if isinstance(m, nn.LayerNorm) and p is m.weight else 0.0))
             elif isinstance(m, (nn.Conv3d, nn.Conv2d, nn.Bilinear)):
                 fan_in = m.weight[0].numel()
                 m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)

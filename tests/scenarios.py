@@ -238,3 +238,137 @@ def audio_fuse_torch(B=2, seed=0):
         if p.grad is not None:
             res["g/audionet." + n] = p.grad.reshape(p.grad.shape[:3]) if p.grad.dim() == 4 else p.grad
     return res
+
+
+# ----------------------------------------------------------------------------- transformer fusion block (AViNet use_transformer=True)
+class _XfRef(torch.nn.Module):
+    """conv_in_1x1 -> tokens = channels -> Transformer -> conv_out_1x1 (model.py:239-247), plain torch."""
+
+    def __init__(self, layers):
+        super().__init__()
+        from oracle import torch_oracle as O
+        self.conv_in_1x1 = torch.nn.Conv3d(1024, 32, 1)
+        self.conv_out_1x1 = torch.nn.Conv3d(32, 1024, 1)
+        self.transformer = O.TransformerOracle(336, 336, 4, layers, 32)
+
+    def forward(self, f):
+        t = self.conv_in_1x1(f).flatten(2).permute(1, 0, 2)
+        t = self.transformer(t).permute(1, 0, 2)
+        return self.conv_out_1x1(t.reshape(t.size(0), t.size(1), 4, 7, 12))
+
+
+def _xf_ref(layers, seed):
+    from oracle import torch_oracle as O
+    ref = O.set_dropout(O.randomize_(_XfRef(layers), seed + 5), 0.0)
+    return ref.train()
+
+
+def xf_block(device, precision, backend=None, B=2, layers=2, seed=0, p=0.0, training=True):
+    """The transformer fusion block of AViNet standalone: a random fused feature in, decoder-input gradient back."""
+    from oracle import torch_oracle as O
+    from vinet_b200 import xfmr as X
+    gen = torch.Generator().manual_seed(seed)
+    ref = _xf_ref(layers, seed)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv_in_1x1 = M.ConvParams(1024, 32, (1, 1, 1), bias=True)
+            self.conv_out_1x1 = M.ConvParams(32, 1024, (1, 1, 1), bias=True)
+            self.transformer = X.Transformer(336, hidden_size=336, nhead=4, num_encoder_layers=layers, max_len=32)
+    m = Holder()
+    m.load_state_dict(ref.state_dict())
+    O.set_dropout(m, p)
+    m.to(device)
+    e = Engine(precision, backend=backend)
+    e.begin(torch.device(device), training, True)
+    fused = fill_act(e, "fused", B, 4, 7, 12, 1024, gen, False, gdtype=torch.float32)
+    out = X.avinet_transformer_plan(e, m, fused)
+    run_tape(e, out, gen)
+    res = {"out": ncdhw(out.buf), "dfused": ncdhw(fused.grad)}
+    for k, v in e.param_grads.items():
+        res["g/" + k] = v.detach().cpu().clone()
+    return res
+
+
+def xf_block_torch(B=2, layers=2, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    ref = _xf_ref(layers, seed)
+    f = bf16r(torch.randn(B, 4, 7, 12, 1024, generator=gen)).permute(0, 4, 1, 2, 3).requires_grad_(True)
+    out = ref(f)
+    go = bf16r(torch.randn(B, 4, 7, 12, 1024, generator=gen)).permute(0, 4, 1, 2, 3)
+    out.backward(go)
+    res = {"out": out.detach(), "dfused": f.grad}
+    for n, prm in ref.named_parameters():
+        res["g/" + n] = prm.grad
+    return res
+
+
+# ----------------------------------------------------------------------------- VideoAudioSaliencyFusionModel's token block
+class _FuRef(torch.nn.Module):
+    """model.py:151-183 between the backbone / SoundNet outputs and the decoder input, plain torch (d = C' features)."""
+
+    def __init__(self, d, layers):
+        super().__init__()
+        from oracle import torch_oracle as O
+        self.conv_in_1x1 = torch.nn.Conv3d(1024, d, 1)
+        self.audio_conv_1x1 = torch.nn.Conv2d(1024, d, 1)
+        self.transformer = O.TransformerOracle(d, d, 4, layers, 339)
+
+    def forward(self, y0, a):
+        v = self.conv_in_1x1(y0).flatten(2)
+        au = self.audio_conv_1x1(a).flatten(2)
+        t = self.transformer(torch.cat((v, au), 2).permute(2, 0, 1)).permute(1, 2, 0)
+        vf = t[..., :336].reshape(t.size(0), t.size(1), 4, 7, 12)
+        af = t[..., 336:].mean(2).view(t.size(0), t.size(1), 1, 1, 1).repeat(1, 1, 4, 7, 12)
+        return torch.cat((vf, af), 1)
+
+
+def _fu_ref(d, layers, seed):
+    from oracle import torch_oracle as O
+    return O.set_dropout(O.randomize_(_FuRef(d, layers), seed + 9), 0.0).train()
+
+
+def fusion_block(device, precision, backend=None, B=2, d=64, layers=1, seed=0):
+    from oracle import torch_oracle as O
+    from vinet_b200 import xfmr as X
+    gen = torch.Generator().manual_seed(seed)
+    ref = _fu_ref(d, layers, seed)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv_in_1x1 = M.ConvParams(1024, d, (1, 1, 1), bias=True)
+            self.audio_conv_1x1 = M.ConvParams(1024, d, (1, 1), bias=True)
+            self.transformer = X.Transformer(d, hidden_size=d, nhead=4, num_encoder_layers=layers, max_len=339)
+    m = Holder()
+    m.load_state_dict(ref.state_dict())
+    O.set_dropout(m, 0.0)
+    m.to(device)
+    e = make_engine(device, precision, backend)
+    y0 = fill_act(e, "y0", B, 4, 7, 12, 1024, gen, True, gdtype=torch.float32)
+    a = torch.randn(B, 1024, 3, generator=gen).to(device)
+    ga = torch.zeros_like(a)
+    out = X.fusion_plan(e, m, y0, a, ga)
+    run_tape(e, out, gen)
+    res = {"out": ncdhw(out.buf), "dy0": ncdhw(y0.grad), "da": ga.cpu().clone()}
+    for k, v in e.param_grads.items():
+        res["g/" + k] = v.detach().cpu().clone()
+    return res
+
+
+def fusion_block_torch(B=2, d=64, layers=1, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    ref = _fu_ref(d, layers, seed)
+    yb = bf16r(torch.randn(B, 4, 7, 12, 1024, generator=gen))
+    sc = torch.rand(1024, generator=gen) + 0.5
+    sh = torch.randn(1024, generator=gen) * 0.3
+    y0 = F.relu(yb.permute(0, 4, 1, 2, 3) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)).requires_grad_(True)
+    a = torch.randn(B, 1024, 3, generator=gen).requires_grad_(True)
+    out = ref(y0, a.unsqueeze(-1))
+    go = bf16r(torch.randn(B, 4, 7, 12, 2 * d, generator=gen)).permute(0, 4, 1, 2, 3)
+    out.backward(go)
+    res = {"out": out.detach(), "dy0": y0.grad, "da": a.grad}
+    for n, prm in ref.named_parameters():
+        res["g/" + n] = prm.grad
+    return res

@@ -255,3 +255,61 @@ def test_split_precision_plan_tracks_fp64():
         errs[prec] = (float(((pm.detach() - p64.detach()).abs() / p64.detach().abs()).max()), float(np.median(eg)))
     assert errs["bf16x6"][0] <= 3 * errs["fp32"][0] + 1e-5, errs
     assert errs["bf16x6"][1] <= 3 * errs["fp32"][1] + 1e-3, errs
+
+
+# ----------------------------------------------------------------------------- transformer fusion variants
+def test_transformer_variants_state_dict_layout_matches_oracle():
+    """Same keys, key ORDER, shapes and dtypes as the reference (the oracle's layout is asserted equal to the executed reference's
+    by oracle/make_golden.py): `load_state_dict` of a reference checkpoint works unchanged."""
+    from vinet_b200 import VideoAudioSaliencyFusionModel, VideoAudioSaliencyModel
+    pairs = [(VideoAudioSaliencyModel(use_transformer=True, soundnet_weights=False), O.AViNetOracle(32, use_transformer=True)),
+             (VideoAudioSaliencyFusionModel(soundnet_weights=False), O.AVFusionOracle())]
+    for mine, ref in pairs:
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        assert torch.equal(a["transformer.pos_encoder.pe"], b["transformer.pos_encoder.pe"])
+        mine.load_state_dict(b)
+
+
+def test_avinet_transformer_block_plan_vs_torch():
+    """use_transformer=True (model.py:239-247): conv_in_1x1 -> 32 channel tokens of 336 features -> encoder -> conv_out_1x1; forward,
+    input gradient and every parameter gradient against PyTorch autograd (dropout 0)."""
+    a, b = S.xf_block("cpu", "fp32", Spec()), S.xf_block_torch()
+    assert set(a) == set(b)
+    assert not S.compare(a, b, 1e-4), S.compare(a, b, 1e-4)
+
+
+def test_fusion_model_token_block_plan_vs_torch():
+    """VideoAudioSaliencyFusionModel (model.py:151-183): visual + audio tokens, encoder, [tokens | mean audio token] decoder input,
+    with a pending BatchNorm + ReLU on the backbone feature (read transform of the token GEMM)."""
+    a, b = S.fusion_block("cpu", "fp32", Spec()), S.fusion_block_torch()
+    assert set(a) == set(b)
+    assert not S.compare(a, b, 1e-4), S.compare(a, b, 1e-4)
+
+
+def test_transformer_dropout_plan():
+    """Train-mode dropout (p = 0.1 like nn.TransformerEncoderLayer): masks keep ~90 %, kept values are scaled by 1/(1-p), every
+    forward draws fresh masks from the device-side counter, eval mode launches none, and the backward stays consistent (finite)."""
+    from oracle.kernel_spec import dropout_keep
+    keep = dropout_keep(200000, 0.1, 1234, 7, 3)
+    assert abs(keep.mean() - 0.9) < 5e-3
+    assert (dropout_keep(200000, 0.1, 1234, 8, 3) != keep).mean() > 0.1          # another step: another mask
+    assert (dropout_keep(200000, 0.1, 1234, 7, 4) != keep).mean() > 0.1          # another site: another mask
+    base = S.xf_block("cpu", "fp32", Spec(), layers=1)
+    d1 = S.xf_block("cpu", "fp32", Spec(), layers=1, p=0.1)
+    ev = S.xf_block("cpu", "fp32", Spec(), layers=1, p=0.1, training=False)
+    assert all(torch.isfinite(v).all() for v in d1.values())
+    assert (d1["out"] - base["out"]).abs().max() > 1e-3                           # dropout changed the result ...
+    assert not S.compare(ev, base, 1e-6, skip=()), "eval mode must not drop"       # ... and is off in eval mode
+    x = torch.arange(1, 1001, dtype=torch.float32)
+    y, mask = torch.empty(1000), torch.empty(1000, dtype=torch.uint8)
+    rng = torch.tensor([5, 0], dtype=torch.int64)
+    sp = Spec()
+    sp.call("vinet_rng_advance", rng.data_ptr(), None)
+    assert rng.tolist() == [5, 1]
+    sp.call("vinet_dropout_fwd", x.data_ptr(), y.data_ptr(), mask.data_ptr(), 1000, 0.25, rng.data_ptr(), 2, None)
+    assert torch.allclose(y, torch.where(mask.bool(), x / 0.75, torch.zeros(())), rtol=1e-6, atol=0) and 0.6 < mask.float().mean() < 0.9
+    g = torch.ones(1000)
+    sp.call("vinet_dropout_bwd", g.data_ptr(), g.data_ptr(), mask.data_ptr(), x.sub(500).data_ptr(), 1000, 0.25, None)
+    assert torch.allclose(g, torch.where(mask.bool() & (x > 500), torch.full((), 1 / 0.75), torch.zeros(())), rtol=1e-6, atol=0)

@@ -11,9 +11,9 @@ from .model import VideoSaliencyModel  # noqa: F401
 from .preprocess import FramePreprocessor, audio_window  # noqa: F401
 
 try:  # AViNet lives in its own module so a ViNet-only user never touches the audio kernels
-    from .avmodel import VideoAudioSaliencyModel  # noqa: F401
+    from .avmodel import VideoAudioSaliencyFusionModel, VideoAudioSaliencyModel  # noqa: F401
 except ImportError:  # pragma: no cover
     pass
 
-__all__ = ["VideoSaliencyModel", "VideoAudioSaliencyModel", "kldiv", "cc", "similarity", "nss", "loss_func",
+__all__ = ["VideoSaliencyModel", "VideoAudioSaliencyModel", "VideoAudioSaliencyFusionModel", "kldiv", "cc", "similarity", "nss", "loss_func",
            "get_loss", "GraphedTrainStep", "GraphedForward", "SlidingWindowSaliency", "FramePreprocessor", "audio_window"]

@@ -1,4 +1,4 @@
-"""Drop-in ``VideoAudioSaliencyModel`` (AViNet, reference model.py:191-249, ``use_transformer=False``).
+"""Drop-in ``VideoAudioSaliencyModel`` (AViNet, reference model.py:191-249; ``use_transformer=True`` through vinet_b200/xfmr.py).
 
 SoundNet (model.py:746-825) runs as seven fp32 conv1d + fused BN/ReLU/MaxPool kernels (csrc/audio.cu);
 its (B,1024,3) output is fused with the max-pooled top backbone feature by the bilinear kernel
@@ -14,6 +14,7 @@ from . import arch
 from . import lib as L
 from .engine import Act
 from .model import BNParams, ConvParams, VideoSaliencyModel, _PlanModule, backbone_plan, decoder_plan, pack_input
+from . import xfmr
 
 
 class SoundNet(nn.Module):
@@ -123,11 +124,14 @@ class VideoAudioSaliencyModel(_PlanModule):
     def __init__(self, use_transformer=False, transformer_in_channel=32, num_encoder_layers=3, nhead=4,
                  use_upsample=True, num_hier=3, num_clips=32, soundnet_weights=None):
         super().__init__()
-        if use_transformer:
-            raise NotImplementedError("use_transformer=True is outside the hot-path scope (SURVEY.md §2.1)")
         self.use_transformer = use_transformer
         self.visual_model = VideoSaliencyModel(transformer_in_channel=transformer_in_channel, nhead=nhead,
                                                use_upsample=use_upsample, num_hier=num_hier, num_clips=num_clips)
+        if use_transformer:                   # model.py:211-221, registered in the reference's order (state_dict key order)
+            self.conv_in_1x1 = ConvParams(1024, transformer_in_channel, (1, 1, 1), bias=True)
+            self.conv_out_1x1 = ConvParams(32, 1024, (1, 1, 1), bias=True)
+            self.transformer = xfmr.Transformer(4 * 7 * 12, hidden_size=4 * 7 * 12, nhead=nhead, num_encoder_layers=num_encoder_layers,
+                                                num_decoder_layers=-1, max_len=transformer_in_channel)
         self.audionet = SoundNet()
         if soundnet_weights is not False:
             path = "./soundnet8_final.pth" if soundnet_weights is None else soundnet_weights
@@ -156,6 +160,59 @@ class VideoAudioSaliencyModel(_PlanModule):
         y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin,
                                        y0_gdtype=torch.float32)
         fused = avfuse_plan(e, "bilinear", y0, a, ga, self.bilinear)
+        if self.use_transformer:
+            fused = xfmr.avinet_transformer_plan(e, self, fused)
+        e.mark_backward_point("decoder")
+        out = decoder_plan(e, "visual_model.decoder.", self.visual_model.decoder, fused, y1, y2, y3)
+        e.end_forward()
+        return out
+
+
+class VideoAudioSaliencyFusionModel(_PlanModule):
+    """Drop-in ``VideoAudioSaliencyFusionModel`` (model.py:116-189): visual and audio tokens through one Transformer
+    (vinet_b200/xfmr.py).  Same constructor and ``state_dict`` as the reference; ``use_transformer`` is stored and ignored like
+    there; ``soundnet_weights`` as in ``VideoAudioSaliencyModel``.  The registered-but-unused ``bilinear`` gets no gradient."""
+
+    _n_extra = 1
+
+    def __init__(self, use_transformer=True, transformer_in_channel=512, num_encoder_layers=3, nhead=4, use_upsample=True, num_hier=3,
+                 num_clips=32, soundnet_weights=None):
+        super().__init__()
+        self.use_transformer = use_transformer
+        self.visual_model = VideoSaliencyModel(transformer_in_channel=transformer_in_channel, nhead=nhead,
+                                               use_upsample=use_upsample, num_hier=num_hier, num_clips=num_clips)
+        self.conv_in_1x1 = ConvParams(1024, transformer_in_channel, (1, 1, 1), bias=True)
+        self.transformer = xfmr.Transformer(transformer_in_channel, hidden_size=transformer_in_channel, nhead=nhead,
+                                            num_encoder_layers=num_encoder_layers, num_decoder_layers=-1, max_len=4 * 7 * 12 + 3)
+        self.audionet = SoundNet()
+        self.audio_conv_1x1 = ConvParams(1024, transformer_in_channel, (1, 1), bias=True)
+        if soundnet_weights is not False:
+            path = "./soundnet8_final.pth" if soundnet_weights is None else soundnet_weights
+            self.audionet.load_state_dict(torch.load(path))
+            print("Loaded SoundNet Weights")
+        for param in self.audionet.parameters():
+            param.requires_grad = True
+        self.bilinear = BilinearParams(42, 3, 4 * 7 * 12)
+
+    def _plan_uses(self, name):
+        return "conv8_" not in name and not name.startswith("bilinear.")
+
+    def forward(self, x, audio):
+        return self._call_plan(x, audio)
+
+    def _run_plan(self, e, record, x, audio):
+        e.generation += 1
+        e.begin(x.device, self.training, record)
+        audio_side = e.fork()
+        e.on_side(True)
+        a, ga = soundnet_plan(e, "audionet.", self.audionet, audio)
+        if audio_side:
+            e._side_active = False
+        xin = pack_input(e, x)
+        y0, y1, y2, y3 = backbone_plan(e, "visual_model.backbone.", self.visual_model.backbone, xin, y0_gdtype=torch.float32)
+        assert (y0.T, y0.H, y0.W, y0.C) == (4, 7, 12, 1024), "the fusion model is hard-wired to 32x224x384 clips (model.py:142,174)"
+        e.join()                 # the audio tokens are read next
+        fused = xfmr.fusion_plan(e, self, y0, a, ga)
         e.mark_backward_point("decoder")
         out = decoder_plan(e, "visual_model.decoder.", self.visual_model.decoder, fused, y1, y2, y3)
         e.end_forward()

@@ -187,7 +187,7 @@ extern "C" int vinet_abi_sizes(int64_t* out, int32_t n) {
                            sizeof(vinet_bn_apply_t), sizeof(vinet_bn_bwd_t),   sizeof(vinet_pool_t),       sizeof(vinet_upsample_t), sizeof(vinet_head_t),
                            sizeof(vinet_loss_t),     sizeof(vinet_conv1d_t),     sizeof(vinet_bn1d_t),     sizeof(vinet_avfuse_t),
                            sizeof(vinet_split_t),    sizeof(vinet_postproc_t), sizeof(vinet_preproc_t),
-                           sizeof(vinet_unpack_t)};
+                           sizeof(vinet_unpack_t),   sizeof(vinet_bgemm_t),    sizeof(vinet_addln_t)};
   const int32_t m = (int32_t)(sizeof(sizes) / sizeof(sizes[0]));
   for (int32_t i = 0; i < n && i < m; ++i) out[i] = sizes[i];
   return m;

@@ -150,6 +150,21 @@ class Unpack(C.Structure):
                 ("win8_kh", _i32), ("win8_kw", _i32), ("begin", _i32)]
 
 
+class Bgemm(C.Structure):
+    _fields_ = [("A", _p), ("sAm", _i64), ("sAk", _i64), ("sAb1", _i64), ("sAb2", _i64), ("a_dtype", _i32), ("a_relu", _i32),
+                ("a_scale", _p), ("a_shift", _p),
+                ("B", _p), ("sBn", _i64), ("sBk", _i64), ("sBb1", _i64), ("sBb2", _i64), ("b_dtype", _i32), ("c_dtype", _i32),
+                ("C", _p), ("sCm", _i64), ("sCn", _i64), ("sCb1", _i64), ("sCb2", _i64),
+                ("M", _i32), ("N", _i32), ("K", _i32), ("nb1", _i32), ("nb2", _i32), ("alpha", _f32), ("relu", _i32),
+                ("bias1", _p), ("s1m", _i64), ("s1n", _i64),
+                ("bias2", _p), ("s2m", _i64), ("s2n", _i64), ("s2b1", _i64), ("s2b2", _i64), ("accumulate", _i32), ("a_xf_on_m", _i32)]
+
+
+class AddLn(C.Structure):
+    _fields_ = [("x", _p), ("y", _p), ("z", _p), ("stat", _p), ("gamma", _p), ("beta", _p), ("eps", _f32), ("n", _i32),
+                ("rows", _i64), ("out", _p), ("gout", _p), ("dz", _p), ("dgamma", _p), ("dbeta", _p)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinet_b200.h
 _S = C.c_void_p  # stream
 SIGNATURES = {
@@ -196,6 +211,14 @@ SIGNATURES = {
     "vinet_bn1d_bwd": (C.c_int, [C.POINTER(Bn1d), _S]),
     "vinet_avfuse_fwd": (C.c_int, [C.POINTER(AvFuse), _S]),
     "vinet_avfuse_bwd": (C.c_int, [C.POINTER(AvFuse), _S]),
+    "vinet_bgemm": (C.c_int, [C.POINTER(Bgemm), _S]),
+    "vinet_softmax_fwd": (C.c_int, [_p, _i64, _i32, _S]),
+    "vinet_softmax_bwd": (C.c_int, [_p, _p, _i64, _i32, _S]),
+    "vinet_dropout_fwd": (C.c_int, [_p, _p, _p, _i64, _f32, _p, C.c_uint32, _S]),
+    "vinet_dropout_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _S]),
+    "vinet_rng_advance": (C.c_int, [_p, _S]),
+    "vinet_add_layernorm_fwd": (C.c_int, [C.POINTER(AddLn), _S]),
+    "vinet_add_layernorm_bwd": (C.c_int, [C.POINTER(AddLn), _S]),
     "vinet_memset_async": (C.c_int, [_p, C.c_int, C.c_size_t, _S]),
     "vinet_axpy_f32": (C.c_int, [_p, _p, _i64, _i32, _S]),
     "vinet_colsum": (C.c_int, [_p, _i64, _i32, _i64, _i32, _p, _p, _S]),
@@ -211,7 +234,7 @@ SIGNATURES = {
 
 # declaration order of the structs in the header (vinet_abi_sizes)
 ABI_STRUCTS = [Src, Gather, Conv, Wgrad, Pack, PackInput, BnStats, BnFinalize, BnApply, BnBwd, Pool, Upsample, Head, Loss,
-               Conv1d, Bn1d, AvFuse, Split, PostProc, PreProc, Unpack]
+               Conv1d, Bn1d, AvFuse, Split, PostProc, PreProc, Unpack, Bgemm, AddLn]
 
 
 class VinetError(RuntimeError):
