@@ -32,6 +32,10 @@ CASES = [
     ("vinet_hier0_train", "vinet", 32, 2, 64, 96, True, 6, 0),
     ("vinet_hier1_eval", "vinet", 32, 1, 64, 96, False, 7, 1),
     ("vinet_hier2_train", "vinet", 32, 2, 96, 64, True, 8, 2),
+    # transformer fusion variants (model.py:211-221,239-247 and model.py:116-189), train mode with every dropout probability set
+    # to 0 on the reference at run time (torch's Philox stream is not part of the contract; see oracle.torch_oracle.set_dropout)
+    ("avinet_xf_train", "avinet_xf", 32, 1, 224, 384, True, 9),
+    ("fusion_train", "fusion", 32, 1, 224, 384, True, 10),
 ]
 
 
@@ -59,16 +63,22 @@ def run_case(name, kind, T, B, H, W, train, seed, num_hier=3):
     if kind == "vinet":
         ref = ref_loader.build_vinet(T, num_hier)
         mine = O.ViNetOracle(T, num_hier)
-    else:
+    elif kind == "avinet":
         ref = ref_loader.build_avinet()
         mine = O.AViNetOracle(T)
+    elif kind == "avinet_xf":
+        ref = O.set_dropout(ref_loader.build_avinet(use_transformer=True), 0.0)
+        mine = O.set_dropout(O.AViNetOracle(T, use_transformer=True), 0.0)
+    else:
+        ref = O.set_dropout(ref_loader.build_fusion(), 0.0)
+        mine = O.set_dropout(O.AVFusionOracle(num_clips=T), 0.0)
     rs, ms = ref.state_dict(), mine.state_dict()
     assert list(rs.keys()) == list(ms.keys()), "state_dict key order differs from the reference"
     for k in rs:
         assert rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype, k
     O.randomize_(mine, seed)
     ref.load_state_dict(mine.state_dict())
-    d = O.make_inputs(B, T, H, W, seed, audio=(kind == "avinet"))
+    d = O.make_inputs(B, T, H, W, seed, audio=(kind != "vinet"))
     args = (d["x"],) if kind == "vinet" else (d["x"], d["audio"])
     _, ref_loss = ref_loader.load()
     rec = {}
@@ -99,8 +109,16 @@ def run_case(name, kind, T, B, H, W, train, seed, num_hier=3):
         full = [pfx + "backbone.base1.0.conv_s.weight", pfx + "backbone.base1.0.bn_s.weight",
                 pfx + "backbone.base2.0.branch2.1.conv_t.weight", pfx + "backbone.base4.1.branch3.1.bn.bias",
                 pfx + "decoder.convtsp4.3.weight"]
-        if kind == "avinet":
+        if kind in ("avinet", "avinet_xf"):
             full += ["bilinear.bias", "audionet.conv1.weight", "audionet.batchnorm7.weight"]
+        if kind == "avinet_xf":
+            full += ["conv_in_1x1.weight", "conv_out_1x1.bias", "transformer.transformer_encoder.layers.0.self_attn.in_proj_bias",
+                     "transformer.transformer_encoder.layers.0.self_attn.out_proj.bias",
+                     "transformer.transformer_encoder.layers.2.norm2.weight", "transformer.transformer_encoder.layers.1.linear1.bias"]
+        if kind == "fusion":
+            full += ["audionet.conv1.weight", "conv_in_1x1.bias", "audio_conv_1x1.bias",
+                     "transformer.transformer_encoder.layers.0.self_attn.in_proj_bias",
+                     "transformer.transformer_encoder.layers.2.norm1.bias", "transformer.transformer_encoder.layers.1.linear2.bias"]
         named = dict(ref.named_parameters())
         for k in full:
             rec["grad/" + k] = named[k].grad.detach().numpy()

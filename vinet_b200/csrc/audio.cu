@@ -3,6 +3,8 @@
 // 0.19 GFLOP per clip: warp-per-output kernels with shuffle reductions, fp32 throughout.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vinet {
@@ -60,8 +62,16 @@ struct A1dOps {
 
 // grid = (tiles over N, tiles over M, K splits); 256 threads, each a 4 x 4 micro-tile.  MODE FWD/DGRAD map M to long contiguous
 // runs in memory, so the m index of the A tile is the fast thread index there; WGRAD reads dy / x along K.
+// Split-K partial sums are combined by atomics (backward: order-dependent in the last bit, like every other gradient reduction
+// here) or, for the FORWARD pass, in a fixed order: the CTAs of one output tile take turns by split index (a per-tile turn
+// counter; CTAs are dispatched in block-id order, so a waiting CTA only ever waits for CTAs dispatched before it), split 0 stores,
+// the others add, the last one resets the counter.  The forward output is then bit-reproducible run to run, which the bf16
+// network behind it turns from a 1e-7 into a 1e-2 matter (tools/av_determinism.py).
+constexpr int A1D_TURN_SLOTS = 64, A1D_TURN_TILES = 512;
+__device__ int g_a1d_turn[A1D_TURN_SLOTS * A1D_TURN_TILES];
+
 template <int MODE>
-__global__ void __launch_bounds__(256) audio_gemm_kernel(const __grid_constant__ vinet_conv1d_t d, int ksplit_len, int atomic) {
+__global__ void __launch_bounds__(256) audio_gemm_kernel(const __grid_constant__ vinet_conv1d_t d, int ksplit_len, int atomic, int* turn) {
   __shared__ float As[A1D_BK][A1D_BM + 4], Bs[A1D_BK][A1D_BN + 4];
   const A1dOps<MODE> op(d);
   const int M = op.M(), N = op.N(), K = op.K();
@@ -102,6 +112,15 @@ __global__ void __launch_bounds__(256) audio_gemm_kernel(const __grid_constant__
     }
     __syncthreads();
   }
+  const bool ordered = turn != nullptr;
+  int* my_turn = ordered ? turn + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
+  if (ordered && blockIdx.z > 0) {
+    if (tid == 0) {
+      while (atomicAdd(my_turn, 0) != (int)blockIdx.z) __nanosleep(32);
+      __threadfence();
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -112,8 +131,20 @@ __global__ void __launch_bounds__(256) audio_gemm_kernel(const __grid_constant__
       if (n >= N) continue;
       float v = acc[i][j];
       if (MODE == A1D_FWD && d.bias && blockIdx.z == 0) v += __ldg(d.bias + n);
-      if (atomic) atomicAdd(op.out(m, n), v); else *op.out(m, n) = v;
+      if (ordered) {
+        float* o = op.out(m, n);
+        __stcg(o, blockIdx.z == 0 ? v : __ldcg(o) + v);      // L2 is the point of coherence between the CTAs of a tile
+      } else if (atomic) {
+        atomicAdd(op.out(m, n), v);
+      } else {
+        *op.out(m, n) = v;
+      }
     }
+  }
+  if (ordered) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(my_turn, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
   }
 }
 
@@ -140,10 +171,28 @@ template <int MODE>
 static int audio_gemm_launch(const vinet_conv1d_t* d, int M, int N, int K, float* out, size_t out_elems, cudaStream_t stream, const char* what) {
   const int tm = (int)cdiv(M, A1D_BM), tn = (int)cdiv(N, A1D_BN);
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * 148, (int64_t)tm * tn), cdiv(K, 4 * A1D_BK)));
+  // forward: ordered (bit-reproducible) combination of the K splits; VINET_AUDIO_FWD_ATOMIC=1 restores the atomics for A/B runs
+  static const bool fwd_atomic = getenv("VINET_AUDIO_FWD_ATOMIC") != nullptr;
+  static std::atomic<unsigned> next_slot{0};
   int len = (int)round_up(cdiv(K, splits), A1D_BK);
   splits = (int)cdiv(K, len);
-  if (splits > 1) cudaMemsetAsync(out, 0, out_elems * sizeof(float), stream);
-  audio_gemm_kernel<MODE><<<dim3((unsigned)tn, (unsigned)tm, (unsigned)splits), 256, 0, stream>>>(*d, len, splits > 1 ? 1 : 0);
+  int* turn = nullptr;
+  if (MODE == A1D_FWD && splits > 1 && !fwd_atomic && (int64_t)tm * tn <= A1D_TURN_TILES) {
+    static int* bases[64] = {nullptr};            // per device; resolved once, outside any stream capture (warm-up steps)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* base = dev < 64 ? bases[dev] : nullptr;
+    if (!base) {
+      if (cudaGetSymbolAddress((void**)&base, g_a1d_turn) != cudaSuccess) {
+        set_error("%s: cudaGetSymbolAddress failed", what);
+        return -1;
+      }
+      if (dev < 64) bases[dev] = base;
+    }
+    turn = base + (next_slot.fetch_add(1, std::memory_order_relaxed) % A1D_TURN_SLOTS) * A1D_TURN_TILES;
+  }
+  if (splits > 1 && !turn) cudaMemsetAsync(out, 0, out_elems * sizeof(float), stream);
+  audio_gemm_kernel<MODE><<<dim3((unsigned)tn, (unsigned)tm, (unsigned)splits), 256, 0, stream>>>(*d, len, splits > 1 ? 1 : 0, turn);
   VINET_LAUNCH_OK(what);
   return 0;
 }

@@ -73,9 +73,14 @@ def gemm(e, M, N, K, A, sA, B, sB, Cp, sC, nb=(1, 1), alpha=1.0, a_dtype=L.F32, 
     e.call("vinet_bgemm", d)
 
 
+def _on_device(t, dev):
+    """`t` lives on the engine's device (an engine begun on torch.device("cuda") holds tensors that report cuda:<current>)."""
+    return t is not None and t.device.type == dev.type and (dev.index is None or t.device.index == dev.index)
+
+
 def ones(e):
     t = e.pool.get("xfmr.one")
-    if t is None or t.device != e.device:
+    if not _on_device(t, e.device):
         t = e.pool["xfmr.one"] = torch.ones(4, dtype=torch.float32, device=e.device)
     return t
 
@@ -102,7 +107,7 @@ def linear_bwd(e, pname, x, rows, k, w, b, dy, n, dx=None, dx_acc=0):
 
 def _rng(e):
     t = e.pool.get("xfmr.rng")
-    if t is None or t.device != e.device:
+    if not _on_device(t, e.device):
         t = e.pool["xfmr.rng"] = torch.tensor([torch.initial_seed() & 0x7FFFFFFF, 0], dtype=torch.int64, device=e.device)
     return t
 
