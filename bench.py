@@ -77,7 +77,10 @@ class ClockSampler(threading.Thread):
 
 
 def workload_name(args, reference=False):
-    what = "ViNet (VideoSaliencyModel)" if args.model == "vinet" else "AViNet (VideoAudioSaliencyModel, SoundNet audio fusion)"
+    what = ("ViNet (VideoSaliencyModel)" if args.model == "vinet" else
+            {"bilinear": "AViNet (VideoAudioSaliencyModel, SoundNet audio fusion)",
+             "transformer": "AViNet (VideoAudioSaliencyModel(use_transformer=True), 3 encoder layers over the 32 channel tokens)",
+             "tokens": "VideoAudioSaliencyFusionModel (336 visual + 3 audio tokens x 512 through 3 encoder layers)"}[args.av_fusion])
     if args.mode == "train":
         return "%s fwd + kldiv + bwd%s" % (what, "" if (args.no_adam or reference) else " + fused Adam")
     return "%s eval forward (no_grad%s)" % (what, "" if reference else ", BatchNorm folded")
@@ -92,10 +95,18 @@ def reference_models(args):
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if os.path.isfile(os.path.join(ref_dir, "model.py")):
         ref_loader.use_dir(ref_dir)
-        m = ref_loader.build_vinet(args.clip_len) if args.model == "vinet" else ref_loader.build_avinet(random_soundnet=True)
+        if args.model == "vinet":
+            m = ref_loader.build_vinet(args.clip_len)
+        elif args.av_fusion == "tokens":
+            m = ref_loader.build_fusion(random_soundnet=True)
+        else:
+            m = ref_loader.build_avinet(random_soundnet=True, use_transformer=args.av_fusion == "transformer")
         _, rl = ref_loader.load()
         return m, rl.kldiv, "reference"
-    m = O.ViNetOracle(args.clip_len) if args.model == "vinet" else O.AViNetOracle(args.clip_len)
+    if args.model == "vinet":
+        m = O.ViNetOracle(args.clip_len)
+    else:
+        m = O.AVFusionOracle() if args.av_fusion == "tokens" else O.AViNetOracle(args.clip_len, use_transformer=args.av_fusion == "transformer")
     return m, O.kldiv, "port"
 
 
@@ -245,6 +256,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--model", default="vinet", choices=["vinet", "avinet"])
+    ap.add_argument("--av-fusion", default="bilinear", choices=["bilinear", "transformer", "tokens"],
+                    help="--model avinet: bilinear = VideoAudioSaliencyModel (config 4); transformer = its use_transformer=True "
+                         "variant (model.py:239-247); tokens = VideoAudioSaliencyFusionModel (model.py:116-189)")
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
     ap.add_argument("--clip-len", type=int, default=32, choices=[8, 16, 32, 48])
     ap.add_argument("--height", type=int, default=224)
@@ -270,7 +284,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from vinet_b200 import GraphedForward, GraphedTrainStep, VideoAudioSaliencyModel, VideoSaliencyModel, kldiv
+    from vinet_b200 import GraphedForward, GraphedTrainStep, VideoAudioSaliencyFusionModel, VideoAudioSaliencyModel, VideoSaliencyModel, kldiv
     from vinet_b200 import lib as L
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -285,8 +299,10 @@ def main():
     T, H, W, B = args.clip_len, args.height, args.width, args.batch
     if args.model == "vinet":
         model = VideoSaliencyModel(num_clips=T)
-    else:
-        model = VideoAudioSaliencyModel(num_clips=T, soundnet_weights=False)   # synthetic benchmark: random SoundNet weights
+    elif args.av_fusion == "tokens":
+        model = VideoAudioSaliencyFusionModel(num_clips=T, soundnet_weights=False)
+    else:                                                                      # synthetic benchmark: random SoundNet weights
+        model = VideoAudioSaliencyModel(use_transformer=args.av_fusion == "transformer", num_clips=T, soundnet_weights=False)
     model = model.to(dev).set_precision(args.precision)
     model.train() if train else model.eval()
     net = model

@@ -514,7 +514,8 @@ typedef struct vinet_bgemm {
   int64_t s1m, s1n;
   const float* bias2; /* optional, per batch */
   int64_t s2m, s2n, s2b1, s2b2;
-  int32_t accumulate; /* 1: C += result (fp32 C only) */
+  int32_t accumulate; /* bit 0: C += result (fp32 C only); bit 1: the reduction order is free (gradients): a long K over few
+                       * output tiles may then be split across CTAs that combine with fp32 atomics */
   int32_t a_xf_on_m;  /* a_scale / a_shift are indexed by A's row m instead of the reduction index k */
 } vinet_bgemm_t;
 int vinet_bgemm(const vinet_bgemm_t* d, vinet_stream_t stream);

@@ -615,7 +615,7 @@ def _bgemm(self, d, stream):
             _, ci = _strided(d.C, L.F32, d.M, d.sCm, d.N, d.sCn, b1 * d.sCb1 + b2 * d.sCb2)
             assert d.c_dtype == L.F32, "the numpy spec keeps fp32 storage"
             flat = _arr(d.C, int(ci.max()) + 1)
-            flat[ci] = (flat[ci] + v if d.accumulate else v).astype(np.float32)
+            flat[ci] = (flat[ci] + v if (d.accumulate & 1) else v).astype(np.float32)
 
 
 def _softmax_fwd(self, s, rows, n, stream):

@@ -1,5 +1,5 @@
 """Per-kernel device-time table of one step (torch.profiler / CUPTI; concurrent, warm caches).
-usage: profile_step.py [B] [vinet|avinet] [train|eval]"""
+usage: profile_step.py [B] [vinet|avinet|avinet_xf|fusion] [train|eval]"""
 import os
 import sys
 import collections
@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
-from vinet_b200 import VideoAudioSaliencyModel, VideoSaliencyModel, kldiv
+from vinet_b200 import VideoAudioSaliencyFusionModel, VideoAudioSaliencyModel, VideoSaliencyModel, kldiv
 
 for kv in os.environ.get("VINET_DEBUG_SET", "").split(","):      # e.g. VINET_DEBUG_SET=3=5 : atomic max-pool backward
     if "=" in kv:
@@ -20,12 +20,14 @@ which = sys.argv[2] if len(sys.argv) > 2 else "vinet"
 mode = sys.argv[3] if len(sys.argv) > 3 else "train"
 dev = torch.device("cuda")
 torch.manual_seed(0)
-model = (VideoSaliencyModel() if which == "vinet" else VideoAudioSaliencyModel(soundnet_weights=False)).to(dev)
+model = {"vinet": lambda: VideoSaliencyModel(), "avinet": lambda: VideoAudioSaliencyModel(soundnet_weights=False),
+         "avinet_xf": lambda: VideoAudioSaliencyModel(use_transformer=True, soundnet_weights=False),
+         "fusion": lambda: VideoAudioSaliencyFusionModel(soundnet_weights=False)}[which]().to(dev)
 model.train() if mode == "train" else model.eval()
 opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, fused=True)
 x = torch.randn(B, 32, 3, 224, 384, device=dev)
 gt = torch.rand(B, 224, 384, device=dev) + 1e-3
-extra = [0.05 * torch.randn(B, 1, 70560, 1, device=dev)] if which == "avinet" else []
+extra = [0.05 * torch.randn(B, 1, 70560, 1, device=dev)] if which != "vinet" else []
 
 
 def step():

@@ -2,24 +2,34 @@
 // three post-norm encoder layers.  Under 1 % of the step's FLOPs, so everything here is plain fp32 FFMA work, written for few
 // launches and no layout copies: ONE strided batched GEMM covers the linear layers, both attention products, the 1x1 convolutions
 // with bias, every permute / flatten / cat / mean / repeat of the reference's forward, and all of their gradients.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vinet {
 
 // ------------------------------------------------------------------ strided batched GEMM
+// These products are small (<= 4 GFLOP) and latency-bound, not FLOP-bound: what matters is loads in flight and CTAs in flight.
+// A k step covers 32 reduction elements (16 independent global loads per thread), the loads of step i + 1 are issued into
+// registers before step i is computed, and outputs with few tiles but a long reduction (weight and bias gradients: K = all token
+// rows) are split along K over up to two waves of CTAs that combine with fp32 atomics (gradients only, never a forward result).
 constexpr int BG_T = 64;   // C tile (BG_T x BG_T), 256 threads, 4 x 4 outputs per thread
-constexpr int BG_K = 16;
+constexpr int BG_K = 32;
 
 __device__ __forceinline__ float bg_load(const void* p, int64_t off, int dtype) {
   return dtype == VINET_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[off]) : __ldg(reinterpret_cast<const float*>(p) + off);
 }
 
-__global__ void __launch_bounds__(256) bgemm_kernel(const vinet_bgemm_t d) {
+// splits > 1: blockIdx.z is a K split of the single batch (k range [z * ksplit_len, ...)), results are added atomically
+__global__ void __launch_bounds__(256) bgemm_kernel(const vinet_bgemm_t d, int ksplit_len, int splits) {
   __shared__ float As[BG_K][BG_T + 4];
   __shared__ float Bs[BG_K][BG_T + 4];
   const int tid = threadIdx.x;
-  const int b1 = blockIdx.z / d.nb2, b2 = blockIdx.z % d.nb2;
+  const int bz = splits > 1 ? 0 : (int)blockIdx.z;
+  const int b1 = bz / d.nb2, b2 = bz % d.nb2;
   const int m0 = blockIdx.y * BG_T, n0 = blockIdx.x * BG_T;
+  const int k_begin = splits > 1 ? (int)blockIdx.z * ksplit_len : 0;
+  const int k_end = splits > 1 ? min(d.K, k_begin + ksplit_len) : d.K;
   const int64_t offA = b1 * d.sAb1 + b2 * d.sAb2, offB = b1 * d.sBb1 + b2 * d.sBb2;
   // the fastest-running thread index follows the unit-stride axis of each operand
   const bool a_kfast = d.sAk == 1, b_kfast = d.sBk == 1;
@@ -29,28 +39,39 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const vinet_bgemm_t d) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < d.K; k0 += BG_K) {
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;
       {
-        const int kk = a_kfast ? (idx & 15) : (idx >> 6), mm = a_kfast ? (idx >> 4) : (idx & 63);
+        const int kk = a_kfast ? (idx & 31) : (idx >> 6), mm = a_kfast ? (idx >> 5) : (idx & 63);
         const int m = m0 + mm, k = k0 + kk;
         float v = 0.f;
-        if (m < d.M && k < d.K) {
+        if (m < d.M && k < k_end) {
           v = bg_load(d.A, offA + m * d.sAm + k * d.sAk, d.a_dtype);
           if (d.a_scale) v = fmaf(v, __ldg(d.a_scale + (d.a_xf_on_m ? m : k)), __ldg(d.a_shift + (d.a_xf_on_m ? m : k)));
           if (d.a_relu) v = fmaxf(v, 0.f);
         }
-        As[kk][mm] = v;
+        ra[i] = v;
       }
       {
-        const int kk = b_kfast ? (idx & 15) : (idx >> 6), nn = b_kfast ? (idx >> 4) : (idx & 63);
+        const int kk = b_kfast ? (idx & 31) : (idx >> 6), nn = b_kfast ? (idx >> 5) : (idx & 63);
         const int n = n0 + nn, k = k0 + kk;
-        Bs[kk][nn] = (n < d.N && k < d.K) ? bg_load(d.B, offB + n * d.sBn + k * d.sBk, d.b_dtype) : 0.f;
+        rb[i] = (n < d.N && k < k_end) ? bg_load(d.B, offB + n * d.sBn + k * d.sBk, d.b_dtype) : 0.f;
       }
     }
+  };
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += BG_K) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      As[a_kfast ? (idx & 31) : (idx >> 6)][a_kfast ? (idx >> 5) : (idx & 63)] = ra[i];
+      Bs[b_kfast ? (idx & 31) : (idx >> 6)][b_kfast ? (idx >> 5) : (idx & 63)] = rb[i];
+    }
     __syncthreads();
+    if (k0 + BG_K < k_end) fetch(k0 + BG_K);        // in flight while this step is computed
 #pragma unroll
     for (int kk = 0; kk < BG_K; ++kk) {
       float a[4], b[4];
@@ -69,6 +90,7 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const vinet_bgemm_t d) {
   // Epilogue through shared memory (As is free now) in four slabs of 16 rows, so that consecutive threads store consecutive
   // addresses whichever of C's two axes has the smaller stride.
   const bool c_nfast = d.sCn <= d.sCm;
+  const bool lead = splits <= 1 || blockIdx.z == 0;     // the bias terms are added once
   float* Ct = &As[0][0];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -84,15 +106,16 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const vinet_bgemm_t d) {
       const int m = m0 + r + 16 * i, n = n0 + c;
       if (m >= d.M || n >= d.N) continue;
       float v = d.alpha * Ct[r * (BG_T + 4) + c];
-      if (d.bias1) v += __ldg(d.bias1 + m * d.s1m + n * d.s1n);
-      if (d.bias2) v += __ldg(d.bias2 + off2 + m * d.s2m + n * d.s2n);
+      if (lead && d.bias1) v += __ldg(d.bias1 + m * d.s1m + n * d.s1n);
+      if (lead && d.bias2) v += __ldg(d.bias2 + off2 + m * d.s2m + n * d.s2n);
       if (d.relu) v = fmaxf(v, 0.f);
       const int64_t o = offC + m * d.sCm + n * d.sCn;
       if (d.c_dtype == VINET_BF16) {
         reinterpret_cast<__nv_bfloat16*>(d.C)[o] = __float2bfloat16_rn(v);
       } else {
         float* cp = reinterpret_cast<float*>(d.C) + o;
-        *cp = d.accumulate ? *cp + v : v;
+        if (splits > 1) atomicAdd(cp, v);
+        else *cp = (d.accumulate & 1) ? *cp + v : v;
       }
     }
   }
@@ -263,11 +286,24 @@ extern "C" int vinet_bgemm(const vinet_bgemm_t* d, vinet_stream_t stream) {
   VINET_CHECK(d->M >= 1 && d->N >= 1 && d->K >= 0 && d->nb1 >= 1 && d->nb2 >= 1, "bgemm: bad shape %d x %d x %d (%d, %d batches)", d->M, d->N, d->K,
               d->nb1, d->nb2);
   VINET_CHECK(d->C && (d->K == 0 || (d->A && d->B)), "bgemm: null operand");
-  VINET_CHECK(!(d->accumulate && d->c_dtype != VINET_F32), "bgemm: accumulation needs an fp32 C");
+  VINET_CHECK(!((d->accumulate & 1) && d->c_dtype != VINET_F32), "bgemm: accumulation needs an fp32 C");
   VINET_CHECK(!d->a_scale == !d->a_shift, "bgemm: a_scale and a_shift come together");
   VINET_CHECK((int64_t)d->nb1 * d->nb2 <= 65535, "bgemm: too many batches");
-  dim3 grid((unsigned)cdiv(d->N, BG_T), (unsigned)cdiv(d->M, BG_T), (unsigned)(d->nb1 * d->nb2));
-  bgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  const int64_t tiles = cdiv(d->N, BG_T) * cdiv(d->M, BG_T);
+  // split K when one wave of CTAs is far from full and the reduction is long - only where the caller allows an order-free
+  // reduction (accumulate bit 1: gradients): fp32 C without ReLU, a single batch, and (unless the call accumulates anyway) a DENSE
+  // C block that one memset can clear
+  const bool dense = (d->sCn == 1 && d->sCm == d->N) || (d->sCm == 1 && d->sCn == d->M) || (d->N == 1 && d->sCm == 1) || (d->M == 1 && d->sCn == 1);
+  int splits = 1, len = d->K;
+  if ((d->accumulate & 2) && d->nb1 * d->nb2 == 1 && d->c_dtype == VINET_F32 && !d->relu && d->K >= 8 * BG_K && tiles <= 74 &&
+      ((d->accumulate & 1) || dense)) {
+    splits = (int)std::min<int64_t>(cdiv(2 * 148, tiles), d->K / (4 * BG_K));
+    len = (int)round_up(cdiv(d->K, splits), BG_K);
+    splits = (int)cdiv(d->K, len);
+  }
+  if (splits > 1 && !(d->accumulate & 1)) cudaMemsetAsync(d->C, 0, (size_t)d->M * d->N * sizeof(float), (cudaStream_t)stream);
+  dim3 grid((unsigned)cdiv(d->N, BG_T), (unsigned)cdiv(d->M, BG_T), (unsigned)(splits > 1 ? splits : d->nb1 * d->nb2));
+  bgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, len, splits);
   VINET_LAUNCH_OK("bgemm");
   return 0;
 }

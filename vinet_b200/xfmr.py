@@ -52,6 +52,19 @@ def _ptr(t, off=0):
     return t.data_ptr() + off * t.element_size()
 
 
+_ORDER_FREE = [False]      # set while a backward closure runs: gradient reductions may be split along K (vinet_bgemm_t.accumulate bit 1)
+
+
+def _backward_pass(fn):
+    def run():
+        _ORDER_FREE[0] = True
+        try:
+            fn()
+        finally:
+            _ORDER_FREE[0] = False
+    return run
+
+
 def gemm(e, M, N, K, A, sA, B, sB, Cp, sC, nb=(1, 1), alpha=1.0, a_dtype=L.F32, b_dtype=L.F32, c_dtype=L.F32, bias1=None, bias2=None,
          relu=0, acc=0, a_xf=None, a_xf_on_m=0):
     """One vinet_bgemm launch.  A / B / Cp are device addresses; sA = (sm, sk[, sb1, sb2]), sB = (sn, sk[, ...]), sC = (sm, sn[, ...])
@@ -61,7 +74,7 @@ def gemm(e, M, N, K, A, sA, B, sB, Cp, sC, nb=(1, 1), alpha=1.0, a_dtype=L.F32, 
     d.A, d.sAm, d.sAk, d.sAb1, d.sAb2, d.a_dtype = A, sA[0], sA[1], sA[2], sA[3], a_dtype
     d.B, d.sBn, d.sBk, d.sBb1, d.sBb2, d.b_dtype = B, sB[0], sB[1], sB[2], sB[3], b_dtype
     d.C, d.sCm, d.sCn, d.sCb1, d.sCb2, d.c_dtype = Cp, sC[0], sC[1], sC[2], sC[3], c_dtype
-    d.M, d.N, d.K, d.nb1, d.nb2, d.alpha, d.relu, d.accumulate = M, N, K, nb[0], nb[1], alpha, relu, acc
+    d.M, d.N, d.K, d.nb1, d.nb2, d.alpha, d.relu, d.accumulate = M, N, K, nb[0], nb[1], alpha, relu, int(acc) | (2 if _ORDER_FREE[0] else 0)
     if a_xf is not None:
         d.a_scale, d.a_shift, d.a_relu = a_xf
         d.a_xf_on_m = a_xf_on_m
@@ -232,7 +245,7 @@ def encoder_plan(e, pfx, tr, x, S, B):
             g = dz1
         gx_box[0] = g
 
-    e.tape.append(backward)
+    e.tape.append(_backward_pass(backward))
     return x, gy, gx_box
 
 
@@ -260,7 +273,7 @@ def avinet_transformer_plan(e, m, fused):
             gemm(e, Pn, Cin, S, _ptr(gx), (1, B * Pn, Pn), _ptr(cin.weight), (1, Cin), fused.gptr(), (fused.ldg, 1, Pn * fused.ldg), nb=(B, 1),
                  acc=0 if first else 1)
             e.param_grads["conv_in_1x1.weight"], e.param_grads["conv_in_1x1.bias"] = gw, gb
-        e.tape.append(conv_in_backward)
+        e.tape.append(_backward_pass(conv_in_backward))
     y, gy, box["gx"] = encoder_plan(e, "transformer.transformer_encoder.layers.", tr, x0, S, B)
     out = e.new_act("xf.out", B, fused.T, fused.H, fused.W, Cout, gdtype=f32)
     gemm(e, Pn, Cout, S, _ptr(y), (1, B * Pn, Pn), _ptr(cout.weight), (S, 1), out.ptr(), (out.ld, 1, Pn * out.ld), nb=(B, 1), c_dtype=e.dt,
@@ -274,7 +287,7 @@ def avinet_transformer_plan(e, m, fused):
             gemm(e, Cout, S, B * Pn, g, (1, ldg), _ptr(y), (B * Pn, 1), _ptr(gw), (S, 1))
             gemm(e, Cout, 1, B * Pn, g, (1, ldg), _ptr(ones(e)), (0, 0), _ptr(gb), (1, 0))
             e.param_grads["conv_out_1x1.weight"], e.param_grads["conv_out_1x1.bias"] = gw, gb
-        e.tape.append(conv_out_backward)
+        e.tape.append(_backward_pass(conv_out_backward))
     return out
 
 
@@ -325,7 +338,7 @@ def fusion_plan(e, m, y0, a, ga):
             gemm(e, na, Cin, d, _ptr(gx, Pn * B * d), (B * d, 1, d), _ptr(ca.weight), (1, Cin), _ptr(ga), (1, na, Cin * na), nb=(B, 1))
             e.param_grads["conv_in_1x1.weight"], e.param_grads["conv_in_1x1.bias"] = gwv, gbv
             e.param_grads["audio_conv_1x1.weight"], e.param_grads["audio_conv_1x1.bias"] = gwa, gba
-        e.tape.append(tokens_backward)
+        e.tape.append(_backward_pass(tokens_backward))
     y, gy, box["gx"] = encoder_plan(e, "transformer.transformer_encoder.layers.", tr, x0, S, B)
     out = e.new_act("fu.out", B, y0.T, y0.H, y0.W, 2 * d, gdtype=f32)
     esz = out.buf.element_size()
@@ -338,5 +351,5 @@ def fusion_plan(e, m, y0, a, ga):
             g, ldg = out.gptr(), out.ldg
             gemm(e, Pn, d, 0, None, (0, 0), None, (0, 0), _ptr(gy), (B * d, 1, d), nb=(B, 1), bias2=(g, ldg, 1, Pn * ldg))
             gemm(e, na, d, Pn, _ptr(ones(e)), (0, 0), g + 4 * d, (1, ldg, Pn * ldg), _ptr(gy, Pn * B * d), (B * d, 1, d), nb=(B, 1), alpha=1.0 / na)
-        e.tape.append(split_backward)
+        e.tape.append(_backward_pass(split_backward))
     return out
