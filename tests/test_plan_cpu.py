@@ -310,6 +310,6 @@ def test_transformer_dropout_plan():
     assert rng.tolist() == [5, 1]
     sp.call("vinet_dropout_fwd", x.data_ptr(), y.data_ptr(), mask.data_ptr(), 1000, 0.25, rng.data_ptr(), 2, None)
     assert torch.allclose(y, torch.where(mask.bool(), x / 0.75, torch.zeros(())), rtol=1e-6, atol=0) and 0.6 < mask.float().mean() < 0.9
-    g = torch.ones(1000)
-    sp.call("vinet_dropout_bwd", g.data_ptr(), g.data_ptr(), mask.data_ptr(), x.sub(500).data_ptr(), 1000, 0.25, None)
+    g, relu_ref = torch.ones(1000), x - 500                    # (kept alive: the call takes raw addresses)
+    sp.call("vinet_dropout_bwd", g.data_ptr(), g.data_ptr(), mask.data_ptr(), relu_ref.data_ptr(), 1000, 0.25, None)
     assert torch.allclose(g, torch.where(mask.bool() & (x > 500), torch.full((), 1 / 0.75), torch.zeros(())), rtol=1e-6, atol=0)

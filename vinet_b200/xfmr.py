@@ -11,8 +11,8 @@ and bias-gradient reduction is one ``vinet_bgemm`` over strided views.  Dropout 
 mode, like ``nn.TransformerEncoderLayer``) uses the library's counter-based generator: statistically equivalent to, not bit-identical
 with, torch's Philox stream (parity tests run with p = 0 or in eval mode).
 """
-import ctypes as C
 import math
+from types import SimpleNamespace
 
 import torch
 import torch.nn as nn
@@ -187,8 +187,9 @@ def encoder_plan(e, pfx, tr, x, S, B):
         ln2.x, ln2.y, ln2.z, ln2.stat, ln2.gamma, ln2.beta = _ptr(x1), _ptr(f), _ptr(z2), _ptr(st2), _ptr(l.norm2.weight), _ptr(l.norm2.bias)
         ln2.eps, ln2.n, ln2.rows, ln2.out = l.norm2.eps, d, R, _ptr(x2)
         e.call("vinet_add_layernorm_fwd", ln2)
-        saved.append((n, l, x, qkv, P, Pd, mask_a, ctx, mask_1, x1, ln1, h, hd, mask_f, mask_2, ln2, (pa, p1, pf, p2), ff,
-                      (z1, st1, z2, st2, ao, f, x2)))        # the last tuple only keeps the buffers referenced
+        # what the backward reads (the descriptors hold raw addresses: `keep` pins the buffers behind them)
+        saved.append(SimpleNamespace(n=n, l=l, xin=x, qkv=qkv, P=P, Pd=Pd, mask_a=mask_a, ctx=ctx, mask_1=mask_1, x1=x1, ln1=ln1, h=h, hd=hd,
+                                     mask_f=mask_f, mask_2=mask_2, ln2=ln2, p=(pa, p1, pf, p2), ff=ff, keep=(z1, st1, z2, st2, ao, f, x2)))
         x = x2
     if not e.record:
         return x, None, None
@@ -197,9 +198,10 @@ def encoder_plan(e, pfx, tr, x, S, B):
 
     def backward():
         g = gy
-        for (n, l, xin, qkv, P, Pd, mask_a, ctx, mask_1, x1, ln1, h, hd, mask_f, mask_2, ln2, (pa, p1, pf, p2), ff, _keep) in reversed(saved):
-            at = l.self_attn
-            pn = n
+        for sv in reversed(saved):
+            n, l, xin, qkv, P, Pd, ctx, x1, ln1, ln2, h, hd, ff = sv.n, sv.l, sv.xin, sv.qkv, sv.P, sv.Pd, sv.ctx, sv.x1, sv.ln1, sv.ln2, sv.h, sv.hd, sv.ff
+            mask_a, mask_1, mask_f, mask_2, (pa, p1, pf, p2) = sv.mask_a, sv.mask_1, sv.mask_f, sv.mask_2, sv.p
+            at, pn = l.self_attn, n
             # ---- norm2(x1 + dropout2(linear2(dropout(relu(linear1(x1))))))
             dz2 = e.buf(n + "dz2", (R, d), f32)
             gg2, gb2 = e.grad_tensor(pn + "norm2.weight", l.norm2.weight, zero=True), e.grad_tensor(pn + "norm2.bias", l.norm2.bias, zero=True)
