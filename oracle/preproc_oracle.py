@@ -70,3 +70,44 @@ def audio_window(excerpt, total=70560):
     lo = total // 2 - n // 2
     out[lo:lo + n] = np.hanning(n).astype(np.float32) * excerpt.astype(np.float32)
     return out
+
+
+def av_excerpt_bounds(n_wav, sample_rate, fps, n_frames):
+    """generate_result_audio_visual.py:56-66 (= dataloader.py:56-70): per-frame audio excerpt start / end sample (1-based frames)."""
+    fs, fps = float(sample_rate), float(fps)
+    n_samples = fs / fps
+    starts, ends = np.zeros(n_frames + 1, dtype=int), np.zeros(n_frames + 1, dtype=int)
+    for vf in range(1, n_frames + 1):
+        starts[vf] = int(max(0, ((vf - 1) * (1.0 / fps) * fs) - n_samples / 2))
+        ends[vf] = int(min(n_wav, abs(((vf - 1) * (1.0 / fps) * fs) + n_samples / 2)))
+    return starts, ends
+
+
+def av_audio_feature(wav, starts, ends, start_idx, clip_len, total=70560):
+    """generate_result_audio_visual.py:86-118 (`get_audio_feature`) for a 1-D waveform: the excerpt of the window whose first frame
+    is `start_idx`, times np.hanning, centred in `total` zeros -> (total,) fp32."""
+    s = starts[start_idx + 1]
+    e = ends[-1] if start_idx + clip_len >= len(ends) else ends[start_idx + clip_len]
+    return audio_window(np.asarray(wav[s:e + 1], np.float32), total)
+
+
+def sliding_window_reference_av(model, frames, clip_len, wav, starts, ends, frame_ids=None):
+    """generate_result_audio_visual.py:177-199 with a callable `model(clip, audio)`: {frame index: (H, W) map} for the frames in
+    `frame_ids` (all when None); the first L-1 frames come from the time-flipped clip AND the time-flipped audio feature."""
+    import torch
+    n = frames.shape[0]
+    out = {}
+    with torch.no_grad():
+        for i in range(clip_len - 1, n):
+            j = i - clip_len + 1
+            want_fwd = frame_ids is None or i in frame_ids
+            want_rev = i < 2 * clip_len - 2 and (frame_ids is None or j in frame_ids)
+            if not (want_fwd or want_rev):
+                continue
+            clip = frames[j:i + 1].unsqueeze(0).permute(0, 2, 1, 3, 4)
+            a = torch.from_numpy(av_audio_feature(wav, starts, ends, j, clip_len)).view(1, 1, -1, 1).to(frames.device)
+            if want_fwd:
+                out[i] = model(clip, a)[0]
+            if want_rev:
+                out[j] = model(torch.flip(clip, [2]), torch.flip(a, [2]))[0]
+    return out

@@ -97,3 +97,40 @@ def test_per_frame_stem_reuse_matches_plain_windows():
     a = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=8, stem_cache=True)(video).cpu()
     c = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=8, stem_cache=False)(video).cpu()
     assert torch.equal(a, c), (a - c).abs().max()
+
+
+def test_audio_visual_sliding_window_matches_reference_loop():
+    """generate_result_audio_visual.py:177-199 through the driver: every window gets the excerpt the reference cuts for it
+    (Hanning-windowed on the device), the first L-1 frames come from time-flipped clips WITH time-flipped audio, windows are
+    batched and graph-replayed.  Checked against the reference's loop (oracle restatement, pinned on the CPU against the reference's
+    own get_audio_feature) calling the same model one clip at a time."""
+    from oracle import preproc_oracle as PR
+    from vinet_b200 import AudioTrack, VideoAudioSaliencyModel
+    T, N, fs, fps = 32, 66, 22050, 15.0
+    ref = O.AViNetOracle(T)
+    O.randomize_(ref, 21)
+    m = VideoAudioSaliencyModel(num_clips=T, soundnet_weights=False)
+    m.load_state_dict(ref.state_dict())
+    m = m.cuda().set_precision("fp32").eval()
+    g = torch.Generator().manual_seed(6)
+    frames = torch.randn(N, 3, 224, 384, generator=g)
+    wav = (0.05 * torch.randn(int(fs * N / fps) + 5, generator=g)).numpy()
+    starts, ends = PR.av_excerpt_bounds(wav.shape[0], fs, fps, N)
+    track = AudioTrack(torch.from_numpy(wav), fs, fps, N)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    idx = [0, 3, N - T]
+    feat = track.features(idx, T, dev).cpu().numpy()
+    rev = track.features(idx, T, dev, flip=True).cpu().numpy()
+    for i, j in enumerate(idx):
+        want = PR.av_audio_feature(wav, starts, ends, j, T)
+        assert np.allclose(feat[i, 0, :, 0], want, rtol=1e-6, atol=1e-9) and np.allclose(rev[i, 0, :, 0], want[::-1], rtol=1e-6, atol=1e-9)
+    sal = SlidingWindowSaliency(m, clip_len=T, windows_per_batch=4)
+    got = sal(frames, audio=track).cpu()
+    assert got.shape == (N, 224, 384) and torch.isfinite(got).all()
+    ids = [0, 7, T - 2, T - 1, T + 9, N - 1]            # flipped clips (first L-1 frames), the first forward window, the last frame
+    want = PR.sliding_window_reference_av(lambda c, a: m(c.cuda(), a.cuda()).cpu(), frames, T, wav, starts, ends, frame_ids=ids)
+    assert sorted(want) == ids
+    for i in ids:
+        assert torch.allclose(got[i], want[i], rtol=1e-4, atol=1e-6), (i, (got[i] - want[i]).abs().max())
+    with pytest.raises(AssertionError):
+        sal(frames)                                     # an audio-visual model needs its sound track

@@ -53,3 +53,44 @@ def test_postprocess_restatement_matches_cv2():
         want = PO.to_uint8(b)
         got = PO.process(smap, size)
         assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+
+
+def _reference_get_audio_feature():
+    """The reference's OWN `get_audio_feature` (generate_result_audio_visual.py:86-118), executed from the reference tree (the
+    module itself imports torchaudio / cv2 at the top, so only the function's source lines are compiled; nothing is copied)."""
+    import os
+    import sys
+    from oracle import ref_loader
+    path = os.path.join(ref_loader.REF_DIR, "generate_result_audio_visual.py")
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not present (GPU box)")
+    src = open(path).read().split("\n")
+    a = next(i for i, l in enumerate(src) if l.startswith("def get_audio_feature"))
+    b = next(i for i in range(a + 1, len(src)) if src[i].startswith("def "))
+    ns = {"torch": torch, "np": np, "sys": sys}
+    exec(compile("\n".join(src[a:b]), "generate_result_audio_visual.py[get_audio_feature]", "exec"), ns)
+    return ns["get_audio_feature"]
+
+
+def test_audio_track_bounds_and_feature_restatement_match_the_reference():
+    """AudioTrack's excerpt arithmetic and the oracle's feature restatement against the executed reference function, over odd /
+    even excerpt lengths, the start of the video (clamped at 0) and its last window."""
+    from oracle import preproc_oracle as PR
+    from vinet_b200 import AudioTrack
+    ref_fn = _reference_get_audio_feature()
+
+    class Args:
+        clip_size = 32
+    for fs, fps, n_frames in [(22050, 15, 70), (16000, 25, 64), (22050, 29.97, 90)]:
+        n_wav = int(fs * n_frames / fps) + 7
+        wav = np.random.default_rng(int(fs + n_frames)).standard_normal(n_wav).astype(np.float32)
+        starts, ends = PR.av_excerpt_bounds(n_wav, fs, fps, n_frames)
+        track = AudioTrack(torch.from_numpy(wav), fs, fps, n_frames)
+        assert track.starts == list(starts) and track.ends == list(ends)
+        data = {"v": {"wav": torch.from_numpy(wav).view(1, -1), "starts": starts, "ends": ends}}
+        for idx in [0, 1, 2, 17, n_frames - 33, n_frames - 32]:
+            want = ref_fn("v", data, Args, idx).view(-1).numpy()
+            got = PR.av_audio_feature(wav, starts, ends, idx, 32)
+            assert np.array_equal(got, want), (fs, fps, idx)
+            s, e = track.bounds(idx, 32)
+            assert (s, e) == (starts[idx + 1], min(ends[min(idx + 32, n_frames)] + 1, n_wav)) and np.count_nonzero(want) <= e - s

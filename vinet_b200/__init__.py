@@ -6,7 +6,7 @@ Public surface mirrors the reference (samyak0210/ViNet): ``VideoSaliencyModel`` 
 """
 from .loss import cc, get_loss, kldiv, loss_func, nss, similarity  # noqa: F401
 from .graph import GraphedForward, GraphedTrainStep  # noqa: F401
-from .inference import SlidingWindowSaliency  # noqa: F401
+from .inference import AudioTrack, SlidingWindowSaliency  # noqa: F401
 from .model import VideoSaliencyModel  # noqa: F401
 from .preprocess import FramePreprocessor, audio_window  # noqa: F401
 
@@ -16,4 +16,4 @@ except ImportError:  # pragma: no cover
     pass
 
 __all__ = ["VideoSaliencyModel", "VideoAudioSaliencyModel", "VideoAudioSaliencyFusionModel", "kldiv", "cc", "similarity", "nss", "loss_func",
-           "get_loss", "GraphedTrainStep", "GraphedForward", "SlidingWindowSaliency", "FramePreprocessor", "audio_window"]
+           "get_loss", "GraphedTrainStep", "GraphedForward", "SlidingWindowSaliency", "AudioTrack", "FramePreprocessor", "audio_window"]
