@@ -313,3 +313,21 @@ def test_transformer_dropout_plan():
     g, relu_ref = torch.ones(1000), x - 500                    # (kept alive: the call takes raw addresses)
     sp.call("vinet_dropout_bwd", g.data_ptr(), g.data_ptr(), mask.data_ptr(), relu_ref.data_ptr(), 1000, 0.25, None)
     assert torch.allclose(g, torch.where(mask.bool() & (x > 500), torch.full((), 1 / 0.75), torch.zeros(())), rtol=1e-6, atol=0)
+
+
+def test_only_gradient_gemms_are_order_free():
+    """vinet_bgemm_t.accumulate bit 1 (the library may split K across CTAs and combine with atomics) is set on the products of the
+    backward pass only: every forward product of the transformer block (they all carry a bias term, or are batched over
+    clips x heads) keeps a fixed reduction order, so forward results stay bit-reproducible."""
+    seen = []
+
+    class Logging(Spec):
+        def bgemm(self, d, stream):
+            seen.append((int(d.accumulate), bool(d.bias1) or bool(d.bias2), d.nb1 * d.nb2, int(d.relu)))
+            Spec.bgemm(self, d, stream)
+    S.xf_block("cpu", "fp32", Logging(), layers=1)
+    free = [s for s in seen if s[0] & 2]
+    assert len(free) >= 10 and all(not bias and not relu for _, bias, _, relu in free)
+    first_free = next(i for i, s in enumerate(seen) if s[0] & 2)
+    assert all(s[0] & 2 for s in seen[first_free:]), "once the tape runs, every product is a gradient"
+    assert all((bias or nb > 1) for _, bias, nb, _ in seen[:first_free]), "forward products"

@@ -12,6 +12,7 @@ mode, like ``nn.TransformerEncoderLayer``) uses the library's counter-based gene
 with, torch's Philox stream (parity tests run with p = 0 or in eval mode).
 """
 import math
+import threading
 from types import SimpleNamespace
 
 import torch
@@ -52,16 +53,18 @@ def _ptr(t, off=0):
     return t.data_ptr() + off * t.element_size()
 
 
-_ORDER_FREE = [False]      # set while a backward closure runs: gradient reductions may be split along K (vinet_bgemm_t.accumulate bit 1)
+# set while a backward closure runs: gradient reductions may be split along K (vinet_bgemm_t.accumulate bit 1).  Per thread:
+# nn.DataParallel runs the replicas' forwards and backwards on one thread per device.
+_STATE = threading.local()
 
 
 def _backward_pass(fn):
     def run():
-        _ORDER_FREE[0] = True
+        _STATE.order_free = True
         try:
             fn()
         finally:
-            _ORDER_FREE[0] = False
+            _STATE.order_free = False
     return run
 
 
@@ -74,7 +77,7 @@ def gemm(e, M, N, K, A, sA, B, sB, Cp, sC, nb=(1, 1), alpha=1.0, a_dtype=L.F32, 
     d.A, d.sAm, d.sAk, d.sAb1, d.sAb2, d.a_dtype = A, sA[0], sA[1], sA[2], sA[3], a_dtype
     d.B, d.sBn, d.sBk, d.sBb1, d.sBb2, d.b_dtype = B, sB[0], sB[1], sB[2], sB[3], b_dtype
     d.C, d.sCm, d.sCn, d.sCb1, d.sCb2, d.c_dtype = Cp, sC[0], sC[1], sC[2], sC[3], c_dtype
-    d.M, d.N, d.K, d.nb1, d.nb2, d.alpha, d.relu, d.accumulate = M, N, K, nb[0], nb[1], alpha, relu, int(acc) | (2 if _ORDER_FREE[0] else 0)
+    d.M, d.N, d.K, d.nb1, d.nb2, d.alpha, d.relu, d.accumulate = M, N, K, nb[0], nb[1], alpha, relu, int(acc) | (2 if getattr(_STATE, "order_free", False) else 0)
     if a_xf is not None:
         d.a_scale, d.a_shift, d.a_relu = a_xf
         d.a_xf_on_m = a_xf_on_m
