@@ -22,17 +22,17 @@ from . import lib as L
 
 
 class PositionalEncoding(nn.Module):
-    """The reference's sinusoidal table (model.py:8-26): buffer ``pe`` of shape (max_len, 1, feat); its Dropout is never applied."""
+    """The reference's sinusoidal table (model.py:8-26) as the buffer ``pe`` of shape (max_len, 1, feat): token s, feature 2i / 2i+1
+    = sin / cos(s * 10000^(-2i / feat)).  The module's Dropout exists but is never applied (model.py:24-26)."""
 
     def __init__(self, feat_size, dropout=0.1, max_len=4):
         super().__init__()
         self.dropout = nn.Dropout(p=dropout)
-        pe = torch.zeros(max_len, feat_size)
-        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0, feat_size, 2).float() * (-math.log(10000.0) / feat_size))
-        pe[:, 0::2] = torch.sin(position * div_term)
-        pe[:, 1::2] = torch.cos(position * div_term)
-        self.register_buffer("pe", pe.unsqueeze(0).transpose(0, 1).contiguous())
+        token = torch.arange(max_len, dtype=torch.float32)[:, None]
+        freq = torch.exp(torch.arange(0, feat_size, 2, dtype=torch.float32) * (-math.log(10000.0) / feat_size))
+        table = torch.zeros(max_len, feat_size)
+        table[:, 0::2], table[:, 1::2] = torch.sin(token * freq), torch.cos(token * freq)
+        self.register_buffer("pe", table[:, None, :].contiguous())
 
 
 class Transformer(nn.Module):
