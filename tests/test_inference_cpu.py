@@ -94,3 +94,50 @@ def test_audio_track_bounds_and_feature_restatement_match_the_reference():
             assert np.array_equal(got, want), (fs, fps, idx)
             s, e = track.bounds(idx, 32)
             assert (s, e) == (starts[idx + 1], min(ends[min(idx + 32, n_frames)] + 1, n_wav)) and np.count_nonzero(want) <= e - s
+
+
+def test_audio_visual_driver_pairs_every_window_with_its_excerpt(monkeypatch):
+    """Host logic of SlidingWindowSaliency for the audio-visual models (generate_result_audio_visual.py:177-199) with a stub model
+    that reports which clip and which audio feature it was given: frame i >= L-1 is predicted from frames i-L+1 .. i with the
+    excerpt of window i-L+1; frame j < L-1 from the time-flipped clip j .. j+L-1 with the time-flipped excerpt of window j."""
+    from oracle import preproc_oracle as PR
+    from vinet_b200 import AudioTrack
+    T, N, fs, fps = 8, 21, 8000, 20.0
+    wav = np.arange(1, int(fs * N / fps) + 1, dtype=np.float32)          # sample k holds k+1: an excerpt identifies its position
+    starts, ends = PR.av_excerpt_bounds(wav.shape[0], fs, fps, N)
+
+    def cpu_features(self, start_indices, clip_len, device, flip=False):  # AudioTrack.features without the CUDA kernel
+        f = torch.stack([torch.from_numpy(PR.av_audio_feature(wav, starts, ends, j, clip_len)) for j in start_indices]).view(-1, 1, 70560, 1)
+        return torch.flip(f, [2]) if flip else f
+    monkeypatch.setattr(AudioTrack, "features", cpu_features)
+
+    class Stub(torch.nn.Module):
+        _n_extra = 1
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, x, a):
+            out = torch.zeros(x.shape[0], 2, 4)
+            out[:, 0, 0], out[:, 0, 1] = x[:, 0, 0, 0, 0], x[:, 0, -1, 0, 0]          # first / last frame of the clip as given
+            nz = (a[:, 0, :, 0] != 0)
+            first = nz.float().argmax(1)
+            last = a.shape[2] - 1 - nz.flip(1).float().argmax(1)
+            out[:, 0, 2], out[:, 0, 3] = a[torch.arange(len(a)), 0, first + 1, 0], a[torch.arange(len(a)), 0, last - 1, 0]
+            out[:, 1, 0], out[:, 1, 1] = first.float(), last.float()
+            return out
+    frames = torch.arange(N, dtype=torch.float32).view(N, 1, 1, 1).expand(N, 3, 2, 4).contiguous()
+    sal = SlidingWindowSaliency(Stub().eval(), clip_len=T, windows_per_batch=3, use_graph=False)
+    got = sal(frames, audio=AudioTrack(torch.from_numpy(wav), fs, fps, N))
+    for i in range(N):
+        j, flipped = (i - T + 1, False) if i >= T - 1 else (i, True)
+        f = PR.av_audio_feature(wav, starts, ends, j, T)
+        f = f[::-1] if flipped else f
+        nz = np.nonzero(f)[0]
+        want_clip = (j + T - 1, j) if flipped else (j, j + T - 1)
+        assert (got[i, 0, 0].item(), got[i, 0, 1].item()) == want_clip, i
+        assert (got[i, 1, 0].item(), got[i, 1, 1].item()) == (nz[0], nz[-1]), i
+        assert got[i, 0, 2].item() == f[nz[0] + 1] and got[i, 0, 3].item() == f[nz[-1] - 1], i
+    with pytest.raises(AssertionError):
+        sal(frames)
