@@ -1,8 +1,9 @@
 """vinet_b200 — B200-native (sm_100a) implementation of the ViNet / AViNet video-saliency hot path.
 
 Public surface mirrors the reference (samyak0210/ViNet): ``VideoSaliencyModel`` (model.py:72),
-``VideoAudioSaliencyModel`` (model.py:191), ``kldiv/cc/similarity/nss`` (loss.py) and
-``loss_func/get_loss`` (utils.py).  Everything computes through ``libvinet_b200.so`` (include/vinet_b200.h).
+``VideoAudioSaliencyModel`` (model.py:191, incl. ``use_transformer=True``), ``VideoAudioSaliencyFusionModel`` (model.py:116),
+``kldiv/cc/similarity/nss`` (loss.py) and ``loss_func/get_loss`` (utils.py); plus the drivers around the path:
+``GraphedTrainStep`` / ``GraphedForward``, ``SlidingWindowSaliency`` (+ ``AudioTrack``), ``FramePreprocessor`` / ``audio_window``.  Everything computes through ``libvinet_b200.so`` (include/vinet_b200.h).
 """
 from .loss import cc, get_loss, kldiv, loss_func, nss, similarity  # noqa: F401
 from .graph import GraphedForward, GraphedTrainStep  # noqa: F401
